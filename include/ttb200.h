@@ -1,0 +1,195 @@
+/*
+ * ttb200 -- B200-native phylogenetic tree-likelihood engine: C ABI.
+ *
+ * This is the drop-in boundary for the tree-likelihood hot path of
+ * 4ment/torchtree.  The reference has no native code and no FFI,
+ * so there is no existing binding to mirror symbol-for-symbol; each entry point
+ * below names the reference function(s) whose work it takes over
+ * (paths relative to the reference checkout):
+ *
+ *   ttb2_create            TreeLikelihoodModel.__init__
+ *                          torchtree/evolution/tree_likelihood.py:283-311
+ *                          (tip partials / tip states + pattern weights are
+ *                          captured once; SitePattern.compute_tips_* results)
+ *   ttb2_set_postorder     TreeModel.postorder / update_traversals
+ *                          torchtree/evolution/tree_model.py:187-195
+ *   ttb2_loglik_mats       calculate_treelikelihood_discrete(_rescaled) and the
+ *                          tip-state variants, tree_likelihood.py:40-75,
+ *                          :78-131, :186-221, :224-278 (matrices supplied by the
+ *                          caller, e.g. from SubstitutionModel.p_t)
+ *   ttb2_loglik_eigen      TreeLikelihoodModel._call, tree_likelihood.py:313-356:
+ *                          bls x site rates -> SymmetricSubstitutionModel.p_t
+ *                          (substitution_model/abstract.py:57-76) -> peeling
+ *   ttb2_grad_mats /       the autograd backward of the above,
+ *   ttb2_grad_eigen        replaced by an analytic pre-order pass
+ *   ttb2_site_loglik       per-pattern log-likelihoods (the tensor the
+ *                          reference reduces at tree_likelihood.py:71-75)
+ *
+ * Conventions
+ *   - all floating point is IEEE fp64; integers are int32 unless stated;
+ *   - every function returns 0 on success, a negative TTB2_E_* code otherwise;
+ *     ttb2_last_error() returns a message for the calling thread's last error;
+ *   - `where` says whether the *data* pointers of that call are host
+ *     (TTB2_HOST: pageable or pinned) or device (TTB2_DEVICE) pointers.  Host
+ *     outputs are complete when the call returns; device outputs are ordered
+ *     on the engine's stream (ttb2_set_stream / ttb2_synchronize);
+ *   - the engine never frees caller memory; the caller never frees engine
+ *     memory; one engine is used from one host thread at a time;
+ *   - shapes use T tips, I=T-1 internal nodes, B=2T-2 branches (branch b is the
+ *     edge above node b), N site patterns, K rate categories, S states,
+ *     D draws (batch of parameter samples);
+ *   - an input that is shared by all draws is passed with its `*_draws`
+ *     argument equal to 1; its gradient is then the sum over draws.
+ *
+ * There is no CPU fallback: every entry point requires a CUDA device.
+ */
+#ifndef TTB200_H
+#define TTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTB2_VERSION 100
+
+#define TTB2_HOST 0
+#define TTB2_DEVICE 1
+
+#define TTB2_OK 0
+#define TTB2_E_INVALID (-1)   /* bad argument / unsupported configuration */
+#define TTB2_E_CUDA (-2)      /* CUDA runtime error (see ttb2_last_error) */
+#define TTB2_E_STATE (-3)     /* call order violated (e.g. grad before loglik) */
+#define TTB2_E_NOMEM (-4)
+
+typedef struct ttb2_engine ttb2_engine;
+
+typedef struct ttb2_config {
+  int32_t tip_count;      /* T  >= 2 */
+  int32_t pattern_count;  /* N  >= 1 (the patterns owned by this engine/shard) */
+  int32_t state_count;    /* S  >= 2 */
+  int32_t category_count; /* K  >= 1 */
+  int32_t max_draws;      /* D_max >= 1 */
+  int32_t code_count;     /* C: rows of code_partials, S+1 <= C <= 255 */
+  int32_t device;         /* CUDA device ordinal */
+  int32_t flags;          /* TTB2_FLAG_* */
+} ttb2_config;
+
+#define TTB2_FLAG_NONE 0
+/* keep per-(node,pattern) data for the gradient pass resident from create()
+ * (otherwise allocated at the first ttb2_grad_* call) */
+#define TTB2_FLAG_PREALLOC_GRAD 1
+/* force the generic-S kernels even when a specialised path exists (testing) */
+#define TTB2_FLAG_FORCE_GENERIC 2
+
+/*
+ * tip_codes      uint8 [T][N]: symbol code of tip t at pattern i
+ * code_partials  double [C][S]: tip conditional-likelihood vector of each code.
+ *                Rows 0..S-1 must be the unit vectors (unambiguous states) and
+ *                row S all ones (gap / unknown: datatype.py:105-111); further
+ *                rows are ambiguity masks (use_ambiguities).
+ * weights        double [N] pattern multiplicities (site_pattern.py:89-95)
+ * postorder      int32 [T-1][3] (node, left, right) triples in post-order;
+ *                tips are 0..T-1, the last triple is the root
+ *                (tree_model.py:37-53, :187-195)
+ * These are host pointers; the data is copied to the device.
+ */
+int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
+                const double* code_partials, const double* weights,
+                const int32_t* postorder, ttb2_engine** out);
+
+/* New topology (same tips): rebuilds the level schedule. Host pointer. */
+int ttb2_set_postorder(ttb2_engine* engine, const int32_t* postorder);
+
+void ttb2_destroy(ttb2_engine* engine);
+
+/* Use `cuda_stream` (a cudaStream_t) for all subsequent work; NULL = the
+ * legacy default stream. */
+int ttb2_set_stream(ttb2_engine* engine, void* cuda_stream);
+int ttb2_synchronize(ttb2_engine* engine);
+
+/*
+ * Log-likelihood with caller-supplied transition matrices.
+ *   mats   [D][B][K][S][S]  rows = parent state (applied as P @ partial)
+ *   freqs  [freq_draws][S]   props [prop_draws][K]
+ *   lnl    [D] (output)
+ */
+int ttb2_loglik_mats(ttb2_engine* engine, int32_t draws, const double* mats,
+                     const double* freqs, int32_t freq_draws,
+                     const double* props, int32_t prop_draws, double* lnl,
+                     int32_t where);
+
+/*
+ * Gradient of sum_d grad_lnl[d] * lnL[d] for the latest ttb2_loglik_mats call.
+ *   grad_lnl [D] or NULL (= ones)
+ *   d_mats   [D][B][K][S][S]; d_freqs [freq_draws][S]; d_props [prop_draws][K]
+ *   any output pointer may be NULL (skipped).
+ */
+int ttb2_grad_mats(ttb2_engine* engine, const double* grad_lnl, double* d_mats,
+                   double* d_freqs, double* d_props, int32_t where);
+
+/*
+ * Log-likelihood from an eigen-decomposed generator, P = V exp(L r t) V^-1
+ * evaluated on the device for every branch x category x draw.
+ *   branch_lengths [D][B]   (already multiplied by clock rates; unrooted trees
+ *                            carry the zero pad for node 2T-3)
+ *   site_rates [rate_draws][K], props [prop_draws][K]
+ *   evec [eig_draws][S][S] = V, ivec [eig_draws][S][S] = V^-1,
+ *   eval [eig_draws][S]; freqs [freq_draws][S]
+ */
+int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws,
+                      const double* branch_lengths, const double* site_rates,
+                      int32_t rate_draws, const double* props,
+                      int32_t prop_draws, const double* evec,
+                      const double* ivec, const double* eval,
+                      int32_t eig_draws, const double* freqs,
+                      int32_t freq_draws, double* lnl, int32_t where);
+
+/*
+ * Gradient for the latest ttb2_loglik_eigen call.
+ *   d_branch_lengths [D][B]; d_site_rates [rate_draws][K];
+ *   d_props [prop_draws][K]; d_freqs [freq_draws][S] (root term only);
+ *   d_q [eig_draws][S][S] = d lnL / d Q for the generator Q = V L V^-1 with all
+ *   S*S entries independent (chain it through the model's Q builder).
+ *   Finite at repeated eigenvalues (divided differences), unlike the
+ *   reference's eigh backward.
+ */
+int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl,
+                    double* d_branch_lengths, double* d_site_rates,
+                    double* d_props, double* d_q, double* d_freqs,
+                    int32_t where);
+
+/* Per-pattern log-likelihoods of the latest loglik call: out [D][N]. */
+int ttb2_site_loglik(ttb2_engine* engine, double* out, int32_t where);
+
+/* Transition matrices used by the latest loglik call: out [D][B][K][S][S]. */
+int ttb2_get_mats(ttb2_engine* engine, double* out, int32_t where);
+
+/*
+ * Optional phase timing with CUDA events on the engine's stream (for bench.py's
+ * live roofline figure).  When enabled, every loglik/grad call records events
+ * around its kernel groups; ttb2_phase_ms synchronises and returns the
+ * durations of the latest call of each kind, in milliseconds:
+ *   out[0] transition matrices   out[1] post-order level kernels
+ *   out[2] root + lnL reduction  out[3] pre-order level kernels (incl. root)
+ *   out[4] gradient contraction / output assembly
+ * and the number of level-kernel launches in out[5] (post-order) and out[6]
+ * (pre-order).
+ */
+#define TTB2_PHASE_COUNT 7
+int ttb2_enable_timing(ttb2_engine* engine, int32_t on);
+int ttb2_phase_ms(ttb2_engine* engine, double* out /*[TTB2_PHASE_COUNT]*/);
+
+/* Kernels launched by this engine since creation (bench `gpu_launches`). */
+int64_t ttb2_launch_count(const ttb2_engine* engine);
+/* Device bytes currently held by this engine. */
+int64_t ttb2_device_bytes(const ttb2_engine* engine);
+
+const char* ttb2_last_error(void);
+int ttb2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTB200_H */

@@ -1,0 +1,113 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/ttb200.h declares, validates arguments, and refuses to compute
+without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, "include", "ttb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ttb2_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from torchtree_b200 import _lib, build
+
+    path = build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.ttb2_version() == 100
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+
+    from torchtree_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_create_validates_arguments_before_touching_the_gpu():
+    from torchtree_b200 import Engine, EngineError
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(6, 10, 4, 2, seed=1)
+    with pytest.raises(EngineError, match="postorder"):
+        Engine(prob.tip_states, prob.weights, prob.postorder[:-1], 4, 2)
+    bad_codes = np.eye(4)[:3]
+    with pytest.raises(EngineError):
+        Engine(prob.tip_states, prob.weights, prob.postorder, 4, 2, code_partials=bad_codes)
+    table = np.concatenate([np.eye(4), np.ones((1, 4))])[::-1].copy()  # wrong row order
+    with pytest.raises(EngineError, match="unit vectors"):
+        Engine(prob.tip_states, prob.weights, prob.postorder, 4, 2, code_partials=table)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    from torchtree_b200 import Engine, EngineError
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(6, 10, 4, 2, seed=1)
+    with pytest.raises(EngineError, match="no CPU fallback"):
+        Engine(prob.tip_states, prob.weights, prob.postorder, 4, 2)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "torchtree_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_codes_from_tip_partials_round_trip():
+    from torchtree_b200 import codes_from_tip_partials
+
+    S = 4
+    cols = {"A": [1, 0, 0, 0], "C": [0, 1, 0, 0], "G": [0, 0, 1, 0], "T": [0, 0, 0, 1],
+            "-": [1, 1, 1, 1], "R": [1, 0, 1, 0], "Y": [0, 1, 0, 1]}
+    seqs = ["ACGT-RYA", "TTGCA-RR"]
+    partials = [np.array([cols[c] for c in s], dtype=np.float64).T for s in seqs]
+    codes, table = codes_from_tip_partials(partials, S)
+    assert codes.dtype == np.uint8 and codes.shape == (2, 8)
+    assert np.array_equal(table[:5], np.concatenate([np.eye(4), np.ones((1, 4))]))
+    for t, s in enumerate(seqs):
+        for i, c in enumerate(s):
+            assert np.array_equal(table[codes[t, i]], cols[c])
+    assert table.shape[0] == 7
+
+
+def test_synthetic_postorder_convention():
+    from torchtree_b200.synthetic import make_problem
+
+    for topo in ("random", "caterpillar", "balanced"):
+        prob = make_problem(37, 5, topology=topo, seed=3)
+        post = prob.postorder
+        T = 37
+        assert post.shape == (T - 1, 3)
+        assert list(post[:, 0]) == list(range(T, 2 * T - 1))  # post-order numbering
+        seen = set(range(T))
+        for node, l, r in post:
+            assert l in seen and r in seen
+            seen.add(node)
+        assert post[-1, 0] == 2 * T - 2
+        assert 2 * T - 3 in post[-1, 1:]  # node 2T-3 is a child of the root
+        assert prob.branch_lengths[0, -1] == 0.0

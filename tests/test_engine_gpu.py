@@ -1,0 +1,189 @@
+"""Parity of the CUDA engine (through the C ABI) against the golden fixtures
+generated from the real reference and against the pinned CPU oracle.
+
+Tolerances (BASELINE.json north_star): log-likelihood relative 1e-10, gradients
+relative 1e-8 (with an absolute floor for ~0 entries), fp64.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (
+    GRAD_RTOL,
+    assert_grad_close,
+    assert_lnl_close,
+    golden_names,
+    load_golden,
+)
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(prob, max_draws=None, flags=0):
+    from torchtree_b200 import Engine
+
+    return Engine(
+        prob.tip_states, prob.weights, prob.postorder, prob.state_count, prob.category_count,
+        code_partials=prob.code_partials, max_draws=max_draws or prob.draws, flags=flags)
+
+
+def _eig(prob):
+    from torchtree_b200 import reversible_eigensystem
+
+    q = torch.tensor(prob.q_matrix)
+    f = torch.tensor(prob.freqs)
+    return reversible_eigensystem(q, f.expand(q.shape[0], -1) if f.shape[0] != q.shape[0] else f)
+
+
+def _reduce(ref, like_rows):
+    ref = np.asarray(ref)
+    if ref.shape[0] != like_rows:
+        ref = ref.sum(0, keepdims=True)
+    return ref
+
+
+@pytest.mark.parametrize("flags", [0, 2], ids=["spec", "generic"])
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_mats_mode(name, flags):
+    """ttb2_loglik_mats / ttb2_grad_mats with the reference's own matrices."""
+    prob, rec = load_golden(name)
+    eng = _engine(prob, flags=flags)
+    lnl = eng.loglik_mats(rec["mats"], prob.freqs, prob.site_props)
+    assert_lnl_close(lnl.numpy(), rec["lnL"], what=name)
+    if "d_mats" not in rec:
+        return
+    d_mats, d_freqs, d_props = eng.grad_mats()
+    assert_grad_close(d_mats.numpy(), rec["d_mats"], what=name + " d_mats")
+    assert_grad_close(d_freqs.numpy(), _reduce(rec["d_freqs_root"], d_freqs.shape[0]),
+                      what=name + " d_freqs")
+    assert_grad_close(d_props.numpy(), _reduce(rec["d_site_props"], d_props.shape[0]),
+                      what=name + " d_props")
+    # site log-likelihoods reproduce the total
+    site = eng.site_loglik().numpy()
+    assert_lnl_close((site * prob.weights).sum(-1), rec["lnL"], what=name + " sites")
+    eng.close()
+
+
+@pytest.mark.parametrize("flags", [0, 2], ids=["spec", "generic"])
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_eigen_mode(name, flags):
+    """ttb2_loglik_eigen / ttb2_grad_eigen: P(t) on the device, gradients w.r.t.
+    branch lengths, site rates, proportions, root frequencies and Q."""
+    from oracle import treelik as orc
+
+    prob, rec = load_golden(name)
+    eng = _engine(prob, flags=flags)
+    evec, ivec, evals = _eig(prob)
+    lnl = eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props,
+                           evec, ivec, evals, prob.freqs)
+    assert_lnl_close(lnl.numpy(), rec["lnL"], what=name)
+    mats = eng.get_mats().numpy()
+    np.testing.assert_allclose(mats, rec["mats"], rtol=1e-9, atol=1e-14)
+    if "d_mats" not in rec:
+        return
+    g = eng.grad_eigen()
+    assert_grad_close(g["branch_lengths"].numpy(), rec["d_branch_lengths"], what=name + " d_bl")
+    assert_grad_close(g["site_rates"].numpy(), _reduce(rec["d_site_rates"], g["site_rates"].shape[0]),
+                      what=name + " d_rates")
+    assert_grad_close(g["props"].numpy(), _reduce(rec["d_site_props"], g["props"].shape[0]),
+                      what=name + " d_props")
+    assert_grad_close(g["freqs"].numpy(), _reduce(rec["d_freqs_root"], g["freqs"].shape[0]),
+                      what=name + " d_freqs_root")
+    # d lnL / d Q: the pinned oracle differentiates expm(Q t) through autograd
+    want = orc.evaluate(prob, want_grad=True, through_q=True)["q_matrix"]
+    if name != "fluA_gtr_w4_init":  # degenerate spectrum: eigh backward is NaN there (F12)
+        assert_grad_close(g["q"].numpy(), want, rtol=1e-7, what=name + " d_q")
+    else:
+        assert np.isfinite(g["q"].numpy()).all()
+    eng.close()
+
+
+def _gtr_chain(rec, eng_grads, prob):
+    """Chain engine gradients to the reference's GTR parameters through torch."""
+    from oracle import treelik as orc
+
+    rates6 = torch.tensor(rec["param_gtr_rates"], requires_grad=True)
+    freqs = torch.tensor(rec["param_gtr_freqs"], requires_grad=True)
+    q = orc.normalise_q(orc.gtr_q_unnorm(rates6, freqs), freqs)
+    q = q.reshape(-1, 4, 4)
+    f2 = freqs.reshape(-1, 4)
+    total = (q * eng_grads["q"]).sum() + (f2 * eng_grads["freqs"]).sum()
+    total.backward()
+    return rates6.grad.numpy(), freqs.grad.numpy()
+
+
+@pytest.mark.parametrize("name", ["fluA_gtr_w4_generic", "fluA_gtr_w4_ambig", "syn40_gtr_w4",
+                                  "syn400_gtr_w4_caterpillar", "syn17_gtr_w3",
+                                  "fluA_gtr_w4_batch3"])
+def test_gtr_parameter_gradients_match_reference(name):
+    """End of the chain: d lnL / d (GTR rates, GTR freqs, Weibull shape, branch
+    lengths) as torchtree's own `like().backward()` produced them."""
+    from oracle import treelik as orc
+
+    prob, rec = load_golden(name)
+    eng = _engine(prob)
+    evec, ivec, evals = _eig(prob)
+    lnl = eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props,
+                           evec, ivec, evals, prob.freqs)
+    assert_lnl_close(lnl.numpy(), rec["model_lnL"], what=name)
+    g = eng.grad_eigen()
+    d_rates6, d_freqs = _gtr_chain(rec, g, prob)
+    assert_grad_close(d_rates6, rec["dparam_gtr_rates"], rtol=1e-7, what=name + " d_gtr_rates")
+    assert_grad_close(d_freqs, rec["dparam_gtr_freqs"], rtol=1e-7, what=name + " d_gtr_freqs")
+    # unrooted branch lengths: the padded last branch is dropped
+    assert_grad_close(g["branch_lengths"].numpy()[..., :-1].reshape(rec["dparam_blens"].shape),
+                      rec["dparam_blens"], what=name + " d_blens")
+    # Weibull shape through the site-rate gradient
+    K = prob.category_count
+    shape = torch.tensor(rec["param_shape"], requires_grad=True)
+    rates, _ = orc.weibull_site_model(shape, K)
+    (rates.reshape(-1, K) * g["site_rates"]).sum().backward()
+    assert_grad_close(shape.grad.numpy(), rec["dparam_shape"], what=name + " d_shape")
+    eng.close()
+
+
+def test_autograd_function_end_to_end():
+    """log_likelihood_eigen as a differentiable torch op on CPU tensors."""
+    from oracle import treelik as orc
+    from torchtree_b200 import log_likelihood_eigen
+
+    prob, rec = load_golden("fluA_gtr_w4_generic")
+    eng = _engine(prob)
+    blens = torch.tensor(rec["param_blens"], requires_grad=True)
+    rates6 = torch.tensor(rec["param_gtr_rates"], requires_grad=True)
+    freqs = torch.tensor(rec["param_gtr_freqs"], requires_grad=True)
+    shape = torch.tensor(rec["param_shape"], requires_grad=True)
+    site_rates, props = orc.weibull_site_model(shape, 4)
+    q = orc.normalise_q(orc.gtr_q_unnorm(rates6, freqs), freqs)
+    bls = torch.cat((blens, torch.zeros(1, dtype=torch.float64)))
+    lnl = log_likelihood_eigen(eng, bls, site_rates, props, q, freqs)
+    assert lnl.shape == (1,)
+    assert_lnl_close(lnl.detach().numpy(), rec["model_lnL"])
+    # a second forward on the same engine before backward: stamp forces a recompute
+    with torch.no_grad():
+        log_likelihood_eigen(eng, bls * 1.1, site_rates, props, q, freqs)
+    lnl.sum().backward()
+    assert_grad_close(blens.grad.numpy(), rec["dparam_blens"], what="d_blens")
+    assert_grad_close(rates6.grad.numpy(), rec["dparam_gtr_rates"], rtol=1e-7, what="d_rates6")
+    assert_grad_close(freqs.grad.numpy(), rec["dparam_gtr_freqs"], rtol=1e-7, what="d_freqs")
+    assert_grad_close(shape.grad.numpy(), rec["dparam_shape"], what="d_shape")
+    eng.close()
+
+
+def test_device_resident_inputs_match_host_inputs():
+    prob, rec = load_golden("syn40_gtr_w4")
+    eng = _engine(prob)
+    evec, ivec, evals = _eig(prob)
+    args = [torch.tensor(a) if not isinstance(a, torch.Tensor) else a
+            for a in (prob.branch_lengths, prob.site_rates, prob.site_props, evec, ivec, evals,
+                      prob.freqs)]
+    host = eng.loglik_eigen(*args).clone()
+    gh = {k: v.clone() for k, v in eng.grad_eigen().items()}
+    dev_args = [a.cuda() for a in args]
+    dev = eng.loglik_eigen(*dev_args)
+    assert dev.is_cuda
+    gd = eng.grad_eigen()
+    assert torch.equal(dev.cpu(), host)
+    for k in gh:
+        assert torch.equal(gd[k].cpu(), gh[k]), k
+    eng.close()

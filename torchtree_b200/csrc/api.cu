@@ -1,0 +1,636 @@
+// C ABI of the ttb200 engine (see include/ttb200.h): engine life-cycle, level
+// schedule, input/output staging and the per-evaluation launch sequences.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "engine.cuh"
+
+namespace ttb2 {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+template <typename T>
+int dev_alloc(Engine& e, T** ptr, size_t count) {
+  *ptr = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t err = cudaMalloc((void**)ptr, count * sizeof(T));
+  if (err != cudaSuccess) {
+    set_error(std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) +
+              " bytes failed: " + cudaGetErrorString(err));
+    return TTB2_E_NOMEM;
+  }
+  e.deviceBytes += (int64_t)(count * sizeof(T));
+  return TTB2_OK;
+}
+
+template <typename T>
+void dev_free(T*& ptr) {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+}
+
+int build_schedule(Engine& e, const int32_t* post) {
+  const Dims& m = e.dm;
+  std::vector<int> level(2 * m.T - 1, -1);
+  for (int t = 0; t < m.T; ++t) level[t] = 0;
+  std::vector<NodeOp> opsv(m.I);
+  std::vector<char> isChild(2 * m.T - 1, 0);
+  for (int j = 0; j < m.I; ++j) {
+    const int node = post[3 * j], l = post[3 * j + 1], r = post[3 * j + 2];
+    if (node < m.T || node > 2 * m.T - 2 || l < 0 || r < 0 || l > 2 * m.T - 2 ||
+        r > 2 * m.T - 2 || l == r) {
+      set_error("postorder: node index out of range at triple " + std::to_string(j));
+      return TTB2_E_INVALID;
+    }
+    if (level[node] != -1) {
+      set_error("postorder: node " + std::to_string(node) + " appears twice");
+      return TTB2_E_INVALID;
+    }
+    if (level[l] < 0 || level[r] < 0) {
+      set_error("postorder: child visited after its parent at triple " + std::to_string(j));
+      return TTB2_E_INVALID;
+    }
+    if (isChild[l] || isChild[r]) {
+      set_error("postorder: a node has two parents at triple " + std::to_string(j));
+      return TTB2_E_INVALID;
+    }
+    isChild[l] = isChild[r] = 1;
+    level[node] = 1 + std::max(level[l], level[r]);
+    opsv[j] = NodeOp{node, l, r, level[node]};
+  }
+  // the last triple must be the root: the only node that is nobody's child
+  for (int n = 0; n < 2 * m.T - 1; ++n) {
+    const bool isRoot = (n == post[3 * (m.I - 1)]);
+    if (!isChild[n] && !isRoot) {
+      set_error("postorder: node " + std::to_string(n) + " is not connected to the root");
+      return TTB2_E_INVALID;
+    }
+  }
+  const NodeOp rootOp = opsv.back();
+  std::stable_sort(opsv.begin(), opsv.end(),
+                   [](const NodeOp& a, const NodeOp& b) { return a.level < b.level; });
+  if (opsv.back().node != rootOp.node) {
+    set_error("postorder: last triple is not the root");
+    return TTB2_E_INVALID;
+  }
+  e.hostOps = opsv;
+  e.levelOff.clear();
+  int cur = 0;
+  for (int j = 0; j < m.I; ++j) {
+    while (cur < opsv[j].level) {
+      e.levelOff.push_back(j);
+      ++cur;
+    }
+  }
+  e.levelOff.push_back(m.I);
+  // levelOff[l-1]..levelOff[l] = ops of level l; drop the leading dummy for level 0
+  // (cur started at 0, the first push is for level 1)
+  return TTB2_OK;
+}
+
+int copy_in(Engine& e, void* dst, const void* src, size_t bytes, int where) {
+  if (bytes == 0) return TTB2_OK;
+  TTB2_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes,
+                                  where == TTB2_HOST ? cudaMemcpyHostToDevice
+                                                     : cudaMemcpyDeviceToDevice,
+                                  e.stream));
+  return TTB2_OK;
+}
+
+int copy_out(Engine& e, void* dst, const void* src, size_t bytes, int where) {
+  if (bytes == 0 || dst == nullptr) return TTB2_OK;
+  TTB2_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes,
+                                  where == TTB2_HOST ? cudaMemcpyDeviceToHost
+                                                     : cudaMemcpyDeviceToDevice,
+                                  e.stream));
+  return TTB2_OK;
+}
+
+int finish(Engine& e, int where) {
+  if (where == TTB2_HOST) TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  return TTB2_OK;
+}
+
+bool bad_draws(int d, int draws) { return !(d == 1 || d == draws); }
+
+int ensure_grad_buffers(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  int rc;
+  if (!e.pre) {
+    const size_t n = (size_t)e.cfg.max_draws * m.I * m.K * m.Npad * m.S;
+    if ((rc = dev_alloc(e, &e.pre, n))) return rc;
+  }
+  const size_t matN = (size_t)e.cfg.max_draws * m.B * m.K * m.S * m.S;
+  if (!e.dmat && (rc = dev_alloc(e, &e.dmat, matN))) return rc;
+  if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)e.cfg.max_draws * (m.K + m.S))))
+    return rc;
+  const size_t need = e.spec4 ? s4_gpart_doubles(e, draws) : gen_gpart_doubles(e, draws);
+  if (need > e.gpartCap) {
+    if (e.gpart) {
+      e.deviceBytes -= (int64_t)(e.gpartCap * sizeof(double));
+      dev_free(e.gpart);
+    }
+    if ((rc = dev_alloc(e, &e.gpart, need))) return rc;
+    e.gpartCap = need;
+  }
+  return TTB2_OK;
+}
+
+int ensure_eigen_grad_buffers(Engine& e) {
+  const Dims& m = e.dm;
+  int rc;
+  const size_t matN = (size_t)e.cfg.max_draws * m.B * m.K * m.S * m.S;
+  if (!e.hpart && (rc = dev_alloc(e, &e.hpart, matN))) return rc;
+  if (!e.gscal && (rc = dev_alloc(e, &e.gscal, (size_t)e.cfg.max_draws * m.B * m.K))) return rc;
+  return TTB2_OK;
+}
+
+int run_forward(Engine& e, int draws, double* lnl, int where) {
+  int rc;
+  mark(e, 1);
+  const int64_t before = e.launches;
+  if (e.spec4) {
+    if ((rc = s4_forward(e, draws))) return rc;
+    e.fwdLevelLaunches = (int)(e.launches - before);
+    mark(e, 2);
+    if ((rc = s4_root(e, draws))) return rc;
+  } else {
+    if ((rc = gen_forward(e, draws))) return rc;
+    e.fwdLevelLaunches = (int)(e.launches - before);
+    mark(e, 2);
+    if ((rc = gen_root(e, draws))) return rc;
+  }
+  mark(e, 3);
+  e.draws = draws;
+  e.preValid = false;
+  if ((rc = copy_out(e, lnl, e.lnl, (size_t)draws * sizeof(double), where))) return rc;
+  return finish(e, where);
+}
+
+int run_backward(Engine& e, const double* grad_lnl, int where) {
+  int rc;
+  const int draws = e.draws;
+  if ((rc = ensure_grad_buffers(e, draws))) return rc;
+  if (grad_lnl) {
+    if ((rc = copy_in(e, e.gradLnl, grad_lnl, (size_t)draws * sizeof(double), where))) return rc;
+  } else {
+    TTB2_CUDA_CHECK(cudaMemcpyAsync(e.gradLnl, e.ones, draws * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, e.stream));
+  }
+  mark(e, 4);
+  if (!e.preValid) {
+    const int64_t before = e.launches;
+    rc = e.spec4 ? s4_backward(e, draws) : gen_backward(e, draws);
+    if (rc) return rc;
+    e.bwdLevelLaunches = (int)(e.launches - before) - 3;  // minus root, root reduce, gpart reduce
+    e.preValid = true;
+  }
+  mark(e, 5);
+  return TTB2_OK;
+}
+
+}  // namespace
+}  // namespace ttb2
+
+using namespace ttb2;
+
+extern "C" {
+
+int ttb2_version(void) { return TTB2_VERSION; }
+
+const char* ttb2_last_error(void) { return g_last_error.c_str(); }
+
+int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
+                const double* code_partials, const double* weights, const int32_t* postorder,
+                ttb2_engine** out) {
+  if (!config || !tip_codes || !code_partials || !weights || !postorder || !out) {
+    set_error("ttb2_create: null argument");
+    return TTB2_E_INVALID;
+  }
+  *out = nullptr;
+  const ttb2_config& c = *config;
+  if (c.tip_count < 2 || c.pattern_count < 1 || c.state_count < 2 || c.category_count < 1 ||
+      c.max_draws < 1 || c.code_count < c.state_count + 1 || c.code_count > 255) {
+    set_error("ttb2_create: invalid configuration (need T>=2, N>=1, S>=2, K>=1, D>=1, "
+              "S+1<=C<=255)");
+    return TTB2_E_INVALID;
+  }
+  if (c.state_count > 64) {
+    set_error("ttb2_create: state_count > 64 is not supported");
+    return TTB2_E_INVALID;
+  }
+  // code table contract: unit vectors then an all-ones row
+  for (int r = 0; r <= c.state_count; ++r)
+    for (int s = 0; s < c.state_count; ++s) {
+      const double want = (r == c.state_count || r == s) ? 1.0 : 0.0;
+      if (code_partials[(size_t)r * c.state_count + s] != want) {
+        set_error("ttb2_create: code_partials rows 0..S-1 must be unit vectors and row S all ones");
+        return TTB2_E_INVALID;
+      }
+    }
+  const size_t TN = (size_t)c.tip_count * c.pattern_count;
+  for (size_t j = 0; j < TN; ++j)
+    if (tip_codes[j] >= c.code_count) {
+      set_error("ttb2_create: tip code out of range of code_partials");
+      return TTB2_E_INVALID;
+    }
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    set_error(std::string("ttb2_create: no CUDA device available (") +
+              cudaGetErrorString(err) + "); this engine has no CPU fallback");
+    return TTB2_E_CUDA;
+  }
+  if (c.device < 0 || c.device >= ndev) {
+    set_error("ttb2_create: device ordinal out of range");
+    return TTB2_E_INVALID;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(c.device));
+
+  Engine* ep = new (std::nothrow) Engine();
+  if (!ep) {
+    set_error("out of host memory");
+    return TTB2_E_NOMEM;
+  }
+  Engine& e = *ep;
+  e.cfg = c;
+  e.device = c.device;
+  Dims& m = e.dm;
+  m.T = c.tip_count;
+  m.I = m.T - 1;
+  m.B = 2 * m.T - 2;
+  m.N = c.pattern_count;
+  m.Npad = (m.N + 31) / 32 * 32;
+  m.S = c.state_count;
+  m.K = c.category_count;
+  m.C = c.code_count;
+  e.spec4 = (m.S == 4) && !(c.flags & TTB2_FLAG_FORCE_GENERIC);
+
+  int rc = build_schedule(e, postorder);
+  if (rc) {
+    delete ep;
+    return rc;
+  }
+
+#define TRY(x)            \
+  do {                    \
+    rc = (x);             \
+    if (rc) {             \
+      ttb2_destroy(reinterpret_cast<ttb2_engine*>(ep)); \
+      return rc;          \
+    }                     \
+  } while (0)
+#define TRY_CUDA(x)                                                     \
+  do {                                                                  \
+    cudaError_t e__ = (x);                                              \
+    if (e__ != cudaSuccess) {                                           \
+      set_error(std::string(#x) + ": " + cudaGetErrorString(e__));      \
+      ttb2_destroy(reinterpret_cast<ttb2_engine*>(ep));                 \
+      return TTB2_E_CUDA;                                               \
+    }                                                                   \
+  } while (0)
+
+  const int D = c.max_draws;
+  TRY(dev_alloc(e, &e.tips, (size_t)m.T * m.Npad));
+  TRY(dev_alloc(e, &e.weights, (size_t)m.Npad));
+  TRY(dev_alloc(e, &e.codeP, (size_t)m.C * m.S));
+  TRY(dev_alloc(e, &e.ops, (size_t)m.I));
+  TRY(dev_alloc(e, &e.partials, (size_t)D * m.I * m.K * m.Npad * m.S));
+  TRY(dev_alloc(e, &e.expo, (size_t)D * m.I * m.Npad));
+  TRY(dev_alloc(e, &e.mats, (size_t)D * m.B * m.K * m.S * m.S));
+  TRY(dev_alloc(e, &e.siteLnl, (size_t)D * m.Npad));
+  const int nblocks = (m.Npad + 127) / 128;
+  e.redPartCap = (size_t)D * nblocks * (m.K + m.S);
+  TRY(dev_alloc(e, &e.redPart, e.redPartCap));
+  TRY(dev_alloc(e, &e.lnl, (size_t)D));
+  TRY(dev_alloc(e, &e.freqs, (size_t)D * m.S));
+  TRY(dev_alloc(e, &e.props, (size_t)D * m.K));
+  TRY(dev_alloc(e, &e.bl, (size_t)D * m.B));
+  TRY(dev_alloc(e, &e.rates, (size_t)D * m.K));
+  TRY(dev_alloc(e, &e.evec, (size_t)D * m.S * m.S));
+  TRY(dev_alloc(e, &e.ivec, (size_t)D * m.S * m.S));
+  TRY(dev_alloc(e, &e.eval, (size_t)D * m.S));
+  TRY(dev_alloc(e, &e.gradLnl, (size_t)D));
+  TRY(dev_alloc(e, &e.ones, (size_t)D));
+  {
+    std::vector<double> ones(D, 1.0);
+    TRY_CUDA(cudaMemcpy(e.ones, ones.data(), D * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  TRY(dev_alloc(e, &e.outBl, (size_t)D * m.B));
+  TRY(dev_alloc(e, &e.outRates, (size_t)D * m.K));
+  TRY(dev_alloc(e, &e.outProps, (size_t)D * m.K));
+  TRY(dev_alloc(e, &e.outFreqs, (size_t)D * m.S));
+  TRY(dev_alloc(e, &e.outQ, (size_t)D * m.S * m.S));
+
+  // tips, padded with the all-ones code S; weights padded with 0
+  {
+    std::vector<uint8_t> padded((size_t)m.T * m.Npad, (uint8_t)m.S);
+    for (int t = 0; t < m.T; ++t)
+      std::memcpy(&padded[(size_t)t * m.Npad], tip_codes + (size_t)t * m.N, m.N);
+    TRY_CUDA(cudaMemcpy(e.tips, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+    std::vector<double> w(m.Npad, 0.0);
+    std::memcpy(w.data(), weights, m.N * sizeof(double));
+    TRY_CUDA(cudaMemcpy(e.weights, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  TRY_CUDA(cudaMemcpy(e.codeP, code_partials, (size_t)m.C * m.S * sizeof(double),
+                      cudaMemcpyHostToDevice));
+  TRY_CUDA(cudaMemcpy(e.ops, e.hostOps.data(), m.I * sizeof(NodeOp), cudaMemcpyHostToDevice));
+  if (c.flags & TTB2_FLAG_PREALLOC_GRAD) {
+    TRY(ensure_grad_buffers(e, D));
+    TRY(ensure_eigen_grad_buffers(e));
+  }
+#undef TRY
+#undef TRY_CUDA
+  *out = reinterpret_cast<ttb2_engine*>(ep);
+  return TTB2_OK;
+}
+
+int ttb2_set_postorder(ttb2_engine* engine, const int32_t* postorder) {
+  if (!engine || !postorder) {
+    set_error("ttb2_set_postorder: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  std::vector<NodeOp> oldOps = e.hostOps;
+  std::vector<int> oldOff = e.levelOff;
+  int rc = build_schedule(e, postorder);
+  if (rc) {
+    e.hostOps = oldOps;
+    e.levelOff = oldOff;
+    return rc;
+  }
+  TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  TTB2_CUDA_CHECK(cudaMemcpy(e.ops, e.hostOps.data(), e.dm.I * sizeof(NodeOp),
+                             cudaMemcpyHostToDevice));
+  e.mode = MODE_NONE;
+  e.preValid = false;
+  return TTB2_OK;
+}
+
+void ttb2_destroy(ttb2_engine* engine) {
+  if (!engine) return;
+  Engine* ep = reinterpret_cast<Engine*>(engine);
+  Engine& e = *ep;
+  cudaSetDevice(e.device);
+  cudaStreamSynchronize(e.stream);
+  dev_free(e.tips); dev_free(e.weights); dev_free(e.codeP); dev_free(e.ops);
+  dev_free(e.partials); dev_free(e.expo); dev_free(e.pre); dev_free(e.mats);
+  dev_free(e.dmat); dev_free(e.gpart); dev_free(e.siteLnl); dev_free(e.redPart);
+  dev_free(e.lnl); dev_free(e.rootGrad); dev_free(e.hpart); dev_free(e.gscal);
+  dev_free(e.freqs); dev_free(e.props); dev_free(e.bl); dev_free(e.rates);
+  dev_free(e.evec); dev_free(e.ivec); dev_free(e.eval); dev_free(e.gradLnl); dev_free(e.ones);
+  dev_free(e.outBl); dev_free(e.outRates); dev_free(e.outProps); dev_free(e.outFreqs);
+  dev_free(e.outQ);
+  for (int j = 0; j < 8; ++j)
+    if (e.ev[j]) cudaEventDestroy(e.ev[j]);
+  delete ep;
+}
+
+int ttb2_set_stream(ttb2_engine* engine, void* cuda_stream) {
+  if (!engine) {
+    set_error("ttb2_set_stream: null engine");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  e.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return TTB2_OK;
+}
+
+int ttb2_synchronize(ttb2_engine* engine) {
+  if (!engine) {
+    set_error("ttb2_synchronize: null engine");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  return TTB2_OK;
+}
+
+int ttb2_loglik_mats(ttb2_engine* engine, int32_t draws, const double* mats,
+                     const double* freqs, int32_t freq_draws, const double* props,
+                     int32_t prop_draws, double* lnl, int32_t where) {
+  if (!engine || !mats || !freqs || !props) {
+    set_error("ttb2_loglik_mats: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  const Dims& m = e.dm;
+  if (draws < 1 || draws > e.cfg.max_draws || bad_draws(freq_draws, draws) ||
+      bad_draws(prop_draws, draws)) {
+    set_error("ttb2_loglik_mats: draws out of range (or a *_draws that is neither 1 nor draws)");
+    return TTB2_E_INVALID;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  mark(e, 0);
+  if ((rc = copy_in(e, e.mats, mats, (size_t)draws * m.B * m.K * m.S * m.S * sizeof(double), where)))
+    return rc;
+  if ((rc = copy_in(e, e.freqs, freqs, (size_t)freq_draws * m.S * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.props, props, (size_t)prop_draws * m.K * sizeof(double), where))) return rc;
+  e.freqDraws = freq_draws;
+  e.propDraws = prop_draws;
+  e.rateDraws = e.eigDraws = 1;
+  e.mode = MODE_MATS;
+  return run_forward(e, draws, lnl, where);
+}
+
+int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws, const double* branch_lengths,
+                      const double* site_rates, int32_t rate_draws, const double* props,
+                      int32_t prop_draws, const double* evec, const double* ivec,
+                      const double* eval, int32_t eig_draws, const double* freqs,
+                      int32_t freq_draws, double* lnl, int32_t where) {
+  if (!engine || !branch_lengths || !site_rates || !props || !evec || !ivec || !eval || !freqs) {
+    set_error("ttb2_loglik_eigen: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  const Dims& m = e.dm;
+  if (draws < 1 || draws > e.cfg.max_draws || bad_draws(freq_draws, draws) ||
+      bad_draws(prop_draws, draws) || bad_draws(rate_draws, draws) ||
+      bad_draws(eig_draws, draws)) {
+    set_error("ttb2_loglik_eigen: draws out of range (or a *_draws that is neither 1 nor draws)");
+    return TTB2_E_INVALID;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  mark(e, 0);
+  const size_t SS = (size_t)m.S * m.S;
+  if ((rc = copy_in(e, e.bl, branch_lengths, (size_t)draws * m.B * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.rates, site_rates, (size_t)rate_draws * m.K * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.props, props, (size_t)prop_draws * m.K * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.evec, evec, eig_draws * SS * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.ivec, ivec, eig_draws * SS * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.eval, eval, (size_t)eig_draws * m.S * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.freqs, freqs, (size_t)freq_draws * m.S * sizeof(double), where))) return rc;
+  e.freqDraws = freq_draws;
+  e.propDraws = prop_draws;
+  e.rateDraws = rate_draws;
+  e.eigDraws = eig_draws;
+  e.mode = MODE_EIGEN;
+  e.draws = draws;
+  if ((rc = small_pmatrix(e, draws))) return rc;
+  return run_forward(e, draws, lnl, where);
+}
+
+int ttb2_grad_mats(ttb2_engine* engine, const double* grad_lnl, double* d_mats,
+                   double* d_freqs, double* d_props, int32_t where) {
+  if (!engine) {
+    set_error("ttb2_grad_mats: null engine");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  const Dims& m = e.dm;
+  if (e.mode == MODE_NONE) {
+    set_error("ttb2_grad_mats: no log-likelihood has been evaluated yet");
+    return TTB2_E_STATE;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  if ((rc = run_backward(e, grad_lnl, where))) return rc;
+  const int draws = e.draws;
+  const size_t matBytes = (size_t)draws * m.B * m.K * m.S * m.S * sizeof(double);
+  if (d_mats) {
+    if (where == TTB2_DEVICE) {
+      if ((rc = small_scale_dmat(e, draws, d_mats))) return rc;
+    } else {
+      // scale into the hpart scratch (same shape as dmat), then copy out
+      if ((rc = ensure_eigen_grad_buffers(e))) return rc;
+      if ((rc = small_scale_dmat(e, draws, e.hpart))) return rc;
+      if ((rc = copy_out(e, d_mats, e.hpart, matBytes, where))) return rc;
+    }
+  }
+  if (d_freqs || d_props) {
+    if ((rc = small_root_outputs(e, draws))) return rc;
+    if ((rc = copy_out(e, d_props, e.outProps, (size_t)e.propDraws * m.K * sizeof(double), where)))
+      return rc;
+    if ((rc = copy_out(e, d_freqs, e.outFreqs, (size_t)e.freqDraws * m.S * sizeof(double), where)))
+      return rc;
+  }
+  return finish(e, where);
+}
+
+int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branch_lengths,
+                    double* d_site_rates, double* d_props, double* d_q, double* d_freqs,
+                    int32_t where) {
+  if (!engine) {
+    set_error("ttb2_grad_eigen: null engine");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  const Dims& m = e.dm;
+  if (e.mode != MODE_EIGEN) {
+    set_error("ttb2_grad_eigen: the latest evaluation was not ttb2_loglik_eigen");
+    return TTB2_E_STATE;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  if ((rc = ensure_eigen_grad_buffers(e))) return rc;
+  if ((rc = run_backward(e, grad_lnl, where))) return rc;
+  const int draws = e.draws;
+  if ((rc = small_eigen_contract(e, draws))) return rc;
+  if ((rc = copy_out(e, d_branch_lengths, e.outBl, (size_t)draws * m.B * sizeof(double), where)))
+    return rc;
+  if ((rc = copy_out(e, d_site_rates, e.outRates, (size_t)e.rateDraws * m.K * sizeof(double), where)))
+    return rc;
+  if ((rc = copy_out(e, d_props, e.outProps, (size_t)e.propDraws * m.K * sizeof(double), where)))
+    return rc;
+  if ((rc = copy_out(e, d_q, e.outQ, (size_t)e.eigDraws * m.S * m.S * sizeof(double), where)))
+    return rc;
+  if ((rc = copy_out(e, d_freqs, e.outFreqs, (size_t)e.freqDraws * m.S * sizeof(double), where)))
+    return rc;
+  mark(e, 6);
+  return finish(e, where);
+}
+
+int ttb2_enable_timing(ttb2_engine* engine, int32_t on) {
+  if (!engine) {
+    set_error("ttb2_enable_timing: null engine");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  if (on) {
+    for (int j = 0; j < 8; ++j)
+      if (!e.ev[j]) TTB2_CUDA_CHECK(cudaEventCreate(&e.ev[j]));
+  }
+  for (int j = 0; j < 8; ++j) e.evSet[j] = false;
+  e.timing = on != 0;
+  return TTB2_OK;
+}
+
+int ttb2_phase_ms(ttb2_engine* engine, double* out) {
+  if (!engine || !out) {
+    set_error("ttb2_phase_ms: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  const int pairs[5][2] = {{0, 1}, {1, 2}, {2, 3}, {4, 5}, {5, 6}};
+  for (int j = 0; j < 5; ++j) {
+    out[j] = 0.0;
+    const int a = pairs[j][0], b = pairs[j][1];
+    if (e.ev[a] && e.ev[b] && e.evSet[a] && e.evSet[b]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e.ev[a], e.ev[b]) == cudaSuccess) out[j] = ms;
+    }
+  }
+  out[5] = e.fwdLevelLaunches;
+  out[6] = e.bwdLevelLaunches;
+  return TTB2_OK;
+}
+
+int ttb2_site_loglik(ttb2_engine* engine, double* out, int32_t where) {
+  if (!engine || !out) {
+    set_error("ttb2_site_loglik: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  if (e.mode == MODE_NONE) {
+    set_error("ttb2_site_loglik: no log-likelihood has been evaluated yet");
+    return TTB2_E_STATE;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  const Dims& m = e.dm;
+  TTB2_CUDA_CHECK(cudaMemcpy2DAsync(
+      out, (size_t)m.N * sizeof(double), e.siteLnl, (size_t)m.Npad * sizeof(double),
+      (size_t)m.N * sizeof(double), e.draws,
+      where == TTB2_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e.stream));
+  return finish(e, where);
+}
+
+int ttb2_get_mats(ttb2_engine* engine, double* out, int32_t where) {
+  if (!engine || !out) {
+    set_error("ttb2_get_mats: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  if (e.mode == MODE_NONE) {
+    set_error("ttb2_get_mats: no log-likelihood has been evaluated yet");
+    return TTB2_E_STATE;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  const Dims& m = e.dm;
+  int rc = copy_out(e, out, e.mats, (size_t)e.draws * m.B * m.K * m.S * m.S * sizeof(double), where);
+  if (rc) return rc;
+  return finish(e, where);
+}
+
+int64_t ttb2_launch_count(const ttb2_engine* engine) {
+  return engine ? reinterpret_cast<const Engine*>(engine)->launches : 0;
+}
+
+int64_t ttb2_device_bytes(const ttb2_engine* engine) {
+  return engine ? reinterpret_cast<const Engine*>(engine)->deviceBytes : 0;
+}
+
+}  // extern "C"

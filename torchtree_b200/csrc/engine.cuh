@@ -1,0 +1,138 @@
+// Internal declarations shared by the ttb200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/ttb200.h"
+
+namespace ttb2 {
+
+// One internal node of the traversal; ops are stored level by level
+// (level = height above the tips; nodes of one level are independent).
+struct NodeOp {
+  int32_t node, left, right, level;
+};
+
+struct Dims {
+  int T;     // tips
+  int I;     // internal nodes T-1
+  int B;     // branches 2T-2
+  int N;     // patterns
+  int Npad;  // patterns padded to a multiple of 32 (padding: all-gap, weight 0)
+  int S;     // states
+  int K;     // rate categories
+  int C;     // tip symbol codes
+};
+
+enum Mode { MODE_NONE = 0, MODE_MATS = 1, MODE_EIGEN = 2 };
+
+struct Engine {
+  ttb2_config cfg{};
+  Dims dm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool spec4 = false;  // S==4 specialised kernels (AoS [k][N][4] layout)
+
+  // static data
+  uint8_t* tips = nullptr;      // [T][Npad]
+  double* weights = nullptr;    // [Npad]
+  double* codeP = nullptr;      // [C][S]
+  NodeOp* ops = nullptr;        // [I] level-sorted
+  std::vector<NodeOp> hostOps;
+  std::vector<int> levelOff;    // ops of level l (1-based height): [levelOff[l-1], levelOff[l])
+
+  // per-evaluation state (sized for max_draws)
+  double* partials = nullptr;   // spec4: [D][I][K][Npad][4]; generic: [D][I][K][S][Npad]
+  int16_t* expo = nullptr;      // [D][I][Npad] power-of-two scale exponents
+  double* pre = nullptr;        // pre-order vectors, same layout as partials
+  double* mats = nullptr;       // [D][B][K][S][S]
+  double* dmat = nullptr;       // d lnL / d mats, same shape
+  double* gpart = nullptr;      // per-chunk partial sums of dmat
+  size_t gpartCap = 0;          // doubles
+  double* siteLnl = nullptr;    // [D][Npad]
+  double* redPart = nullptr;    // per-block partials of pattern reductions
+  size_t redPartCap = 0;
+  double* lnl = nullptr;        // [D]
+  double* rootGrad = nullptr;   // [D][K+S] (d_props | d_freqs) per draw
+  double* hpart = nullptr;      // [D][B*K][S][S] (M o Phi) per branch x category
+  double* gscal = nullptr;      // [D][B*K] d lnL / d (r t)
+  // staged inputs
+  double* freqs = nullptr;      // [Dmax][S]
+  double* props = nullptr;      // [Dmax][K]
+  double* bl = nullptr;         // [Dmax][B]
+  double* rates = nullptr;      // [Dmax][K]
+  double* evec = nullptr;       // [Dmax][S][S]
+  double* ivec = nullptr;
+  double* eval = nullptr;       // [Dmax][S]
+  double* gradLnl = nullptr;    // [Dmax]
+  double* ones = nullptr;       // [Dmax] default grad_lnl
+  // staged outputs (small)
+  double* outBl = nullptr;      // [Dmax][B]
+  double* outRates = nullptr;   // [Dmax][K]
+  double* outProps = nullptr;   // [Dmax][K]
+  double* outFreqs = nullptr;   // [Dmax][S]
+  double* outQ = nullptr;       // [Dmax][S][S]
+
+  int draws = 0, freqDraws = 0, propDraws = 0, rateDraws = 0, eigDraws = 0;
+  Mode mode = MODE_NONE;
+  bool preValid = false;
+
+  int64_t launches = 0;
+  int64_t deviceBytes = 0;
+
+  // optional phase timing (ttb2_enable_timing)
+  bool timing = false;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool evSet[8] = {false, false, false, false, false, false, false, false};
+  int fwdLevelLaunches = 0, bwdLevelLaunches = 0;
+};
+
+// event slots: 0 start-fwd, 1 after pmatrix, 2 after post-order levels, 3 after root,
+//              4 start-bwd, 5 after pre-order levels, 6 after contraction
+inline void mark(Engine& e, int slot) {
+  if (e.timing && e.ev[slot]) {
+    cudaEventRecord(e.ev[slot], e.stream);
+    e.evSet[slot] = true;
+  }
+}
+
+void set_error(const std::string& msg);
+
+#define TTB2_CUDA_CHECK(expr)                                                  \
+  do {                                                                         \
+    cudaError_t err__ = (expr);                                                \
+    if (err__ != cudaSuccess) {                                                \
+      ttb2::set_error(std::string(#expr) + ": " + cudaGetErrorString(err__) + \
+                      " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+      return TTB2_E_CUDA;                                                      \
+    }                                                                          \
+  } while (0)
+
+// ---- launchers (each returns a TTB2_* status) ------------------------------
+// S = 4 specialised path (kernels_s4.cu)
+int s4_forward(Engine& e, int draws);
+int s4_root(Engine& e, int draws);
+int s4_backward(Engine& e, int draws);
+size_t s4_gpart_doubles(const Engine& e, int draws);
+
+// generic-S path (kernels_gen.cu)
+int gen_forward(Engine& e, int draws);
+int gen_root(Engine& e, int draws);
+int gen_backward(Engine& e, int draws);
+size_t gen_gpart_doubles(const Engine& e, int draws);
+
+// small kernels (kernels_small.cu)
+int small_pmatrix(Engine& e, int draws);
+int small_reduce_lnl(Engine& e, int draws, int nblocks);
+int small_root_grad_reduce(Engine& e, int draws, int nblocks);
+int small_gpart_reduce(Engine& e, int draws, int nchunk);
+int small_scale_dmat(Engine& e, int draws, double* out);
+int small_eigen_contract(Engine& e, int draws);
+int small_root_outputs(Engine& e, int draws);
+
+int pattern_chunks(const Engine& e, int draws, int threads);
+
+}  // namespace ttb2

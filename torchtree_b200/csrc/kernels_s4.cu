@@ -1,0 +1,601 @@
+// 4-state (nucleotide) level-synchronous peeling kernels for sm_100a.
+//
+// Layout: conditional-likelihood vectors are stored [draw][inode][k][pattern][4]
+// so that one pattern's 4-state vector is one 32-byte fp64x4 access
+// (LDG/STG.256) and a warp touches 1 KB of contiguous memory per category.
+// Patterns map to threads.  Per-branch transition matrices (or, for tip
+// children, the K x C table P . tipvector[code]) are staged in shared memory.
+// Rescaling uses exact power-of-two factors: s = 2^e with e taken from the
+// exponent field of max_{k,s} partial, stored as int16 per (node, pattern).
+//
+// Replaces: calculate_treelikelihood_discrete_rescaled and the tip-state
+// variants (torchtree/evolution/tree_likelihood.py:186-278) for the post-order
+// pass, and the autograd tape by the pre-order pass of
+// SURVEY Appendix B.
+#include "engine.cuh"
+
+namespace ttb2 {
+
+namespace {
+
+constexpr int FWD_THREADS = 128;
+constexpr int BWD_THREADS = 256;
+constexpr int ROOT_THREADS = 128;
+
+struct __align__(32) V4 {
+  double x, y, z, w;
+};
+
+__device__ __forceinline__ V4 ldg4(const double* p) {
+  V4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void stg4(double* p, const V4& v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x),
+               "d"(v.y), "d"(v.z), "d"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ V4 lds4(const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  return V4{a.x, a.y, b.x, b.y};
+}
+
+// u = P v, P row-major 4x4 in shared memory (warp-uniform address: broadcast)
+__device__ __forceinline__ V4 matvec(const double* P, const V4& v) {
+  V4 u;
+  u.x = fma(P[3], v.w, fma(P[2], v.z, fma(P[1], v.y, P[0] * v.x)));
+  u.y = fma(P[7], v.w, fma(P[6], v.z, fma(P[5], v.y, P[4] * v.x)));
+  u.z = fma(P[11], v.w, fma(P[10], v.z, fma(P[9], v.y, P[8] * v.x)));
+  u.w = fma(P[15], v.w, fma(P[14], v.z, fma(P[13], v.y, P[12] * v.x)));
+  return u;
+}
+
+// u = P^T v
+__device__ __forceinline__ V4 matvec_t(const double* P, const V4& v) {
+  V4 u;
+  u.x = fma(P[12], v.w, fma(P[8], v.z, fma(P[4], v.y, P[0] * v.x)));
+  u.y = fma(P[13], v.w, fma(P[9], v.z, fma(P[5], v.y, P[1] * v.x)));
+  u.z = fma(P[14], v.w, fma(P[10], v.z, fma(P[6], v.y, P[2] * v.x)));
+  u.w = fma(P[15], v.w, fma(P[11], v.z, fma(P[7], v.y, P[3] * v.x)));
+  return u;
+}
+
+__device__ __forceinline__ V4 mul4(const V4& a, const V4& b) {
+  return V4{a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w};
+}
+
+__device__ __forceinline__ V4 scale4(const V4& a, double f) {
+  return V4{a.x * f, a.y * f, a.z * f, a.w * f};
+}
+
+__device__ __forceinline__ double max4(const V4& a) {
+  return fmax(fmax(a.x, a.y), fmax(a.z, a.w));
+}
+
+// Shared-memory table of one child for all K categories.
+//   internal child: tab[k][16] = P_k (row-major)
+//   tip child     : tab[k][code][4] = P_k . codeP[code]
+template <int K>
+__device__ __forceinline__ void build_child_table(double* tab, const double* P,
+                                                  bool tip, const double* codeP,
+                                                  int C) {
+  if (!tip) {
+    for (int j = threadIdx.x; j < K * 16; j += blockDim.x) tab[j] = P[j];
+  } else {
+    for (int j = threadIdx.x; j < K * C * 4; j += blockDim.x) {
+      const int s = j & 3;
+      const int code = (j >> 2) % C;
+      const int k = (j >> 2) / C;
+      const double* row = P + k * 16 + s * 4;
+      const double* cp = codeP + code * 4;
+      tab[j] = fma(row[3], cp[3], fma(row[2], cp[2], fma(row[1], cp[1], row[0] * cp[0])));
+    }
+  }
+}
+
+__host__ __device__ inline int child_table_doubles(int K, int C) {
+  return K * (C > 4 ? C : 4) * 4;
+}
+
+// ---------------------------------------------------------------------------
+// post-order: one launch per level, grid (pattern blocks, nodes of level, draws)
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(FWD_THREADS)
+fwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
+            const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+            const double* __restrict__ codeP, double* __restrict__ partials,
+            int16_t* __restrict__ expo, int T, int Npad, int C, int B) {
+  extern __shared__ double sm[];
+  const NodeOp op = ops[opBegin + blockIdx.y];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int tabN = child_table_doubles(K, C);
+  double* tabL = sm;
+  double* tabR = sm + tabN;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  build_child_table<K>(tabL, matsD + (size_t)op.left * K * 16, tipL, codeP, C);
+  build_child_table<K>(tabR, matsD + (size_t)op.right * K * 16, tipR, codeP, C);
+  __syncthreads();
+
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  double* base = partials + (size_t)d * I * nodeStride;
+
+  V4 a[K], b[K];
+  int codeL = 0, codeR = 0;
+  if (tipL) {
+    codeL = tips[(size_t)op.left * Npad + i];
+  } else {
+    const double* p = base + (size_t)(op.left - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+    for (int k = 0; k < K; ++k) a[k] = ldg4(p + (size_t)k * Npad * 4);
+  }
+  if (tipR) {
+    codeR = tips[(size_t)op.right * Npad + i];
+  } else {
+    const double* p = base + (size_t)(op.right - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+    for (int k = 0; k < K; ++k) b[k] = ldg4(p + (size_t)k * Npad * 4);
+  }
+
+  V4 out[K];
+  double m = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const V4 ul = tipL ? lds4(tabL + (k * C + codeL) * 4) : matvec(tabL + k * 16, a[k]);
+    const V4 ur = tipR ? lds4(tabR + (k * C + codeR) * 4) : matvec(tabR + k * 16, b[k]);
+    out[k] = mul4(ul, ur);
+    m = fmax(m, max4(out[k]));
+  }
+  // exact power-of-two rescaling: m * f in [0.5, 1)
+  int eb = (__double2hiint(m) >> 20) & 0x7ff;
+  eb = eb > 2044 ? 2044 : eb;
+  const double f = __hiloint2double((2045 - eb) << 20, 0);
+  double* q = base + (size_t)(op.node - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+  for (int k = 0; k < K; ++k) stg4(q + (size_t)k * Npad * 4, scale4(out[k], f));
+  expo[((size_t)d * I + (op.node - T)) * Npad + i] = (int16_t)(eb - 1022);
+}
+
+// generic-K fallback (K not instantiated): two sweeps over the categories
+__global__ void __launch_bounds__(FWD_THREADS)
+fwd4_kernel_anyk(const NodeOp* __restrict__ ops, int opBegin,
+                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                 const double* __restrict__ codeP, double* __restrict__ partials,
+                 int16_t* __restrict__ expo, int T, int Npad, int C, int B, int K) {
+  extern __shared__ double sm[];
+  const NodeOp op = ops[opBegin + blockIdx.y];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int tabN = child_table_doubles(K, C);
+  double* tabL = sm;
+  double* tabR = sm + tabN;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  for (int side = 0; side < 2; ++side) {
+    double* tab = side ? tabR : tabL;
+    const int child = side ? op.right : op.left;
+    const bool tip = side ? tipR : tipL;
+    const double* P = matsD + (size_t)child * K * 16;
+    if (!tip) {
+      for (int j = threadIdx.x; j < K * 16; j += blockDim.x) tab[j] = P[j];
+    } else {
+      for (int j = threadIdx.x; j < K * C * 4; j += blockDim.x) {
+        const int s = j & 3, code = (j >> 2) % C, k = (j >> 2) / C;
+        const double* row = P + k * 16 + s * 4;
+        const double* cp = codeP + code * 4;
+        tab[j] = fma(row[3], cp[3], fma(row[2], cp[2], fma(row[1], cp[1], row[0] * cp[0])));
+      }
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  double* base = partials + (size_t)d * I * nodeStride;
+  const int codeL = tipL ? tips[(size_t)op.left * Npad + i] : 0;
+  const int codeR = tipR ? tips[(size_t)op.right * Npad + i] : 0;
+  const double* pl = base + (size_t)(tipL ? 0 : op.left - T) * nodeStride + (size_t)i * 4;
+  const double* pr = base + (size_t)(tipR ? 0 : op.right - T) * nodeStride + (size_t)i * 4;
+  double* q = base + (size_t)(op.node - T) * nodeStride + (size_t)i * 4;
+  double m = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const V4 ul = tipL ? lds4(tabL + (k * C + codeL) * 4)
+                       : matvec(tabL + k * 16, ldg4(pl + (size_t)k * Npad * 4));
+    const V4 ur = tipR ? lds4(tabR + (k * C + codeR) * 4)
+                       : matvec(tabR + k * 16, ldg4(pr + (size_t)k * Npad * 4));
+    const V4 o = mul4(ul, ur);
+    m = fmax(m, max4(o));
+    stg4(q + (size_t)k * Npad * 4, o);
+  }
+  int eb = (__double2hiint(m) >> 20) & 0x7ff;
+  eb = eb > 2044 ? 2044 : eb;
+  const double f = __hiloint2double((2045 - eb) << 20, 0);
+  for (int k = 0; k < K; ++k) {
+    double* qq = q + (size_t)k * Npad * 4;
+    V4 o;
+    // plain (coherent) loads: this thread wrote these values above
+    o.x = qq[0]; o.y = qq[1]; o.z = qq[2]; o.w = qq[3];
+    stg4(qq, scale4(o, f));
+  }
+  expo[((size_t)d * I + (op.node - T)) * Npad + i] = (int16_t)(eb - 1022);
+}
+
+// ---------------------------------------------------------------------------
+// block-level sum of one double per thread; result valid in thread 0
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) t += red[w];
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+// root: site log-likelihoods + per-block weighted partial sums
+//   lnL_i = log(sum_k rho_k pi . p~_root[k,:,i]) + ln2 * sum_n e_n[i]
+// (tree_likelihood.py:215-221)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROOT_THREADS)
+root4_kernel(const double* __restrict__ partials, const int16_t* __restrict__ expo,
+             const double* __restrict__ freqs, int freqDraws,
+             const double* __restrict__ props, int propDraws,
+             const double* __restrict__ weights, double* __restrict__ siteLnl,
+             double* __restrict__ blockPart, int T, int Npad, int K, int rootInode) {
+  __shared__ double red[ROOT_THREADS / 32];
+  const int d = blockIdx.y;
+  const int I = T - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* fr = freqs + (freqDraws > 1 ? (size_t)d * 4 : 0);
+  const double* pr = props + (propDraws > 1 ? (size_t)d * K : 0);
+  double contrib = 0.0;
+  if (i < Npad) {
+    const size_t nodeStride = (size_t)K * Npad * 4;
+    const double* p = partials + ((size_t)d * I + rootInode) * nodeStride + (size_t)i * 4;
+    double L = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const V4 v = ldg4(p + (size_t)k * Npad * 4);
+      const double dot = fma(fr[3], v.w, fma(fr[2], v.z, fma(fr[1], v.y, fr[0] * v.x)));
+      L = fma(pr[k], dot, L);
+    }
+    int esum = 0;
+    const int16_t* e = expo + (size_t)d * I * Npad + i;
+    for (int n = 0; n < I; ++n) esum += e[(size_t)n * Npad];
+    const double site = log(L) + (double)esum * 0.693147180559945309417232121458;
+    siteLnl[(size_t)d * Npad + i] = site;
+    const double w = weights[i];
+    contrib = (w != 0.0) ? w * site : 0.0;
+  }
+  const double t = block_sum(contrib, red);
+  if (threadIdx.x == 0) blockPart[(size_t)d * gridDim.x + blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------
+// pre-order root: q^_root[k,s,i] = rho_k pi_s / (L~_i * 2^{e_root});
+// per-block partials of d lnL / d rho_k and the root term of d lnL / d pi_s
+// 
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROOT_THREADS)
+root4_bwd_kernel(const double* __restrict__ partials, const int16_t* __restrict__ expo,
+                 const double* __restrict__ freqs, int freqDraws,
+                 const double* __restrict__ props, int propDraws,
+                 const double* __restrict__ weights, double* __restrict__ pre,
+                 double* __restrict__ blockPart, int T, int Npad, int K, int rootInode) {
+  __shared__ double red[ROOT_THREADS / 32];
+  const int d = blockIdx.y;
+  const int I = T - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* fr = freqs + (freqDraws > 1 ? (size_t)d * 4 : 0);
+  const double* pr = props + (propDraws > 1 ? (size_t)d * K : 0);
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const bool live = i < Npad;
+  double w = 0.0, invL = 0.0;
+  const double* p = nullptr;
+  if (live) {
+    p = partials + ((size_t)d * I + rootInode) * nodeStride + (size_t)i * 4;
+    double L = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const V4 v = ldg4(p + (size_t)k * Npad * 4);
+      const double dot = fma(fr[3], v.w, fma(fr[2], v.z, fma(fr[1], v.y, fr[0] * v.x)));
+      L = fma(pr[k], dot, L);
+    }
+    invL = 1.0 / L;
+    w = weights[i];
+    const int e = expo[((size_t)d * I + rootInode) * Npad + i];
+    const double scale = invL * __hiloint2double((1023 - e) << 20, 0);
+    double* q = pre + ((size_t)d * I + rootInode) * nodeStride + (size_t)i * 4;
+    for (int k = 0; k < K; ++k) {
+      const double c = pr[k] * scale;
+      stg4(q + (size_t)k * Npad * 4, V4{c * fr[0], c * fr[1], c * fr[2], c * fr[3]});
+    }
+  }
+  // d/d rho_k = sum_i w_i (pi . p~[k]) / L~ ; d/d pi_s = sum_i w_i sum_k rho_k p~[k,s] / L~
+  const double wl = (w != 0.0) ? w * invL : 0.0;
+  double* out = blockPart + ((size_t)d * gridDim.x + blockIdx.x) * (K + 4);
+  V4 accF{0.0, 0.0, 0.0, 0.0};
+  for (int k = 0; k < K; ++k) {
+    V4 v{0.0, 0.0, 0.0, 0.0};
+    if (live && wl != 0.0) v = ldg4(p + (size_t)k * Npad * 4);
+    const double dot = fma(fr[3], v.w, fma(fr[2], v.z, fma(fr[1], v.y, fr[0] * v.x)));
+    const double t = block_sum(wl * dot, red);
+    if (threadIdx.x == 0) out[k] = t;
+    const double c = wl * pr[k];
+    accF.x = fma(c, v.x, accF.x);
+    accF.y = fma(c, v.y, accF.y);
+    accF.z = fma(c, v.z, accF.z);
+    accF.w = fma(c, v.w, accF.w);
+  }
+  double t;
+  t = block_sum(accF.x, red); if (threadIdx.x == 0) out[K + 0] = t;
+  t = block_sum(accF.y, red); if (threadIdx.x == 0) out[K + 1] = t;
+  t = block_sum(accF.z, red); if (threadIdx.x == 0) out[K + 2] = t;
+  t = block_sum(accF.w, red); if (threadIdx.x == 0) out[K + 3] = t;
+}
+
+// ---------------------------------------------------------------------------
+// pre-order level kernel: grid (pattern chunks, nodes of level x K, draws).
+// For parent n with children l, r:
+//   u_c = P_c p~_c ; m_l = q^_n o u_r ; m_r = q^_n o u_l
+//   G_c += w_i m_c (x) p~_c          (= d lnL / d P_c[k], rows = parent state)
+//   q^_c = P_c^T m_c * 2^{-e_c}      (internal children only)
+// ---------------------------------------------------------------------------
+// Sum 32 per-thread values across the warp with a halving butterfly
+// (31 shuffles instead of 160); on return lane L holds the total of v[L].
+__device__ __forceinline__ double warp_transpose_sum(double (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const double send = upper ? v[j] : v[j + half];
+      const double keep = upper ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(BWD_THREADS)
+bwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
+            const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+            const double* __restrict__ codeP, const double* __restrict__ partials,
+            const int16_t* __restrict__ expo, const double* __restrict__ weights,
+            double* __restrict__ pre, double* __restrict__ gpart, int T, int Npad,
+            int C, int B, int K, int chunkPatterns, int nChunk) {
+  extern __shared__ double sm[];
+  // sm: Pl[16] Pr[16] | cp[C][4] | ul_tab[C][4] ur_tab[C][4] | red[8][32]
+  double* Pl = sm;
+  double* Pr = sm + 16;
+  double* cp = sm + 32;
+  double* tabL = cp + C * 4;
+  double* tabR = tabL + C * 4;
+  double* red = tabR + C * 4;
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
+  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
+  for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
+  __syncthreads();
+  if (tipL || tipR) {
+    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
+      const int s = j & 3, code = j >> 2;
+      const double* c = cp + code * 4;
+      const double* rl = Pl + s * 4;
+      const double* rr = Pr + s * 4;
+      tabL[j] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
+      tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
+    }
+    __syncthreads();
+  }
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const size_t kOff = (size_t)k * Npad * 4;
+  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
+  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
+  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  double* ql = tipL ? nullptr : pre + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
+  double* qr = tipR ? nullptr : pre + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  const int16_t* el = tipL ? nullptr : expo + ((size_t)d * I + (op.left - T)) * Npad;
+  const int16_t* er = tipR ? nullptr : expo + ((size_t)d * I + (op.right - T)) * Npad;
+  const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
+  const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
+
+  double g[32];  // g[0..15] = G_l (row-major, row = parent state), g[16..31] = G_r
+#pragma unroll
+  for (int j = 0; j < 32; ++j) g[j] = 0.0;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const V4 q = ldg4(qn + (size_t)i * 4);
+    const double w = weights[i];
+    V4 vl, vr, ul, ur;
+    if (tipL) {
+      const int code = tl[i];
+      vl = lds4(cp + code * 4);
+      ul = lds4(tabL + code * 4);
+    } else {
+      vl = ldg4(pl + (size_t)i * 4);
+      ul = matvec(Pl, vl);
+    }
+    if (tipR) {
+      const int code = tr[i];
+      vr = lds4(cp + code * 4);
+      ur = lds4(tabR + code * 4);
+    } else {
+      vr = ldg4(prr + (size_t)i * 4);
+      ur = matvec(Pr, vr);
+    }
+    const V4 ml = mul4(q, ur);
+    const V4 mr = mul4(q, ul);
+    if (!tipL) {
+      const int e = el[i];
+      stg4(ql + (size_t)i * 4, scale4(matvec_t(Pl, ml), __hiloint2double((1023 - e) << 20, 0)));
+    }
+    if (!tipR) {
+      const int e = er[i];
+      stg4(qr + (size_t)i * 4, scale4(matvec_t(Pr, mr), __hiloint2double((1023 - e) << 20, 0)));
+    }
+    if (w != 0.0) {
+      const V4 a = scale4(ml, w);
+      const V4 b = scale4(mr, w);
+      g[0] = fma(a.x, vl.x, g[0]);   g[1] = fma(a.x, vl.y, g[1]);
+      g[2] = fma(a.x, vl.z, g[2]);   g[3] = fma(a.x, vl.w, g[3]);
+      g[4] = fma(a.y, vl.x, g[4]);   g[5] = fma(a.y, vl.y, g[5]);
+      g[6] = fma(a.y, vl.z, g[6]);   g[7] = fma(a.y, vl.w, g[7]);
+      g[8] = fma(a.z, vl.x, g[8]);   g[9] = fma(a.z, vl.y, g[9]);
+      g[10] = fma(a.z, vl.z, g[10]); g[11] = fma(a.z, vl.w, g[11]);
+      g[12] = fma(a.w, vl.x, g[12]); g[13] = fma(a.w, vl.y, g[13]);
+      g[14] = fma(a.w, vl.z, g[14]); g[15] = fma(a.w, vl.w, g[15]);
+      g[16] = fma(b.x, vr.x, g[16]); g[17] = fma(b.x, vr.y, g[17]);
+      g[18] = fma(b.x, vr.z, g[18]); g[19] = fma(b.x, vr.w, g[19]);
+      g[20] = fma(b.y, vr.x, g[20]); g[21] = fma(b.y, vr.y, g[21]);
+      g[22] = fma(b.y, vr.z, g[22]); g[23] = fma(b.y, vr.w, g[23]);
+      g[24] = fma(b.z, vr.x, g[24]); g[25] = fma(b.z, vr.y, g[25]);
+      g[26] = fma(b.z, vr.z, g[26]); g[27] = fma(b.z, vr.w, g[27]);
+      g[28] = fma(b.w, vr.x, g[28]); g[29] = fma(b.w, vr.y, g[29]);
+      g[30] = fma(b.w, vr.z, g[30]); g[31] = fma(b.w, vr.w, g[31]);
+    }
+  }
+
+  const double mine = warp_transpose_sum(g);  // lane j: warp total of g[j]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  red[warp * 32 + lane] = mine;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w2 = 0; w2 < nw; ++w2) t += red[w2 * 32 + threadIdx.x];
+    const int branch = threadIdx.x < 16 ? op.left : op.right;
+    const int entry = threadIdx.x & 15;
+    // gpart [d][branch][k][chunk][16]
+    gpart[((((size_t)d * B + branch) * K + k) * nChunk + blockIdx.x) * 16 + entry] = t;
+  }
+}
+
+template <int K>
+void launch_fwd(Engine& e, int draws, int opBegin, int count, size_t smem) {
+  const Dims& m = e.dm;
+  dim3 grid((m.Npad + FWD_THREADS - 1) / FWD_THREADS, count, draws);
+  fwd4_kernel<K><<<grid, FWD_THREADS, smem, e.stream>>>(
+      e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B);
+}
+
+}  // namespace
+
+int s4_forward(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const size_t smem = 2 * (size_t)child_table_doubles(m.K, m.C) * sizeof(double);
+  const int nLevels = (int)e.levelOff.size() - 1;
+  for (int l = 0; l < nLevels; ++l) {
+    const int opBegin = e.levelOff[l];
+    const int count = e.levelOff[l + 1] - opBegin;
+    // grid.y is limited to 65535
+    for (int done = 0; done < count; done += 65535) {
+      const int c = (count - done) < 65535 ? (count - done) : 65535;
+      switch (m.K) {
+        case 1: launch_fwd<1>(e, draws, opBegin + done, c, smem); break;
+        case 2: launch_fwd<2>(e, draws, opBegin + done, c, smem); break;
+        case 3: launch_fwd<3>(e, draws, opBegin + done, c, smem); break;
+        case 4: launch_fwd<4>(e, draws, opBegin + done, c, smem); break;
+        case 5: launch_fwd<5>(e, draws, opBegin + done, c, smem); break;
+        case 6: launch_fwd<6>(e, draws, opBegin + done, c, smem); break;
+        case 8: launch_fwd<8>(e, draws, opBegin + done, c, smem); break;
+        default: {
+          dim3 grid((m.Npad + FWD_THREADS - 1) / FWD_THREADS, c, draws);
+          fwd4_kernel_anyk<<<grid, FWD_THREADS, smem, e.stream>>>(
+              e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo,
+              m.T, m.Npad, m.C, m.B, m.K);
+        }
+      }
+      ++e.launches;
+    }
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+int s4_root(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int nblocks = (m.Npad + ROOT_THREADS - 1) / ROOT_THREADS;
+  dim3 grid(nblocks, draws);
+  const int rootInode = e.hostOps.back().node - m.T;
+  root4_kernel<<<grid, ROOT_THREADS, 0, e.stream>>>(
+      e.partials, e.expo, e.freqs, e.freqDraws, e.props, e.propDraws, e.weights,
+      e.siteLnl, e.redPart, m.T, m.Npad, m.K, rootInode);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return small_reduce_lnl(e, draws, nblocks);
+}
+
+size_t s4_gpart_doubles(const Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int nChunk = pattern_chunks(e, draws, BWD_THREADS);
+  return (size_t)draws * m.B * m.K * nChunk * 16;
+}
+
+int s4_backward(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int rootInode = e.hostOps.back().node - m.T;
+  {
+    const int nblocks = (m.Npad + ROOT_THREADS - 1) / ROOT_THREADS;
+    dim3 grid(nblocks, draws);
+    root4_bwd_kernel<<<grid, ROOT_THREADS, 0, e.stream>>>(
+        e.partials, e.expo, e.freqs, e.freqDraws, e.props, e.propDraws, e.weights,
+        e.pre, e.redPart, m.T, m.Npad, m.K, rootInode);
+    ++e.launches;
+    TTB2_CUDA_CHECK(cudaGetLastError());
+    int rc = small_root_grad_reduce(e, draws, nblocks);
+    if (rc) return rc;
+  }
+  const int nChunk = pattern_chunks(e, draws, BWD_THREADS);
+  int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
+  chunkPatterns = (chunkPatterns + 31) / 32 * 32;
+  const size_t smem = (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
+  const int nLevels = (int)e.levelOff.size() - 1;
+  const int maxNodes = 65535 / m.K;
+  for (int l = nLevels - 1; l >= 0; --l) {
+    const int opBegin = e.levelOff[l];
+    const int count = e.levelOff[l + 1] - opBegin;
+    for (int done = 0; done < count; done += maxNodes) {
+      const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+      dim3 grid(nChunk, c * m.K, draws);
+      bwd4_kernel<<<grid, BWD_THREADS, smem, e.stream>>>(
+          e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo,
+          e.weights, e.pre, e.gpart, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      ++e.launches;
+    }
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return small_gpart_reduce(e, draws, nChunk);
+}
+
+}  // namespace ttb2

@@ -1,0 +1,409 @@
+// Small per-evaluation kernels: transition matrices for every branch x rate
+// category x draw in one launch, deterministic second-stage reductions, and the
+// contraction of d lnL / d P into branch-length, site-rate and generator
+// gradients.  All are O(B K S^3) or O(N) and negligible next to the peeling.
+#include "engine.cuh"
+
+namespace ttb2 {
+
+namespace {
+
+constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ double block_sum256(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) t += red[w];
+  }
+  return t;
+}
+
+// P[d][b][k] = V diag(exp(lambda * t_b * r_k)) V^-1
+// (SymmetricSubstitutionModel.p_t, substitution_model/abstract.py:57-76, with
+// the eigen-system supplied by the host; tree_likelihood.py:346 for t*r)
+__global__ void pmatrix_kernel(const double* __restrict__ bl,
+                               const double* __restrict__ rates, int rateDraws,
+                               const double* __restrict__ evec,
+                               const double* __restrict__ ivec,
+                               const double* __restrict__ eval, int eigDraws,
+                               double* __restrict__ mats, int B, int K, int S) {
+  extern __shared__ double ex[];
+  const int bk = blockIdx.x;
+  const int b = bk / K, k = bk - b * K;
+  const int d = blockIdx.y;
+  const int de = eigDraws > 1 ? d : 0;
+  const double t = bl[(size_t)d * B + b] * rates[(size_t)(rateDraws > 1 ? d : 0) * K + k];
+  const double* lam = eval + (size_t)de * S;
+  for (int m = threadIdx.x; m < S; m += blockDim.x) ex[m] = exp(lam[m] * t);
+  __syncthreads();
+  const double* V = evec + (size_t)de * S * S;
+  const double* Vi = ivec + (size_t)de * S * S;
+  double* P = mats + (((size_t)d * B + b) * K + k) * S * S;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, j = idx - i * S;
+    double acc = 0.0;
+    for (int m = 0; m < S; ++m) acc = fma(V[i * S + m] * ex[m], Vi[m * S + j], acc);
+    P[idx] = acc;
+  }
+}
+
+// out[d] = sum_j part[d][j]   (fixed order: deterministic)
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_rows_kernel(const double* __restrict__ part, double* __restrict__ out, int n,
+                   int width, int col) {
+  // part is [rows][n][width]; reduces column `col + blockIdx.x` of row blockIdx.y
+  __shared__ double red[RED_THREADS / 32];
+  const int c = col + blockIdx.x;
+  const double* p = part + (size_t)blockIdx.y * n * width + c;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) acc += p[(size_t)j * width];
+  const double t = block_sum256(acc, red);
+  if (threadIdx.x == 0) out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+}
+
+// dmat[d][b][k][e] = sum_chunk gpart[d][b][k][chunk][e]
+__global__ void gpart_reduce_kernel(const double* __restrict__ gpart,
+                                    double* __restrict__ dmat, size_t items, int nChunk,
+                                    int SS) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= items * SS) return;
+  const size_t item = idx / SS;
+  const int e = (int)(idx - item * SS);
+  const double* p = gpart + item * nChunk * SS + e;
+  double acc = 0.0;
+  for (int c = 0; c < nChunk; ++c) acc += p[(size_t)c * SS];
+  dmat[idx] = acc;
+}
+
+// out[d][j] = g[d] * in[d][j]
+__global__ void scale_rows_kernel(const double* __restrict__ in, const double* __restrict__ g,
+                                  double* __restrict__ out, size_t width, int draws) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= width * draws) return;
+  out[idx] = in[idx] * g[idx / width];
+}
+
+// out[od][j] = sum_d g[d] in[d][j*stride + off]  (od == 1)  or  g[d] in[d][...] (od == D)
+__global__ void combine_draws_kernel(const double* __restrict__ in, const double* __restrict__ g,
+                                     double* __restrict__ out, int width, int inWidth, int off,
+                                     int draws, int outDraws) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (outDraws > 1) {
+    if (idx >= width * draws) return;
+    const int d = idx / width, j = idx - d * width;
+    out[idx] = g[d] * in[(size_t)d * inWidth + off + j];
+  } else {
+    if (idx >= width) return;
+    double acc = 0.0;
+    for (int d = 0; d < draws; ++d) acc = fma(g[d], in[(size_t)d * inWidth + off + idx], acc);
+    out[idx] = acc;
+  }
+}
+
+// Per branch x category: M = V^T G V^-T (eigenbasis),
+//   gscal = sum_i M_ii lambda_i exp(lambda_i tau)        (= tr(G^T Q P), d/d tau)
+//   hpart = M o Phi(tau), Phi_ij = (e^{l_i tau} - e^{l_j tau}) / (l_i - l_j),
+//           Phi_ii = tau e^{l_i tau}   (divided differences, expm1 form: finite
+//           and accurate at repeated eigenvalues -- SURVEY F12, Appendix B)
+__global__ void eigen_contract_kernel(const double* __restrict__ dmat,
+                                      const double* __restrict__ bl,
+                                      const double* __restrict__ rates, int rateDraws,
+                                      const double* __restrict__ evec,
+                                      const double* __restrict__ ivec,
+                                      const double* __restrict__ eval, int eigDraws,
+                                      double* __restrict__ hpart, double* __restrict__ gscal,
+                                      int B, int K, int S) {
+  extern __shared__ double sm[];
+  double* sG = sm;              // [S][S]
+  double* sT = sG + S * S;      // [S][S] tmp = V^T G
+  double* sV = sT + S * S;      // [S][S]
+  double* sVi = sV + S * S;     // [S][S]
+  double* sLam = sVi + S * S;   // [S]
+  double* sEx = sLam + S;       // [S]
+  __shared__ double red[32];
+  const int bk = blockIdx.x;
+  const int b = bk / K, k = bk - b * K;
+  const int d = blockIdx.y;
+  const int de = eigDraws > 1 ? d : 0;
+  const double tau = bl[(size_t)d * B + b] * rates[(size_t)(rateDraws > 1 ? d : 0) * K + k];
+  const size_t item = ((size_t)d * B + b) * K + k;
+  const double* G = dmat + item * S * S;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    sG[idx] = G[idx];
+    sV[idx] = evec[(size_t)de * S * S + idx];
+    sVi[idx] = ivec[(size_t)de * S * S + idx];
+  }
+  for (int m = threadIdx.x; m < S; m += blockDim.x) {
+    const double l = eval[(size_t)de * S + m];
+    sLam[m] = l;
+    sEx[m] = exp(l * tau);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, c = idx - i * S;
+    double acc = 0.0;
+    for (int a = 0; a < S; ++a) acc = fma(sV[a * S + i], sG[a * S + c], acc);
+    sT[idx] = acc;
+  }
+  __syncthreads();
+  double diag = 0.0;
+  double* H = hpart + item * S * S;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, j = idx - i * S;
+    double m = 0.0;
+    for (int c = 0; c < S; ++c) m = fma(sT[i * S + c], sVi[j * S + c], m);
+    double phi;
+    if (i == j) {
+      phi = tau * sEx[i];
+      diag = fma(m, sLam[i] * sEx[i], diag);
+    } else {
+      const double a = sLam[i] * tau, bb = sLam[j] * tau;
+      const double hi = a > bb ? a : bb;
+      const double x = -fabs(a - bb);  // <= 0
+      const double ratio = (x > -1e-9) ? 1.0 + 0.5 * x : expm1(x) / x;
+      phi = tau * exp(hi) * ratio;
+    }
+    H[idx] = m * phi;
+  }
+  const double t = block_sum256(diag, red);
+  if (threadIdx.x == 0) gscal[item] = t;
+}
+
+// d_bl[d][b] = g[d] * sum_k r_k gscal[d][b][k]
+__global__ void branch_grad_kernel(const double* __restrict__ gscal,
+                                   const double* __restrict__ rates, int rateDraws,
+                                   const double* __restrict__ g, double* __restrict__ out,
+                                   int B, int K, int draws) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * draws) return;
+  const int d = idx / B;
+  const double* r = rates + (size_t)(rateDraws > 1 ? d : 0) * K;
+  const double* gs = gscal + (size_t)idx * K;
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) acc = fma(r[k], gs[k], acc);
+  out[idx] = g[d] * acc;
+}
+
+// d_rate[od][k] = sum_d g[d] sum_b t[d][b] gscal[d][b][k]   (one block per (k, od))
+__global__ void __launch_bounds__(RED_THREADS)
+rate_grad_kernel(const double* __restrict__ gscal, const double* __restrict__ bl,
+                 const double* __restrict__ g, double* __restrict__ out, int B, int K,
+                 int draws, int outDraws) {
+  __shared__ double red[RED_THREADS / 32];
+  const int k = blockIdx.x;
+  const int od = blockIdx.y;
+  const int d0 = outDraws > 1 ? od : 0;
+  const int d1 = outDraws > 1 ? od + 1 : draws;
+  double acc = 0.0;
+  for (int d = d0; d < d1; ++d) {
+    double a = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+      a = fma(bl[(size_t)d * B + b], gscal[((size_t)d * B + b) * K + k], a);
+    acc = fma(g[d], a, acc);
+  }
+  const double t = block_sum256(acc, red);
+  if (threadIdx.x == 0) out[(size_t)od * K + k] = t;
+}
+
+// H[od][e] = sum_d g[d] sum_item hpart[d][item][e]  (one block per (e, od))
+__global__ void __launch_bounds__(RED_THREADS)
+h_reduce_kernel(const double* __restrict__ hpart, const double* __restrict__ g,
+                double* __restrict__ H, int items, int SS, int draws, int outDraws) {
+  __shared__ double red[RED_THREADS / 32];
+  const int e = blockIdx.x;
+  const int od = blockIdx.y;
+  const int d0 = outDraws > 1 ? od : 0;
+  const int d1 = outDraws > 1 ? od + 1 : draws;
+  double acc = 0.0;
+  for (int d = d0; d < d1; ++d) {
+    double a = 0.0;
+    for (int it = threadIdx.x; it < items; it += blockDim.x)
+      a += hpart[((size_t)d * items + it) * SS + e];
+    acc = fma(g[d], a, acc);
+  }
+  const double t = block_sum256(acc, red);
+  if (threadIdx.x == 0) H[(size_t)od * SS + e] = t;
+}
+
+// dQ = V^-T H V^T  (one block per eigen-system)
+// (H and dQ may alias: H is fully staged in shared memory before dQ is written)
+__global__ void q_grad_kernel(const double* H, const double* __restrict__ evec,
+                              const double* __restrict__ ivec, double* dQ, int S) {
+  extern __shared__ double sm[];
+  double* sH = sm;
+  double* sT = sH + S * S;
+  double* sV = sT + S * S;
+  double* sVi = sV + S * S;
+  const size_t off = (size_t)blockIdx.x * S * S;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    sH[idx] = H[off + idx];
+    sV[idx] = evec[off + idx];
+    sVi[idx] = ivec[off + idx];
+  }
+  __syncthreads();
+  // T[a][j] = sum_i Vi[i][a] H[i][j]
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int a = idx / S, j = idx - a * S;
+    double acc = 0.0;
+    for (int i = 0; i < S; ++i) acc = fma(sVi[i * S + a], sH[i * S + j], acc);
+    sT[idx] = acc;
+  }
+  __syncthreads();
+  // dQ[a][b] = sum_j T[a][j] V[b][j]
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int a = idx / S, b = idx - a * S;
+    double acc = 0.0;
+    for (int j = 0; j < S; ++j) acc = fma(sT[a * S + j], sV[b * S + j], acc);
+    dQ[off + idx] = acc;
+  }
+}
+
+int round_threads(int n, int cap) {
+  int t = (n + 31) / 32 * 32;
+  if (t < 32) t = 32;
+  return t > cap ? cap : t;
+}
+
+}  // namespace
+
+int pattern_chunks(const Engine& e, int draws, int threads) {
+  const Dims& m = e.dm;
+  int want = (2 * 148 + m.K * draws - 1) / (m.K * draws);
+  const int maxChunks = (m.Npad + threads - 1) / threads;
+  if (want > maxChunks) want = maxChunks;
+  if (want < 1) want = 1;
+  return want;
+}
+
+int small_pmatrix(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  dim3 grid(m.B * m.K, draws);
+  const int threads = round_threads(m.S * m.S, 256);
+  pmatrix_kernel<<<grid, threads, m.S * sizeof(double), e.stream>>>(
+      e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.mats, m.B, m.K, m.S);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+int small_reduce_lnl(Engine& e, int draws, int nblocks) {
+  dim3 grid(1, draws);
+  reduce_rows_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.redPart, e.lnl, nblocks, 1, 0);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+int small_root_grad_reduce(Engine& e, int draws, int nblocks) {
+  const Dims& m = e.dm;
+  dim3 grid(m.K + m.S, draws);
+  reduce_rows_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.redPart, e.rootGrad, nblocks,
+                                                          m.K + m.S, 0);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+int small_gpart_reduce(Engine& e, int draws, int nChunk) {
+  const Dims& m = e.dm;
+  const size_t items = (size_t)draws * m.B * m.K;
+  const int SS = m.S * m.S;
+  const size_t total = items * SS;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  gpart_reduce_kernel<<<blocks, threads, 0, e.stream>>>(e.gpart, e.dmat, items, nChunk, SS);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+int small_scale_dmat(Engine& e, int draws, double* out) {
+  const Dims& m = e.dm;
+  const size_t width = (size_t)m.B * m.K * m.S * m.S;
+  const size_t total = width * draws;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  scale_rows_kernel<<<blocks, threads, 0, e.stream>>>(e.dmat, e.gradLnl, out, width, draws);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+// rootGrad [D][K+S] -> outProps [propDraws][K], outFreqs [freqDraws][S]
+int small_root_outputs(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int w = m.K + m.S;
+  {
+    const int n = m.K * (e.propDraws > 1 ? draws : 1);
+    combine_draws_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
+        e.rootGrad, e.gradLnl, e.outProps, m.K, w, 0, draws, e.propDraws > 1 ? draws : 1);
+    ++e.launches;
+  }
+  {
+    const int n = m.S * (e.freqDraws > 1 ? draws : 1);
+    combine_draws_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
+        e.rootGrad, e.gradLnl, e.outFreqs, m.S, w, m.K, draws, e.freqDraws > 1 ? draws : 1);
+    ++e.launches;
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+int small_eigen_contract(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int SS = m.S * m.S;
+  {
+    dim3 grid(m.B * m.K, draws);
+    const int threads = round_threads(SS, 256);
+    const size_t smem = (4 * (size_t)SS + 2 * m.S) * sizeof(double);
+    if (smem > 48 * 1024)
+      TTB2_CUDA_CHECK(cudaFuncSetAttribute(eigen_contract_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    eigen_contract_kernel<<<grid, threads, smem, e.stream>>>(
+        e.dmat, e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.hpart,
+        e.gscal, m.B, m.K, m.S);
+    ++e.launches;
+  }
+  {
+    const int n = m.B * draws;
+    branch_grad_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
+        e.gscal, e.rates, e.rateDraws, e.gradLnl, e.outBl, m.B, m.K, draws);
+    ++e.launches;
+  }
+  {
+    const int od = e.rateDraws > 1 ? draws : 1;
+    dim3 grid(m.K, od);
+    rate_grad_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
+                                                        m.B, m.K, draws, od);
+    ++e.launches;
+  }
+  {
+    const int od = e.eigDraws > 1 ? draws : 1;
+    dim3 grid(SS, od);
+    // reuse outQ as H then transform in place via a second buffer: H lives in hpart's
+    // tail?  keep it simple: H is written to e.outQ, dQ overwrites it after staging in smem
+    h_reduce_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.hpart, e.gradLnl, e.outQ,
+                                                       m.B * m.K, SS, draws, od);
+    ++e.launches;
+    const int threads = round_threads(SS, 256);
+    const size_t smem = 4 * (size_t)SS * sizeof(double);
+    if (smem > 48 * 1024)
+      TTB2_CUDA_CHECK(cudaFuncSetAttribute(q_grad_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    q_grad_kernel<<<od, threads, smem, e.stream>>>(e.outQ, e.evec, e.ivec, e.outQ, m.S);
+    ++e.launches;
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return small_root_outputs(e, draws);
+}
+
+}  // namespace ttb2
