@@ -212,10 +212,16 @@ def log_likelihood_no_categories(tips, weights, postorder, mats, freqs):
 # whole evaluation on a flattened Problem (torchtree_b200.synthetic.Problem)
 # ----------------------------------------------------------------------------
 def evaluate(problem, want_grad: bool = True, rescale: bool = True, tip_states=False,
-             through_q: bool = True):
+             through_q: bool = True, route: str = "eigh"):
     """logL (and autograd gradient, like the reference: SURVEY 3.4) of a
     flattened problem.  Mirrors TreeLikelihoodModel._call
     (tree_likelihood.py:313-356): mats = p_t(bls[...,B,1] * rates[...,1,K]).
+
+    route="eigh" is the reference's reversible route; its gradient w.r.t. the
+    generator is only the part `eigh` sees (the lower triangle of the
+    symmetrised matrix, returned symmetrised).  route="expm" evaluates
+    P = matrix_exp(Q t) (abstract.py:89-94) whose autograd gives the full
+    unconstrained d lnL / d Q -- the truth the engine's d_q is compared with.
 
     Returns dict with lnL [D] and gradients w.r.t. branch_lengths [D,B],
     site_rates, site_props, freqs (root term only when through_q, i.e. with Q
@@ -230,7 +236,9 @@ def evaluate(problem, want_grad: bool = True, rescale: bool = True, tip_states=F
     weights = torch.tensor(problem.weights, dtype=torch_f64)
 
     t = bl.unsqueeze(-1) * rates.expand(D, -1).unsqueeze(-2)  # [D,B,K]
-    if through_q:
+    if route == "expm":
+        mats = p_t_expm(q.expand(D, -1, -1), t)
+    elif through_q:
         # Q is an independent input: P = expm(Q t) evaluated through the
         # reversible eigen route with a *detached* symmetrising pi, so that
         # d lnL / d freqs is the root term only and d lnL / d Q is the full

@@ -19,7 +19,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
-BUILD = os.path.join(PKG, "build")
+BUILD = os.path.join(PKG, "_obj")
 LIB = os.path.join(LIBDIR, "libttb200.so")
 SOURCES = ["api.cu", "kernels_s4.cu", "kernels_small.cu", "kernels_gen.cu"]
 HEADERS = [os.path.join(CSRC, "engine.cuh"), os.path.join(PKG, "..", "include", "ttb200.h")]
