@@ -1,0 +1,265 @@
+"""The torchtree plug-in class against the REAL reference (authoring container
+only: needs /root/reference).  There is no GPU here, so the two engine entry
+points the glue calls are replaced by the pinned CPU oracle (test-only
+injection); what is verified is everything *around* the engine: JSON parsing,
+class registration / type resolution, tip-code extraction, the flattening of
+torchtree's sub-models, batch shapes, the output contract and the gradient
+hand-back to torchtree Parameters."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.reference
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = "/root/reference/data"
+
+
+@pytest.fixture(scope="module")
+def torchtree_env():
+    sys.path.insert(0, os.path.join(REPO, "oracle", "dendropy_shim"))
+    sys.path.insert(0, "/root/reference")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
+    sys.path.remove("/root/reference")
+    sys.path.remove(os.path.join(REPO, "oracle", "dendropy_shim"))
+
+
+class FakeEngine:
+    """Carries what Engine() was given; the oracle does the arithmetic."""
+
+    def __init__(self, tip_codes, weights, postorder, state_count, category_count,
+                 code_partials=None, max_draws=1, device=0, flags=0):
+        from torchtree_b200.engine import default_code_partials
+
+        self.tip_codes, self.weights, self.postorder = tip_codes, weights, postorder
+        self.S, self.K, self.max_draws = state_count, category_count, max_draws
+        self.code_partials = default_code_partials(state_count) if code_partials is None \
+            else code_partials
+
+    def set_postorder(self, postorder):
+        self.postorder = postorder
+
+    def close(self):
+        pass
+
+
+def _tips(engine):
+    from oracle import treelik as orc
+
+    return orc.tip_partials_from_states(engine.tip_codes, engine.S, engine.code_partials)
+
+
+def fake_eigen(engine, bls, rates, props, q, freqs):
+    from oracle import treelik as orc
+
+    D = bls.shape[0]
+    t = bls.unsqueeze(-1) * rates.reshape(-1, 1, engine.K)
+    # same contract as the engine: P depends on Q only, all S*S entries of Q
+    # independent (matrix_exp autograd), freqs enter at the root only
+    mats = orc.p_t_expm(q.expand(max(q.shape[0], 1), -1, -1), t)
+    return orc.log_likelihood(
+        _tips(engine), torch.tensor(engine.weights), engine.postorder, mats,
+        freqs.expand(D, -1).unsqueeze(-2), props.expand(D, -1)[..., None, None]).squeeze(-1)
+
+
+def fake_mats(engine, mats, freqs, props):
+    from oracle import treelik as orc
+
+    D = mats.shape[0]
+    return orc.log_likelihood(
+        _tips(engine), torch.tensor(engine.weights), engine.postorder, mats,
+        freqs.expand(D, -1).unsqueeze(-2), props.expand(D, -1)[..., None, None]).squeeze(-1)
+
+
+@pytest.fixture
+def patched(torchtree_env, monkeypatch):
+    import torchtree_b200.flatten as flatten
+    import torchtree_b200.tree_likelihood as tlmod
+
+    monkeypatch.setattr(flatten, "log_likelihood_eigen", fake_eigen)
+    monkeypatch.setattr(flatten, "log_likelihood_mats", fake_mats)
+    monkeypatch.setattr(tlmod, "Engine", FakeEngine)
+    return tlmod
+
+
+def _flu_json(tree_type="unrooted", model="GTR", batch=None):
+    taxa = []
+    with open(DATA + "/fluA.fa") as fp:
+        for line in fp:
+            if line.startswith(">"):
+                name = line[1:].strip()
+                taxa.append({"id": name, "type": "Taxon",
+                             "attributes": {"date": float(name.split("_")[-1])}})
+    with open(DATA + "/fluA.tree") as fp:
+        newick = fp.read().strip()
+    rng = np.random.default_rng(5)
+    T = len(taxa)
+    shape = (2 * T - 3,) if batch is None else (batch, 2 * T - 3)
+    objs = [
+        {"id": "taxa", "type": "Taxa", "taxa": taxa},
+        {"id": "alignment", "type": "Alignment", "datatype": "nucleotide",
+         "file": DATA + "/fluA.fa", "taxa": "taxa"},
+    ]
+    like = {
+        "id": "like", "type": "TreeLikelihoodModel",
+        "tree_model": {"id": "tree", "type": "UnRootedTreeModel", "newick": newick,
+                       "taxa": "taxa",
+                       "branch_lengths": {"id": "blens", "type": "Parameter",
+                                          "tensor": rng.uniform(0.01, 0.1, shape).tolist()}},
+        "site_model": {"id": "sm", "type": "WeibullSiteModel", "categories": 4,
+                       "shape": {"id": "shape", "type": "Parameter",
+                                 "tensor": [0.7] if batch is None else [[0.7]] * batch}},
+        "site_pattern": {"id": "sp", "type": "SitePattern", "alignment": "alignment"},
+    }
+    if model == "GTR":
+        like["substitution_model"] = {
+            "id": "gtr", "type": "GTR",
+            "rates": {"id": "rates", "type": "Parameter",
+                      "tensor": [0.9, 3.1, 0.6, 1.3, 4.2, 1.0]},
+            "frequencies": {"id": "freqs", "type": "Parameter",
+                            "tensor": [0.33, 0.19, 0.22, 0.26]}}
+    elif model == "JC69":
+        like["substitution_model"] = {"id": "jc", "type": "JC69"}
+    return objs, like
+
+
+def _build(objs, like, like_type):
+    from torchtree.core.utils import process_objects
+
+    dic = {}
+    for o in objs:
+        process_objects(json.loads(json.dumps(o)), dic)
+    data = json.loads(json.dumps(like))
+    data["type"] = like_type
+    process_objects(data, dic)
+    return dic
+
+
+def _grads(dic, names):
+    for n in names:
+        dic[n].requires_grad = True
+    val = dic["like"]()
+    val.sum().backward()
+    return val.detach().clone(), {n: dic[n].grad.clone() for n in names}
+
+
+@pytest.mark.parametrize("batch", [None, 3])
+def test_dropin_equals_reference_on_fluA_gtr(patched, batch):
+    objs, like = _flu_json(batch=batch)
+    ref = _build(objs, like, "torchtree.evolution.tree_likelihood.TreeLikelihoodModel")
+    new = _build(objs, like, "torchtree_b200.TreeLikelihoodModel")
+    assert type(new["like"]).__module__ == "torchtree_b200.tree_likelihood"
+    names = ["blens", "shape", "rates", "freqs"]
+    v_ref, g_ref = _grads(ref, names)
+    v_new, g_new = _grads(new, names)
+    assert v_new.shape == v_ref.shape  # sample_shape + (1,)
+    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0)
+    for n in names:
+        assert g_new[n].shape == g_ref[n].shape
+        assert torch.allclose(g_new[n], g_ref[n], rtol=1e-7, atol=1e-7 * g_ref[n].abs().max()), n
+
+
+def test_tip_states_and_ambiguities_flags(patched):
+    objs, like = _flu_json()
+    for extra in ({"use_tip_states": True}, {"use_ambiguities": True}):
+        cfg = dict(like, **extra)
+        ref = _build(objs, cfg, "torchtree.evolution.tree_likelihood.TreeLikelihoodModel")
+        new = _build(objs, cfg, "torchtree_b200.TreeLikelihoodModel")
+        assert torch.allclose(new["like"](), ref["like"](), rtol=1e-11, atol=0), extra
+
+
+def test_install_overrides_bare_and_dotted_type_names(patched):
+    from torchtree.core.utils import REGISTERED_CLASSES, get_class
+
+    import torchtree.evolution.tree_likelihood as refmod
+
+    saved_reg = dict(REGISTERED_CLASSES)
+    saved_cls = refmod.TreeLikelihoodModel
+    try:
+        patched.install(override_reference=True)
+        assert get_class("TreeLikelihoodModel") is patched.TreeLikelihoodModel
+        assert get_class("torchtree.evolution.tree_likelihood.TreeLikelihoodModel") \
+            is patched.TreeLikelihoodModel
+        assert get_class("torchtree_b200.TreeLikelihoodModel") is patched.TreeLikelihoodModel
+        assert get_class("LG").__name__ == "LG"
+        objs, like = _flu_json(model="JC69")
+        dic = _build(objs, like, "TreeLikelihoodModel")
+        assert isinstance(dic["like"], patched.TreeLikelihoodModel)
+        assert dic["like"]().shape == (1,)
+    finally:
+        REGISTERED_CLASSES.clear()
+        REGISTERED_CLASSES.update(saved_reg)
+        refmod.TreeLikelihoodModel = saved_cls
+
+
+def test_cli_plugin_rewrites_type(torchtree_env):
+    import argparse
+
+    from torchtree.cli.plugin_manager import PluginManager
+
+    import torchtree_b200
+
+    sys.path.insert(0, REPO)
+    pm = PluginManager()
+    pm.load_plugins()
+    assert "torchtree_b200" in pm._plugins
+    parser = argparse.ArgumentParser()
+    sub = parser.add_subparsers()
+    for name in ("advi", "hmc", "map", "mcmc"):
+        sub.add_parser(name)
+    pm.load_arguments(sub)
+    args = parser.parse_args(["advi", "--b200"])
+    data = {"id": "like", "type": "TreeLikelihoodModel"}
+    for plugin in pm.plugins():
+        plugin.process_tree_likelihood(args, data)
+    assert data["type"] == "torchtree_b200.TreeLikelihoodModel"
+    args = parser.parse_args(["map"])
+    data = {"id": "like", "type": "TreeLikelihoodModel"}
+    for plugin in pm.plugins():
+        plugin.process_tree_likelihood(args, data)
+    assert data["type"] == "TreeLikelihoodModel"
+
+
+def test_time_tree_with_strict_clock(patched):
+    """test/test_tree_likelihood.py:268-342 through the drop-in class."""
+    from torchtree import Parameter
+    from torchtree.evolution.branch_model import StrictClockModel
+    from torchtree.evolution.site_model import WeibullSiteModel
+    from torchtree.evolution.site_pattern import SitePattern
+    from torchtree.evolution.substitution_model import JC69
+    from torchtree.evolution.taxa import Taxa, Taxon
+    from torchtree.evolution.tree_model import ReparameterizedTimeTreeModel
+
+    taxa_list = []
+    with open(DATA + "/fluA.fa") as fp:
+        for line in fp:
+            if line.startswith(">"):
+                t = line[1:].strip()
+                taxa_list.append(Taxon(t, {"date": float(t.split("_")[-1])}))
+    dic = {"taxa": Taxa("taxa", taxa_list)}
+    with open(DATA + "/fluA.tree") as fp:
+        newick = fp.read().strip()
+    tree_model = ReparameterizedTimeTreeModel.from_json(
+        ReparameterizedTimeTreeModel.json_factory(
+            "tree_model", newick, "taxa", ratios=[0.5] * 67, root_height=[20.0],
+            **{"keep_branch_lengths": True}), dic)
+    sp = SitePattern.from_json({
+        "id": "sp", "type": "SitePattern",
+        "alignment": {"id": "a", "type": "Alignment", "datatype": "nucleotide",
+                      "file": DATA + "/fluA.fa", "taxa": "taxa"}}, dic)
+    site_model = WeibullSiteModel("sm", Parameter(None, torch.tensor([[0.1]])), 4)
+    clock = StrictClockModel(None, Parameter(None, torch.tensor([[0.001]])), tree_model)
+    like = patched.TreeLikelihoodModel("like", sp, tree_model, JC69("jc"), site_model, clock)
+    assert torch.allclose(torch.tensor([-4618.2062529058]), like())
+    clock._rates.tensor = clock._rates.tensor.repeat(3, 1)
+    site_model._parameter.tensor = site_model._parameter.tensor.repeat(3, 1)
+    tree_model._internal_heights.tensor = tree_model._internal_heights.tensor.repeat(3, 68)
+    like.lp_needs_update = True
+    assert torch.allclose(torch.tensor([[-4618.2062529058] * 3]), like())

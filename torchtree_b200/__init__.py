@@ -15,3 +15,18 @@ from .function import (  # noqa: F401
     reversible_eigensystem,
 )
 from ._lib import EngineError  # noqa: F401
+
+
+def __getattr__(name):
+    # resolved lazily so that the engine can be used where torchtree is absent;
+    # `"type": "torchtree_b200.TreeLikelihoodModel"` reaches this through
+    # torchtree.core.utils.get_class (core/utils.py:116-125)
+    if name == "TreeLikelihoodModel":
+        from .tree_likelihood import TreeLikelihoodModel
+
+        return TreeLikelihoodModel
+    if name == "install":
+        from .tree_likelihood import install
+
+        return install
+    raise AttributeError(name)

@@ -1,0 +1,47 @@
+"""torchtree-cli plug-in hooks (torchtree/cli/plugin.py:4-16,
+plugin_manager.py:10-23): adds `--b200` to the advi/hmc/map/mcmc sub-commands and
+rewrites the generated tree-likelihood block to the B200 class.
+
+Also provides `main()`: `python -m torchtree_b200.cli cfg.json` runs the stock
+torchtree runner with the drop-in installed, so that *existing* JSON files
+(bare or dotted reference type names) run unchanged on the engine.
+"""
+from __future__ import annotations
+
+import sys
+
+from torchtree.cli.plugin import Plugin
+
+
+class B200Plugin(Plugin):
+    def load_arguments(self, subparsers):
+        for name, parser in subparsers._name_parser_map.items():
+            if name in ("advi", "hmc", "map", "mcmc"):
+                parser.add_argument(
+                    "--b200", action="store_true",
+                    help="compute the tree likelihood with the torchtree_b200 CUDA engine")
+                parser.add_argument(
+                    "--b200_device", type=int, default=0,
+                    help="CUDA device ordinal used by the torchtree_b200 engine")
+
+    def process_tree_likelihood(self, arg, data):
+        if getattr(arg, "b200", False):
+            data["type"] = "torchtree_b200.TreeLikelihoodModel"
+            if getattr(arg, "b200_device", 0):
+                data["device"] = arg.b200_device
+
+
+def main(argv=None):
+    """torchtree runner with the drop-in installed (console entry point)."""
+    from torchtree.torchtree import main as torchtree_main
+
+    from .tree_likelihood import install
+
+    install(override_reference=True)
+    if argv is not None:
+        sys.argv = [sys.argv[0]] + list(argv)
+    torchtree_main()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,9 +94,13 @@ def log_likelihood_eigen(engine: Engine, branch_lengths, site_rates, site_props,
     independent; d/d freqs is the root term only -- chain the rest through the
     caller's Q builder (which is where the reference's graph does it too).
     """
+    q_norm, freqs = _lead(q_norm, 2), _lead(freqs, 1)
+    if freqs.shape[0] > q_norm.shape[0]:
+        # one eigen-system per frequency draw: give Q the same leading dimension
+        q_norm = q_norm.expand(freqs.shape[0], -1, -1)
     return _EigenLikelihood.apply(
         engine, _lead(branch_lengths, 1), _lead(site_rates, 1), _lead(site_props, 1),
-        _lead(q_norm, 2), _lead(freqs, 1))
+        q_norm, freqs)
 
 
 def log_likelihood_mats(engine: Engine, mats, freqs, site_props):
