@@ -82,6 +82,13 @@ typedef struct ttb2_config {
 #define TTB2_FLAG_PREALLOC_GRAD 1
 /* force the generic-S kernels even when a specialised path exists (testing) */
 #define TTB2_FLAG_FORCE_GENERIC 2
+/* 4-state models, eigen mode: use the experimental fused whole-tree traversal
+ * kernels (one persistent launch per sweep, 2 instead of 5 vectors of HBM
+ * traffic per node) instead of the per-level kernels */
+#define TTB2_FLAG_FUSED 4
+/* 4-state pre-order kernel: accumulate d lnL / d P with plain fp64 FMAs instead
+ * of fp64 tensor-core MMAs (testing / comparison) */
+#define TTB2_FLAG_NO_MMA 8
 
 /*
  * tip_codes      uint8 [T][N]: symbol code of tip t at pattern i

@@ -42,7 +42,7 @@ def _reduce(ref, like_rows):
     return ref
 
 
-@pytest.mark.parametrize("flags", [0, 2], ids=["spec", "generic"])
+@pytest.mark.parametrize("flags", [0, 2, 8], ids=["levels", "generic", "levels-simt"])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_mats_mode(name, flags):
     """ttb2_loglik_mats / ttb2_grad_mats with the reference's own matrices."""
@@ -64,7 +64,7 @@ def test_golden_mats_mode(name, flags):
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [0, 2], ids=["spec", "generic"])
+@pytest.mark.parametrize("flags", [0, 2, 4, 8], ids=["levels", "generic", "fused", "levels-simt"])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_eigen_mode(name, flags):
     """ttb2_loglik_eigen / ttb2_grad_eigen: P(t) on the device, gradients w.r.t.
@@ -114,13 +114,14 @@ def _gtr_chain(rec, eng_grads, prob):
 @pytest.mark.parametrize("name", ["fluA_gtr_w4_generic", "fluA_gtr_w4_ambig", "syn40_gtr_w4",
                                   "syn400_gtr_w4_caterpillar", "syn17_gtr_w3",
                                   "fluA_gtr_w4_batch3"])
-def test_gtr_parameter_gradients_match_reference(name):
+@pytest.mark.parametrize("flags", [0, 4, 8], ids=["levels", "fused", "levels-simt"])
+def test_gtr_parameter_gradients_match_reference(name, flags):
     """End of the chain: d lnL / d (GTR rates, GTR freqs, Weibull shape, branch
     lengths) as torchtree's own `like().backward()` produced them."""
     from oracle import treelik as orc
 
     prob, rec = load_golden(name)
-    eng = _engine(prob)
+    eng = _engine(prob, flags=flags)
     evec, ivec, evals = _eig(prob)
     lnl = eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props,
                            evec, ivec, evals, prob.freqs)
@@ -185,4 +186,44 @@ def test_device_resident_inputs_match_host_inputs():
     assert torch.equal(dev.cpu(), host)
     for k in gh:
         assert torch.equal(gd[k].cpu(), gh[k]), k
+    eng.close()
+
+
+def test_grad_mats_after_fused_eigen_forward():
+    """d lnL / d P requested after an eigen-mode (fused) forward: the engine
+    falls back to the per-level sweeps for that call."""
+    prob, rec = load_golden("syn40_gtr_w4")
+    eng = _engine(prob, flags=4)
+    evec, ivec, evals = _eig(prob)
+    eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props, evec, ivec, evals,
+                     prob.freqs)
+    d_mats, d_freqs, d_props = eng.grad_mats()
+    assert_grad_close(d_mats.numpy(), rec["d_mats"], what="d_mats")
+    g = eng.grad_eigen()
+    assert_grad_close(g["branch_lengths"].numpy(), rec["d_branch_lengths"], what="d_bl")
+    eng.close()
+
+
+def test_fused_without_q_gradient():
+    """grad_eigen with d_q skipped (models without free substitution parameters)."""
+    import ctypes
+
+    from torchtree_b200 import _lib
+
+    prob, rec = load_golden("fluA_gtr_w4_generic")
+    eng = _engine(prob, flags=4)
+    evec, ivec, evals = _eig(prob)
+    eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props, evec, ivec, evals,
+                     prob.freqs)
+    out = dict(branch_lengths=torch.empty((1, prob.branch_count), dtype=torch.float64),
+               site_rates=torch.empty((1, 4), dtype=torch.float64),
+               props=torch.empty((1, 4), dtype=torch.float64), q=None,
+               freqs=torch.empty((1, 4), dtype=torch.float64))
+    eng.grad_eigen(out=out)
+    assert_grad_close(out["branch_lengths"].numpy(), rec["d_branch_lengths"], what="d_bl")
+    assert_grad_close(out["site_rates"].numpy(), rec["d_site_rates"], what="d_rates")
+    g = eng.grad_eigen()  # now with d_q: must recompute the sweep with H accumulation
+    from oracle import treelik as orc
+    want = orc.evaluate(prob, want_grad=True, route="expm")["q_matrix"]
+    assert_grad_close(g["q"].numpy(), want, rtol=1e-7, what="d_q")
     eng.close()

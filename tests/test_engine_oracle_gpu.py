@@ -42,19 +42,21 @@ def _check(prob, flags=0, q_rtol=1e-7):
     eng.close()
 
 
+@pytest.mark.parametrize("flags", [0, 4, 8], ids=["levels", "fused", "levels-simt"])
 @pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8])
-def test_category_counts(K):
+def test_category_counts(K, flags):
     from torchtree_b200.synthetic import make_problem
 
-    _check(make_problem(33, 257, 4, K, seed=100 + K, gap_fraction=0.05))
+    _check(make_problem(33, 257, 4, K, seed=100 + K, gap_fraction=0.05), flags=flags)
 
 
+@pytest.mark.parametrize("flags", [0, 4, 8], ids=["levels", "fused", "levels-simt"])
 @pytest.mark.parametrize("topology", ["random", "caterpillar", "balanced"])
-def test_topologies_with_rescaling(topology):
+def test_topologies_with_rescaling(topology, flags):
     from torchtree_b200.synthetic import make_problem
 
     # iid tips on >= 300 taxa underflow without rescaling
-    _check(make_problem(320, 96, 4, 4, seed=7, topology=topology))
+    _check(make_problem(320, 96, 4, 4, seed=7, topology=topology), flags=flags)
 
 
 def test_ragged_pattern_counts_and_single_pattern():
@@ -73,8 +75,9 @@ def test_two_tips_tree():
 def test_batched_draws_with_per_draw_models():
     from torchtree_b200.synthetic import make_problem
 
-    _check(make_problem(25, 130, 4, 4, draws=5, seed=17, per_draw_model=True))
-    _check(make_problem(25, 130, 4, 4, draws=5, seed=18, per_draw_model=False))
+    for flags in (0, 4, 8):
+        _check(make_problem(25, 130, 4, 4, draws=5, seed=17, per_draw_model=True), flags=flags)
+        _check(make_problem(25, 130, 4, 4, draws=5, seed=18, per_draw_model=False), flags=flags)
 
 
 def test_generic_kernels_equal_specialised_for_nucleotides():
@@ -190,3 +193,31 @@ def test_nan_in_nan_out():
     eng, out = _run(prob, want_grad=False)
     assert np.isnan(out["lnL"]).all()
     eng.close()
+
+
+def test_fused_equals_level_kernels():
+    """Whole-tree traversal kernels vs per-level kernels on the same problem
+    (different rescaling granularity, same likelihood)."""
+    from torchtree_b200.synthetic import make_problem
+
+    for topo in ("random", "caterpillar", "balanced"):
+        prob = make_problem(200, 700, 4, 4, seed=31, topology=topo, gap_fraction=0.02)
+        e1, a = _run(prob, flags=4)
+        e2, b = _run(prob, flags=0)
+        assert_lnl_close(a["lnL"], b["lnL"], rtol=1e-13)
+        for k in ("branch_lengths", "site_rates", "props", "freqs", "q"):
+            assert_grad_close(a[k], b[k], rtol=1e-10, what=topo + " " + k)
+        e1.close(); e2.close()
+
+
+def test_invariant_category_zero_rate():
+    """Rate-0 category (InvariantSiteModel, site_model.py:77-112): P = I exactly,
+    so variable patterns have an all-zero vector in that category."""
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(30, 200, 4, 4, seed=77)
+    prob.site_rates = prob.site_rates.copy()
+    prob.site_rates[0, 0] = 0.0
+    prob.site_rates /= (prob.site_rates * prob.site_props).sum()
+    for flags in (0, 4, 8):
+        _check(prob, flags=flags)

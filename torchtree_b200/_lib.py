@@ -15,6 +15,8 @@ TTB2_HOST = 0
 TTB2_DEVICE = 1
 TTB2_FLAG_PREALLOC_GRAD = 1
 TTB2_FLAG_FORCE_GENERIC = 2
+TTB2_FLAG_FUSED = 4
+TTB2_FLAG_NO_MMA = 8
 
 
 class Ttb2Config(ctypes.Structure):

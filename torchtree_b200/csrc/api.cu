@@ -129,7 +129,8 @@ int ensure_grad_buffers(Engine& e, int draws) {
   if (!e.dmat && (rc = dev_alloc(e, &e.dmat, matN))) return rc;
   if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)e.cfg.max_draws * (m.K + m.S))))
     return rc;
-  const size_t need = e.spec4 ? s4_gpart_doubles(e, draws) : gen_gpart_doubles(e, draws);
+  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32))) return rc;
+  const size_t need = planned_gpart_doubles(e, draws);
   if (need > e.gpartCap) {
     if (e.gpart) {
       e.deviceBytes -= (int64_t)(e.gpartCap * sizeof(double));
@@ -145,15 +146,109 @@ int ensure_eigen_grad_buffers(Engine& e) {
   const Dims& m = e.dm;
   int rc;
   const size_t matN = (size_t)e.cfg.max_draws * m.B * m.K * m.S * m.S;
-  if (!e.hpart && (rc = dev_alloc(e, &e.hpart, matN))) return rc;
+  if (!e.hpart) {
+    if ((rc = dev_alloc(e, &e.hpart, matN))) return rc;
+    e.hpartCap = matN;
+  }
   if (!e.gscal && (rc = dev_alloc(e, &e.gscal, (size_t)e.cfg.max_draws * m.B * m.K))) return rc;
+  return TTB2_OK;
+}
+
+int upload_fused_programs(Engine& e) {
+  const Dims& m = e.dm;
+  e.fusedOK = false;
+  if (!e.spec4 || !(e.cfg.flags & TTB2_FLAG_FUSED)) return TTB2_OK;
+  int rc = fused_build_programs(e);
+  if (rc) return rc;
+  if (!fused_supported(e)) return TTB2_OK;
+  if (!e.fwdProg) {
+    const int D = e.cfg.max_draws;
+    if ((rc = dev_alloc(e, &e.fwdProg, (size_t)m.I))) return rc;
+    if ((rc = dev_alloc(e, &e.bwdProg, (size_t)m.I))) return rc;
+    if ((rc = dev_alloc(e, &e.expoK, (size_t)D * m.I * m.K * m.Npad))) return rc;
+    if ((rc = dev_alloc(e, &e.esum, (size_t)D * m.K * m.Npad))) return rc;
+    if ((rc = dev_alloc(e, &e.fusedCounter, (size_t)1))) return rc;
+    const size_t tipWords = (size_t)fused_tip_groups(e) * m.Npad;
+    if ((rc = dev_alloc(e, &e.tipsF4, tipWords))) return rc;
+    if ((rc = dev_alloc(e, &e.tipsB4, tipWords))) return rc;
+    if ((rc = dev_alloc(e, &e.tipOrder, (size_t)m.T))) return rc;
+    if ((rc = dev_alloc(e, &e.streamF, (size_t)D * m.K * m.I * 32))) return rc;
+  }
+  TTB2_CUDA_CHECK(cudaMemcpy(e.fwdProg, e.hostFwdProg.data(), m.I * sizeof(FusedRec),
+                             cudaMemcpyHostToDevice));
+  TTB2_CUDA_CHECK(cudaMemcpy(e.bwdProg, e.hostBwdProg.data(), m.I * sizeof(FusedRec),
+                             cudaMemcpyHostToDevice));
+  if ((rc = fused_pack_tips(e))) return rc;
+  e.fusedOK = true;
+  return TTB2_OK;
+}
+
+int ensure_fused_grad_buffers(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int D = e.cfg.max_draws;
+  int rc;
+  if (!e.qroot && (rc = dev_alloc(e, &e.qroot, (size_t)D * m.K * m.Npad * 4))) return rc;
+  if (!e.aux && (rc = dev_alloc(e, &e.aux, (size_t)D * m.B * m.K * 20))) return rc;
+  if (!e.streamB && (rc = dev_alloc(e, &e.streamB, (size_t)D * m.K * m.I * 80))) return rc;
+  if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)D * (m.K + m.S)))) return rc;
+  if (!e.gscal && (rc = dev_alloc(e, &e.gscal, (size_t)D * m.B * m.K))) return rc;
+  const size_t hneed = std::max((size_t)D * m.B * m.K * m.S * m.S,
+                                (size_t)D * (m.Npad / 32) * m.K * 16);
+  if (hneed > e.hpartCap) {
+    if (e.hpart) {
+      e.deviceBytes -= (int64_t)(e.hpartCap * sizeof(double));
+      dev_free(e.hpart);
+    }
+    if ((rc = dev_alloc(e, &e.hpart, hneed))) return rc;
+    e.hpartCap = hneed;
+  }
+  const size_t need = fused_gspart_doubles(e, draws);
+  if (need > e.gpartCap) {
+    if (e.gpart) {
+      e.deviceBytes -= (int64_t)(e.gpartCap * sizeof(double));
+      dev_free(e.gpart);
+    }
+    if ((rc = dev_alloc(e, &e.gpart, need))) return rc;
+    e.gpartCap = need;
+  }
+  return TTB2_OK;
+}
+
+int run_forward_levels(Engine& e, int draws) {
+  int rc;
+  const int64_t before = e.launches;
+  if (e.spec4) {
+    if ((rc = s4_forward(e, draws))) return rc;
+    e.fwdLevelLaunches = (int)(e.launches - before);
+    mark(e, 2);
+    if ((rc = s4_root(e, draws))) return rc;
+  } else {
+    if ((rc = gen_forward(e, draws))) return rc;
+    e.fwdLevelLaunches = (int)(e.launches - before);
+    mark(e, 2);
+    if ((rc = gen_root(e, draws))) return rc;
+  }
+  e.lastFused = false;
   return TTB2_OK;
 }
 
 int run_forward(Engine& e, int draws, double* lnl, int where) {
   int rc;
   mark(e, 1);
+  if (e.fusedOK && e.mode == MODE_EIGEN) {
+    if ((rc = fused_forward(e, draws))) return rc;
+    e.fwdLevelLaunches = 1;
+    mark(e, 2);
+    if ((rc = fused_root(e, draws))) return rc;
+    e.lastFused = true;
+    mark(e, 3);
+    e.draws = draws;
+    e.preValid = false;
+    if ((rc = copy_out(e, lnl, e.lnl, (size_t)draws * sizeof(double), where))) return rc;
+    return finish(e, where);
+  }
   const int64_t before = e.launches;
+  e.lastFused = false;
   if (e.spec4) {
     if ((rc = s4_forward(e, draws))) return rc;
     e.fwdLevelLaunches = (int)(e.launches - before);
@@ -172,9 +267,40 @@ int run_forward(Engine& e, int draws, double* lnl, int where) {
   return finish(e, where);
 }
 
+int stage_grad_lnl(Engine& e, const double* grad_lnl, int where) {
+  if (grad_lnl)
+    return copy_in(e, e.gradLnl, grad_lnl, (size_t)e.draws * sizeof(double), where);
+  TTB2_CUDA_CHECK(cudaMemcpyAsync(e.gradLnl, e.ones, e.draws * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, e.stream));
+  return TTB2_OK;
+}
+
+// pre-order sweep of the fused path (eigen mode only)
+int run_backward_fused(Engine& e, const double* grad_lnl, bool needQ, int where) {
+  int rc;
+  const int draws = e.draws;
+  if ((rc = ensure_fused_grad_buffers(e, draws))) return rc;
+  if ((rc = stage_grad_lnl(e, grad_lnl, where))) return rc;
+  mark(e, 4);
+  if (!e.preValid || (needQ && !e.lastNeedQ)) {
+    if ((rc = fused_backward(e, draws, needQ))) return rc;
+    e.bwdLevelLaunches = 1;
+    e.preValid = true;
+    e.lastNeedQ = needQ;
+  }
+  mark(e, 5);
+  return TTB2_OK;
+}
+
 int run_backward(Engine& e, const double* grad_lnl, int where) {
   int rc;
   const int draws = e.draws;
+  if (e.lastFused) {
+    // d lnL / d P was requested after a fused forward: the per-level pre-order
+    // pass needs the per-pattern exponents of the per-level post-order pass
+    if ((rc = run_forward_levels(e, draws))) return rc;
+    e.preValid = false;
+  }
   if ((rc = ensure_grad_buffers(e, draws))) return rc;
   if (grad_lnl) {
     if ((rc = copy_in(e, e.gradLnl, grad_lnl, (size_t)draws * sizeof(double), where))) return rc;
@@ -340,9 +466,20 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
   TRY_CUDA(cudaMemcpy(e.codeP, code_partials, (size_t)m.C * m.S * sizeof(double),
                       cudaMemcpyHostToDevice));
   TRY_CUDA(cudaMemcpy(e.ops, e.hostOps.data(), m.I * sizeof(NodeOp), cudaMemcpyHostToDevice));
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device) == cudaSuccess &&
+        sms > 0)
+      e.smCount = sms;
+  }
+  TRY(upload_fused_programs(e));
   if (c.flags & TTB2_FLAG_PREALLOC_GRAD) {
-    TRY(ensure_grad_buffers(e, D));
-    TRY(ensure_eigen_grad_buffers(e));
+    if (e.fusedOK) {
+      TRY(ensure_fused_grad_buffers(e, D));
+    } else {
+      TRY(ensure_grad_buffers(e, D));
+      TRY(ensure_eigen_grad_buffers(e));
+    }
   }
 #undef TRY
 #undef TRY_CUDA
@@ -370,7 +507,9 @@ int ttb2_set_postorder(ttb2_engine* engine, const int32_t* postorder) {
                              cudaMemcpyHostToDevice));
   e.mode = MODE_NONE;
   e.preValid = false;
-  return TTB2_OK;
+  e.lastFused = false;
+  e.chunkPlanDraws = 0;
+  return upload_fused_programs(e);
 }
 
 void ttb2_destroy(ttb2_engine* engine) {
@@ -387,6 +526,11 @@ void ttb2_destroy(ttb2_engine* engine) {
   dev_free(e.evec); dev_free(e.ivec); dev_free(e.eval); dev_free(e.gradLnl); dev_free(e.ones);
   dev_free(e.outBl); dev_free(e.outRates); dev_free(e.outProps); dev_free(e.outFreqs);
   dev_free(e.outQ);
+  dev_free(e.fwdProg); dev_free(e.bwdProg); dev_free(e.expoK); dev_free(e.esum);
+  dev_free(e.qroot); dev_free(e.aux); dev_free(e.fusedCounter);
+  dev_free(e.tipsF4); dev_free(e.tipsB4); dev_free(e.tipOrder);
+  dev_free(e.streamF); dev_free(e.streamB);
+  dev_free(e.chunkBase); dev_free(e.chunkCount);
   for (int j = 0; j < 8; ++j)
     if (e.ev[j]) cudaEventDestroy(e.ev[j]);
   delete ep;
@@ -533,10 +677,16 @@ int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branc
   }
   TTB2_CUDA_CHECK(cudaSetDevice(e.device));
   int rc;
-  if ((rc = ensure_eigen_grad_buffers(e))) return rc;
-  if ((rc = run_backward(e, grad_lnl, where))) return rc;
   const int draws = e.draws;
-  if ((rc = small_eigen_contract(e, draws))) return rc;
+  if (e.lastFused) {
+    const bool needQ = d_q != nullptr;
+    if ((rc = run_backward_fused(e, grad_lnl, needQ, where))) return rc;
+    if ((rc = small_fused_outputs(e, draws, needQ))) return rc;
+  } else {
+    if ((rc = ensure_eigen_grad_buffers(e))) return rc;
+    if ((rc = run_backward(e, grad_lnl, where))) return rc;
+    if ((rc = small_eigen_contract(e, draws))) return rc;
+  }
   if ((rc = copy_out(e, d_branch_lengths, e.outBl, (size_t)draws * m.B * sizeof(double), where)))
     return rc;
   if ((rc = copy_out(e, d_site_rates, e.outRates, (size_t)e.rateDraws * m.K * sizeof(double), where)))

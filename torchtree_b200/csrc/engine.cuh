@@ -29,6 +29,15 @@ struct Dims {
 
 enum Mode { MODE_NONE = 0, MODE_MATS = 1, MODE_EIGEN = 2 };
 
+// One step of a fused traversal program (kernels_fused.cu), 16 bytes.
+//   post-order: aux = storage position of the node's vector;
+//               slots = (slot of left child, slot of right child, output slot)
+//   pre-order : aux = node id; slots = (slot of q^_node, slot for q^_left, q^_right)
+// slot bytes are signed, -1 = not applicable (tip child / root output).
+struct __align__(16) FusedRec {
+  int32_t left, right, aux, slots;
+};
+
 struct Engine {
   ttb2_config cfg{};
   Dims dm{};
@@ -52,6 +61,14 @@ struct Engine {
   double* dmat = nullptr;       // d lnL / d mats, same shape
   double* gpart = nullptr;      // per-chunk partial sums of dmat
   size_t gpartCap = 0;          // doubles
+  // pattern-chunk plan of the per-level pre-order kernels (depends on draws)
+  std::vector<int> levelChunks;     // chunks per level
+  std::vector<int> hostChunkBase;   // [B] offset (in chunk slots) of branch b, category 0
+  std::vector<int> hostChunkCount;  // [B] chunks of branch b
+  int* chunkBase = nullptr;
+  int* chunkCount = nullptr;
+  int chunkPlanDraws = 0;           // draws the uploaded plan was made for (0 = none)
+  size_t chunkTotal = 0;            // chunk slots per draw (sum over branches of K * chunks)
   double* siteLnl = nullptr;    // [D][Npad]
   double* redPart = nullptr;    // per-block partials of pattern reductions
   size_t redPartCap = 0;
@@ -75,6 +92,28 @@ struct Engine {
   double* outProps = nullptr;   // [Dmax][K]
   double* outFreqs = nullptr;   // [Dmax][S]
   double* outQ = nullptr;       // [Dmax][S][S]
+
+  // fused-traversal path (S = 4, eigen mode)
+  int smCount = 148;
+  int fusedSlots = 0;
+  bool fusedOK = false;      // programs built and the stack fits in shared memory
+  bool lastFused = false;    // the latest forward used the fused path
+  bool lastNeedQ = false;
+  std::vector<FusedRec> hostFwdProg, hostBwdProg;
+  std::vector<int> hostTipOrderF, hostTipOrderB;
+  FusedRec* fwdProg = nullptr;
+  FusedRec* bwdProg = nullptr;
+  uint32_t* tipsF4 = nullptr;   // [groups][Npad] tip codes, 4 per word, post-order use order
+  uint32_t* tipsB4 = nullptr;   // same, pre-order use order
+  int* tipOrder = nullptr;      // [T] scratch
+  double* streamF = nullptr;    // [D][K][I][32] P_l, P_r in post-order program order
+  double* streamB = nullptr;    // [D][K][I][80] P_l, P_r, aux_l, aux_r in pre-order order
+  int16_t* expoK = nullptr;     // [D][I][K][Npad] per-(pattern, category) exponents
+  int* esum = nullptr;          // [D][K][Npad] exponent sums of the chains
+  double* qroot = nullptr;      // [D][K][Npad][4] q^ of the root
+  double* aux = nullptr;        // [D][B][K][20] Phi / lambda e^{lambda tau} (or Q P)
+  int* fusedCounter = nullptr;  // dynamic work distribution
+  size_t hpartCap = 0;
 
   int draws = 0, freqDraws = 0, propDraws = 0, rateDraws = 0, eigDraws = 0;
   Mode mode = MODE_NONE;
@@ -116,23 +155,37 @@ void set_error(const std::string& msg);
 int s4_forward(Engine& e, int draws);
 int s4_root(Engine& e, int draws);
 int s4_backward(Engine& e, int draws);
-size_t s4_gpart_doubles(const Engine& e, int draws);
 
 // generic-S path (kernels_gen.cu)
 int gen_forward(Engine& e, int draws);
 int gen_root(Engine& e, int draws);
 int gen_backward(Engine& e, int draws);
-size_t gen_gpart_doubles(const Engine& e, int draws);
 
 // small kernels (kernels_small.cu)
 int small_pmatrix(Engine& e, int draws);
 int small_reduce_lnl(Engine& e, int draws, int nblocks);
 int small_root_grad_reduce(Engine& e, int draws, int nblocks);
-int small_gpart_reduce(Engine& e, int draws, int nchunk);
+int small_gpart_reduce(Engine& e, int draws);
 int small_scale_dmat(Engine& e, int draws, double* out);
 int small_eigen_contract(Engine& e, int draws);
 int small_root_outputs(Engine& e, int draws);
 
-int pattern_chunks(const Engine& e, int draws, int threads);
+// Plans how many pattern chunks every level's pre-order launch uses (enough CTAs
+// to fill the GPU on small levels, long-lived CTAs on large ones) and uploads the
+// per-branch offsets into the partial-sum buffer.  `granule` = patterns a chunk
+// must be a multiple of.
+int plan_chunks(Engine& e, int draws, int granule);
+size_t planned_gpart_doubles(const Engine& e, int draws);
+
+// fused-traversal path (kernels_fused.cu)
+int fused_build_programs(Engine& e);
+int fused_pack_tips(Engine& e);
+int fused_tip_groups(const Engine& e);
+bool fused_supported(const Engine& e);
+int fused_forward(Engine& e, int draws);
+int fused_root(Engine& e, int draws);
+int fused_backward(Engine& e, int draws, bool needQ);
+size_t fused_gspart_doubles(const Engine& e, int draws);
+int small_fused_outputs(Engine& e, int draws, bool needQ);
 
 }  // namespace ttb2

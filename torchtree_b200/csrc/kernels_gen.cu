@@ -215,8 +215,9 @@ gen_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
                const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
                const double* __restrict__ partials, const int16_t* __restrict__ expo,
                const double* __restrict__ weights, double* __restrict__ pre,
-               double* __restrict__ gpart, int T, int Npad, int B, int K, int S,
-               int chunkPatterns, int nChunk) {
+               double* __restrict__ gpart, const int* __restrict__ chunkBase,
+               size_t chunkTotal, int T, int Npad, int B, int K, int S, int chunkPatterns,
+               int nChunk) {
   extern __shared__ double sm[];
   const int SS = S * S;
   double* Pl = sm;
@@ -331,8 +332,10 @@ gen_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       }
     }
   }
-  double* outL = gpart + ((((size_t)d * B + op.left) * K + k) * nChunk + blockIdx.x) * SS;
-  double* outR = gpart + ((((size_t)d * B + op.right) * K + k) * nChunk + blockIdx.x) * SS;
+  double* outL = gpart + ((size_t)d * chunkTotal + chunkBase[op.left] + (size_t)k * nChunk +
+                          blockIdx.x) * SS;
+  double* outR = gpart + ((size_t)d * chunkTotal + chunkBase[op.right] + (size_t)k * nChunk +
+                          blockIdx.x) * SS;
 #pragma unroll
   for (int j = 0; j < GEN_MAX_OWN; ++j) {
     const int idx = threadIdx.x + j * GEN_THREADS;
@@ -398,12 +401,6 @@ int gen_root(Engine& e, int draws) {
   return small_reduce_lnl(e, draws, nblocks);
 }
 
-size_t gen_gpart_doubles(const Engine& e, int draws) {
-  const Dims& m = e.dm;
-  const int nChunk = pattern_chunks(e, draws, TP);
-  return (size_t)draws * m.B * m.K * nChunk * m.S * m.S;
-}
-
 int gen_backward(Engine& e, int draws) {
   const Dims& m = e.dm;
   const int rootInode = e.hostOps.back().node - m.T;
@@ -418,9 +415,6 @@ int gen_backward(Engine& e, int draws) {
     int rc = small_root_grad_reduce(e, draws, nblocks);
     if (rc) return rc;
   }
-  const int nChunk = pattern_chunks(e, draws, TP);
-  int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
-  chunkPatterns = (chunkPatterns + TP - 1) / TP * TP;
   const size_t smem = bwd_smem(m);
   if (smem > 48 * 1024)
     TTB2_CUDA_CHECK(cudaFuncSetAttribute(gen_bwd_kernel,
@@ -430,17 +424,21 @@ int gen_backward(Engine& e, int draws) {
   for (int l = nLevels - 1; l >= 0; --l) {
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
+    const int nChunk = e.levelChunks[l];
+    int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
+    chunkPatterns = (chunkPatterns + TP - 1) / TP * TP;
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
       gen_bwd_kernel<<<grid, GEN_THREADS, smem, e.stream>>>(
           e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
-          e.pre, e.gpart, m.T, m.Npad, m.B, m.K, m.S, chunkPatterns, nChunk);
+          e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B, m.K, m.S, chunkPatterns,
+          nChunk);
       ++e.launches;
     }
   }
   TTB2_CUDA_CHECK(cudaGetLastError());
-  return small_gpart_reduce(e, draws, nChunk);
+  return small_gpart_reduce(e, draws);
 }
 
 }  // namespace ttb2

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(FWD_THREADS)
 fwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
             const double* __restrict__ mats, const uint8_t* __restrict__ tips,
             const double* __restrict__ codeP, double* __restrict__ partials,
-            int16_t* __restrict__ expo, int T, int Npad, int C, int B) {
+            int16_t* __restrict__ expo, int T, int Npad, int C, int B, int ppt) {
   extern __shared__ double sm[];
   const NodeOp op = ops[opBegin + blockIdx.y];
   const int d = blockIdx.z;
@@ -125,45 +125,48 @@ fwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
   build_child_table<K>(tabR, matsD + (size_t)op.right * K * 16, tipR, codeP, C);
   __syncthreads();
 
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Npad) return;
   const size_t nodeStride = (size_t)K * Npad * 4;
   double* base = partials + (size_t)d * I * nodeStride;
+  const int i0 = blockIdx.x * (FWD_THREADS * ppt) + threadIdx.x;
+#pragma unroll 1
+  for (int it = 0; it < ppt; ++it) {
+    const int i = i0 + it * FWD_THREADS;
+    if (i >= Npad) break;
+    V4 a[K], b[K];
+    int codeL = 0, codeR = 0;
+    if (tipL) {
+      codeL = tips[(size_t)op.left * Npad + i];
+    } else {
+      const double* p = base + (size_t)(op.left - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+      for (int k = 0; k < K; ++k) a[k] = ldg4(p + (size_t)k * Npad * 4);
+    }
+    if (tipR) {
+      codeR = tips[(size_t)op.right * Npad + i];
+    } else {
+      const double* p = base + (size_t)(op.right - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+      for (int k = 0; k < K; ++k) b[k] = ldg4(p + (size_t)k * Npad * 4);
+    }
 
-  V4 a[K], b[K];
-  int codeL = 0, codeR = 0;
-  if (tipL) {
-    codeL = tips[(size_t)op.left * Npad + i];
-  } else {
-    const double* p = base + (size_t)(op.left - T) * nodeStride + (size_t)i * 4;
+    V4 out[K];
+    double m = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) a[k] = ldg4(p + (size_t)k * Npad * 4);
+    for (int k = 0; k < K; ++k) {
+      const V4 ul = tipL ? lds4(tabL + (k * C + codeL) * 4) : matvec(tabL + k * 16, a[k]);
+      const V4 ur = tipR ? lds4(tabR + (k * C + codeR) * 4) : matvec(tabR + k * 16, b[k]);
+      out[k] = mul4(ul, ur);
+      m = fmax(m, max4(out[k]));
+    }
+    // exact power-of-two rescaling: m * f in [0.5, 1)
+    int eb = (__double2hiint(m) >> 20) & 0x7ff;
+    eb = eb > 2044 ? 2044 : eb;
+    const double f = __hiloint2double((2045 - eb) << 20, 0);
+    double* q = base + (size_t)(op.node - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+    for (int k = 0; k < K; ++k) stg4(q + (size_t)k * Npad * 4, scale4(out[k], f));
+    expo[((size_t)d * I + (op.node - T)) * Npad + i] = (int16_t)(eb - 1022);
   }
-  if (tipR) {
-    codeR = tips[(size_t)op.right * Npad + i];
-  } else {
-    const double* p = base + (size_t)(op.right - T) * nodeStride + (size_t)i * 4;
-#pragma unroll
-    for (int k = 0; k < K; ++k) b[k] = ldg4(p + (size_t)k * Npad * 4);
-  }
-
-  V4 out[K];
-  double m = 0.0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const V4 ul = tipL ? lds4(tabL + (k * C + codeL) * 4) : matvec(tabL + k * 16, a[k]);
-    const V4 ur = tipR ? lds4(tabR + (k * C + codeR) * 4) : matvec(tabR + k * 16, b[k]);
-    out[k] = mul4(ul, ur);
-    m = fmax(m, max4(out[k]));
-  }
-  // exact power-of-two rescaling: m * f in [0.5, 1)
-  int eb = (__double2hiint(m) >> 20) & 0x7ff;
-  eb = eb > 2044 ? 2044 : eb;
-  const double f = __hiloint2double((2045 - eb) << 20, 0);
-  double* q = base + (size_t)(op.node - T) * nodeStride + (size_t)i * 4;
-#pragma unroll
-  for (int k = 0; k < K; ++k) stg4(q + (size_t)k * Npad * 4, scale4(out[k], f));
-  expo[((size_t)d * I + (op.node - T)) * Npad + i] = (int16_t)(eb - 1022);
 }
 
 // generic-K fallback (K not instantiated): two sweeps over the categories
@@ -378,7 +381,8 @@ bwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
             const double* __restrict__ mats, const uint8_t* __restrict__ tips,
             const double* __restrict__ codeP, const double* __restrict__ partials,
             const int16_t* __restrict__ expo, const double* __restrict__ weights,
-            double* __restrict__ pre, double* __restrict__ gpart, int T, int Npad,
+            double* __restrict__ pre, double* __restrict__ gpart,
+            const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
             int C, int B, int K, int chunkPatterns, int nChunk) {
   extern __shared__ double sm[];
   // sm: Pl[16] Pr[16] | cp[C][4] | ul_tab[C][4] ur_tab[C][4] | red[8][32]
@@ -496,17 +500,205 @@ bwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
     for (int w2 = 0; w2 < nw; ++w2) t += red[w2 * 32 + threadIdx.x];
     const int branch = threadIdx.x < 16 ? op.left : op.right;
     const int entry = threadIdx.x & 15;
-    // gpart [d][branch][k][chunk][16]
-    gpart[((((size_t)d * B + branch) * K + k) * nChunk + blockIdx.x) * 16 + entry] = t;
+    // gpart [d][chunkBase[branch] + k * nChunk + chunk][16]
+    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+          entry] = t;
   }
 }
 
-template <int K>
-void launch_fwd(Engine& e, int draws, int opBegin, int count, size_t smem) {
+// fp64 tensor-core variant of the pre-order kernel.  The per-branch sums
+//   G_l = sum_i (w_i m_l,i) (x) p~_l,i ,  G_r = sum_i (w_i m_r,i) (x) p~_r,i
+// are rank-1 updates over patterns, i.e. one 8x8 += [8 x 4 patterns][4 patterns x 8]
+// product per group of four patterns with rows (w m_l | w m_r) and columns
+// (p~_l | p~_r): the diagonal 4x4 blocks of the DMMA accumulator are G_l and G_r.
+// The accumulator costs 2 registers per lane instead of 32 fp64 accumulators per
+// thread, and the block reduction shrinks to one 8x8 tile per warp.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int BWDM_THREADS = 128;
+constexpr int MMA_LD = 36;               // row stride (doubles) of the staging tiles
+constexpr int MMA_STAGE = 2 * 8 * MMA_LD;  // doubles per warp: X and Y tiles
+
+__global__ void __launch_bounds__(BWDM_THREADS, 4)
+bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
+                const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                const double* __restrict__ codeP, const double* __restrict__ partials,
+                const int16_t* __restrict__ expo, const double* __restrict__ weights,
+                double* __restrict__ pre, double* __restrict__ gpart,
+                const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
+                int C, int B, int K, int chunkPatterns, int nChunk) {
+  extern __shared__ __align__(16) double sm[];
+  // sm: Pl[16] Pr[16] | cp[C][4] | tabL[C][4] tabR[C][4] | stage[warps][2][8][36] | red[warps][64]
+  constexpr int NW = BWDM_THREADS / 32;
+  double* Pl = sm;
+  double* Pr = sm + 16;
+  double* cp = sm + 32;
+  double* tabL = cp + C * 4;
+  double* tabR = tabL + C * 4;
+  double* stage = tabR + C * 4;
+  double* red = stage + NW * MMA_STAGE;
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
+  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
+  for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
+  __syncthreads();
+  if (tipL || tipR) {
+    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
+      const int s = j & 3, code = j >> 2;
+      const double* c = cp + code * 4;
+      const double* rl = Pl + s * 4;
+      const double* rr = Pr + s * 4;
+      tabL[j] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
+      tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
+    }
+    __syncthreads();
+  }
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const size_t kOff = (size_t)k * Npad * 4;
+  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
+  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
+  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  double* ql = tipL ? nullptr : pre + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
+  double* qr = tipR ? nullptr : pre + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  const int16_t* el = tipL ? nullptr : expo + ((size_t)d * I + (op.left - T)) * Npad;
+  const int16_t* er = tipR ? nullptr : expo + ((size_t)d * I + (op.right - T)) * Npad;
+  const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
+  const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // staging tiles [8 rows][32 patterns], row stride 36 doubles: the per-pattern
+  // stores (lane = pattern) and the MMA fragment loads (lane -> row lane>>2,
+  // pattern 4t + (lane&3)) are both bank-conflict free
+  double* sX = stage + warp * MMA_STAGE;   // rows: w m_l[0..3] | w m_r[0..3]
+  double* sY = sX + MMA_STAGE / 2;         // rows: p~_l[0..3]  | p~_r[0..3]
+  const int fragOff = (lane >> 2) * MMA_LD + (lane & 3);
+  double c0 = 0.0, c1 = 0.0;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+
+  // software pipeline: the global loads of iteration j+1 are in flight while
+  // iteration j is computed
+  struct Inputs {
+    V4 q, vl, vr;
+    double w;
+    int el, er;  // scale exponent (internal child) or tip code (tip child)
+  };
+  auto fetch = [&](int i, Inputs& in) {
+    if (i < end) {
+      in.q = ldg4(qn + (size_t)i * 4);
+      in.w = weights[i];
+      if (tipL) in.el = tl[i];
+      else { in.vl = ldg4(pl + (size_t)i * 4); in.el = el[i]; }
+      if (tipR) in.er = tr[i];
+      else { in.vr = ldg4(prr + (size_t)i * 4); in.er = er[i]; }
+    }
+  };
+  Inputs cur;
+  fetch(begin + warp * 32 + lane, cur);
+  // warp-uniform trip count: every lane executes the MMAs
+  for (int base = begin + warp * 32; base < end; base += BWDM_THREADS) {
+    const int i = base + lane;
+    Inputs nxt;
+    fetch(i + BWDM_THREADS, nxt);
+    V4 xl{0.0, 0.0, 0.0, 0.0}, xr = xl, vl = xl, vr = xl;
+    if (i < end) {
+      V4 ul, ur;
+      if (tipL) {
+        vl = lds4(cp + cur.el * 4);
+        ul = lds4(tabL + cur.el * 4);
+      } else {
+        vl = cur.vl;
+        ul = matvec(Pl, vl);
+      }
+      if (tipR) {
+        vr = lds4(cp + cur.er * 4);
+        ur = lds4(tabR + cur.er * 4);
+      } else {
+        vr = cur.vr;
+        ur = matvec(Pr, vr);
+      }
+      const V4 ml = mul4(cur.q, ur);
+      const V4 mr = mul4(cur.q, ul);
+      if (!tipL)
+        stg4(ql + (size_t)i * 4,
+             scale4(matvec_t(Pl, ml), __hiloint2double((1023 - cur.el) << 20, 0)));
+      if (!tipR)
+        stg4(qr + (size_t)i * 4,
+             scale4(matvec_t(Pr, mr), __hiloint2double((1023 - cur.er) << 20, 0)));
+      if (cur.w != 0.0) {
+        xl = scale4(ml, cur.w);
+        xr = scale4(mr, cur.w);
+      } else {
+        vl = V4{0.0, 0.0, 0.0, 0.0};
+        vr = vl;
+      }
+    }
+    __syncwarp();
+    sX[0 * MMA_LD + lane] = xl.x; sX[1 * MMA_LD + lane] = xl.y;
+    sX[2 * MMA_LD + lane] = xl.z; sX[3 * MMA_LD + lane] = xl.w;
+    sX[4 * MMA_LD + lane] = xr.x; sX[5 * MMA_LD + lane] = xr.y;
+    sX[6 * MMA_LD + lane] = xr.z; sX[7 * MMA_LD + lane] = xr.w;
+    sY[0 * MMA_LD + lane] = vl.x; sY[1 * MMA_LD + lane] = vl.y;
+    sY[2 * MMA_LD + lane] = vl.z; sY[3 * MMA_LD + lane] = vl.w;
+    sY[4 * MMA_LD + lane] = vr.x; sY[5 * MMA_LD + lane] = vr.y;
+    sY[6 * MMA_LD + lane] = vr.z; sY[7 * MMA_LD + lane] = vr.w;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dmma884(c0, c1, sX[t * 4 + fragOff], sY[t * 4 + fragOff]);
+    cur = nxt;
+  }
+  // accumulator fragment: row = lane>>2, cols = (lane&3)*2 + {0,1}
+  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = c0;
+  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = c1;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int child = threadIdx.x >> 4;
+    const int s = (threadIdx.x >> 2) & 3, sp = threadIdx.x & 3;
+    const int idx = (child * 4 + s) * 8 + child * 4 + sp;
+    double t = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 64 + idx];
+    const int branch = child ? op.right : op.left;
+    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+          (threadIdx.x & 15)] = t;
+  }
+}
+
+// patterns per thread of a post-order launch: long-lived CTAs on large levels
+// (amortises the shared-memory table build), ~8 CTAs per SM on small ones
+int fwd_patterns_per_thread(const Engine& e, int draws, int levelCount) {
   const Dims& m = e.dm;
-  dim3 grid((m.Npad + FWD_THREADS - 1) / FWD_THREADS, count, draws);
+  const long target = (long)e.smCount * 8;
+  long ppt = ((long)m.Npad * levelCount * draws) / ((long)FWD_THREADS * target);
+  if (ppt < 1) ppt = 1;
+  if (ppt > 64) ppt = 64;
+  return (int)ppt;
+}
+
+template <int K>
+void launch_fwd(Engine& e, int draws, int opBegin, int count, size_t smem, int ppt) {
+  const Dims& m = e.dm;
+  const int per = FWD_THREADS * ppt;
+  dim3 grid((m.Npad + per - 1) / per, count, draws);
   fwd4_kernel<K><<<grid, FWD_THREADS, smem, e.stream>>>(
-      e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B);
+      e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B, ppt);
 }
 
 }  // namespace
@@ -518,17 +710,18 @@ int s4_forward(Engine& e, int draws) {
   for (int l = 0; l < nLevels; ++l) {
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
+    const int ppt = fwd_patterns_per_thread(e, draws, count);
     // grid.y is limited to 65535
     for (int done = 0; done < count; done += 65535) {
       const int c = (count - done) < 65535 ? (count - done) : 65535;
       switch (m.K) {
-        case 1: launch_fwd<1>(e, draws, opBegin + done, c, smem); break;
-        case 2: launch_fwd<2>(e, draws, opBegin + done, c, smem); break;
-        case 3: launch_fwd<3>(e, draws, opBegin + done, c, smem); break;
-        case 4: launch_fwd<4>(e, draws, opBegin + done, c, smem); break;
-        case 5: launch_fwd<5>(e, draws, opBegin + done, c, smem); break;
-        case 6: launch_fwd<6>(e, draws, opBegin + done, c, smem); break;
-        case 8: launch_fwd<8>(e, draws, opBegin + done, c, smem); break;
+        case 1: launch_fwd<1>(e, draws, opBegin + done, c, smem, ppt); break;
+        case 2: launch_fwd<2>(e, draws, opBegin + done, c, smem, ppt); break;
+        case 3: launch_fwd<3>(e, draws, opBegin + done, c, smem, ppt); break;
+        case 4: launch_fwd<4>(e, draws, opBegin + done, c, smem, ppt); break;
+        case 5: launch_fwd<5>(e, draws, opBegin + done, c, smem, ppt); break;
+        case 6: launch_fwd<6>(e, draws, opBegin + done, c, smem, ppt); break;
+        case 8: launch_fwd<8>(e, draws, opBegin + done, c, smem, ppt); break;
         default: {
           dim3 grid((m.Npad + FWD_THREADS - 1) / FWD_THREADS, c, draws);
           fwd4_kernel_anyk<<<grid, FWD_THREADS, smem, e.stream>>>(
@@ -556,12 +749,6 @@ int s4_root(Engine& e, int draws) {
   return small_reduce_lnl(e, draws, nblocks);
 }
 
-size_t s4_gpart_doubles(const Engine& e, int draws) {
-  const Dims& m = e.dm;
-  const int nChunk = pattern_chunks(e, draws, BWD_THREADS);
-  return (size_t)draws * m.B * m.K * nChunk * 16;
-}
-
 int s4_backward(Engine& e, int draws) {
   const Dims& m = e.dm;
   const int rootInode = e.hostOps.back().node - m.T;
@@ -576,26 +763,34 @@ int s4_backward(Engine& e, int draws) {
     int rc = small_root_grad_reduce(e, draws, nblocks);
     if (rc) return rc;
   }
-  const int nChunk = pattern_chunks(e, draws, BWD_THREADS);
-  int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
-  chunkPatterns = (chunkPatterns + 31) / 32 * 32;
-  const size_t smem = (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
+  const bool useMma = !(e.cfg.flags & TTB2_FLAG_NO_MMA);
+  const size_t smem = useMma
+      ? (32 + 3 * (size_t)m.C * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) * sizeof(double)
+      : (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
   const int nLevels = (int)e.levelOff.size() - 1;
   const int maxNodes = 65535 / m.K;
   for (int l = nLevels - 1; l >= 0; --l) {
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
+    const int nChunk = e.levelChunks[l];
+    int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
+    chunkPatterns = (chunkPatterns + 31) / 32 * 32;
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      bwd4_kernel<<<grid, BWD_THREADS, smem, e.stream>>>(
-          e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo,
-          e.weights, e.pre, e.gpart, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      if (useMma)
+        bwd4_mma_kernel<<<grid, BWDM_THREADS, smem, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
+            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      else
+        bwd4_kernel<<<grid, BWD_THREADS, smem, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
+            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
       ++e.launches;
     }
   }
   TTB2_CUDA_CHECK(cudaGetLastError());
-  return small_gpart_reduce(e, draws, nChunk);
+  return small_gpart_reduce(e, draws);
 }
 
 }  // namespace ttb2

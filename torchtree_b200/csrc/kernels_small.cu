@@ -2,6 +2,8 @@
 // category x draw in one launch, deterministic second-stage reductions, and the
 // contraction of d lnL / d P into branch-length, site-rate and generator
 // gradients.  All are O(B K S^3) or O(N) and negligible next to the peeling.
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace ttb2 {
@@ -68,17 +70,23 @@ reduce_rows_kernel(const double* __restrict__ part, double* __restrict__ out, in
   if (threadIdx.x == 0) out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
 }
 
-// dmat[d][b][k][e] = sum_chunk gpart[d][b][k][chunk][e]
+// dmat[d][b][k][e] = sum_chunk gpart[d][chunkBase[b] + k * chunkCount[b] + chunk][e]
 __global__ void gpart_reduce_kernel(const double* __restrict__ gpart,
-                                    double* __restrict__ dmat, size_t items, int nChunk,
-                                    int SS) {
+                                    const int* __restrict__ chunkBase,
+                                    const int* __restrict__ chunkCount,
+                                    double* __restrict__ dmat, size_t chunkTotal, int B, int K,
+                                    int SS, int draws) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= items * SS) return;
+  if (idx >= (size_t)draws * B * K * SS) return;
   const size_t item = idx / SS;
   const int e = (int)(idx - item * SS);
-  const double* p = gpart + item * nChunk * SS + e;
+  const int k = (int)(item % K);
+  const int b = (int)((item / K) % B);
+  const size_t d = item / ((size_t)K * B);
+  const int n = chunkCount[b];
+  const double* p = gpart + (d * chunkTotal + chunkBase[b] + (size_t)k * n) * SS + e;
   double acc = 0.0;
-  for (int c = 0; c < nChunk; ++c) acc += p[(size_t)c * SS];
+  for (int c = 0; c < n; ++c) acc += p[(size_t)c * SS];
   dmat[idx] = acc;
 }
 
@@ -273,13 +281,49 @@ int round_threads(int n, int cap) {
 
 }  // namespace
 
-int pattern_chunks(const Engine& e, int draws, int threads) {
+int plan_chunks(Engine& e, int draws, int granule) {
   const Dims& m = e.dm;
-  int want = (2 * 148 + m.K * draws - 1) / (m.K * draws);
-  const int maxChunks = (m.Npad + threads - 1) / threads;
-  if (want > maxChunks) want = maxChunks;
-  if (want < 1) want = 1;
-  return want;
+  if (e.chunkPlanDraws == draws && e.chunkBase) return TTB2_OK;
+  const int nLevels = (int)e.levelOff.size() - 1;
+  // aim for ~8 CTAs per SM in every launch; never less than 2 granules per chunk
+  const long target = (long)e.smCount * 8;
+  const int maxChunks = std::max(1, m.Npad / (2 * granule));
+  e.levelChunks.assign(nLevels, 1);
+  e.hostChunkBase.assign(m.B + 1, 0);
+  e.hostChunkCount.assign(m.B + 1, 0);
+  for (int l = 0; l < nLevels; ++l) {
+    const long count = e.levelOff[l + 1] - e.levelOff[l];
+    long want = (target + count * m.K * draws - 1) / (count * m.K * draws);
+    if (want > maxChunks) want = maxChunks;
+    if (want < 1) want = 1;
+    e.levelChunks[l] = (int)want;
+    for (int j = e.levelOff[l]; j < e.levelOff[l + 1]; ++j) {
+      e.hostChunkCount[e.hostOps[j].left] = (int)want;
+      e.hostChunkCount[e.hostOps[j].right] = (int)want;
+    }
+  }
+  size_t total = 0;
+  for (int b = 0; b < m.B; ++b) {
+    e.hostChunkBase[b] = (int)total;
+    total += (size_t)m.K * e.hostChunkCount[b];
+  }
+  e.chunkTotal = total;
+  if (!e.chunkBase) {
+    TTB2_CUDA_CHECK(cudaMalloc((void**)&e.chunkBase, (m.B + 1) * sizeof(int)));
+    TTB2_CUDA_CHECK(cudaMalloc((void**)&e.chunkCount, (m.B + 1) * sizeof(int)));
+    e.deviceBytes += 2 * (int64_t)(m.B + 1) * sizeof(int);
+  }
+  TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  TTB2_CUDA_CHECK(cudaMemcpy(e.chunkBase, e.hostChunkBase.data(), (m.B + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice));
+  TTB2_CUDA_CHECK(cudaMemcpy(e.chunkCount, e.hostChunkCount.data(), (m.B + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice));
+  e.chunkPlanDraws = draws;
+  return TTB2_OK;
+}
+
+size_t planned_gpart_doubles(const Engine& e, int draws) {
+  return (size_t)draws * e.chunkTotal * e.dm.S * e.dm.S;
 }
 
 int small_pmatrix(Engine& e, int draws) {
@@ -311,14 +355,15 @@ int small_root_grad_reduce(Engine& e, int draws, int nblocks) {
   return TTB2_OK;
 }
 
-int small_gpart_reduce(Engine& e, int draws, int nChunk) {
+int small_gpart_reduce(Engine& e, int draws) {
   const Dims& m = e.dm;
   const size_t items = (size_t)draws * m.B * m.K;
   const int SS = m.S * m.S;
   const size_t total = items * SS;
   const int threads = 256;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  gpart_reduce_kernel<<<blocks, threads, 0, e.stream>>>(e.gpart, e.dmat, items, nChunk, SS);
+  gpart_reduce_kernel<<<blocks, threads, 0, e.stream>>>(e.gpart, e.chunkBase, e.chunkCount, e.dmat,
+                                                       e.chunkTotal, m.B, m.K, SS, draws);
   ++e.launches;
   TTB2_CUDA_CHECK(cudaGetLastError());
   return TTB2_OK;
@@ -401,6 +446,41 @@ int small_eigen_contract(Engine& e, int draws) {
                                            (int)smem));
     q_grad_kernel<<<od, threads, smem, e.stream>>>(e.outQ, e.evec, e.ivec, e.outQ, m.S);
     ++e.launches;
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return small_root_outputs(e, draws);
+}
+
+// Outputs of the fused pre-order sweep: gscal [D][B][K] and (needQ) hpart
+// [D][nBlocks*K][16] are already on the device; assemble the same outputs as
+// small_eigen_contract.
+int small_fused_outputs(Engine& e, int draws, bool needQ) {
+  const Dims& m = e.dm;
+  const int SS = m.S * m.S;
+  {
+    const int n = m.B * draws;
+    branch_grad_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
+        e.gscal, e.rates, e.rateDraws, e.gradLnl, e.outBl, m.B, m.K, draws);
+    ++e.launches;
+  }
+  {
+    const int od = e.rateDraws > 1 ? draws : 1;
+    dim3 grid(m.K, od);
+    rate_grad_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
+                                                        m.B, m.K, draws, od);
+    ++e.launches;
+  }
+  const int od = e.eigDraws > 1 ? draws : 1;
+  if (needQ) {
+    dim3 grid(SS, od);
+    h_reduce_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.hpart, e.gradLnl, e.outQ,
+                                                       (m.Npad / 32) * m.K, SS, draws, od);
+    ++e.launches;
+    q_grad_kernel<<<od, 32, 4 * (size_t)SS * sizeof(double), e.stream>>>(e.outQ, e.evec, e.ivec,
+                                                                         e.outQ, m.S);
+    ++e.launches;
+  } else {
+    TTB2_CUDA_CHECK(cudaMemsetAsync(e.outQ, 0, (size_t)od * SS * sizeof(double), e.stream));
   }
   TTB2_CUDA_CHECK(cudaGetLastError());
   return small_root_outputs(e, draws);

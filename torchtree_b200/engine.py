@@ -255,7 +255,7 @@ class Engine:
             )
         _lib.check(self._lib.ttb2_grad_eigen(
             self._h, _ptr(g), _ptr(out["branch_lengths"]), _ptr(out["site_rates"]),
-            _ptr(out["props"]), _ptr(out["q"]), _ptr(out["freqs"]), sh["where"]),
+            _ptr(out["props"]), _ptr(out.get("q")), _ptr(out["freqs"]), sh["where"]),
             "ttb2_grad_eigen")
         return out
 
