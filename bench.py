@@ -221,8 +221,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- problem, sharded by patterns ----
-    per = (args.patterns + world - 1) // world
-    lo, hi = rank * per, min(args.patterns, (rank + 1) * per)
+    from torchtree_b200.sharded import shard_range
+
+    lo, hi = shard_range(args.patterns, rank, world)
     prob = build_problem(args, lo, hi)
     units_total = args.patterns * (args.taxa - 1) * args.categories
     eng = Engine(prob.tip_states, prob.weights, prob.postorder, 4, args.categories,
@@ -351,13 +352,13 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "bwd4_kernel (pre-order level sweep)",
+                "bound": "hbm", "kernel": "bwd4_mma_kernel (pre-order sweep, one launch per tree level)",
                 "achieved": ach_pre, "peak": peak, "unit": "GB/s", "frac": ach_pre / peak,
                 "peak_kind": peak_kind, "traffic": None,
                 "algorithmic_bytes_per_unit": BYTES_PER_UNIT_PRE,
                 "launches_per_step": ph["preorder_launches"],
                 "avg_launch_ms": ph_pre / max(1, ph["preorder_launches"]),
-                "postorder": {"kernel": "fwd4_kernel", "achieved": ach_post,
+                "postorder": {"kernel": "fwd4_kernel<4> (post-order sweep)", "achieved": ach_post,
                               "frac": ach_post / peak,
                               "algorithmic_bytes_per_unit": BYTES_PER_UNIT_POST,
                               "launches_per_step": ph["postorder_launches"], "ms": ph_post},

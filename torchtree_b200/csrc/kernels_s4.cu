@@ -12,6 +12,8 @@
 // variants (torchtree/evolution/tree_likelihood.py:186-278) for the post-order
 // pass, and the autograd tape by the pre-order pass of
 // SURVEY Appendix B.
+#include <cstdlib>
+
 #include "engine.cuh"
 
 namespace ttb2 {
@@ -107,7 +109,7 @@ __host__ __device__ inline int child_table_doubles(int K, int C) {
 // post-order: one launch per level, grid (pattern blocks, nodes of level, draws)
 // ---------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(FWD_THREADS)
+__global__ void __launch_bounds__(FWD_THREADS, (K <= 4 ? 4 : 2))
 fwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
             const double* __restrict__ mats, const uint8_t* __restrict__ tips,
             const double* __restrict__ codeP, double* __restrict__ partials,
@@ -523,7 +525,8 @@ constexpr int BWDM_THREADS = 128;
 constexpr int MMA_LD = 36;               // row stride (doubles) of the staging tiles
 constexpr int MMA_STAGE = 2 * 8 * MMA_LD;  // doubles per warp: X and Y tiles
 
-__global__ void __launch_bounds__(BWDM_THREADS, 4)
+template <bool PREFETCH, int MINBLOCKS>
+__global__ void __launch_bounds__(BWDM_THREADS, MINBLOCKS)
 bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
                 const double* __restrict__ codeP, const double* __restrict__ partials,
@@ -616,7 +619,7 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   for (int base = begin + warp * 32; base < end; base += BWDM_THREADS) {
     const int i = base + lane;
     Inputs nxt;
-    fetch(i + BWDM_THREADS, nxt);
+    if (PREFETCH) fetch(i + BWDM_THREADS, nxt);
     V4 xl{0.0, 0.0, 0.0, 0.0}, xr = xl, vl = xl, vr = xl;
     if (i < end) {
       V4 ul, ur;
@@ -662,7 +665,8 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < 8; ++t) dmma884(c0, c1, sX[t * 4 + fragOff], sY[t * 4 + fragOff]);
-    cur = nxt;
+    if (PREFETCH) cur = nxt;
+    else fetch(i + BWDM_THREADS, cur);
   }
   // accumulator fragment: row = lane>>2, cols = (lane&3)*2 + {0,1}
   red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = c0;
@@ -764,6 +768,7 @@ int s4_backward(Engine& e, int draws) {
     if (rc) return rc;
   }
   const bool useMma = !(e.cfg.flags & TTB2_FLAG_NO_MMA);
+  static const int variant = getenv("TTB2_BWD_VARIANT") ? atoi(getenv("TTB2_BWD_VARIANT")) : 0;
   const size_t smem = useMma
       ? (32 + 3 * (size_t)m.C * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) * sizeof(double)
       : (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
@@ -778,8 +783,20 @@ int s4_backward(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      if (useMma)
-        bwd4_mma_kernel<<<grid, BWDM_THREADS, smem, e.stream>>>(
+      if (useMma && variant == 1)
+        bwd4_mma_kernel<false, 6><<<grid, BWDM_THREADS, smem, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
+            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      else if (useMma && variant == 2)
+        bwd4_mma_kernel<false, 8><<<grid, BWDM_THREADS, smem, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
+            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      else if (useMma && variant == 3)
+        bwd4_mma_kernel<true, 5><<<grid, BWDM_THREADS, smem, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
+            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      else if (useMma)
+        bwd4_mma_kernel<true, 4><<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
       else
