@@ -89,6 +89,12 @@ typedef struct ttb2_config {
 /* 4-state pre-order kernel: accumulate d lnL / d P with plain fp64 FMAs instead
  * of fp64 tensor-core MMAs (testing / comparison) */
 #define TTB2_FLAG_NO_MMA 8
+/* 4-state models: tabulate "cherries" (nodes whose two children are tips) by
+ * tip-code pair instead of storing their vectors per pattern.  Removes a third
+ * of the post-order HBM traffic on random trees (post-order sweep 4.2 -> 3.4 ms
+ * on config 2) but the extra shared-memory lookups slow the L1-bound pre-order
+ * kernel more than that (8.1 -> 10.0 ms), so it is opt-in. */
+#define TTB2_FLAG_CHERRY 16
 
 /*
  * tip_codes      uint8 [T][N]: symbol code of tip t at pattern i

@@ -42,7 +42,7 @@ def _check(prob, flags=0, q_rtol=1e-7):
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [0, 4, 8], ids=["levels", "fused", "levels-simt"])
+@pytest.mark.parametrize("flags", [0, 4, 8, 16], ids=["levels", "fused", "levels-simt", "cherry"])
 @pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_category_counts(K, flags):
     from torchtree_b200.synthetic import make_problem
@@ -50,7 +50,7 @@ def test_category_counts(K, flags):
     _check(make_problem(33, 257, 4, K, seed=100 + K, gap_fraction=0.05), flags=flags)
 
 
-@pytest.mark.parametrize("flags", [0, 4, 8], ids=["levels", "fused", "levels-simt"])
+@pytest.mark.parametrize("flags", [0, 4, 8, 16], ids=["levels", "fused", "levels-simt", "cherry"])
 @pytest.mark.parametrize("topology", ["random", "caterpillar", "balanced"])
 def test_topologies_with_rescaling(topology, flags):
     from torchtree_b200.synthetic import make_problem
@@ -75,7 +75,7 @@ def test_two_tips_tree():
 def test_batched_draws_with_per_draw_models():
     from torchtree_b200.synthetic import make_problem
 
-    for flags in (0, 4, 8):
+    for flags in (0, 4, 8, 16):
         _check(make_problem(25, 130, 4, 4, draws=5, seed=17, per_draw_model=True), flags=flags)
         _check(make_problem(25, 130, 4, 4, draws=5, seed=18, per_draw_model=False), flags=flags)
 
@@ -219,5 +219,5 @@ def test_invariant_category_zero_rate():
     prob.site_rates = prob.site_rates.copy()
     prob.site_rates[0, 0] = 0.0
     prob.site_rates /= (prob.site_rates * prob.site_props).sum()
-    for flags in (0, 4, 8):
+    for flags in (0, 4, 8, 16):
         _check(prob, flags=flags)

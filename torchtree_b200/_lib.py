@@ -17,6 +17,7 @@ TTB2_FLAG_PREALLOC_GRAD = 1
 TTB2_FLAG_FORCE_GENERIC = 2
 TTB2_FLAG_FUSED = 4
 TTB2_FLAG_NO_MMA = 8
+TTB2_FLAG_CHERRY = 16
 
 
 class Ttb2Config(ctypes.Structure):

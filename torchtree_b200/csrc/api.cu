@@ -157,6 +157,10 @@ int ensure_eigen_grad_buffers(Engine& e) {
 int upload_fused_programs(Engine& e) {
   const Dims& m = e.dm;
   e.fusedOK = false;
+  {
+    int rc0 = s4_build_cherries(e);
+    if (rc0) return rc0;
+  }
   if (!e.spec4 || !(e.cfg.flags & TTB2_FLAG_FUSED)) return TTB2_OK;
   int rc = fused_build_programs(e);
   if (rc) return rc;
@@ -465,6 +469,18 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
   }
   TRY_CUDA(cudaMemcpy(e.codeP, code_partials, (size_t)m.C * m.S * sizeof(double),
                       cudaMemcpyHostToDevice));
+  {
+    std::vector<int> masks(m.C, 0);
+    e.codes01 = m.S <= 32;
+    for (int cc = 0; cc < m.C; ++cc)
+      for (int s2 = 0; s2 < m.S; ++s2) {
+        const double v = code_partials[(size_t)cc * m.S + s2];
+        if (v != 0.0 && v != 1.0) e.codes01 = false;
+        if (v != 0.0 && s2 < 32) masks[cc] |= 1 << s2;
+      }
+    TRY(dev_alloc(e, &e.codeMask, (size_t)m.C));
+    TRY_CUDA(cudaMemcpy(e.codeMask, masks.data(), m.C * sizeof(int), cudaMemcpyHostToDevice));
+  }
   TRY_CUDA(cudaMemcpy(e.ops, e.hostOps.data(), m.I * sizeof(NodeOp), cudaMemcpyHostToDevice));
   {
     int sms = 0;
@@ -518,7 +534,7 @@ void ttb2_destroy(ttb2_engine* engine) {
   Engine& e = *ep;
   cudaSetDevice(e.device);
   cudaStreamSynchronize(e.stream);
-  dev_free(e.tips); dev_free(e.weights); dev_free(e.codeP); dev_free(e.ops);
+  dev_free(e.tips); dev_free(e.weights); dev_free(e.codeP); dev_free(e.codeMask); dev_free(e.ops);
   dev_free(e.partials); dev_free(e.expo); dev_free(e.pre); dev_free(e.mats);
   dev_free(e.dmat); dev_free(e.gpart); dev_free(e.siteLnl); dev_free(e.redPart);
   dev_free(e.lnl); dev_free(e.rootGrad); dev_free(e.hpart); dev_free(e.gscal);
@@ -531,6 +547,7 @@ void ttb2_destroy(ttb2_engine* engine) {
   dev_free(e.tipsF4); dev_free(e.tipsB4); dev_free(e.tipOrder);
   dev_free(e.streamF); dev_free(e.streamB);
   dev_free(e.chunkBase); dev_free(e.chunkCount);
+  dev_free(e.cherryIdx); dev_free(e.cherryInfo); dev_free(e.cherryVec); dev_free(e.cherryExp);
   for (int j = 0; j < 8; ++j)
     if (e.ev[j]) cudaEventDestroy(e.ev[j]);
   delete ep;

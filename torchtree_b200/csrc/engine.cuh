@@ -49,6 +49,8 @@ struct Engine {
   uint8_t* tips = nullptr;      // [T][Npad]
   double* weights = nullptr;    // [Npad]
   double* codeP = nullptr;      // [C][S]
+  int* codeMask = nullptr;      // [C] bit s set iff codeP[c][s] != 0 (S <= 32)
+  bool codes01 = false;         // every entry of codeP is exactly 0 or 1
   NodeOp* ops = nullptr;        // [I] level-sorted
   std::vector<NodeOp> hostOps;
   std::vector<int> levelOff;    // ops of level l (1-based height): [levelOff[l-1], levelOff[l])
@@ -92,6 +94,14 @@ struct Engine {
   double* outProps = nullptr;   // [Dmax][K]
   double* outFreqs = nullptr;   // [Dmax][S]
   double* outQ = nullptr;       // [Dmax][S][S]
+
+  // cherry fusion (kernels_s4.cu): level-1 nodes tabulated by tip-code pair
+  bool cherryOn = false;
+  int nCherry = 0;
+  int* cherryIdx = nullptr;     // [I]
+  int* cherryInfo = nullptr;    // [nCherry][3] (left tip, right tip, node)
+  double* cherryVec = nullptr;  // [D][nCherry][K][C*C][4]
+  int* cherryExp = nullptr;     // [D][nCherry][C*C]
 
   // fused-traversal path (S = 4, eigen mode)
   int smCount = 148;
@@ -152,6 +162,7 @@ void set_error(const std::string& msg);
 
 // ---- launchers (each returns a TTB2_* status) ------------------------------
 // S = 4 specialised path (kernels_s4.cu)
+int s4_build_cherries(Engine& e);
 int s4_forward(Engine& e, int draws);
 int s4_root(Engine& e, int draws);
 int s4_backward(Engine& e, int draws);

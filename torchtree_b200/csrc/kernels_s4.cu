@@ -13,6 +13,7 @@
 // pass, and the autograd tape by the pre-order pass of
 // SURVEY Appendix B.
 #include <cstdlib>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -508,6 +509,385 @@ bwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Level 1 (both children are tips; a third of all nodes of a random tree).
+// The generic kernels spend their time in shared-memory lookups and MMA staging
+// there, while the only HBM traffic is one vector per unit -- so level 1 gets
+// its own kernels.
+// ---------------------------------------------------------------------------
+// post-order: the node's vector depends only on the pair of tip codes, so the
+// CTA builds the table pair[cL][cR] -> (K scaled vectors, exponent) once and
+// every pattern is two byte loads, K table reads and K 32-byte stores.
+template <int K>
+__global__ void __launch_bounds__(FWD_THREADS, 4)
+fwd4_tips_kernel(const NodeOp* __restrict__ ops, int opBegin,
+                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                 const double* __restrict__ codeP, double* __restrict__ partials,
+                 int16_t* __restrict__ expo, int T, int Npad, int C, int B, int ppt) {
+  extern __shared__ double sm[];
+  const NodeOp op = ops[opBegin + blockIdx.y];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int tabN = child_table_doubles(K, C);
+  double* tabL = sm;
+  double* tabR = sm + tabN;
+  // pair table, transposed so that lanes with different code pairs read
+  // consecutive 16-byte words: pair2[(k*2 + half)][pc] (double2)
+  double2* pair2 = reinterpret_cast<double2*>(tabR + tabN);
+  int* pexp = reinterpret_cast<int*>(pair2 + (size_t)C * C * K * 2);  // [C*C]
+  const int CC = C * C;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  build_child_table<K>(tabL, matsD + (size_t)op.left * K * 16, true, codeP, C);
+  build_child_table<K>(tabR, matsD + (size_t)op.right * K * 16, true, codeP, C);
+  __syncthreads();
+  for (int pc = threadIdx.x; pc < C * C; pc += blockDim.x) {
+    const int cl = pc / C, cr = pc - cl * C;
+    V4 out[K];
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      out[k] = mul4(lds4(tabL + (k * C + cl) * 4), lds4(tabR + (k * C + cr) * 4));
+      m = fmax(m, max4(out[k]));
+    }
+    int eb = (__double2hiint(m) >> 20) & 0x7ff;
+    eb = eb > 2044 ? 2044 : eb;
+    const double f = __hiloint2double((2045 - eb) << 20, 0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      pair2[(k * 2 + 0) * CC + pc] = make_double2(out[k].x * f, out[k].y * f);
+      pair2[(k * 2 + 1) * CC + pc] = make_double2(out[k].z * f, out[k].w * f);
+    }
+    pexp[pc] = eb - 1022;
+  }
+  __syncthreads();
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  double* q = partials + ((size_t)d * I + (op.node - T)) * nodeStride;
+  int16_t* eo = expo + ((size_t)d * I + (op.node - T)) * Npad;
+  const uint8_t* tl = tips + (size_t)op.left * Npad;
+  const uint8_t* tr = tips + (size_t)op.right * Npad;
+  const int i0 = blockIdx.x * (FWD_THREADS * ppt) + threadIdx.x;
+#pragma unroll 2
+  for (int it = 0; it < ppt; ++it) {
+    const int i = i0 + it * FWD_THREADS;
+    if (i >= Npad) break;
+    const int pc = (int)tl[i] * C + (int)tr[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double2 lo = pair2[(k * 2 + 0) * CC + pc];
+      const double2 hi = pair2[(k * 2 + 1) * CC + pc];
+      stg4(q + ((size_t)k * Npad + i) * 4, V4{lo.x, lo.y, hi.x, hi.y});
+    }
+    eo[i] = (int16_t)pexp[pc];
+  }
+}
+
+// pre-order: no child vectors to read and no q^ to write; with 0/1 tip vectors
+// G_c[s][s'] = sum_i [s' in code_i] w_i m_c,i[s], accumulated with predicated
+// adds in registers (bit s' of codeMask[code] = codeP[code][s'] != 0).
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+bwd4_tips_kernel(const NodeOp* __restrict__ ops, int opBegin,
+                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                 const double* __restrict__ codeP, const int* __restrict__ codeMask,
+                 const double* __restrict__ weights, const double* __restrict__ pre,
+                 double* __restrict__ gpart, const int* __restrict__ chunkBase,
+                 size_t chunkTotal, int T, int Npad, int C, int B, int K, int chunkPatterns,
+                 int nChunk) {
+  extern __shared__ double sm[];
+  // sm: Pl[16] Pr[16] | tabL[C][4] tabR[C][4] | red[8][32] | masks[C] (int)
+  double* Pl = sm;
+  double* Pr = sm + 16;
+  double* tabL = sm + 32;
+  double* tabR = tabL + C * 4;
+  double* red = tabR + C * 4;
+  int* masks = reinterpret_cast<int*>(red + (BWD_THREADS / 32) * 32);
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
+  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
+  for (int j = threadIdx.x; j < C; j += blockDim.x) masks[j] = codeMask[j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
+    const int s = j & 3, code = j >> 2;
+    const double* c = codeP + code * 4;
+    const double* rl = Pl + s * 4;
+    const double* rr = Pr + s * 4;
+    tabL[j] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
+    tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
+  }
+  __syncthreads();
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const double* qn = pre + ((size_t)d * I + (op.node - T)) * nodeStride + (size_t)k * Npad * 4;
+  const uint8_t* tl = tips + (size_t)op.left * Npad;
+  const uint8_t* tr = tips + (size_t)op.right * Npad;
+
+  double g[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) g[j] = 0.0;
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  // software pipeline: the loads of the next pattern are in flight while the
+  // current one is accumulated
+  struct Inputs {
+    V4 q;
+    double w;
+    int cl, cr;
+  };
+  auto fetch = [&](int i, Inputs& in) {
+    if (i < end) {
+      in.q = ldg4(qn + (size_t)i * 4);
+      in.w = weights[i];
+      in.cl = tl[i];
+      in.cr = tr[i];
+    } else {
+      in.q = V4{0.0, 0.0, 0.0, 0.0};
+      in.w = 0.0;
+      in.cl = 0;
+      in.cr = 0;
+    }
+  };
+  Inputs cur;
+  fetch(begin + threadIdx.x, cur);
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    Inputs nxt;
+    fetch(i + blockDim.x, nxt);
+    const V4 ul = lds4(tabL + cur.cl * 4);
+    const V4 ur = lds4(tabR + cur.cr * 4);
+    const int ml_mask = masks[cur.cl], mr_mask = masks[cur.cr];
+    const V4 a = scale4(mul4(cur.q, ur), cur.w);  // w m_l
+    const V4 b = scale4(mul4(cur.q, ul), cur.w);  // w m_r
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double sl = (ml_mask >> c) & 1 ? 1.0 : 0.0;
+      const double sr = (mr_mask >> c) & 1 ? 1.0 : 0.0;
+      g[0 + c] = fma(a.x, sl, g[0 + c]);
+      g[4 + c] = fma(a.y, sl, g[4 + c]);
+      g[8 + c] = fma(a.z, sl, g[8 + c]);
+      g[12 + c] = fma(a.w, sl, g[12 + c]);
+      g[16 + c] = fma(b.x, sr, g[16 + c]);
+      g[20 + c] = fma(b.y, sr, g[20 + c]);
+      g[24 + c] = fma(b.z, sr, g[24 + c]);
+      g[28 + c] = fma(b.w, sr, g[28 + c]);
+    }
+    cur = nxt;
+  }
+  const double mine = warp_transpose_sum(g);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  red[warp * 32 + lane] = mine;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w2 = 0; w2 < nw; ++w2) t += red[w2 * 32 + threadIdx.x];
+    const int branch = threadIdx.x < 16 ? op.left : op.right;
+    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+          (threadIdx.x & 15)] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Cherry fusion.  A "cherry" is an internal node whose two children are tips.
+// Its (rescaled) vector is a pure function of the pair of tip codes, so it is
+// tabulated once per evaluation -- cherryVec[d][c][k][cL*C+cR][4] and the scale
+// exponent cherryExp[d][c][cL*C+cR] -- and never stored per pattern: parents
+// treat a cherry child like a tip with C*C symbol codes.  On a random tree a
+// third of the internal nodes are cherries, so a third of the post-order
+// writes/reads and of the pre-order child reads disappear from HBM.
+// ---------------------------------------------------------------------------
+struct CherryArgs {
+  const int* idx;      // [I] cherry index of internal node (node - T), or -1
+  const int* info;     // [n][3] (left tip, right tip, node)
+  const double* vec;   // [D][n][K][CC][4]
+  const int* exps;     // [D][n][CC]
+  int n;               // number of cherries (0 = fusion off)
+  int CC;              // C * C
+};
+
+__global__ void __launch_bounds__(128)
+cherry_table_kernel(const int* __restrict__ info, const double* __restrict__ mats,
+                    const double* __restrict__ codeP, double* __restrict__ vec,
+                    int* __restrict__ exps, int n, int C, int B, int K) {
+  extern __shared__ double sm[];  // tabL[K][C][4] tabR[K][C][4]
+  const int c = blockIdx.x, d = blockIdx.y;
+  const int CC = C * C;
+  double* tabL = sm;
+  double* tabR = sm + K * C * 4;
+  const int tipL = info[c * 3], tipR = info[c * 3 + 1];
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  for (int j = threadIdx.x; j < 2 * K * C * 4; j += blockDim.x) {
+    const int side = j / (K * C * 4);
+    const int r = j - side * (K * C * 4);
+    const int s = r & 3, code = (r >> 2) % C, k = (r >> 2) / C;
+    const double* row = matsD + ((size_t)(side ? tipR : tipL) * K + k) * 16 + s * 4;
+    const double* cp = codeP + code * 4;
+    (side ? tabR : tabL)[r] = fma(row[3], cp[3], fma(row[2], cp[2], fma(row[1], cp[1], row[0] * cp[0])));
+  }
+  __syncthreads();
+  for (int pc = threadIdx.x; pc < CC; pc += blockDim.x) {
+    const int cl = pc / C, cr = pc - cl * C;
+    double m = 0.0;
+    for (int k = 0; k < K; ++k)
+      m = fmax(m, max4(mul4(lds4(tabL + (k * C + cl) * 4), lds4(tabR + (k * C + cr) * 4))));
+    int eb = (__double2hiint(m) >> 20) & 0x7ff;
+    eb = eb > 2044 ? 2044 : eb;
+    const double f = __hiloint2double((2045 - eb) << 20, 0);
+    for (int k = 0; k < K; ++k) {
+      const V4 o = scale4(mul4(lds4(tabL + (k * C + cl) * 4), lds4(tabR + (k * C + cr) * 4)), f);
+      double* dst = vec + ((((size_t)d * n + c) * K + k) * CC + pc) * 4;
+      dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w;
+    }
+    exps[((size_t)d * n + c) * CC + pc] = eb - 1022;
+  }
+}
+
+// per-pattern scale exponents of the cherries (2 bytes per pattern; the only
+// per-pattern data a cherry keeps -- read by the root sum and the pre-order pass)
+__global__ void __launch_bounds__(256)
+cherry_expo_kernel(const int* __restrict__ info, const int* __restrict__ exps,
+                   const uint8_t* __restrict__ tips, int16_t* __restrict__ expo, int n, int C,
+                   int T, int Npad) {
+  const int c = blockIdx.y, d = blockIdx.z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  const int tipL = info[c * 3], tipR = info[c * 3 + 1], node = info[c * 3 + 2];
+  const int pc = (int)tips[(size_t)tipL * Npad + i] * C + (int)tips[(size_t)tipR * Npad + i];
+  expo[((size_t)d * (T - 1) + (node - T)) * Npad + i] = (int16_t)exps[((size_t)d * n + c) * (C * C) + pc];
+}
+
+// child kinds
+enum { KIND_STORED = 0, KIND_TIP = 1, KIND_CHERRY = 2 };
+
+__device__ __forceinline__ int child_kind(int child, int T, const CherryArgs& ch, int& cidx) {
+  cidx = -1;
+  if (child < T) return KIND_TIP;
+  if (ch.n > 0) {
+    cidx = ch.idx[child - T];
+    if (cidx >= 0) return KIND_CHERRY;
+  }
+  return KIND_STORED;
+}
+
+// tab[(k*NC + code)*4 + s] = sum_s' P_k[s][s'] vec_k[code][s']   (tip / cherry child)
+// tab[k*16 + ..] = P_k                                             (stored child)
+template <int K>
+__device__ __forceinline__ void build_child_table_c(double* tab, const double* P, int kind,
+                                                    const double* codeP, int C,
+                                                    const double* cvec, int CC, int NC) {
+  if (kind == KIND_STORED) {
+    for (int j = threadIdx.x; j < K * 16; j += blockDim.x) tab[j] = P[j];
+    return;
+  }
+  // coded child: two double2 planes per category, tab2[(k*2 + half)*NC + code], so
+  // that lanes holding different codes read different 16-byte words
+  const int n = kind == KIND_TIP ? C : CC;
+  for (int j = threadIdx.x; j < K * n * 4; j += blockDim.x) {
+    const int s = j & 3;
+    const int code = (j >> 2) % n;
+    const int k = (j >> 2) / n;
+    const double* row = P + k * 16 + s * 4;
+    const double* v = kind == KIND_TIP ? codeP + code * 4 : cvec + ((size_t)k * CC + code) * 4;
+    tab[(((k * 2 + (s >> 1)) * NC + code) << 1) + (s & 1)] =
+        fma(row[3], v[3], fma(row[2], v[2], fma(row[1], v[1], row[0] * v[0])));
+  }
+}
+
+__device__ __forceinline__ V4 lds4_planes(const double* tab, int k, int NC, int code) {
+  const double2 lo = *reinterpret_cast<const double2*>(tab + (((k * 2 + 0) * NC + code) << 1));
+  const double2 hi = *reinterpret_cast<const double2*>(tab + (((k * 2 + 1) * NC + code) << 1));
+  return V4{lo.x, lo.y, hi.x, hi.y};
+}
+
+// post-order level kernel, cherry-aware (levels >= 2 when fusion is on)
+template <int K>
+__global__ void __launch_bounds__(FWD_THREADS, (K <= 4 ? 4 : 2))
+fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
+             const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
+             double* __restrict__ partials, int16_t* __restrict__ expo, CherryArgs ch, int T,
+             int Npad, int C, int B, int ppt) {
+  extern __shared__ double sm[];
+  const NodeOp op = ops[opBegin + blockIdx.y];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int NC = ch.CC > C ? ch.CC : C;
+  const int tabN = K * (NC > 4 ? NC : 4) * 4;
+  double* tabL = sm;
+  double* tabR = sm + tabN;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  int cidxL, cidxR;
+  const int kindL = child_kind(op.left, T, ch, cidxL);
+  const int kindR = child_kind(op.right, T, ch, cidxR);
+  const double* cvL = kindL == KIND_CHERRY ? ch.vec + ((size_t)d * ch.n + cidxL) * K * ch.CC * 4 : nullptr;
+  const double* cvR = kindR == KIND_CHERRY ? ch.vec + ((size_t)d * ch.n + cidxR) * K * ch.CC * 4 : nullptr;
+  build_child_table_c<K>(tabL, matsD + (size_t)op.left * K * 16, kindL, codeP, C, cvL, ch.CC, NC);
+  build_child_table_c<K>(tabR, matsD + (size_t)op.right * K * 16, kindR, codeP, C, cvR, ch.CC, NC);
+  __syncthreads();
+  // tip rows whose bytes form the child's symbol code
+  const uint8_t* l0 = nullptr; const uint8_t* l1 = nullptr;
+  const uint8_t* r0 = nullptr; const uint8_t* r1 = nullptr;
+  if (kindL == KIND_TIP) l0 = tips + (size_t)op.left * Npad;
+  if (kindL == KIND_CHERRY) {
+    l0 = tips + (size_t)ch.info[cidxL * 3] * Npad;
+    l1 = tips + (size_t)ch.info[cidxL * 3 + 1] * Npad;
+  }
+  if (kindR == KIND_TIP) r0 = tips + (size_t)op.right * Npad;
+  if (kindR == KIND_CHERRY) {
+    r0 = tips + (size_t)ch.info[cidxR * 3] * Npad;
+    r1 = tips + (size_t)ch.info[cidxR * 3 + 1] * Npad;
+  }
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  double* base = partials + (size_t)d * I * nodeStride;
+  const int i0 = blockIdx.x * (FWD_THREADS * ppt) + threadIdx.x;
+#pragma unroll 1
+  for (int it = 0; it < ppt; ++it) {
+    const int i = i0 + it * FWD_THREADS;
+    if (i >= Npad) break;
+    V4 a[K], b[K];
+    int codeL = 0, codeR = 0;
+    if (kindL == KIND_STORED) {
+      const double* p = base + (size_t)(op.left - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+      for (int k = 0; k < K; ++k) a[k] = ldg4(p + (size_t)k * Npad * 4);
+    } else {
+      codeL = l0[i];
+      if (kindL == KIND_CHERRY) codeL = codeL * C + l1[i];
+    }
+    if (kindR == KIND_STORED) {
+      const double* p = base + (size_t)(op.right - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+      for (int k = 0; k < K; ++k) b[k] = ldg4(p + (size_t)k * Npad * 4);
+    } else {
+      codeR = r0[i];
+      if (kindR == KIND_CHERRY) codeR = codeR * C + r1[i];
+    }
+    V4 out[K];
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const V4 ul = kindL != KIND_STORED ? lds4_planes(tabL, k, NC, codeL) : matvec(tabL + k * 16, a[k]);
+      const V4 ur = kindR != KIND_STORED ? lds4_planes(tabR, k, NC, codeR) : matvec(tabR + k * 16, b[k]);
+      out[k] = mul4(ul, ur);
+      m = fmax(m, max4(out[k]));
+    }
+    int eb = (__double2hiint(m) >> 20) & 0x7ff;
+    eb = eb > 2044 ? 2044 : eb;
+    const double f = __hiloint2double((2045 - eb) << 20, 0);
+    double* q = base + (size_t)(op.node - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+    for (int k = 0; k < K; ++k) stg4(q + (size_t)k * Npad * 4, scale4(out[k], f));
+    expo[((size_t)d * I + (op.node - T)) * Npad + i] = (int16_t)(eb - 1022);
+  }
+}
+
 // fp64 tensor-core variant of the pre-order kernel.  The per-branch sums
 //   G_l = sum_i (w_i m_l,i) (x) p~_l,i ,  G_r = sum_i (w_i m_r,i) (x) p~_r,i
 // are rank-1 updates over patterns, i.e. one 8x8 += [8 x 4 patterns][4 patterns x 8]
@@ -525,7 +905,7 @@ constexpr int BWDM_THREADS = 128;
 constexpr int MMA_LD = 36;               // row stride (doubles) of the staging tiles
 constexpr int MMA_STAGE = 2 * 8 * MMA_LD;  // doubles per warp: X and Y tiles
 
-template <bool PREFETCH, int MINBLOCKS>
+template <bool PREFETCH, int MINBLOCKS, bool PREG>
 __global__ void __launch_bounds__(BWDM_THREADS, MINBLOCKS)
 bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
@@ -583,6 +963,15 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
   const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
 
+  // optional: both transition matrices in registers (no shared-memory broadcasts
+  // in the pattern loop)
+  double rPl[16], rPr[16];
+  if (PREG) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { rPl[j] = Pl[j]; rPr[j] = Pr[j]; }
+  }
+  const double* mPl = PREG ? rPl : Pl;
+  const double* mPr = PREG ? rPr : Pr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // staging tiles [8 rows][32 patterns], row stride 36 doubles: the per-pattern
   // stores (lane = pattern) and the MMA fragment loads (lane -> row lane>>2,
@@ -628,23 +1017,23 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
         ul = lds4(tabL + cur.el * 4);
       } else {
         vl = cur.vl;
-        ul = matvec(Pl, vl);
+        ul = matvec(mPl, vl);
       }
       if (tipR) {
         vr = lds4(cp + cur.er * 4);
         ur = lds4(tabR + cur.er * 4);
       } else {
         vr = cur.vr;
-        ur = matvec(Pr, vr);
+        ur = matvec(mPr, vr);
       }
       const V4 ml = mul4(cur.q, ur);
       const V4 mr = mul4(cur.q, ul);
       if (!tipL)
         stg4(ql + (size_t)i * 4,
-             scale4(matvec_t(Pl, ml), __hiloint2double((1023 - cur.el) << 20, 0)));
+             scale4(matvec_t(mPl, ml), __hiloint2double((1023 - cur.el) << 20, 0)));
       if (!tipR)
         stg4(qr + (size_t)i * 4,
-             scale4(matvec_t(Pr, mr), __hiloint2double((1023 - cur.er) << 20, 0)));
+             scale4(matvec_t(mPr, mr), __hiloint2double((1023 - cur.er) << 20, 0)));
       if (cur.w != 0.0) {
         xl = scale4(ml, cur.w);
         xr = scale4(mr, cur.w);
@@ -696,36 +1085,319 @@ int fwd_patterns_per_thread(const Engine& e, int draws, int levelCount) {
   return (int)ppt;
 }
 
+// pre-order level kernel, cherry-aware: a cherry child is handled like a tip with
+// C*C symbol codes (vectors from cherryVec), except that it still receives q^.
+__global__ void __launch_bounds__(BWDM_THREADS, 4)
+bwd4c_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
+                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                 const double* __restrict__ codeP, const double* __restrict__ partials,
+                 const int16_t* __restrict__ expo, const double* __restrict__ weights,
+                 double* __restrict__ pre, double* __restrict__ gpart,
+                 const int* __restrict__ chunkBase, size_t chunkTotal, CherryArgs ch, int T,
+                 int Npad, int C, int B, int K, int chunkPatterns, int nChunk) {
+  extern __shared__ __align__(16) double sm[];
+  // sm: Pl[16] Pr[16] | vecL[NC][4] vecR[NC][4] tabL[NC][4] tabR[NC][4] | stage | red
+  constexpr int NW = BWDM_THREADS / 32;
+  const int NC = ch.CC > C ? ch.CC : C;
+  double* Pl = sm;
+  double* Pr = sm + 16;
+  double* vecL = sm + 32;
+  double* vecR = vecL + NC * 4;
+  double* tabL = vecR + NC * 4;
+  double* tabR = tabL + NC * 4;
+  double* stage = tabR + NC * 4;
+  double* red = stage + NW * MMA_STAGE;
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  int cidxL, cidxR;
+  const int kindL = child_kind(op.left, T, ch, cidxL);
+  const int kindR = child_kind(op.right, T, ch, cidxR);
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
+  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
+  {
+    const int nL = kindL == KIND_TIP ? C : (kindL == KIND_CHERRY ? ch.CC : 0);
+    const int nR = kindR == KIND_TIP ? C : (kindR == KIND_CHERRY ? ch.CC : 0);
+    const double* srcL = kindL == KIND_TIP ? codeP
+                         : ch.vec + (((size_t)d * ch.n + (cidxL < 0 ? 0 : cidxL)) * K + k) * ch.CC * 4;
+    const double* srcR = kindR == KIND_TIP ? codeP
+                         : ch.vec + (((size_t)d * ch.n + (cidxR < 0 ? 0 : cidxR)) * K + k) * ch.CC * 4;
+    __syncthreads();  // Pl, Pr visible
+    // plane layout [half][code] (double2): conflict-free for lanes with distinct codes
+    for (int j = threadIdx.x; j < nL * 4; j += blockDim.x) {
+      const int s = j & 3, code = j >> 2;
+      const double* c = srcL + code * 4;
+      const double* rl = Pl + s * 4;
+      const int dst = (((s >> 1) * NC + code) << 1) + (s & 1);
+      vecL[dst] = c[s];
+      tabL[dst] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
+    }
+    for (int j = threadIdx.x; j < nR * 4; j += blockDim.x) {
+      const int s = j & 3, code = j >> 2;
+      const double* c = srcR + code * 4;
+      const double* rr = Pr + s * 4;
+      const int dst = (((s >> 1) * NC + code) << 1) + (s & 1);
+      vecR[dst] = c[s];
+      tabR[dst] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
+    }
+    __syncthreads();
+  }
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const size_t kOff = (size_t)k * Npad * 4;
+  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
+  const bool storedL = kindL == KIND_STORED, storedR = kindR == KIND_STORED;
+  const bool tipL = kindL == KIND_TIP, tipR = kindR == KIND_TIP;
+  const double* pl = storedL ? partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff : nullptr;
+  const double* prr = storedR ? partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff : nullptr;
+  double* ql = tipL ? nullptr : pre + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
+  double* qr = tipR ? nullptr : pre + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  const int16_t* el = tipL ? nullptr : expo + ((size_t)d * I + (op.left - T)) * Npad;
+  const int16_t* er = tipR ? nullptr : expo + ((size_t)d * I + (op.right - T)) * Npad;
+  const uint8_t* l0 = nullptr; const uint8_t* l1 = nullptr;
+  const uint8_t* r0 = nullptr; const uint8_t* r1 = nullptr;
+  if (tipL) l0 = tips + (size_t)op.left * Npad;
+  if (kindL == KIND_CHERRY) {
+    l0 = tips + (size_t)ch.info[cidxL * 3] * Npad;
+    l1 = tips + (size_t)ch.info[cidxL * 3 + 1] * Npad;
+  }
+  if (tipR) r0 = tips + (size_t)op.right * Npad;
+  if (kindR == KIND_CHERRY) {
+    r0 = tips + (size_t)ch.info[cidxR * 3] * Npad;
+    r1 = tips + (size_t)ch.info[cidxR * 3 + 1] * Npad;
+  }
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sX = stage + warp * MMA_STAGE;
+  double* sY = sX + MMA_STAGE / 2;
+  const int fragOff = (lane >> 2) * MMA_LD + (lane & 3);
+  double c0 = 0.0, c1 = 0.0;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+
+  struct Inputs {
+    V4 q, vl, vr;
+    double w;
+    int el, er;      // scale exponents (stored / cherry children)
+    int cl, cr;      // symbol codes (tip / cherry children)
+  };
+  auto fetch = [&](int i, Inputs& in) {
+    if (i < end) {
+      in.q = ldg4(qn + (size_t)i * 4);
+      in.w = weights[i];
+      if (storedL) in.vl = ldg4(pl + (size_t)i * 4);
+      else { in.cl = l0[i]; if (l1) in.cl = in.cl * C + l1[i]; }
+      if (!tipL) in.el = el[i];
+      if (storedR) in.vr = ldg4(prr + (size_t)i * 4);
+      else { in.cr = r0[i]; if (r1) in.cr = in.cr * C + r1[i]; }
+      if (!tipR) in.er = er[i];
+    }
+  };
+  Inputs cur;
+  fetch(begin + warp * 32 + lane, cur);
+  for (int base = begin + warp * 32; base < end; base += BWDM_THREADS) {
+    const int i = base + lane;
+    Inputs nxt;
+    fetch(i + BWDM_THREADS, nxt);
+    V4 xl{0.0, 0.0, 0.0, 0.0}, xr = xl, vl = xl, vr = xl;
+    if (i < end) {
+      V4 ul, ur;
+      if (storedL) {
+        vl = cur.vl;
+        ul = matvec(Pl, vl);
+      } else {
+        vl = lds4_planes(vecL, 0, NC, cur.cl);
+        ul = lds4_planes(tabL, 0, NC, cur.cl);
+      }
+      if (storedR) {
+        vr = cur.vr;
+        ur = matvec(Pr, vr);
+      } else {
+        vr = lds4_planes(vecR, 0, NC, cur.cr);
+        ur = lds4_planes(tabR, 0, NC, cur.cr);
+      }
+      const V4 ml = mul4(cur.q, ur);
+      const V4 mr = mul4(cur.q, ul);
+      if (!tipL)
+        stg4(ql + (size_t)i * 4,
+             scale4(matvec_t(Pl, ml), __hiloint2double((1023 - cur.el) << 20, 0)));
+      if (!tipR)
+        stg4(qr + (size_t)i * 4,
+             scale4(matvec_t(Pr, mr), __hiloint2double((1023 - cur.er) << 20, 0)));
+      if (cur.w != 0.0) {
+        xl = scale4(ml, cur.w);
+        xr = scale4(mr, cur.w);
+      } else {
+        vl = V4{0.0, 0.0, 0.0, 0.0};
+        vr = vl;
+      }
+    }
+    __syncwarp();
+    sX[0 * MMA_LD + lane] = xl.x; sX[1 * MMA_LD + lane] = xl.y;
+    sX[2 * MMA_LD + lane] = xl.z; sX[3 * MMA_LD + lane] = xl.w;
+    sX[4 * MMA_LD + lane] = xr.x; sX[5 * MMA_LD + lane] = xr.y;
+    sX[6 * MMA_LD + lane] = xr.z; sX[7 * MMA_LD + lane] = xr.w;
+    sY[0 * MMA_LD + lane] = vl.x; sY[1 * MMA_LD + lane] = vl.y;
+    sY[2 * MMA_LD + lane] = vl.z; sY[3 * MMA_LD + lane] = vl.w;
+    sY[4 * MMA_LD + lane] = vr.x; sY[5 * MMA_LD + lane] = vr.y;
+    sY[6 * MMA_LD + lane] = vr.z; sY[7 * MMA_LD + lane] = vr.w;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dmma884(c0, c1, sX[t * 4 + fragOff], sY[t * 4 + fragOff]);
+    cur = nxt;
+  }
+  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = c0;
+  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = c1;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int child = threadIdx.x >> 4;
+    const int s = (threadIdx.x >> 2) & 3, sp = threadIdx.x & 3;
+    const int idx = (child * 4 + s) * 8 + child * 4 + sp;
+    double t = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 64 + idx];
+    const int branch = child ? op.right : op.left;
+    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+          (threadIdx.x & 15)] = t;
+  }
+}
+
+CherryArgs cherry_args(const Engine& e) {
+  CherryArgs ch;
+  ch.idx = e.cherryIdx;
+  ch.info = e.cherryInfo;
+  ch.vec = e.cherryVec;
+  ch.exps = e.cherryExp;
+  ch.n = e.cherryOn ? e.nCherry : 0;
+  ch.CC = e.cherryOn ? e.dm.C * e.dm.C : 0;
+  return ch;
+}
+
 template <int K>
-void launch_fwd(Engine& e, int draws, int opBegin, int count, size_t smem, int ppt) {
+void launch_fwdc(Engine& e, int draws, int opBegin, int count, int ppt) {
+  const Dims& m = e.dm;
+  const CherryArgs ch = cherry_args(e);
+  const int NC = ch.CC > m.C ? ch.CC : m.C;
+  const size_t smem = 2 * (size_t)K * (NC > 4 ? NC : 4) * 4 * sizeof(double);
+  const int per = FWD_THREADS * ppt;
+  dim3 grid((m.Npad + per - 1) / per, count, draws);
+  fwd4c_kernel<K><<<grid, FWD_THREADS, smem, e.stream>>>(
+      e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, ch, m.T, m.Npad, m.C, m.B, ppt);
+}
+
+template <int K>
+void launch_fwd(Engine& e, int draws, int opBegin, int count, size_t smem, int ppt,
+                bool tipLevel) {
   const Dims& m = e.dm;
   const int per = FWD_THREADS * ppt;
   dim3 grid((m.Npad + per - 1) / per, count, draws);
+  const size_t pairBytes = smem + ((size_t)m.C * m.C * K * 4) * sizeof(double) +
+                           (size_t)m.C * m.C * sizeof(int);
+  if (tipLevel && pairBytes <= 40 * 1024) {
+    fwd4_tips_kernel<K><<<grid, FWD_THREADS, pairBytes, e.stream>>>(
+        e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B, ppt);
+    return;
+  }
   fwd4_kernel<K><<<grid, FWD_THREADS, smem, e.stream>>>(
       e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B, ppt);
 }
 
 }  // namespace
 
+// cherries = level-1 nodes (both children tips) other than the root, when the
+// pair alphabet is small enough for the shared-memory tables
+int s4_build_cherries(Engine& e) {
+  const Dims& m = e.dm;
+  e.cherryOn = false;
+  e.nCherry = 0;
+  const bool allowed = e.spec4 && (e.cfg.flags & TTB2_FLAG_CHERRY) &&
+                       !(e.cfg.flags & TTB2_FLAG_NO_MMA) && m.C * m.C <= 64 &&
+                       m.T > 2 && (m.K <= 6 || m.K == 8);
+  if (!allowed) return TTB2_OK;
+  std::vector<int> idx(m.I, -1), info;
+  const int root = e.hostOps.back().node;
+  for (int j = e.levelOff[0]; j < e.levelOff[1]; ++j) {
+    const NodeOp& op = e.hostOps[j];
+    if (op.node == root || op.left >= m.T || op.right >= m.T) return TTB2_OK;  // unexpected
+    idx[op.node - m.T] = e.nCherry++;
+    info.push_back(op.left);
+    info.push_back(op.right);
+    info.push_back(op.node);
+  }
+  if (e.nCherry == 0) return TTB2_OK;
+  const int D = e.cfg.max_draws;
+  const int CC = m.C * m.C;
+  if (e.cherryIdx) { cudaFree(e.cherryIdx); e.cherryIdx = nullptr; }
+  if (e.cherryInfo) { cudaFree(e.cherryInfo); e.cherryInfo = nullptr; }
+  if (e.cherryVec) { cudaFree(e.cherryVec); e.cherryVec = nullptr; }
+  if (e.cherryExp) { cudaFree(e.cherryExp); e.cherryExp = nullptr; }
+  TTB2_CUDA_CHECK(cudaMalloc((void**)&e.cherryIdx, m.I * sizeof(int)));
+  TTB2_CUDA_CHECK(cudaMalloc((void**)&e.cherryInfo, info.size() * sizeof(int)));
+  TTB2_CUDA_CHECK(cudaMalloc((void**)&e.cherryVec, (size_t)D * e.nCherry * m.K * CC * 4 * sizeof(double)));
+  TTB2_CUDA_CHECK(cudaMalloc((void**)&e.cherryExp, (size_t)D * e.nCherry * CC * sizeof(int)));
+  TTB2_CUDA_CHECK(cudaMemcpy(e.cherryIdx, idx.data(), m.I * sizeof(int), cudaMemcpyHostToDevice));
+  TTB2_CUDA_CHECK(cudaMemcpy(e.cherryInfo, info.data(), info.size() * sizeof(int),
+                             cudaMemcpyHostToDevice));
+  e.cherryOn = true;
+  return TTB2_OK;
+}
+
 int s4_forward(Engine& e, int draws) {
   const Dims& m = e.dm;
   const size_t smem = 2 * (size_t)child_table_doubles(m.K, m.C) * sizeof(double);
   const int nLevels = (int)e.levelOff.size() - 1;
-  for (int l = 0; l < nLevels; ++l) {
+  if (e.cherryOn) {
+    // tabulate the cherries (level 1) instead of computing them per pattern
+    dim3 grid(e.nCherry, draws);
+    cherry_table_kernel<<<grid, 128, 2 * (size_t)m.K * m.C * 4 * sizeof(double), e.stream>>>(
+        e.cherryInfo, e.mats, e.codeP, e.cherryVec, e.cherryExp, e.nCherry, m.C, m.B, m.K);
+    ++e.launches;
+    dim3 grid2((m.Npad + 255) / 256, e.nCherry, draws);
+    cherry_expo_kernel<<<grid2, 256, 0, e.stream>>>(e.cherryInfo, e.cherryExp, e.tips, e.expo,
+                                                    e.nCherry, m.C, m.T, m.Npad);
+    ++e.launches;
+  }
+  for (int l = e.cherryOn ? 1 : 0; l < nLevels; ++l) {
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
     const int ppt = fwd_patterns_per_thread(e, draws, count);
+    if (e.cherryOn && (m.K <= 6 || m.K == 8)) {
+      for (int done = 0; done < count; done += 65535) {
+        const int c = (count - done) < 65535 ? (count - done) : 65535;
+        switch (m.K) {
+          case 1: launch_fwdc<1>(e, draws, opBegin + done, c, ppt); break;
+          case 2: launch_fwdc<2>(e, draws, opBegin + done, c, ppt); break;
+          case 3: launch_fwdc<3>(e, draws, opBegin + done, c, ppt); break;
+          case 4: launch_fwdc<4>(e, draws, opBegin + done, c, ppt); break;
+          case 5: launch_fwdc<5>(e, draws, opBegin + done, c, ppt); break;
+          case 6: launch_fwdc<6>(e, draws, opBegin + done, c, ppt); break;
+          default: launch_fwdc<8>(e, draws, opBegin + done, c, ppt); break;
+        }
+        ++e.launches;
+      }
+      continue;
+    }
+    const bool tipLevel = (l == 0) && !(e.cfg.flags & TTB2_FLAG_NO_MMA);  // level 1: tip-tip nodes
     // grid.y is limited to 65535
     for (int done = 0; done < count; done += 65535) {
       const int c = (count - done) < 65535 ? (count - done) : 65535;
       switch (m.K) {
-        case 1: launch_fwd<1>(e, draws, opBegin + done, c, smem, ppt); break;
-        case 2: launch_fwd<2>(e, draws, opBegin + done, c, smem, ppt); break;
-        case 3: launch_fwd<3>(e, draws, opBegin + done, c, smem, ppt); break;
-        case 4: launch_fwd<4>(e, draws, opBegin + done, c, smem, ppt); break;
-        case 5: launch_fwd<5>(e, draws, opBegin + done, c, smem, ppt); break;
-        case 6: launch_fwd<6>(e, draws, opBegin + done, c, smem, ppt); break;
-        case 8: launch_fwd<8>(e, draws, opBegin + done, c, smem, ppt); break;
+        case 1: launch_fwd<1>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
+        case 2: launch_fwd<2>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
+        case 3: launch_fwd<3>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
+        case 4: launch_fwd<4>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
+        case 5: launch_fwd<5>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
+        case 6: launch_fwd<6>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
+        case 8: launch_fwd<8>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
         default: {
           dim3 grid((m.Npad + FWD_THREADS - 1) / FWD_THREADS, c, draws);
           fwd4_kernel_anyk<<<grid, FWD_THREADS, smem, e.stream>>>(
@@ -783,22 +1455,38 @@ int s4_backward(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      if (useMma && variant == 1)
-        bwd4_mma_kernel<false, 6><<<grid, BWDM_THREADS, smem, e.stream>>>(
+      if (useMma && l == 0 && e.codes01) {
+        const size_t smemT = (32 + 2 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
+                             (size_t)m.C * sizeof(int);
+        bwd4_tips_kernel<<<grid, BWD_THREADS, smemT, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre, e.gpart,
+            e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      } else if (useMma && e.cherryOn) {
+        const CherryArgs ch = cherry_args(e);
+        const int NC = ch.CC > m.C ? ch.CC : m.C;
+        const size_t smemC = (32 + 4 * (size_t)NC * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) *
+                             sizeof(double);
+        bwd4c_mma_kernel<<<grid, BWDM_THREADS, smemC, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
+            e.gpart, e.chunkBase, e.chunkTotal, ch, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns,
+            nChunk);
+      } else if (useMma && variant == 4) {
+        bwd4_mma_kernel<false, 4, false><<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      else if (useMma && variant == 2)
-        bwd4_mma_kernel<false, 8><<<grid, BWDM_THREADS, smem, e.stream>>>(
+      } else if (useMma && variant == 5) {
+        bwd4_mma_kernel<false, 3, true><<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      else if (useMma && variant == 3)
-        bwd4_mma_kernel<true, 5><<<grid, BWDM_THREADS, smem, e.stream>>>(
+      } else if (useMma && variant == 6) {
+        bwd4_mma_kernel<true, 3, true><<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      else if (useMma)
-        bwd4_mma_kernel<true, 4><<<grid, BWDM_THREADS, smem, e.stream>>>(
+      } else if (useMma) {
+        bwd4_mma_kernel<true, 4, false><<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      }
       else
         bwd4_kernel<<<grid, BWD_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
