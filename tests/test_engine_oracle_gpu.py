@@ -93,12 +93,14 @@ def test_generic_kernels_equal_specialised_for_nucleotides():
     e1.close(); e2.close()
 
 
+@pytest.mark.parametrize("flags", [0, 8], ids=["mma", "simt"])
 @pytest.mark.parametrize("S,K,T,N", [(20, 4, 14, 70), (61, 4, 9, 40), (20, 1, 30, 33),
-                                     (7, 3, 10, 64), (2, 2, 10, 64)])
-def test_other_state_counts(S, K, T, N):
+                                     (7, 3, 10, 64), (2, 2, 10, 64), (8, 2, 12, 100),
+                                     (64, 1, 6, 33), (21, 3, 40, 700)])
+def test_other_state_counts(S, K, T, N, flags):
     from torchtree_b200.synthetic import make_problem
 
-    _check(make_problem(T, N, S, K, seed=S + K, gap_fraction=0.05), q_rtol=1e-6)
+    _check(make_problem(T, N, S, K, seed=S + K, gap_fraction=0.05), flags=flags, q_rtol=1e-6)
 
 
 def test_weights_linearity_and_shard_additivity():

@@ -172,6 +172,11 @@ int gen_forward(Engine& e, int draws);
 int gen_root(Engine& e, int draws);
 int gen_backward(Engine& e, int draws);
 
+// fp64 tensor-core path for 8 <= S <= 64 (kernels_gmma.cu); shares the generic layout
+bool gmma_supported(const Engine& e);
+int gmma_forward(Engine& e, int draws);
+int gmma_backward_levels(Engine& e, int draws);
+
 // small kernels (kernels_small.cu)
 int small_pmatrix(Engine& e, int draws);
 int small_reduce_lnl(Engine& e, int draws, int nblocks);
