@@ -74,15 +74,56 @@ def timing(cfg, steps):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    eng.enable_timing(True)
+    step()
+    phases = eng.phase_ms()
+    eng.enable_timing(False)
     bytes_per_unit = 5 * cfg["S"] * 8
     out = {
         "ms_per_eval": ms, "units": prob.units, "units_per_s": prob.units / (ms * 1e-3),
         "evals_per_s": 1e3 / ms,
         "hbm_frac_of_measured": prob.units * bytes_per_unit / (ms * 1e-3) / 1e9 / PEAK_GBS,
         "device_GB": eng.device_bytes / 1e9,
+        "phases_ms": {k: round(v, 3) for k, v in phases.items()},
     }
     eng.close()
     return out
+
+
+def config1_flu():
+    """Config 1 shape on the real fluA data (golden fixture): 69 taxa, 238 patterns,
+    GTR + 4 categories, unrooted; parity against the reference's own outputs."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from helpers import load_golden
+
+    prob, rec = load_golden("fluA_gtr_w4_generic")
+    eng = Engine(prob.tip_states, prob.weights, prob.postorder, 4, 4,
+                 code_partials=prob.code_partials, max_draws=1, flags=1)
+    e = eig(prob)
+    lnl, g = evaluate(eng, prob, e)
+    rel = abs(lnl.item() - rec["lnL"][0]) / abs(rec["lnL"][0])
+    gerr = float(np.max(np.abs(g["branch_lengths"].numpy() - rec["d_branch_lengths"]) /
+                        np.maximum(np.abs(rec["d_branch_lengths"]), 1e-8 * np.abs(rec["d_branch_lengths"]).max())))
+    host = [torch.tensor(a) if not isinstance(a, torch.Tensor) else a
+            for a in (prob.branch_lengths, prob.site_rates, prob.site_props, *e, prob.freqs)]
+    for _ in range(20):
+        eng.loglik_eigen(*host); eng.grad_eigen()
+    t0 = time.perf_counter()
+    n = 200
+    for _ in range(n):
+        eng.loglik_eigen(*host); eng.grad_eigen()
+    ms = (time.perf_counter() - t0) / n * 1e3
+    line = {"config": "config1_fluA_gtr_w4", "note": "real fluA data (69 taxa, 238 patterns), host "
+            "tensors in/out through the C ABI (launch-bound: %d kernel launches per evaluation)"
+            % (eng.launch_count // 221),
+            "shape": {"T": 69, "N": 238, "S": 4, "K": 4, "D": 1},
+            "parity": {"lnL_rel_err_vs_reference": rel, "branch_grad_max_rel_err": gerr,
+                       "ok": bool(rel <= 1e-10 and gerr <= 1e-8)},
+            "timing": {"ms_per_eval_e2e": ms, "evals_per_s": 1e3 / ms,
+                       "reference_cpu_ms_per_eval": 25.0,
+                       "reference_note": "SURVEY section 6: 0.025 s logL+grad on 8 CPU threads"}}
+    eng.close()
+    print(json.dumps(line), flush=True)
 
 
 CONFIGS = {
@@ -100,6 +141,8 @@ if __name__ == "__main__":
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
+    if not a.only or a.only == "config1":
+        config1_flu()
     for name, cfg in CONFIGS.items():
         if a.only and a.only != name:
             continue

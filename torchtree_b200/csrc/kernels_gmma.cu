@@ -93,10 +93,39 @@ __device__ __forceinline__ void gm_mma_atb(double& c0, double& c1, const double*
   for (int kt = 0; kt < ksteps; ++kt) dmma884(c0, c1, a[kt * 4 * lda], b[kt * 4 * GM_LDT]);
 }
 
+// grouped variants: one A fragment feeds NTG pattern tiles (NTG independent
+// accumulator chains, 1 + NTG shared-memory loads per NTG MMAs)
+template <int NTG>
+__device__ __forceinline__ void gm_mma_ab_g(double (&c)[NTG][2], const double* A, int lda,
+                                            const double* Bt, int mt, int nt0, int ksteps,
+                                            int lane) {
+  const double* a = A + (mt * 8 + (lane >> 2)) * lda + (lane & 3);
+  const double* b = Bt + (lane & 3) * GM_LDT + nt0 * 8 + (lane >> 2);
+  for (int kt = 0; kt < ksteps; ++kt) {
+    const double av = a[kt * 4];
+#pragma unroll
+    for (int n = 0; n < NTG; ++n) dmma884(c[n][0], c[n][1], av, b[kt * 4 * GM_LDT + n * 8]);
+  }
+}
+
+template <int NTG>
+__device__ __forceinline__ void gm_mma_atb_g(double (&c)[NTG][2], const double* A, int lda,
+                                             const double* Bt, int mt, int nt0, int ksteps,
+                                             int lane) {
+  const double* a = A + (lane & 3) * lda + mt * 8 + (lane >> 2);
+  const double* b = Bt + (lane & 3) * GM_LDT + nt0 * 8 + (lane >> 2);
+  for (int kt = 0; kt < ksteps; ++kt) {
+    const double av = a[kt * 4 * lda];
+#pragma unroll
+    for (int n = 0; n < NTG; ++n) dmma884(c[n][0], c[n][1], av, b[kt * 4 * GM_LDT + n * 8]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // post-order.  grid (pattern tiles, nodes of level, draws)
 // shared: Pl Pr [Sp*PLD] | cl cr [R*LDT] | out [K][Sp][LDT] | wmax [8*32]
 // ---------------------------------------------------------------------------
+template <int NTG>
 __global__ void __launch_bounds__(GM_THREADS)
 gm_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
               const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
@@ -133,14 +162,20 @@ gm_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     gm_stage_tile(cr, tipR, tips + (size_t)(tipR ? op.right : 0) * Npad, codeP,
                   base + (size_t)(tipR ? 0 : op.right - T) * nodeStride + k * plane, i0, Npad, g);
     __syncthreads();
-    for (int item = warp; item < MT * 4; item += GM_WARPS) {
-      const int mt = item >> 2, nt = item & 3;
-      double l0 = 0.0, l1 = 0.0, r0 = 0.0, r1 = 0.0;
-      gm_mma_ab(l0, l1, Pl, g.PLD, cl, mt, nt, KT, lane);
-      gm_mma_ab(r0, r1, Pr, g.PLD, cr, mt, nt, KT, lane);
-      double* o = out + ((size_t)k * g.Sp + mt * 8 + (lane >> 2)) * GM_LDT + nt * 8 + (lane & 3) * 2;
-      o[0] = l0 * r0;
-      o[1] = l1 * r1;
+    constexpr int NG = 4 / NTG;  // groups of pattern tiles
+    for (int item = warp; item < MT * NG; item += GM_WARPS) {
+      const int mt = item / NG, nt0 = (item - mt * NG) * NTG;
+      double accL[NTG][2], accR[NTG][2];
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
+      gm_mma_ab_g<NTG>(accL, Pl, g.PLD, cl, mt, nt0, KT, lane);
+      gm_mma_ab_g<NTG>(accR, Pr, g.PLD, cr, mt, nt0, KT, lane);
+      double* o = out + ((size_t)k * g.Sp + mt * 8 + (lane >> 2)) * GM_LDT + nt0 * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) {
+        o[n * 8] = accL[n][0] * accR[n][0];
+        o[n * 8 + 1] = accL[n][1] * accR[n][1];
+      }
     }
   }
   __syncthreads();
@@ -169,6 +204,7 @@ gm_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
 // pre-order.  grid (pattern chunks, nodes of level x K, draws)
 // shared: Pl Pr [Sp*PLD] | tq vl vr ml mr [R*LDT each] | ws[32] | el er [32] (int)
 // ---------------------------------------------------------------------------
+template <int NTG>
 __global__ void __launch_bounds__(GM_THREADS)
 gm_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
               const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
@@ -205,7 +241,6 @@ gm_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
 
   // persistent G accumulators: items (child, mt, mt2) dealt round-robin to the warps
-  const int nG = 2 * MT * MT;
   double acc[GM_MAXACC][2];
 #pragma unroll
   for (int j = 0; j < GM_MAXACC; ++j) acc[j][0] = acc[j][1] = 0.0;
@@ -231,17 +266,23 @@ gm_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     }
     __syncthreads();
     // U phase: u_l = P_l v_l, u_r = P_r v_r;  m_l = q^ o u_r, m_r = q^ o u_l
-    for (int item = warp; item < MT * 4; item += GM_WARPS) {
-      const int mt = item >> 2, nt = item & 3;
-      double l0 = 0.0, l1 = 0.0, r0 = 0.0, r1 = 0.0;
-      gm_mma_ab(l0, l1, Pl, g.PLD, vl, mt, nt, KT, lane);
-      gm_mma_ab(r0, r1, Pr, g.PLD, vr, mt, nt, KT, lane);
-      const int off = (mt * 8 + (lane >> 2)) * GM_LDT + nt * 8 + (lane & 3) * 2;
-      const double q0 = tq[off], q1 = tq[off + 1];
-      ml[off] = q0 * r0;
-      ml[off + 1] = q1 * r1;
-      mr[off] = q0 * l0;
-      mr[off + 1] = q1 * l1;
+    constexpr int NG = 4 / NTG;
+    for (int item = warp; item < MT * NG; item += GM_WARPS) {
+      const int mt = item / NG, nt0 = (item - mt * NG) * NTG;
+      double accL[NTG][2], accR[NTG][2];
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
+      gm_mma_ab_g<NTG>(accL, Pl, g.PLD, vl, mt, nt0, KT, lane);
+      gm_mma_ab_g<NTG>(accR, Pr, g.PLD, vr, mt, nt0, KT, lane);
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) {
+        const int off = (mt * 8 + (lane >> 2)) * GM_LDT + (nt0 + n) * 8 + (lane & 3) * 2;
+        const double q0 = tq[off], q1 = tq[off + 1];
+        ml[off] = q0 * accR[n][0];
+        ml[off + 1] = q1 * accR[n][1];
+        mr[off] = q0 * accL[n][0];
+        mr[off + 1] = q1 * accL[n][1];
+      }
     }
     __syncthreads();
     // Q phase: q^_c = P_c^T m_c * 2^{-e_c}  (internal children)
@@ -251,52 +292,66 @@ gm_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
       const double* mm = side ? mr : ml;
       const int child = side ? op.right : op.left;
       double* qout = pre + drawBase + (size_t)(child - T) * nodeStride + k * plane + i0;
-      for (int item = warp; item < MT * 4; item += GM_WARPS) {
-        const int mt = item >> 2, nt = item & 3;
-        double c0 = 0.0, c1 = 0.0;
-        gm_mma_atb(c0, c1, P, g.PLD, mm, mt, nt, KTr, lane);
+      for (int item = warp; item < MT * NG; item += GM_WARPS) {
+        const int mt = item / NG, nt0 = (item - mt * NG) * NTG;
+        double c[NTG][2];
+#pragma unroll
+        for (int n = 0; n < NTG; ++n) c[n][0] = c[n][1] = 0.0;
+        gm_mma_atb_g<NTG>(c, P, g.PLD, mm, mt, nt0, KTr, lane);
         const int row = mt * 8 + (lane >> 2);
-        const int col = nt * 8 + (lane & 3) * 2;
         if (row < S) {
-          const double f0 = __hiloint2double((1023 - se[side * 32 + col]) << 20, 0);
-          const double f1 = __hiloint2double((1023 - se[side * 32 + col + 1]) << 20, 0);
-          *reinterpret_cast<double2*>(qout + (size_t)row * Npad + col) =
-              make_double2(c0 * f0, c1 * f1);
+#pragma unroll
+          for (int n = 0; n < NTG; ++n) {
+            const int col = (nt0 + n) * 8 + (lane & 3) * 2;
+            const double f0 = __hiloint2double((1023 - se[side * 32 + col]) << 20, 0);
+            const double f1 = __hiloint2double((1023 - se[side * 32 + col + 1]) << 20, 0);
+            *reinterpret_cast<double2*>(qout + (size_t)row * Npad + col) =
+                make_double2(c[n][0] * f0, c[n][1] * f1);
+          }
         }
       }
     }
-    // G phase: G_c[s][t] += sum_p (w_p m_c[s][p]) v_c[t][p]
+    // G phase: G_c[s][t] += sum_p (w_p m_c[s][p]) v_c[t][p].  A warp owns up to two
+    // (child, row tile) combos and all their column tiles: one A fragment (w o m)
+    // feeds MT independent accumulator chains.
 #pragma unroll
-    for (int j = 0; j < GM_MAXACC; ++j) {
-      const int item = warp + j * GM_WARPS;
-      if (item < nG) {
-        const int side = item / (MT * MT);
-        const int r = item - side * MT * MT;
-        const int mt = r / MT, mt2 = r - mt * MT;
+    for (int cj = 0; cj < 2; ++cj) {
+      const int combo = warp + cj * GM_WARPS;
+      if (combo < 2 * MT) {
+        const int side = combo / MT;
+        const int mt = combo - side * MT;
         const double* mm = (side ? mr : ml) + (mt * 8 + (lane >> 2)) * GM_LDT + (lane & 3);
-        const double* vv = (side ? vr : vl) + (mt2 * 8 + (lane >> 2)) * GM_LDT + (lane & 3);
+        const double* vv = (side ? vr : vl) + (lane >> 2) * GM_LDT + (lane & 3);
         const double* wp = ws + (lane & 3);
 #pragma unroll
-        for (int kt = 0; kt < GM_TP / 4; ++kt)
-          dmma884(acc[j][0], acc[j][1], mm[kt * 4] * wp[kt * 4], vv[kt * 4]);
+        for (int kt = 0; kt < GM_TP / 4; ++kt) {
+          const double av = mm[kt * 4] * wp[kt * 4];
+#pragma unroll
+          for (int mt2 = 0; mt2 < 8; ++mt2)
+            if (mt2 < MT)
+              dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av,
+                      vv[mt2 * 8 * GM_LDT + kt * 4]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < GM_MAXACC; ++j) {
-    const int item = warp + j * GM_WARPS;
-    if (item < nG) {
-      const int side = item / (MT * MT);
-      const int r = item - side * MT * MT;
-      const int mt = r / MT, mt2 = r - mt * MT;
+  for (int cj = 0; cj < 2; ++cj) {
+    const int combo = warp + cj * GM_WARPS;
+    if (combo < 2 * MT) {
+      const int side = combo / MT;
+      const int mt = combo - side * MT;
       const int branch = side ? op.right : op.left;
       double* o = gpart + ((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk +
                            blockIdx.x) * SS;
       const int row = mt * 8 + (lane >> 2);
-      const int col = mt2 * 8 + (lane & 3) * 2;
-      if (row < S) {
-        if (col < S) o[row * S + col] = acc[j][0];
-        if (col + 1 < S) o[row * S + col + 1] = acc[j][1];
+#pragma unroll
+      for (int mt2 = 0; mt2 < 8; ++mt2) {
+        if (mt2 < MT && row < S) {
+          const int col = mt2 * 8 + (lane & 3) * 2;
+          if (col < S) o[row * S + col] = acc[cj * 8 + mt2][0];
+          if (col + 1 < S) o[row * S + col + 1] = acc[cj * 8 + mt2][1];
+        }
       }
     }
   }
@@ -326,9 +381,12 @@ bool gmma_supported(const Engine& e) {
 int gmma_forward(Engine& e, int draws) {
   const Dims& m = e.dm;
   const size_t smem = gm_fwd_smem(m);
+  const int MT = gm_shape(m.S).Sp / 8;
+  const int ntg = MT >= 8 ? 4 : (MT >= 4 ? 2 : 1);
+  auto kern = ntg == 4 ? gm_fwd_kernel<4> : (ntg == 2 ? gm_fwd_kernel<2> : gm_fwd_kernel<1>);
   if (smem > 48 * 1024)
-    TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_fwd_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TTB2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
   const int nLevels = (int)e.levelOff.size() - 1;
   for (int l = 0; l < nLevels; ++l) {
     const int opBegin = e.levelOff[l];
@@ -336,7 +394,7 @@ int gmma_forward(Engine& e, int draws) {
     for (int done = 0; done < count; done += 65535) {
       const int c = (count - done) < 65535 ? (count - done) : 65535;
       dim3 grid(m.Npad / GM_TP, c, draws);
-      gm_fwd_kernel<<<grid, GM_THREADS, smem, e.stream>>>(
+      kern<<<grid, GM_THREADS, smem, e.stream>>>(
           e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.B,
           m.K, m.S);
       ++e.launches;
@@ -350,9 +408,12 @@ int gmma_forward(Engine& e, int draws) {
 int gmma_backward_levels(Engine& e, int draws) {
   const Dims& m = e.dm;
   const size_t smem = gm_bwd_smem(m);
+  const int MT = gm_shape(m.S).Sp / 8;
+  const int ntg = MT >= 8 ? 4 : (MT >= 4 ? 2 : 1);
+  auto kern = ntg == 4 ? gm_bwd_kernel<4> : (ntg == 2 ? gm_bwd_kernel<2> : gm_bwd_kernel<1>);
   if (smem > 48 * 1024)
-    TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_bwd_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TTB2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
   const int nLevels = (int)e.levelOff.size() - 1;
   const int maxNodes = 65535 / m.K;
   for (int l = nLevels - 1; l >= 0; --l) {
@@ -364,7 +425,7 @@ int gmma_backward_levels(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      gm_bwd_kernel<<<grid, GM_THREADS, smem, e.stream>>>(
+      kern<<<grid, GM_THREADS, smem, e.stream>>>(
           e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
           e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B, m.K, m.S, chunkPatterns, nChunk);
       ++e.launches;
