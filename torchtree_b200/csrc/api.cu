@@ -258,6 +258,12 @@ int run_forward(Engine& e, int draws, double* lnl, int where) {
     e.fwdLevelLaunches = (int)(e.launches - before);
     mark(e, 2);
     if ((rc = s4_root(e, draws))) return rc;
+  } else if (gmma_supported(e)) {
+    if (!e.expoK && (rc = dev_alloc(e, &e.expoK, gmma_expo_elems(e)))) return rc;
+    if ((rc = gmma_forward2(e, draws))) return rc;
+    e.fwdLevelLaunches = (int)(e.launches - before);
+    mark(e, 2);
+    if ((rc = gmma_root2(e, draws))) return rc;
   } else {
     if ((rc = gen_forward(e, draws))) return rc;
     e.fwdLevelLaunches = (int)(e.launches - before);
@@ -315,7 +321,8 @@ int run_backward(Engine& e, const double* grad_lnl, int where) {
   mark(e, 4);
   if (!e.preValid) {
     const int64_t before = e.launches;
-    rc = e.spec4 ? s4_backward(e, draws) : gen_backward(e, draws);
+    rc = e.spec4 ? s4_backward(e, draws)
+                 : (gmma_supported(e) ? gmma_backward2(e, draws) : gen_backward(e, draws));
     if (rc) return rc;
     e.bwdLevelLaunches = (int)(e.launches - before) - 3;  // minus root, root reduce, gpart reduce
     e.preValid = true;

@@ -176,6 +176,11 @@ int gen_backward(Engine& e, int draws);
 bool gmma_supported(const Engine& e);
 int gmma_forward(Engine& e, int draws);
 int gmma_backward_levels(Engine& e, int draws);
+// v2: per-(pattern, category) rescaling, pipelined staging (own root kernels, expoK layout)
+size_t gmma_expo_elems(const Engine& e);
+int gmma_forward2(Engine& e, int draws);
+int gmma_root2(Engine& e, int draws);
+int gmma_backward2(Engine& e, int draws);
 
 // small kernels (kernels_small.cu)
 int small_pmatrix(Engine& e, int draws);

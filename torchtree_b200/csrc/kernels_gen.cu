@@ -359,7 +359,6 @@ size_t bwd_smem(const Dims& m) {
 
 int gen_forward(Engine& e, int draws) {
   const Dims& m = e.dm;
-  if (gmma_supported(e)) return gmma_forward(e, draws);
   if (m.S > 64) {
     set_error("generic kernels support at most 64 states");
     return TTB2_E_INVALID;
@@ -415,11 +414,6 @@ int gen_backward(Engine& e, int draws) {
     TTB2_CUDA_CHECK(cudaGetLastError());
     int rc = small_root_grad_reduce(e, draws, nblocks);
     if (rc) return rc;
-  }
-  if (gmma_supported(e)) {
-    int rc = gmma_backward_levels(e, draws);
-    if (rc) return rc;
-    return small_gpart_reduce(e, draws);
   }
   const size_t smem = bwd_smem(m);
   if (smem > 48 * 1024)

@@ -12,6 +12,8 @@
 //
 // Layout in HBM is the generic one ([draw][inode][k][s][pattern], kernels_gen.cu)
 // and the root / reduction kernels are shared with it.
+#include <climits>
+
 #include "engine.cuh"
 
 namespace ttb2 {
@@ -357,6 +359,406 @@ gm_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   }
 }
 
+// ===========================================================================
+// Version 2: per-(pattern, category) rescaling + software-pipelined staging.
+// Every (node, category) is independent of the other categories (their chains
+// are recombined at the root with their exponent sums, like the fused 4-state
+// path), so a CTA owns (node, k, chunk of pattern tiles): the two transition
+// matrices are staged once and the child tiles stream through a double buffer
+// filled with cp.async while the previous tile is in the tensor cores.
+// Exponents: expoK [draw][inode][k][pattern] (int16).
+// ===========================================================================
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// asynchronous version of gm_stage_tile (tips and padding rows are written directly)
+template <int NW>
+__device__ __forceinline__ void gm_stage_tile_async(double* tile, bool tip, const uint8_t* tipRow,
+                                                    const double* codeP, const double* plane,
+                                                    int i0, int Npad, const GmShape g) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = i0 + lane;
+  if (tip) {
+    const double* cp = codeP + (size_t)tipRow[i] * g.S;
+    for (int s = warp; s < g.R; s += NW) tile[s * GM_LDT + lane] = s < g.S ? cp[s] : 0.0;
+  } else {
+    for (int s = warp; s < g.R; s += NW) {
+      if (s < g.S) cp_async8(tile + s * GM_LDT + lane, plane + (size_t)s * Npad + i);
+      else tile[s * GM_LDT + lane] = 0.0;
+    }
+  }
+}
+
+// post-order v2.  grid (pattern chunks, nodes of level x K, draws)
+// shared: Pl Pr [Sp*PLD] | cl[2] cr[2] [R*LDT] | out [Sp*LDT] | wmax [8*32]
+template <int NTG, int NW, int CS>
+__global__ void __launch_bounds__(NW * 32)
+gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
+               const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
+               double* __restrict__ partials, int16_t* __restrict__ expoK, int T, int Npad, int B,
+               int K, int Srt, int chunkPatterns) {
+  extern __shared__ double sm[];
+  const int S = CS ? CS : Srt;  // compile-time state count for the common alphabets
+  const GmShape g = gm_shape(S);
+  const int SS = S * S;
+  const int tileN = g.R * GM_LDT;
+  double* Pl = sm;
+  double* Pr = Pl + g.Sp * g.PLD;
+  double* cl = Pr + g.Sp * g.PLD;   // two buffers
+  double* cr = cl + 2 * tileN;      // two buffers
+  double* out = cr + 2 * tileN;
+  double* wmax = out + tileN;
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const size_t plane = (size_t)S * Npad;
+  const size_t nodeStride = (size_t)K * plane;
+  double* base = partials + (size_t)d * I * nodeStride + k * plane;
+  const double* matsD = mats + (size_t)d * B * K * SS;
+  const int MT = g.Sp / 8, KT = g.Kp / 4;
+  const uint8_t* tl = tips + (size_t)(tipL ? op.left : 0) * Npad;
+  const uint8_t* tr = tips + (size_t)(tipR ? op.right : 0) * Npad;
+  const double* pl = base + (size_t)(tipL ? 0 : op.left - T) * nodeStride;
+  const double* pr = base + (size_t)(tipR ? 0 : op.right - T) * nodeStride;
+  double* qn = base + (size_t)(op.node - T) * nodeStride;
+  int16_t* en = expoK + (((size_t)d * I + (op.node - T)) * K + k) * Npad;
+
+  gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
+  gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  if (begin < end) {
+    gm_stage_tile_async<NW>(cl, tipL, tl, codeP, pl, begin, Npad, g);
+    gm_stage_tile_async<NW>(cr, tipR, tr, codeP, pr, begin, Npad, g);
+  }
+  cp_async_commit();
+  int buf = 0;
+  for (int i0 = begin; i0 < end; i0 += GM_TP, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // tile `buf` (and P on the first trip) visible; `out` free
+    if (i0 + GM_TP < end) {
+      gm_stage_tile_async<NW>(cl + (buf ^ 1) * tileN, tipL, tl, codeP, pl, i0 + GM_TP, Npad, g);
+      gm_stage_tile_async<NW>(cr + (buf ^ 1) * tileN, tipR, tr, codeP, pr, i0 + GM_TP, Npad, g);
+    }
+    cp_async_commit();
+    const double* tcl = cl + buf * tileN;
+    const double* tcr = cr + buf * tileN;
+    constexpr int NG = 4 / NTG;
+    for (int item = warp; item < MT * NG; item += NW) {
+      const int mt = item / NG, nt0 = (item - mt * NG) * NTG;
+      double accL[NTG][2], accR[NTG][2];
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
+      gm_mma_ab_g<NTG>(accL, Pl, g.PLD, tcl, mt, nt0, KT, lane);
+      gm_mma_ab_g<NTG>(accR, Pr, g.PLD, tcr, mt, nt0, KT, lane);
+      double* o = out + (mt * 8 + (lane >> 2)) * GM_LDT + nt0 * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) {
+        o[n * 8] = accL[n][0] * accR[n][0];
+        o[n * 8 + 1] = accL[n][1] * accR[n][1];
+      }
+    }
+    __syncthreads();
+    double m = 0.0;
+    for (int s2 = warp; s2 < S; s2 += NW) m = fmax(m, out[s2 * GM_LDT + lane]);
+    wmax[warp * 32 + lane] = m;
+    __syncthreads();
+    double mm = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mm = fmax(mm, wmax[w * 32 + lane]);
+    const int eb = (__double2hiint(mm) >> 20) & 0x7ff;
+    const int e = (mm > 0.0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
+    const double f = __hiloint2double((1023 - e) << 20, 0);
+    for (int s2 = warp; s2 < S; s2 += NW)
+      qn[(size_t)s2 * Npad + i0 + lane] = out[s2 * GM_LDT + lane] * f;
+    if (warp == 0) en[i0 + lane] = (int16_t)e;
+  }
+}
+
+// root v2: recombine the per-category chains (cf. fused_root_kernel)
+constexpr int GMR_THREADS = 128;
+
+__device__ __forceinline__ double gm_block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) t += red[w];
+  }
+  return t;
+}
+
+__device__ __forceinline__ double gm_chain_weight(int diff) {
+  return diff < -1000 ? 0.0 : __hiloint2double((1023 + (diff > 1000 ? 1000 : diff)) << 20, 0);
+}
+
+constexpr int GM_MAXK = 16;
+
+// WITH_PRE: also writes q^_root and the per-block partials of d/d rho, root d/d pi
+template <bool WITH_PRE>
+__global__ void __launch_bounds__(GMR_THREADS)
+gm_root2_kernel(const double* __restrict__ partials, const int16_t* __restrict__ expoK,
+                const double* __restrict__ freqs, int freqDraws,
+                const double* __restrict__ props, int propDraws,
+                const double* __restrict__ weights, double* __restrict__ siteLnl,
+                double* __restrict__ pre, double* __restrict__ blockPart, int T, int Npad, int K,
+                int S, int rootInode) {
+  __shared__ double red[GMR_THREADS / 32];
+  const int d = blockIdx.y;
+  const int I = T - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* fr = freqs + (freqDraws > 1 ? (size_t)d * S : 0);
+  const double* pr = props + (propDraws > 1 ? (size_t)d * K : 0);
+  const size_t plane = (size_t)S * Npad;
+  const bool live = i < Npad;
+  const double* p = partials + ((size_t)d * I + rootInode) * K * plane + (live ? i : 0);
+  double dots[GM_MAXK];
+  int es[GM_MAXK];
+  double w = 0.0, invL = 0.0, site = 0.0;
+  int emax = INT_MIN;
+  if (live) {
+    for (int k = 0; k < K; ++k) {
+      double dot = 0.0;
+      for (int s = 0; s < S; ++s) dot = fma(fr[s], p[k * plane + (size_t)s * Npad], dot);
+      dots[k] = dot;
+      int e = 0;
+      const int16_t* ep = expoK + ((size_t)d * I * K + k) * Npad + i;
+      for (int n = 0; n < I; ++n) e += ep[(size_t)n * K * Npad];
+      es[k] = e;
+      if (dot > 0.0 && pr[k] > 0.0) emax = max(emax, e);
+    }
+    double L = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double cw = dots[k] > 0.0 ? gm_chain_weight(es[k] - emax) : 0.0;
+      L = fma(pr[k] * cw, dots[k], L);
+    }
+    site = log(L) + (double)emax * 0.693147180559945309417232121458;
+    invL = 1.0 / L;
+    w = weights[i];
+    if (!WITH_PRE) siteLnl[(size_t)d * Npad + i] = site;
+  }
+  if (!WITH_PRE) {
+    const double t = gm_block_sum((live && w != 0.0) ? w * site : 0.0, red);
+    if (threadIdx.x == 0) blockPart[(size_t)d * gridDim.x + blockIdx.x] = t;
+    return;
+  }
+  if (live) {
+    double* q = pre + ((size_t)d * I + rootInode) * K * plane + i;
+    for (int k = 0; k < K; ++k) {
+      const double cw = dots[k] > 0.0 ? gm_chain_weight(es[k] - emax) : 0.0;
+      const int e = expoK[(((size_t)d * I + rootInode) * K + k) * Npad + i];
+      const double c = pr[k] * cw * invL * __hiloint2double((1023 - e) << 20, 0);
+      for (int s = 0; s < S; ++s) q[k * plane + (size_t)s * Npad] = c * fr[s];
+    }
+  }
+  const double wl = (live && w != 0.0) ? w * invL : 0.0;
+  double* out = blockPart + ((size_t)d * gridDim.x + blockIdx.x) * (K + S);
+  for (int k = 0; k < K; ++k) {
+    double v = 0.0;
+    if (wl != 0.0 && dots[k] > 0.0) v = wl * gm_chain_weight(es[k] - emax) * dots[k];
+    const double t = gm_block_sum(v, red);
+    if (threadIdx.x == 0) out[k] = t;
+  }
+  for (int s = 0; s < S; ++s) {
+    double acc = 0.0;
+    if (wl != 0.0)
+      for (int k = 0; k < K; ++k)
+        if (dots[k] > 0.0)
+          acc = fma(pr[k] * gm_chain_weight(es[k] - emax), p[k * plane + (size_t)s * Npad], acc);
+    const double t = gm_block_sum(wl * acc, red);
+    if (threadIdx.x == 0) out[K + s] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pre-order v2 (per-category exponents, double-buffered cp.async staging).
+// shared: Pl Pr [Sp*PLD] | tq[2] vl[2] vr[2] ml mr [R*LDT each] | ws[2][32] | el er [2][32] (int)
+// ---------------------------------------------------------------------------
+template <int NTG, int NW, int CS>
+__global__ void __launch_bounds__(NW * 32)
+gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
+              const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
+              const double* __restrict__ partials, const int16_t* __restrict__ expoK,
+              const double* __restrict__ weights, double* __restrict__ pre,
+              double* __restrict__ gpart, const int* __restrict__ chunkBase, size_t chunkTotal,
+              int T, int Npad, int B, int K, int Srt, int chunkPatterns, int nChunk) {
+  extern __shared__ double sm[];
+  const int S = CS ? CS : Srt;
+  const GmShape g = gm_shape(S);
+  const int SS = S * S;
+  double* Pl = sm;
+  double* Pr = Pl + g.Sp * g.PLD;
+  const int tileN = g.R * GM_LDT;
+  double* tqB = Pr + g.Sp * g.PLD;   // 2 buffers each
+  double* vlB = tqB + 2 * tileN;
+  double* vrB = vlB + 2 * tileN;
+  double* ml = vrB + 2 * tileN;
+  double* mr = ml + tileN;
+  double* wsB = mr + tileN;          // [2][32]
+  int* seB = reinterpret_cast<int*>(wsB + 64);  // [2][el[32], er[32]]
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const size_t plane = (size_t)S * Npad;
+  const size_t nodeStride = (size_t)K * plane;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const double* matsD = mats + (size_t)d * B * K * SS;
+  const int MT = g.Sp / 8, KT = g.Kp / 4, KTr = g.Sp / 4;
+  gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
+  gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+
+  // persistent G accumulators: items (child, mt, mt2) dealt round-robin to the warps
+  double acc[GM_MAXACC][2];
+#pragma unroll
+  for (int j = 0; j < GM_MAXACC; ++j) acc[j][0] = acc[j][1] = 0.0;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  const double* qsrc = pre + drawBase + (size_t)(op.node - T) * nodeStride + k * plane;
+  const double* lsrc = partials + drawBase + (size_t)(tipL ? 0 : op.left - T) * nodeStride + k * plane;
+  const double* rsrc = partials + drawBase + (size_t)(tipR ? 0 : op.right - T) * nodeStride + k * plane;
+  const uint8_t* tl = tips + (size_t)(tipL ? op.left : 0) * Npad;
+  const uint8_t* tr = tips + (size_t)(tipR ? op.right : 0) * Npad;
+  const int16_t* elp = tipL ? nullptr : expoK + (((size_t)d * I + (op.left - T)) * K + k) * Npad;
+  const int16_t* erp = tipR ? nullptr : expoK + (((size_t)d * I + (op.right - T)) * K + k) * Npad;
+  auto stage = [&](int b, int i0) {
+    gm_stage_tile_async<NW>(tqB + b * tileN, false, nullptr, codeP, qsrc, i0, Npad, g);
+    gm_stage_tile_async<NW>(vlB + b * tileN, tipL, tl, codeP, lsrc, i0, Npad, g);
+    gm_stage_tile_async<NW>(vrB + b * tileN, tipR, tr, codeP, rsrc, i0, Npad, g);
+    if (warp == 0) {
+      const int i = i0 + lane;
+      wsB[b * 32 + lane] = weights[i];
+      seB[b * 64 + lane] = tipL ? 0 : (int)elp[i];
+      seB[b * 64 + 32 + lane] = tipR ? 0 : (int)erp[i];
+    }
+  };
+  if (begin < end) stage(0, begin);
+  cp_async_commit();
+  int buf = 0;
+  for (int i0 = begin; i0 < end; i0 += GM_TP, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // buffers `buf` visible; ml/mr and buffers `buf^1` free
+    if (i0 + GM_TP < end) stage(buf ^ 1, i0 + GM_TP);
+    cp_async_commit();
+    const double* tq = tqB + buf * tileN;
+    const double* vl = vlB + buf * tileN;
+    const double* vr = vrB + buf * tileN;
+    const double* ws = wsB + buf * 32;
+    const int* se = seB + buf * 64;
+    // U phase: u_l = P_l v_l, u_r = P_r v_r;  m_l = q^ o u_r, m_r = q^ o u_l
+    constexpr int NG = 4 / NTG;
+    for (int item = warp; item < MT * NG; item += NW) {
+      const int mt = item / NG, nt0 = (item - mt * NG) * NTG;
+      double accL[NTG][2], accR[NTG][2];
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
+      gm_mma_ab_g<NTG>(accL, Pl, g.PLD, vl, mt, nt0, KT, lane);
+      gm_mma_ab_g<NTG>(accR, Pr, g.PLD, vr, mt, nt0, KT, lane);
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) {
+        const int off = (mt * 8 + (lane >> 2)) * GM_LDT + (nt0 + n) * 8 + (lane & 3) * 2;
+        const double q0 = tq[off], q1 = tq[off + 1];
+        ml[off] = q0 * accR[n][0];
+        ml[off + 1] = q1 * accR[n][1];
+        mr[off] = q0 * accL[n][0];
+        mr[off + 1] = q1 * accL[n][1];
+      }
+    }
+    __syncthreads();
+    // Q phase: q^_c = P_c^T m_c * 2^{-e_c}  (internal children)
+    for (int side = 0; side < 2; ++side) {
+      if (side ? tipR : tipL) continue;
+      const double* P = side ? Pr : Pl;
+      const double* mm = side ? mr : ml;
+      const int child = side ? op.right : op.left;
+      double* qout = pre + drawBase + (size_t)(child - T) * nodeStride + k * plane + i0;
+      for (int item = warp; item < MT * NG; item += NW) {
+        const int mt = item / NG, nt0 = (item - mt * NG) * NTG;
+        double c[NTG][2];
+#pragma unroll
+        for (int n = 0; n < NTG; ++n) c[n][0] = c[n][1] = 0.0;
+        gm_mma_atb_g<NTG>(c, P, g.PLD, mm, mt, nt0, KTr, lane);
+        const int row = mt * 8 + (lane >> 2);
+        if (row < S) {
+#pragma unroll
+          for (int n = 0; n < NTG; ++n) {
+            const int col = (nt0 + n) * 8 + (lane & 3) * 2;
+            const double f0 = __hiloint2double((1023 - se[side * 32 + col]) << 20, 0);
+            const double f1 = __hiloint2double((1023 - se[side * 32 + col + 1]) << 20, 0);
+            *reinterpret_cast<double2*>(qout + (size_t)row * Npad + col) =
+                make_double2(c[n][0] * f0, c[n][1] * f1);
+          }
+        }
+      }
+    }
+    // G phase: G_c[s][t] += sum_p (w_p m_c[s][p]) v_c[t][p].  A warp owns up to two
+    // (child, row tile) combos and all their column tiles: one A fragment (w o m)
+    // feeds MT independent accumulator chains.
+#pragma unroll
+    for (int cj = 0; cj < 2; ++cj) {
+      const int combo = warp + cj * NW;
+      if (combo < 2 * MT) {
+        const int side = combo / MT;
+        const int mt = combo - side * MT;
+        const double* mm = (side ? mr : ml) + (mt * 8 + (lane >> 2)) * GM_LDT + (lane & 3);
+        const double* vv = (side ? vr : vl) + (lane >> 2) * GM_LDT + (lane & 3);
+        const double* wp = ws + (lane & 3);
+#pragma unroll
+        for (int kt = 0; kt < GM_TP / 4; ++kt) {
+          const double av = mm[kt * 4] * wp[kt * 4];
+#pragma unroll
+          for (int mt2 = 0; mt2 < 8; ++mt2)
+            if (mt2 < MT)
+              dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av,
+                      vv[mt2 * 8 * GM_LDT + kt * 4]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int cj = 0; cj < 2; ++cj) {
+    const int combo = warp + cj * NW;
+    if (combo < 2 * MT) {
+      const int side = combo / MT;
+      const int mt = combo - side * MT;
+      const int branch = side ? op.right : op.left;
+      double* o = gpart + ((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk +
+                           blockIdx.x) * SS;
+      const int row = mt * 8 + (lane >> 2);
+#pragma unroll
+      for (int mt2 = 0; mt2 < 8; ++mt2) {
+        if (mt2 < MT && row < S) {
+          const int col = mt2 * 8 + (lane & 3) * 2;
+          if (col < S) o[row * S + col] = acc[cj * 8 + mt2][0];
+          if (col + 1 < S) o[row * S + col + 1] = acc[cj * 8 + mt2][1];
+        }
+      }
+    }
+  }
+}
+
 size_t gm_fwd_smem(const Dims& m) {
   const GmShape g = gm_shape(m.S);
   return (2 * (size_t)g.Sp * g.PLD + 2 * (size_t)g.R * GM_LDT + (size_t)m.K * g.Sp * GM_LDT +
@@ -369,13 +771,137 @@ size_t gm_bwd_smem(const Dims& m) {
          64 * sizeof(int);
 }
 
+size_t gm_fwd2_smem(const Dims& m) {
+  const GmShape g = gm_shape(m.S);
+  return (2 * (size_t)g.Sp * g.PLD + 5 * (size_t)g.R * GM_LDT + GM_WARPS * 32) * sizeof(double);
+}
+
+size_t gm_bwd2_smem(const Dims& m) {
+  const GmShape g = gm_shape(m.S);
+  return (2 * (size_t)g.Sp * g.PLD + 8 * (size_t)g.R * GM_LDT + 64) * sizeof(double) +
+         128 * sizeof(int);
+}
+
 }  // namespace
 
 bool gmma_supported(const Engine& e) {
   const Dims& m = e.dm;
   return !e.spec4 && m.S >= 8 && m.S <= 64 && !(e.cfg.flags & TTB2_FLAG_NO_MMA) &&
-         !(e.cfg.flags & TTB2_FLAG_FORCE_GENERIC) && gm_fwd_smem(m) <= 227 * 1024 &&
-         gm_bwd_smem(m) <= 227 * 1024;
+         !(e.cfg.flags & TTB2_FLAG_FORCE_GENERIC) && m.K <= GM_MAXK &&
+         gm_fwd2_smem(m) <= 227 * 1024 && gm_bwd2_smem(m) <= 227 * 1024;
+}
+
+size_t gmma_expo_elems(const Engine& e) {
+  const Dims& m = e.dm;
+  return (size_t)e.cfg.max_draws * m.I * m.K * m.Npad;
+}
+
+// chunk of patterns per post-order CTA (enough CTAs to fill the GPU, long-lived otherwise)
+static int gm_fwd_chunk(const Engine& e, int draws, int count) {
+  const Dims& m = e.dm;
+  const long target = (long)e.smCount * 8;
+  long chunks = (target + (long)count * m.K * draws - 1) / ((long)count * m.K * draws);
+  const long maxChunks = m.Npad / GM_TP;
+  if (chunks > maxChunks) chunks = maxChunks;
+  if (chunks < 1) chunks = 1;
+  int chunkPatterns = (int)((m.Npad + chunks - 1) / chunks);
+  return (chunkPatterns + GM_TP - 1) / GM_TP * GM_TP;
+}
+
+int gmma_forward2(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const size_t smem = gm_fwd2_smem(m);
+  const int MT = gm_shape(m.S).Sp / 8;
+  const int ntg = MT >= 8 ? 4 : (MT >= 4 ? 2 : 1);
+  const int nw = MT >= 5 ? 8 : 4;  // small state spaces: fewer, busier warps per CTA
+  auto kern = m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
+              : m.S == 20 ? gm_fwd2_kernel<1, 4, 20>
+              : ntg == 4  ? gm_fwd2_kernel<4, 8, 0>
+              : nw == 8   ? gm_fwd2_kernel<2, 8, 0>
+              : ntg == 2  ? gm_fwd2_kernel<2, 4, 0>
+                          : gm_fwd2_kernel<1, 4, 0>;
+  if (smem > 48 * 1024)
+    TTB2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+  const int nLevels = (int)e.levelOff.size() - 1;
+  const int maxNodes = 65535 / m.K;
+  for (int l = 0; l < nLevels; ++l) {
+    const int opBegin = e.levelOff[l];
+    const int count = e.levelOff[l + 1] - opBegin;
+    const int chunkPatterns = gm_fwd_chunk(e, draws, count);
+    const int nChunk = (m.Npad + chunkPatterns - 1) / chunkPatterns;
+    for (int done = 0; done < count; done += maxNodes) {
+      const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+      dim3 grid(nChunk, c * m.K, draws);
+      kern<<<grid, nw * 32, smem, e.stream>>>(e.ops, opBegin + done, e.mats, e.tips, e.codeP,
+                                              e.partials, e.expoK, m.T, m.Npad, m.B, m.K, m.S,
+                                              chunkPatterns);
+      ++e.launches;
+    }
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+int gmma_root2(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int nblocks = (m.Npad + GMR_THREADS - 1) / GMR_THREADS;
+  dim3 grid(nblocks, draws);
+  const int rootInode = e.hostOps.back().node - m.T;
+  gm_root2_kernel<false><<<grid, GMR_THREADS, 0, e.stream>>>(
+      e.partials, e.expoK, e.freqs, e.freqDraws, e.props, e.propDraws, e.weights, e.siteLnl,
+      nullptr, e.redPart, m.T, m.Npad, m.K, m.S, rootInode);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return small_reduce_lnl(e, draws, nblocks);
+}
+
+int gmma_backward2(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int rootInode = e.hostOps.back().node - m.T;
+  {
+    const int nblocks = (m.Npad + GMR_THREADS - 1) / GMR_THREADS;
+    dim3 grid(nblocks, draws);
+    gm_root2_kernel<true><<<grid, GMR_THREADS, 0, e.stream>>>(
+        e.partials, e.expoK, e.freqs, e.freqDraws, e.props, e.propDraws, e.weights, e.siteLnl,
+        e.pre, e.redPart, m.T, m.Npad, m.K, m.S, rootInode);
+    ++e.launches;
+    TTB2_CUDA_CHECK(cudaGetLastError());
+    int rc = small_root_grad_reduce(e, draws, nblocks);
+    if (rc) return rc;
+  }
+  const size_t smem = gm_bwd2_smem(m);
+  const int MT = gm_shape(m.S).Sp / 8;
+  const int ntg = MT >= 8 ? 4 : (MT >= 4 ? 2 : 1);
+  const int nw = MT >= 5 ? 8 : 4;
+  auto kern = m.S == 61 ? gm_bwd2_kernel<4, 8, 61>
+              : m.S == 20 ? gm_bwd2_kernel<1, 4, 20>
+              : ntg == 4  ? gm_bwd2_kernel<4, 8, 0>
+              : nw == 8   ? gm_bwd2_kernel<2, 8, 0>
+              : ntg == 2  ? gm_bwd2_kernel<2, 4, 0>
+                          : gm_bwd2_kernel<1, 4, 0>;
+  if (smem > 48 * 1024)
+    TTB2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+  const int nLevels = (int)e.levelOff.size() - 1;
+  const int maxNodes = 65535 / m.K;
+  for (int l = nLevels - 1; l >= 0; --l) {
+    const int opBegin = e.levelOff[l];
+    const int count = e.levelOff[l + 1] - opBegin;
+    const int nChunk = e.levelChunks[l];
+    int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
+    chunkPatterns = (chunkPatterns + GM_TP - 1) / GM_TP * GM_TP;
+    for (int done = 0; done < count; done += maxNodes) {
+      const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+      dim3 grid(nChunk, c * m.K, draws);
+      kern<<<grid, nw * 32, smem, e.stream>>>(
+          e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, e.weights, e.pre,
+          e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B, m.K, m.S, chunkPatterns, nChunk);
+      ++e.launches;
+    }
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return small_gpart_reduce(e, draws);
 }
 
 int gmma_forward(Engine& e, int draws) {
