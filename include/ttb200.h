@@ -95,6 +95,10 @@ typedef struct ttb2_config {
  * on config 2) but the extra shared-memory lookups slow the L1-bound pre-order
  * kernel more than that (8.1 -> 10.0 ms), so it is opt-in. */
 #define TTB2_FLAG_CHERRY 16
+/* do not replay the per-evaluation kernel sequence from a CUDA graph (the default
+ * captures the eigen-mode forward and backward sequences once per shape and
+ * replays them: one graph launch instead of ~25-80 kernel launches) */
+#define TTB2_FLAG_NO_GRAPH 32
 
 /*
  * tip_codes      uint8 [T][N]: symbol code of tip t at pattern i

@@ -64,7 +64,7 @@ def test_golden_mats_mode(name, flags):
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [0, 2, 4, 8, 16], ids=["levels", "generic", "fused", "levels-simt", "cherry"])
+@pytest.mark.parametrize("flags", [0, 2, 4, 8, 16, 32], ids=["levels", "generic", "fused", "levels-simt", "cherry", "nograph"])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_eigen_mode(name, flags):
     """ttb2_loglik_eigen / ttb2_grad_eigen: P(t) on the device, gradients w.r.t.

@@ -134,9 +134,36 @@ def test_bitwise_reproducible():
     prob = make_problem(100, 3000, 4, 4, seed=2)
     e1, a = _run(prob)
     e2, b = _run(prob)
+    e3, c = _run(prob, flags=32)  # without CUDA-graph replay: same kernels, same bits
     for k in a:
         assert np.array_equal(a[k], b[k]), k
-    e1.close(); e2.close()
+        assert np.array_equal(a[k], c[k]), k
+    e1.close(); e2.close(); e3.close()
+
+
+def test_graph_replay_many_evaluations():
+    """The captured graphs are replayed with new parameter values every call."""
+    from oracle import treelik as orc
+    from torchtree_b200 import Engine, reversible_eigensystem
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(40, 300, 4, 4, seed=12)
+    eng = Engine(prob.tip_states, prob.weights, prob.postorder, 4, 4)
+    evec, ivec, evals = reversible_eigensystem(torch.tensor(prob.q_matrix),
+                                               torch.tensor(prob.freqs))
+    rng = np.random.default_rng(0)
+    for it in range(6):
+        prob.branch_lengths = prob.branch_lengths * rng.uniform(0.8, 1.25, prob.branch_lengths.shape)
+        prob.branch_lengths[:, -1] = 0.0
+        lnl = eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props,
+                               evec, ivec, evals, prob.freqs)
+        if it % 2 == 0:  # forward-only calls interleaved with forward+backward
+            continue
+        g = eng.grad_eigen()
+        want = orc.evaluate(prob, want_grad=True, through_q=True)
+        assert_lnl_close(lnl.numpy(), want["lnL"])
+        assert_grad_close(g["branch_lengths"].numpy(), want["branch_lengths"], what="d_bl")
+    eng.close()
 
 
 def test_headline_size_properties():
@@ -223,3 +250,62 @@ def test_invariant_category_zero_rate():
     prob.site_rates /= (prob.site_rates * prob.site_props).sum()
     for flags in (0, 4, 8, 16):
         _check(prob, flags=flags)
+
+
+@pytest.mark.parametrize("S", [4, 20])
+def test_set_postorder_rebuilds_schedule(S):
+    """Topology change on a live engine (TreeModel.update_traversals,
+    tree_model.py:187-195): same tips, new post-order."""
+    import dataclasses
+
+    from oracle import treelik as orc
+    from torchtree_b200 import Engine, reversible_eigensystem
+    from torchtree_b200.synthetic import make_problem
+
+    a = make_problem(30, 200, S, 3, seed=41, topology="random")
+    b = make_problem(30, 200, S, 3, seed=42, topology="caterpillar")
+    b = dataclasses.replace(b, tip_states=a.tip_states, weights=a.weights)
+    eng = Engine(a.tip_states, a.weights, a.postorder, S, 3)
+    for prob in (a, b, a):
+        eng.set_postorder(prob.postorder)
+        evec, ivec, evals = reversible_eigensystem(torch.tensor(prob.q_matrix),
+                                                   torch.tensor(prob.freqs))
+        lnl = eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props,
+                               evec, ivec, evals, prob.freqs)
+        g = eng.grad_eigen()
+        want = orc.evaluate(prob, want_grad=True, through_q=True)
+        assert_lnl_close(lnl.numpy(), want["lnL"])
+        assert_grad_close(g["branch_lengths"].numpy(), want["branch_lengths"], what="d_bl")
+    eng.close()
+
+
+def test_varying_draw_counts_on_one_engine():
+    """An engine sized for 6 draws evaluates 1, 6, 2 draws in turn (ELBO with many
+    draws, then a logger / convergence check with one)."""
+    import dataclasses
+
+    from oracle import treelik as orc
+    from torchtree_b200 import Engine, reversible_eigensystem
+    from torchtree_b200.synthetic import make_problem
+
+    full = make_problem(21, 150, 4, 4, draws=6, seed=51)
+    eng = Engine(full.tip_states, full.weights, full.postorder, 4, 4, max_draws=6)
+    evec, ivec, evals = reversible_eigensystem(torch.tensor(full.q_matrix),
+                                               torch.tensor(full.freqs))
+    for d in (1, 6, 2):
+        prob = dataclasses.replace(full, branch_lengths=full.branch_lengths[:d].copy())
+        lnl = eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props,
+                               evec, ivec, evals, prob.freqs)
+        g = eng.grad_eigen()
+        want = orc.evaluate(prob, want_grad=True, through_q=True)
+        assert_lnl_close(lnl.numpy(), want["lnL"])
+        assert_grad_close(g["branch_lengths"].numpy(), want["branch_lengths"], what="d_bl")
+        assert_grad_close(g["site_rates"].numpy(), want["site_rates"], what="d_rates")
+    eng.close()
+
+
+@pytest.mark.parametrize("S,K", [(20, 16), (20, 17), (4, 16), (4, 11)])
+def test_many_categories(S, K):
+    from torchtree_b200.synthetic import make_problem
+
+    _check(make_problem(9, 70, S, K, seed=61, weibull_shape=1.5), q_rtol=1e-6)

@@ -18,6 +18,7 @@ TTB2_FLAG_FORCE_GENERIC = 2
 TTB2_FLAG_FUSED = 4
 TTB2_FLAG_NO_MMA = 8
 TTB2_FLAG_CHERRY = 16
+TTB2_FLAG_NO_GRAPH = 32
 
 
 class Ttb2Config(ctypes.Structure):

@@ -118,6 +118,8 @@ int finish(Engine& e, int where) {
 
 bool bad_draws(int d, int draws) { return !(d == 1 || d == draws); }
 
+void drop_graphs(Engine& e);
+
 int ensure_grad_buffers(Engine& e, int draws) {
   const Dims& m = e.dm;
   int rc;
@@ -129,9 +131,12 @@ int ensure_grad_buffers(Engine& e, int draws) {
   if (!e.dmat && (rc = dev_alloc(e, &e.dmat, matN))) return rc;
   if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)e.cfg.max_draws * (m.K + m.S))))
     return rc;
+  const int planBefore = e.chunkPlanDraws;
   if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32))) return rc;
+  if (planBefore != e.chunkPlanDraws) drop_graphs(e);
   const size_t need = planned_gpart_doubles(e, draws);
   if (need > e.gpartCap) {
+    drop_graphs(e);
     if (e.gpart) {
       e.deviceBytes -= (int64_t)(e.gpartCap * sizeof(double));
       dev_free(e.gpart);
@@ -275,6 +280,69 @@ int run_forward(Engine& e, int draws, double* lnl, int where) {
   e.preValid = false;
   if ((rc = copy_out(e, lnl, e.lnl, (size_t)draws * sizeof(double), where))) return rc;
   return finish(e, where);
+}
+
+// ---- CUDA-graph replay ----------------------------------------------------
+void drop_graphs(Engine& e) {
+  if (e.gFwd.exec) cudaGraphExecDestroy(e.gFwd.exec);
+  if (e.gBwd.exec) cudaGraphExecDestroy(e.gBwd.exec);
+  e.gFwd = Engine::GraphSlot();
+  e.gBwd = Engine::GraphSlot();
+}
+
+bool graphs_enabled(const Engine& e) {
+  return !(e.cfg.flags & TTB2_FLAG_NO_GRAPH) && !e.timing && e.ownStream != nullptr;
+}
+
+bool slot_matches(const Engine::GraphSlot& g, const Engine& e, int draws) {
+  return g.exec && g.draws == draws && g.fd == e.freqDraws && g.pd == e.propDraws &&
+         g.rd == e.rateDraws && g.ed == e.eigDraws;
+}
+
+// Runs `body` (a sequence of kernel launches on e.stream) through a cached CUDA
+// graph: captured on the engine's own stream the first time a shape is seen, then
+// replayed.  The user's stream is ordered before and after with events.
+template <typename Body>
+int run_graphed(Engine& e, Engine::GraphSlot& slot, int draws, Body body) {
+  if (!graphs_enabled(e)) return body();
+  cudaStream_t user = e.stream;
+  if (!slot_matches(slot, e, draws)) {
+    if (slot.exec) cudaGraphExecDestroy(slot.exec);
+    slot = Engine::GraphSlot();
+    const int64_t before = e.launches;
+    TTB2_CUDA_CHECK(cudaStreamBeginCapture(e.ownStream, cudaStreamCaptureModeThreadLocal));
+    e.stream = e.ownStream;
+    const int rc = body();
+    e.stream = user;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t err = cudaStreamEndCapture(e.ownStream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (err != cudaSuccess || !graph) {
+      set_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(err));
+      return TTB2_E_CUDA;
+    }
+    const cudaError_t ierr = cudaGraphInstantiate(&slot.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ierr != cudaSuccess) {
+      slot.exec = nullptr;
+      set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ierr));
+      return TTB2_E_CUDA;
+    }
+    slot.kernels = e.launches - before;
+    e.launches = before;  // counted per replay below
+    slot.draws = draws;
+    slot.fd = e.freqDraws; slot.pd = e.propDraws; slot.rd = e.rateDraws; slot.ed = e.eigDraws;
+  }
+  TTB2_CUDA_CHECK(cudaEventRecord(e.evIn, user));
+  TTB2_CUDA_CHECK(cudaStreamWaitEvent(e.ownStream, e.evIn, 0));
+  TTB2_CUDA_CHECK(cudaGraphLaunch(slot.exec, e.ownStream));
+  TTB2_CUDA_CHECK(cudaEventRecord(e.evOut, e.ownStream));
+  TTB2_CUDA_CHECK(cudaStreamWaitEvent(user, e.evOut, 0));
+  e.launches += slot.kernels;
+  return TTB2_OK;
 }
 
 int stage_grad_lnl(Engine& e, const double* grad_lnl, int where) {
@@ -496,6 +564,9 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
       e.smCount = sms;
   }
   TRY(upload_fused_programs(e));
+  TRY_CUDA(cudaStreamCreateWithFlags(&e.ownStream, cudaStreamNonBlocking));
+  TRY_CUDA(cudaEventCreateWithFlags(&e.evIn, cudaEventDisableTiming));
+  TRY_CUDA(cudaEventCreateWithFlags(&e.evOut, cudaEventDisableTiming));
   if (c.flags & TTB2_FLAG_PREALLOC_GRAD) {
     if (e.fusedOK) {
       TRY(ensure_fused_grad_buffers(e, D));
@@ -532,6 +603,7 @@ int ttb2_set_postorder(ttb2_engine* engine, const int32_t* postorder) {
   e.preValid = false;
   e.lastFused = false;
   e.chunkPlanDraws = 0;
+  drop_graphs(e);
   return upload_fused_programs(e);
 }
 
@@ -557,6 +629,10 @@ void ttb2_destroy(ttb2_engine* engine) {
   dev_free(e.cherryIdx); dev_free(e.cherryInfo); dev_free(e.cherryVec); dev_free(e.cherryExp);
   for (int j = 0; j < 8; ++j)
     if (e.ev[j]) cudaEventDestroy(e.ev[j]);
+  drop_graphs(e);
+  if (e.evIn) cudaEventDestroy(e.evIn);
+  if (e.evOut) cudaEventDestroy(e.evOut);
+  if (e.ownStream) cudaStreamDestroy(e.ownStream);
   delete ep;
 }
 
@@ -645,8 +721,21 @@ int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws, const double* branch_l
   e.eigDraws = eig_draws;
   e.mode = MODE_EIGEN;
   e.draws = draws;
-  if ((rc = small_pmatrix(e, draws))) return rc;
-  return run_forward(e, draws, lnl, where);
+  if (e.fusedOK || !e.spec4 && !gmma_supported(e)) {
+    if ((rc = small_pmatrix(e, draws))) return rc;
+    return run_forward(e, draws, lnl, where);
+  }
+  if (!e.spec4 && !e.expoK && (rc = dev_alloc(e, &e.expoK, gmma_expo_elems(e)))) return rc;
+  rc = run_graphed(e, e.gFwd, draws, [&]() -> int {
+    int r = small_pmatrix(e, draws);
+    if (r) return r;
+    return run_forward(e, draws, nullptr, TTB2_DEVICE);
+  });
+  if (rc) return rc;
+  e.draws = draws;
+  e.preValid = false;
+  if ((rc = copy_out(e, lnl, e.lnl, (size_t)draws * sizeof(double), where))) return rc;
+  return finish(e, where);
 }
 
 int ttb2_grad_mats(ttb2_engine* engine, const double* grad_lnl, double* d_mats,
@@ -706,10 +795,21 @@ int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branc
     const bool needQ = d_q != nullptr;
     if ((rc = run_backward_fused(e, grad_lnl, needQ, where))) return rc;
     if ((rc = small_fused_outputs(e, draws, needQ))) return rc;
-  } else {
+  } else if (e.preValid || !graphs_enabled(e) || !(e.spec4 || gmma_supported(e))) {
     if ((rc = ensure_eigen_grad_buffers(e))) return rc;
     if ((rc = run_backward(e, grad_lnl, where))) return rc;
     if ((rc = small_eigen_contract(e, draws))) return rc;
+  } else {
+    if ((rc = ensure_eigen_grad_buffers(e))) return rc;
+    if ((rc = ensure_grad_buffers(e, draws))) return rc;  // allocations + chunk plan: not capturable
+    if ((rc = stage_grad_lnl(e, grad_lnl, where))) return rc;
+    rc = run_graphed(e, e.gBwd, draws, [&]() -> int {
+      int r = e.spec4 ? s4_backward(e, draws) : gmma_backward2(e, draws);
+      if (r) return r;
+      return small_eigen_contract(e, draws);
+    });
+    if (rc) return rc;
+    e.preValid = true;
   }
   if ((rc = copy_out(e, d_branch_lengths, e.outBl, (size_t)draws * m.B * sizeof(double), where)))
     return rc;

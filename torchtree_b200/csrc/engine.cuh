@@ -132,6 +132,16 @@ struct Engine {
   int64_t launches = 0;
   int64_t deviceBytes = 0;
 
+  // CUDA-graph replay of the eigen-mode kernel sequences (api.cu)
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    int draws = -1, fd = -1, pd = -1, rd = -1, ed = -1;
+    int64_t kernels = 0;
+  };
+  GraphSlot gFwd, gBwd;
+  cudaStream_t ownStream = nullptr;   // capture / replay stream
+  cudaEvent_t evIn = nullptr, evOut = nullptr;
+
   // optional phase timing (ttb2_enable_timing)
   bool timing = false;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
