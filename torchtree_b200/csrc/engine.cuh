@@ -184,9 +184,7 @@ int gen_backward(Engine& e, int draws);
 
 // fp64 tensor-core path for 8 <= S <= 64 (kernels_gmma.cu); shares the generic layout
 bool gmma_supported(const Engine& e);
-int gmma_forward(Engine& e, int draws);
-int gmma_backward_levels(Engine& e, int draws);
-// v2: per-(pattern, category) rescaling, pipelined staging (own root kernels, expoK layout)
+// per-(pattern, category) rescaling, pipelined staging (own root kernels, expoK layout)
 size_t gmma_expo_elems(const Engine& e);
 int gmma_forward2(Engine& e, int draws);
 int gmma_root2(Engine& e, int draws);
