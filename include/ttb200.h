@@ -198,6 +198,19 @@ int ttb2_get_mats(ttb2_engine* engine, double* out, int32_t where);
 int ttb2_enable_timing(ttb2_engine* engine, int32_t on);
 int ttb2_phase_ms(ttb2_engine* engine, double* out /*[TTB2_PHASE_COUNT]*/);
 
+/*
+ * Site-pattern compression (host code, no GPU needed): the unique columns of an
+ * alignment in the reference's order with their multiplicities -- replaces
+ * `compress`, torchtree/evolution/site_pattern.py:69-97.
+ *   sequences [taxa][length] bytes (taxa in Taxa order); a site is `group`
+ *   consecutive characters (3 for codons, site_pattern.py:79-82)
+ *   patterns  [taxa][n][group] bytes, out (caller allocates taxa*length bytes)
+ *   weights   [n] out (caller allocates length/group doubles)
+ */
+int ttb2_compress_patterns(const uint8_t* sequences, int32_t taxa, int64_t length,
+                           int32_t group, uint8_t* patterns, double* weights,
+                           int64_t* pattern_count);
+
 /* Kernels launched by this engine since creation (bench `gpu_launches`). */
 int64_t ttb2_launch_count(const ttb2_engine* engine);
 /* Device bytes currently held by this engine. */

@@ -55,6 +55,7 @@ EXPORTED_SYMBOLS = (
     "ttb2_get_mats",
     "ttb2_enable_timing",
     "ttb2_phase_ms",
+    "ttb2_compress_patterns",
     "ttb2_launch_count",
     "ttb2_device_bytes",
     "ttb2_last_error",
@@ -107,6 +108,8 @@ def load():
     lib.ttb2_enable_timing.restype = c_int32
     lib.ttb2_phase_ms.argtypes = [vp, vp]
     lib.ttb2_phase_ms.restype = c_int32
+    lib.ttb2_compress_patterns.argtypes = [vp, c_int32, c_int64, c_int32, vp, vp, vp]
+    lib.ttb2_compress_patterns.restype = c_int32
     lib.ttb2_launch_count.argtypes = [vp]
     lib.ttb2_launch_count.restype = c_int64
     lib.ttb2_device_bytes.argtypes = [vp]

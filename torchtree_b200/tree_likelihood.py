@@ -47,7 +47,17 @@ class TreeLikelihoodModel(CallableModel):
         self.use_ambiguities = use_ambiguities
         self.device_index = int(device)
         state_count = subst_model.frequencies.shape[-1]
-        if use_tip_states:
+        if type(site_pattern) is SitePattern:
+            # stock SitePattern: compress natively (patterns.py, ttb2_compress_patterns)
+            # instead of the per-character Python loops of site_pattern.py:69-151
+            from .patterns import tip_codes_from_alignment
+            codes, table, weights = tip_codes_from_alignment(
+                site_pattern.alignment, use_ambiguities and not use_tip_states,
+                site_pattern.indices)
+            self._tip_codes = codes
+            self._code_partials = None if use_tip_states else table
+            self.weights = torch.from_numpy(weights).to(torch.int64)
+        elif use_tip_states:
             # integer codes, gaps = S (site_pattern.py:127-151)
             states, self.weights = site_pattern.compute_tips_states()
             self._tip_codes = torch.stack(list(states)).clamp(max=state_count).to(torch.uint8).numpy()
