@@ -1074,6 +1074,394 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Pre-order level kernel in DMMA fragment layout: no shared-memory staging and no
+// transition-matrix broadcasts in the pattern loop.
+//
+// A warp step handles 8 patterns; lane = (p = lane>>2 pattern, c = lane&3).  With
+// m8n8k4 (A[8x4]: lane holds A[p][c]; B[4x8]: lane holds B[c][p]; C[8x8]: lane
+// holds C[p][2c], C[p][2c+1]) the whole node update is four MMAs whose constant
+// operands are one double per lane each:
+//   U  = p~_l . [P_l^T | 0] + p~_r . [0 | P_r^T]     -> C cols 0-3 = u_l, 4-7 = u_r
+//        (the A operands p~[p][c] are one coalesced 256-byte load per child)
+//   M  = q^_n o U (lane-local)                        -> cols 0-3 = m_r, 4-7 = m_l
+//   O  = M[:, {0,2,4,6}] . W_even + M[:, {1,3,5,7}] . W_odd,  W = diag(P_r, P_l)
+//        (the reduction index is permuted so that every lane feeds the two C values
+//         it already holds as A operands: no transpose between the products)
+//                                                     -> cols 0-3 = q^_r, 4-7 = q^_l
+// Lanes c<2 therefore own the right child's outputs and lanes c>=2 the left
+// child's.  G = sum_i w m (x) p~ needs the child's whole p~ vector next to the
+// lane's two m values: a quad all-gather (three shuffles) and 8 FMAs per lane.
+constexpr int BWDF_THREADS = 128;
+
+template <int MINBLOCKS>
+__global__ void __launch_bounds__(BWDF_THREADS, MINBLOCKS)
+bwd4_frag_kernel(const NodeOp* __restrict__ ops, int opBegin,
+                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                 const double* __restrict__ codeP, const double* __restrict__ partials,
+                 const int16_t* __restrict__ expo, const double* __restrict__ weights,
+                 double* __restrict__ pre, double* __restrict__ gpart,
+                 const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
+                 int C, int B, int K, int chunkPatterns, int nChunk) {
+  extern __shared__ __align__(16) double sm[];
+  // sm: cp[C][4] | red[warps][32]
+  constexpr int NW = BWDF_THREADS / 32;
+  double* cp = sm;
+  double* red = sm + C * 4;
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+  if (tipL || tipR) {
+    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
+    __syncthreads();
+  }
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = lane >> 2, c = lane & 3;
+  const bool rside = c < 2;        // this lane produces m_r, q^_r, G_r
+  const int s0 = (c & 1) * 2;      // first of the two states it holds
+  // constant B fragments (lane holds B[k = c][n = p])
+  const double b1 = p < 4 ? gPl[p * 4 + c] : 0.0;          // [P_l^T | 0]
+  const double b2 = p >= 4 ? gPr[(p - 4) * 4 + c] : 0.0;   // [0 | P_r^T]
+  double ba, bb;                                           // W rows 2c, 2c+1
+  if (rside) {
+    ba = p < 4 ? gPr[(2 * c) * 4 + p] : 0.0;
+    bb = p < 4 ? gPr[(2 * c + 1) * 4 + p] : 0.0;
+  } else {
+    ba = p >= 4 ? gPl[(2 * c - 4) * 4 + (p - 4)] : 0.0;
+    bb = p >= 4 ? gPl[(2 * c - 3) * 4 + (p - 4)] : 0.0;
+  }
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const size_t kOff = (size_t)k * Npad * 4;
+  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
+  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
+  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
+  const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
+  // the child this lane writes to
+  const int mine = rside ? op.right : op.left;
+  const bool store = mine >= T;
+  double* qc = store ? pre + drawBase + (size_t)(mine - T) * nodeStride + kOff : nullptr;
+  const int16_t* ec = store ? expo + ((size_t)d * I + (mine - T)) * Npad : nullptr;
+
+  double g[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[i][j] = 0.0;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+
+  // chunk boundaries and Npad are multiples of 32: a warp block is never ragged
+  for (int base = begin + warp * 32; base < end; base += BWDF_THREADS) {
+    double al[4], ar[4], w[4];
+    double2 q[4];
+    int ex[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = base + t * 8 + p;
+      al[t] = tipL ? cp[tl[i] * 4 + c] : __ldg(pl + (size_t)i * 4 + c);
+      ar[t] = tipR ? cp[tr[i] * 4 + c] : __ldg(prr + (size_t)i * 4 + c);
+      q[t] = __ldg(reinterpret_cast<const double2*>(qn + (size_t)i * 4 + s0));
+      w[t] = __ldg(weights + i);
+      ex[t] = store ? (int)ec[i] : 0;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = base + t * 8 + p;
+      double u0 = 0.0, u1 = 0.0;
+      dmma884(u0, u1, al[t], b1);
+      dmma884(u0, u1, ar[t], b2);
+      const double m0 = q[t].x * u0, m1 = q[t].y * u1;
+      double o0 = 0.0, o1 = 0.0;
+      dmma884(o0, o1, m0, ba);
+      dmma884(o0, o1, m1, bb);
+      if (store) {
+        const double f = __hiloint2double((1023 - ex[t]) << 20, 0);
+        *reinterpret_cast<double2*>(qc + (size_t)i * 4 + s0) = make_double2(o0 * f, o1 * f);
+      }
+      const bool live = w[t] != 0.0;
+      const double own = live ? (rside ? ar[t] : al[t]) : 0.0;
+      const double oth = live ? (rside ? al[t] : ar[t]) : 0.0;
+      const double wm0 = live ? w[t] * m0 : 0.0;
+      const double wm1 = live ? w[t] * m1 : 0.0;
+      // x[j] = p~_child[c ^ j]
+      const double x1 = __shfl_xor_sync(0xffffffffu, own, 1);
+      const double x2 = __shfl_xor_sync(0xffffffffu, oth, 2);
+      const double x3 = __shfl_xor_sync(0xffffffffu, oth, 3);
+      g[0][0] = fma(wm0, own, g[0][0]); g[1][0] = fma(wm1, own, g[1][0]);
+      g[0][1] = fma(wm0, x1, g[0][1]);  g[1][1] = fma(wm1, x1, g[1][1]);
+      g[0][2] = fma(wm0, x2, g[0][2]);  g[1][2] = fma(wm1, x2, g[1][2]);
+      g[0][3] = fma(wm0, x3, g[0][3]);  g[1][3] = fma(wm1, x3, g[1][3]);
+    }
+  }
+  // sum over the 8 pattern rows of the warp, then over warps (fixed order)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double v = g[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      // G_child[s = s0 + i][s' = c ^ j]
+      if (p == 0) red[warp * 32 + (rside ? 16 : 0) + (s0 + i) * 4 + (c ^ j)] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int child = threadIdx.x >> 4;
+    double t = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 32 + threadIdx.x];
+    const int branch = child ? op.right : op.left;
+    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+          (threadIdx.x & 15)] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Same arithmetic as bwd4_frag_kernel, with the three input vectors of a 32-pattern
+// block (q^_n, p~_l, p~_r: 1 KB each, contiguous) brought in by bulk asynchronous
+// copies (cp.async.bulk -> SASS UBLKCP) into a per-warp ring of shared-memory slots,
+// completion tracked by one mbarrier per slot.  Every warp is its own producer and
+// consumer, so there is no CTA-wide synchronisation in the pattern loop, and the
+// loads in flight do not occupy registers: STAGES-1 blocks (3 KB each) per warp.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+// slot (bytes): q^_n 1024 | p~_l 1024 | p~_r 1024 | w 256 | e_l 64 | e_r 64 | code_l 32 | code_r 32
+constexpr int BWDT_SLOT = 448;      // doubles per slot (3584 bytes)
+constexpr int BWDT_W = 384;         // double offset of the weights
+constexpr int BWDT_EL = 3328, BWDT_ER = 3392, BWDT_CL = 3456, BWDT_CR = 3488;  // byte offsets
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int STAGES, int MINBLOCKS>
+__global__ void __launch_bounds__(BWDF_THREADS, MINBLOCKS)
+bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
+                const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                const double* __restrict__ codeP, const double* __restrict__ partials,
+                const int16_t* __restrict__ expo, const double* __restrict__ weights,
+                double* __restrict__ pre, double* __restrict__ gpart,
+                const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
+                int C, int B, int K, int chunkPatterns, int nChunk) {
+  extern __shared__ __align__(128) double sm[];
+  // sm: slots[warps][STAGES][448] | red[warps][32] | cp[C][4] | mbarriers[warps][STAGES]
+  constexpr int NW = BWDF_THREADS / 32;
+  double* slots = sm;
+  double* red = slots + NW * STAGES * BWDT_SLOT;
+  double* cp = red + NW * 32;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cp + C * 4);
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) mbar_init(smem_u32(bars + warp * STAGES + st), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (tipL || tipR)
+    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
+  __syncthreads();
+
+  const int p = lane >> 2, c = lane & 3;
+  const bool rside = c < 2;
+  const int s0 = (c & 1) * 2;
+  const double b1 = p < 4 ? gPl[p * 4 + c] : 0.0;
+  const double b2 = p >= 4 ? gPr[(p - 4) * 4 + c] : 0.0;
+  double ba, bb;
+  if (rside) {
+    ba = p < 4 ? gPr[(2 * c) * 4 + p] : 0.0;
+    bb = p < 4 ? gPr[(2 * c + 1) * 4 + p] : 0.0;
+  } else {
+    ba = p >= 4 ? gPl[(2 * c - 4) * 4 + (p - 4)] : 0.0;
+    bb = p >= 4 ? gPl[(2 * c - 3) * 4 + (p - 4)] : 0.0;
+  }
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const size_t kOff = (size_t)k * Npad * 4;
+  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
+  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
+  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  const int mine = rside ? op.right : op.left;
+  const bool store = mine >= T;
+  double* qc = store ? pre + drawBase + (size_t)(mine - T) * nodeStride + kOff : nullptr;
+
+  // the one 16-byte piece of per-pattern side data this lane copies per block
+  const char* sideSrc = nullptr;   // source at pattern 0
+  int sideDst = 0, sideScale = 0;  // byte offset in the slot; source bytes per pattern
+  if (lane < 16) {
+    sideSrc = reinterpret_cast<const char*>(weights) + lane * 16;
+    sideDst = BWDT_W * 8 + lane * 16; sideScale = 8;
+  } else if (lane < 20) {
+    if (!tipL) sideSrc = reinterpret_cast<const char*>(expo + ((size_t)d * I + (op.left - T)) * Npad) + (lane - 16) * 16;
+    sideDst = BWDT_EL + (lane - 16) * 16; sideScale = 2;
+  } else if (lane < 24) {
+    if (!tipR) sideSrc = reinterpret_cast<const char*>(expo + ((size_t)d * I + (op.right - T)) * Npad) + (lane - 20) * 16;
+    sideDst = BWDT_ER + (lane - 20) * 16; sideScale = 2;
+  } else if (lane < 26) {
+    if (tipL) sideSrc = reinterpret_cast<const char*>(tips + (size_t)op.left * Npad) + (lane - 24) * 16;
+    sideDst = BWDT_CL + (lane - 24) * 16; sideScale = 1;
+  } else if (lane < 28) {
+    if (tipR) sideSrc = reinterpret_cast<const char*>(tips + (size_t)op.right * Npad) + (lane - 26) * 16;
+    sideDst = BWDT_CR + (lane - 26) * 16; sideScale = 1;
+  }
+
+  double g[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[i][j] = 0.0;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  const int first = begin + warp * 32;
+  const int nb = first < end ? (end - first + BWDF_THREADS - 1) / BWDF_THREADS : 0;
+  double* mySlots = slots + warp * STAGES * BWDT_SLOT;
+  const uint32_t myBars = smem_u32(bars + warp * STAGES);
+  const uint32_t txBytes = 1024u + (tipL ? 0u : 1024u) + (tipR ? 0u : 1024u);
+
+  // all lanes; exactly one cp.async group is committed per call (possibly empty)
+  auto issue = [&](int blk) {
+    if (blk < nb) {
+      const int st = blk % STAGES;
+      const int i0 = first + blk * BWDF_THREADS;
+      const uint32_t dst = smem_u32(mySlots + st * BWDT_SLOT);
+      if (sideSrc) cp_async16(dst + sideDst, sideSrc + (size_t)i0 * sideScale);
+      if (lane == 0) {
+        const size_t off = (size_t)i0 * 4;
+        const uint32_t bar = myBars + st * 8;
+        mbar_expect_tx(bar, txBytes);
+        bulk_g2s(dst, qn + off, 1024u, bar);
+        if (!tipL) bulk_g2s(dst + 1024u, pl + off, 1024u, bar);
+        if (!tipR) bulk_g2s(dst + 2048u, prr + off, 1024u, bar);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int blk = 0; blk < STAGES; ++blk) issue(blk);
+
+  for (int blk = 0; blk < nb; ++blk) {
+    const int base = first + blk * BWDF_THREADS;
+    const int st = blk % STAGES;
+    const double* slot = mySlots + st * BWDT_SLOT;
+    const char* slotB = reinterpret_cast<const char*>(slot);
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+    __syncwarp();
+    mbar_wait(myBars + st * 8, (uint32_t)((blk / STAGES) & 1));
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = t * 8 + p;
+      const int i = base + j;
+      const double2 q = *reinterpret_cast<const double2*>(slot + j * 4 + s0);
+      const double al = tipL ? cp[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CL)[j] * 4 + c]
+                             : slot[128 + t * 32 + lane];
+      const double ar = tipR ? cp[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CR)[j] * 4 + c]
+                             : slot[256 + t * 32 + lane];
+      const double w = slot[BWDT_W + j];
+      double u0 = 0.0, u1 = 0.0;
+      dmma884(u0, u1, al, b1);
+      dmma884(u0, u1, ar, b2);
+      const double m0 = q.x * u0, m1 = q.y * u1;
+      double o0 = 0.0, o1 = 0.0;
+      dmma884(o0, o1, m0, ba);
+      dmma884(o0, o1, m1, bb);
+      if (store) {
+        const int ex = reinterpret_cast<const int16_t*>(slotB + (rside ? BWDT_ER : BWDT_EL))[j];
+        const double f = __hiloint2double((1023 - ex) << 20, 0);
+        *reinterpret_cast<double2*>(qc + (size_t)i * 4 + s0) = make_double2(o0 * f, o1 * f);
+      }
+      const bool live = w != 0.0;
+      const double own = live ? (rside ? ar : al) : 0.0;
+      const double oth = live ? (rside ? al : ar) : 0.0;
+      const double wm0 = live ? w * m0 : 0.0;
+      const double wm1 = live ? w * m1 : 0.0;
+      const double x1 = __shfl_xor_sync(0xffffffffu, own, 1);
+      const double x2 = __shfl_xor_sync(0xffffffffu, oth, 2);
+      const double x3 = __shfl_xor_sync(0xffffffffu, oth, 3);
+      g[0][0] = fma(wm0, own, g[0][0]); g[1][0] = fma(wm1, own, g[1][0]);
+      g[0][1] = fma(wm0, x1, g[0][1]);  g[1][1] = fma(wm1, x1, g[1][1]);
+      g[0][2] = fma(wm0, x2, g[0][2]);  g[1][2] = fma(wm1, x2, g[1][2]);
+      g[0][3] = fma(wm0, x3, g[0][3]);  g[1][3] = fma(wm1, x3, g[1][3]);
+    }
+    __syncwarp();   // every lane has read the slot: it can be refilled
+    issue(blk + STAGES);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double v = g[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (p == 0) red[warp * 32 + (rside ? 16 : 0) + (s0 + i) * 4 + (c ^ j)] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int child = threadIdx.x >> 4;
+    double t = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 32 + threadIdx.x];
+    const int branch = child ? op.right : op.left;
+    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+          (threadIdx.x & 15)] = t;
+  }
+}
+
 // patterns per thread of a post-order launch: long-lived CTAs on large levels
 // (amortises the shared-memory table build), ~8 CTAs per SM on small ones
 int fwd_patterns_per_thread(const Engine& e, int draws, int levelCount) {
@@ -1441,6 +1829,7 @@ int s4_backward(Engine& e, int draws) {
   }
   const bool useMma = !(e.cfg.flags & TTB2_FLAG_NO_MMA);
   static const int variant = getenv("TTB2_BWD_VARIANT") ? atoi(getenv("TTB2_BWD_VARIANT")) : 0;
+  static const bool tipsViaTma = getenv("TTB2_BWD_TIPS_TMA") != nullptr;
   const size_t smem = useMma
       ? (32 + 3 * (size_t)m.C * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) * sizeof(double)
       : (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
@@ -1455,7 +1844,7 @@ int s4_backward(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      if (useMma && l == 0 && e.codes01) {
+      if (useMma && l == 0 && e.codes01 && variant != 2 && !tipsViaTma) {
         const size_t smemT = (32 + 2 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
                              (size_t)m.C * sizeof(int);
         bwd4_tips_kernel<<<grid, BWD_THREADS, smemT, e.stream>>>(
@@ -1470,6 +1859,41 @@ int s4_backward(Engine& e, int draws) {
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, ch, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns,
             nChunk);
+      } else if (useMma && (variant == 0 || (variant >= 7 && variant <= 9))) {
+        constexpr int NWF = BWDF_THREADS / 32;
+        auto smemOf = [&](int stages) {
+          return ((size_t)NWF * stages * BWDT_SLOT + NWF * 32 + (size_t)m.C * 4) * sizeof(double) +
+                 (size_t)NWF * stages * sizeof(uint64_t);
+        };
+#define TTB2_LAUNCH_TMA(ST, MB)                                                                  \
+        do {                                                                                     \
+          static bool attr = false;                                                              \
+          if (!attr) {                                                                           \
+            cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>,                                        \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOf(ST));  \
+            attr = true;                                                                         \
+          }                                                                                      \
+          bwd4_tma_kernel<ST, MB><<<grid, BWDF_THREADS, smemOf(ST), e.stream>>>(                 \
+              e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,     \
+              e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,             \
+              chunkPatterns, nChunk);                                                            \
+        } while (0)
+        if (variant == 8) TTB2_LAUNCH_TMA(4, 4);
+        else if (variant == 9) TTB2_LAUNCH_TMA(2, 6);
+        else TTB2_LAUNCH_TMA(3, 5);
+#undef TTB2_LAUNCH_TMA
+      } else if (useMma && variant != 1 && (l > 0 || variant == 2)) {
+        const size_t smemF = ((size_t)m.C * 4 + (BWDF_THREADS / 32) * 32) * sizeof(double);
+        if (variant == 3)
+          bwd4_frag_kernel<8><<<grid, BWDF_THREADS, smemF, e.stream>>>(
+              e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
+              e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
+              chunkPatterns, nChunk);
+        else
+          bwd4_frag_kernel<6><<<grid, BWDF_THREADS, smemF, e.stream>>>(
+              e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
+              e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
+              chunkPatterns, nChunk);
       } else if (useMma && variant == 4) {
         bwd4_mma_kernel<false, 4, false><<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
