@@ -203,7 +203,7 @@ int small_root_outputs(Engine& e, int draws);
 // to fill the GPU on small levels, long-lived CTAs on large ones) and uploads the
 // per-branch offsets into the partial-sum buffer.  `granule` = patterns a chunk
 // must be a multiple of.
-int plan_chunks(Engine& e, int draws, int granule);
+int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm);
 size_t planned_gpart_doubles(const Engine& e, int draws);
 
 // fused-traversal path (kernels_fused.cu)

@@ -1462,6 +1462,156 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Pre-order kernel for nodes whose two children are tips (level 1), bulk-copy
+// pipelined: same arithmetic as bwd4_tips_kernel (lane = pattern, predicated
+// accumulation of G in registers), but q^_n arrives through a per-warp ring of
+// shared-memory slots filled by cp.async.bulk, weights and tip codes by 16-byte
+// cp.async, so that several blocks per warp are in flight without holding registers.
+// slot (bytes): q^_n 1024 | w 256 | code_l 32 | code_r 32 | pad -> 1408
+constexpr int BTT_SLOT = 1408;
+constexpr int BTT_W = 1024, BTT_CL = 1280, BTT_CR = 1312;
+
+template <int STAGES>
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+bwd4_tips_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
+                     const double* __restrict__ mats, const uint8_t* __restrict__ tips,
+                     const double* __restrict__ codeP, const int* __restrict__ codeMask,
+                     const double* __restrict__ weights, const double* __restrict__ pre,
+                     double* __restrict__ gpart, const int* __restrict__ chunkBase,
+                     size_t chunkTotal, int T, int Npad, int C, int B, int K,
+                     int chunkPatterns, int nChunk) {
+  extern __shared__ __align__(128) double sm[];
+  // sm: slots[warps][STAGES][1408 B] | Pl[16] Pr[16] | tabL[C][4] tabR[C][4] | red[warps][32]
+  //     | mbarriers[warps][STAGES] | masks[C] (int)
+  constexpr int NW = BWD_THREADS / 32;
+  char* slots = reinterpret_cast<char*>(sm);
+  double* Pl = sm + NW * STAGES * (BTT_SLOT / 8);
+  double* Pr = Pl + 16;
+  double* tabL = Pr + 16;
+  double* tabR = tabL + C * 4;
+  double* red = tabR + C * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 32);
+  int* masks = reinterpret_cast<int*>(bars + NW * STAGES);
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
+  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
+  for (int j = threadIdx.x; j < C; j += blockDim.x) masks[j] = codeMask[j];
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) mbar_init(smem_u32(bars + warp * STAGES + st), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const double* qn = pre + ((size_t)d * I + (op.node - T)) * nodeStride + (size_t)k * Npad * 4;
+  const char* sideSrc = nullptr;
+  int sideDst = 0, sideScale = 0;
+  if (lane < 16) {
+    sideSrc = reinterpret_cast<const char*>(weights) + lane * 16;
+    sideDst = BTT_W + lane * 16; sideScale = 8;
+  } else if (lane < 18) {
+    sideSrc = reinterpret_cast<const char*>(tips + (size_t)op.left * Npad) + (lane - 16) * 16;
+    sideDst = BTT_CL + (lane - 16) * 16; sideScale = 1;
+  } else if (lane < 20) {
+    sideSrc = reinterpret_cast<const char*>(tips + (size_t)op.right * Npad) + (lane - 18) * 16;
+    sideDst = BTT_CR + (lane - 18) * 16; sideScale = 1;
+  }
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  const int first = begin + warp * 32;
+  const int nb = first < end ? (end - first + BWD_THREADS - 1) / BWD_THREADS : 0;
+  char* mySlots = slots + warp * STAGES * BTT_SLOT;
+  const uint32_t myBars = smem_u32(bars + warp * STAGES);
+  auto issue = [&](int blk) {
+    if (blk < nb) {
+      const int st = blk % STAGES;
+      const int i0 = first + blk * BWD_THREADS;
+      const uint32_t dst = smem_u32(mySlots + st * BTT_SLOT);
+      if (sideSrc) cp_async16(dst + sideDst, sideSrc + (size_t)i0 * sideScale);
+      if (lane == 0) {
+        const uint32_t bar = myBars + st * 8;
+        mbar_expect_tx(bar, 1024u);
+        bulk_g2s(dst, qn + (size_t)i0 * 4, 1024u, bar);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int blk = 0; blk < STAGES; ++blk) issue(blk);
+
+  // transition tables while the first blocks are in flight
+  for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
+    const int s = j & 3, code = j >> 2;
+    const double* c = codeP + code * 4;
+    const double* rl = Pl + s * 4;
+    const double* rr = Pr + s * 4;
+    tabL[j] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
+    tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
+  }
+  __syncthreads();
+
+  double g[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) g[j] = 0.0;
+  for (int blk = 0; blk < nb; ++blk) {
+    const int st = blk % STAGES;
+    const char* slot = mySlots + st * BTT_SLOT;
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+    __syncwarp();
+    mbar_wait(myBars + st * 8, (uint32_t)((blk / STAGES) & 1));
+    const V4 q = lds4(reinterpret_cast<const double*>(slot) + lane * 4);
+    const double w = reinterpret_cast<const double*>(slot + BTT_W)[lane];
+    const int cl = reinterpret_cast<const uint8_t*>(slot + BTT_CL)[lane];
+    const int cr = reinterpret_cast<const uint8_t*>(slot + BTT_CR)[lane];
+    __syncwarp();
+    issue(blk + STAGES);
+    const V4 ul = lds4(tabL + cl * 4);
+    const V4 ur = lds4(tabR + cr * 4);
+    const int ml_mask = masks[cl], mr_mask = masks[cr];
+    const V4 qw = scale4(q, w);
+    const V4 a = mul4(qw, ur);  // w m_l
+    const V4 b = mul4(qw, ul);  // w m_r
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double sl = (ml_mask >> c) & 1 ? 1.0 : 0.0;
+      const double sr = (mr_mask >> c) & 1 ? 1.0 : 0.0;
+      g[0 + c] = fma(a.x, sl, g[0 + c]);
+      g[4 + c] = fma(a.y, sl, g[4 + c]);
+      g[8 + c] = fma(a.z, sl, g[8 + c]);
+      g[12 + c] = fma(a.w, sl, g[12 + c]);
+      g[16 + c] = fma(b.x, sr, g[16 + c]);
+      g[20 + c] = fma(b.y, sr, g[20 + c]);
+      g[24 + c] = fma(b.z, sr, g[24 + c]);
+      g[28 + c] = fma(b.w, sr, g[28 + c]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const double mine = warp_transpose_sum(g);
+  red[warp * 32 + lane] = mine;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 32 + threadIdx.x];
+    const int branch = threadIdx.x < 16 ? op.left : op.right;
+    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+          (threadIdx.x & 15)] = t;
+  }
+}
+
 // patterns per thread of a post-order launch: long-lived CTAs on large levels
 // (amortises the shared-memory table build), ~8 CTAs per SM on small ones
 int fwd_patterns_per_thread(const Engine& e, int draws, int levelCount) {
@@ -1830,6 +1980,7 @@ int s4_backward(Engine& e, int draws) {
   const bool useMma = !(e.cfg.flags & TTB2_FLAG_NO_MMA);
   static const int variant = getenv("TTB2_BWD_VARIANT") ? atoi(getenv("TTB2_BWD_VARIANT")) : 0;
   static const bool tipsViaTma = getenv("TTB2_BWD_TIPS_TMA") != nullptr;
+  static const int tipsVariant = getenv("TTB2_TIPS_VARIANT") ? atoi(getenv("TTB2_TIPS_VARIANT")) : 0;
   const size_t smem = useMma
       ? (32 + 3 * (size_t)m.C * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) * sizeof(double)
       : (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
@@ -1844,7 +1995,24 @@ int s4_backward(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      if (useMma && l == 0 && e.codes01 && variant != 2 && !tipsViaTma) {
+      if (useMma && l == 0 && e.codes01 && variant != 2 && !tipsViaTma && tipsVariant != 1) {
+        constexpr int ST = 4;
+        auto smemTips = [&](int codes) {
+          return (size_t)(BWD_THREADS / 32) * ST * BTT_SLOT +
+                 (32 + 2 * (size_t)codes * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
+                 (size_t)(BWD_THREADS / 32) * ST * sizeof(uint64_t) + (size_t)codes * sizeof(int);
+        };
+        const size_t smemT = smemTips(m.C);
+        static bool attr = false;
+        if (!attr) {   // sized for the largest code table (uint8 codes)
+          cudaFuncSetAttribute(bwd4_tips_tma_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smemTips(256));
+          attr = true;
+        }
+        bwd4_tips_tma_kernel<ST><<<grid, BWD_THREADS, smemT, e.stream>>>(
+            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre, e.gpart,
+            e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      } else if (useMma && l == 0 && e.codes01 && variant != 2 && !tipsViaTma) {
         const size_t smemT = (32 + 2 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
                              (size_t)m.C * sizeof(int);
         bwd4_tips_kernel<<<grid, BWD_THREADS, smemT, e.stream>>>(
@@ -1861,8 +2029,8 @@ int s4_backward(Engine& e, int draws) {
             nChunk);
       } else if (useMma && (variant == 0 || (variant >= 7 && variant <= 9))) {
         constexpr int NWF = BWDF_THREADS / 32;
-        auto smemOf = [&](int stages) {
-          return ((size_t)NWF * stages * BWDT_SLOT + NWF * 32 + (size_t)m.C * 4) * sizeof(double) +
+        auto smemOf = [&](int stages, int codes) {
+          return ((size_t)NWF * stages * BWDT_SLOT + NWF * 32 + (size_t)codes * 4) * sizeof(double) +
                  (size_t)NWF * stages * sizeof(uint64_t);
         };
 #define TTB2_LAUNCH_TMA(ST, MB)                                                                  \
@@ -1870,10 +2038,11 @@ int s4_backward(Engine& e, int draws) {
           static bool attr = false;                                                              \
           if (!attr) {                                                                           \
             cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>,                                        \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOf(ST));  \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
+                                 (int)smemOf(ST, 256));                                          \
             attr = true;                                                                         \
           }                                                                                      \
-          bwd4_tma_kernel<ST, MB><<<grid, BWDF_THREADS, smemOf(ST), e.stream>>>(                 \
+          bwd4_tma_kernel<ST, MB><<<grid, BWDF_THREADS, smemOf(ST, m.C), e.stream>>>(            \
               e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,     \
               e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,             \
               chunkPatterns, nChunk);                                                            \

@@ -4,6 +4,7 @@
 // gradients.  All are O(B K S^3) or O(N) and negligible next to the peeling.
 #include <algorithm>
 
+#include <cstdlib>
 #include "engine.cuh"
 
 namespace ttb2 {
@@ -281,12 +282,15 @@ int round_threads(int n, int cap) {
 
 }  // namespace
 
-int plan_chunks(Engine& e, int draws, int granule) {
+int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm) {
   const Dims& m = e.dm;
   if (e.chunkPlanDraws == draws && e.chunkBase) return TTB2_OK;
   const int nLevels = (int)e.levelOff.size() - 1;
-  // aim for ~8 CTAs per SM in every launch; never less than 2 granules per chunk
-  const long target = (long)e.smCount * 8;
+  // never less than 2 granules per chunk
+  // ctasPerSm: CTAs per SM aimed at in every launch (several waves keep the tail short)
+  static const int envPerSm = getenv("TTB2_CHUNK_TARGET") ? atoi(getenv("TTB2_CHUNK_TARGET")) : 0;
+  const int perSm = envPerSm > 0 ? envPerSm : ctasPerSm;
+  const long target = (long)e.smCount * perSm;
   const int maxChunks = std::max(1, m.Npad / (2 * granule));
   e.levelChunks.assign(nLevels, 1);
   e.hostChunkBase.assign(m.B + 1, 0);
