@@ -34,6 +34,9 @@ import torch  # noqa: E402
 METRIC = "fp64 logL+grad patterns*nodes*cats/s"
 UNIT = "patterns*nodes*cats/s"
 BYTES_PER_UNIT = 160.0  # 5 vectors x 4 states x 8 B per (pattern, node, cat)
+# ncu dram__bytes_read.sum + dram__bytes_write.sum over the pre-order sweep of one step at
+# the headline size on one GPU (profiles/r01_tma_dram_bytes.csv)
+NCU_PREORDER_SWEEP_BYTES = 38.07e9
 BYTES_PER_UNIT_PRE = 96.0  # pre-order sweep share (3 vectors)
 BYTES_PER_UNIT_POST = 64.0  # post-order sweep share (2 vectors)
 
@@ -51,6 +54,8 @@ def parse_args():
     ap.add_argument("--cpu-patterns", type=int, default=8000,
                     help="patterns of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine-flags", type=int, default=0,
+                    help="extra TTB2_FLAG_* bits for experiments (32 = no CUDA graphs)")
     return ap.parse_args()
 
 
@@ -227,7 +232,7 @@ def main():
     prob = build_problem(args, lo, hi)
     units_total = args.patterns * (args.taxa - 1) * args.categories
     eng = Engine(prob.tip_states, prob.weights, prob.postorder, 4, args.categories,
-                 max_draws=1, device=local_rank, flags=1)
+                 max_draws=1, device=local_rank, flags=1 | args.engine_flags)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
 
@@ -352,9 +357,18 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "bwd4_mma_kernel (pre-order sweep, one launch per tree level)",
+                "bound": "hbm",
+                "kernel": "bwd4_tma_kernel<3,5> (pre-order sweep, one launch per tree level; "
+                          "level 1 is bwd4_tips_tma_kernel<4>)",
                 "achieved": ach_pre, "peak": peak, "unit": "GB/s", "frac": ach_pre / peak,
-                "peak_kind": peak_kind, "traffic": None,
+                "peak_kind": peak_kind,
+                "traffic": (NCU_PREORDER_SWEEP_BYTES / max(1, ph["preorder_launches"])
+                            if world == 1 and args.taxa == 1000 and args.patterns == 100_000
+                            and args.categories == 4 else None),
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read+write summed over the "
+                                "pre-order sweep / launches, profiles/r01_tma_dram_bytes.csv)",
+                "algorithmic_bytes_per_launch": units_rank * BYTES_PER_UNIT_PRE
+                / max(1, ph["preorder_launches"]),
                 "algorithmic_bytes_per_unit": BYTES_PER_UNIT_PRE,
                 "launches_per_step": ph["preorder_launches"],
                 "avg_launch_ms": ph_pre / max(1, ph["preorder_launches"]),
@@ -365,6 +379,10 @@ def main():
                 "whole_step": {"achieved": ach_step, "frac": ach_step / peak,
                                "algorithmic_bytes_per_unit": BYTES_PER_UNIT},
             },
+            "phases_ms": {"note": "CUDA events between kernel groups, ordinary launches (the timed "
+                                  "steps above replay CUDA graphs)",
+                          **{k: (round(v, 4) if isinstance(v, float) else v)
+                             for k, v in ph.items()}},
             "device_bytes": eng.device_bytes,
         }
         if world == 1 and not args.no_cpu_baseline:

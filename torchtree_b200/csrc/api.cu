@@ -290,8 +290,15 @@ void drop_graphs(Engine& e) {
   e.gBwd = Engine::GraphSlot();
 }
 
-bool graphs_enabled(const Engine& e) {
-  return !(e.cfg.flags & TTB2_FLAG_NO_GRAPH) && !e.timing && e.ownStream != nullptr;
+// Graph replay pays when an evaluation is launch-bound (fluA: 79 launches of a few
+// microseconds each, 0.53 -> 0.37 ms).  When the level kernels run for milliseconds the
+// host is far ahead of the device anyway and replay only adds its own launch and
+// event-ordering cost (measured +0.1 ms on 1000 taxa x 100k patterns), so large
+// problems use ordinary stream launches.
+bool graphs_enabled(const Engine& e, int draws) {
+  if ((e.cfg.flags & TTB2_FLAG_NO_GRAPH) || e.timing || e.ownStream == nullptr) return false;
+  const double units = (double)e.dm.Npad * e.dm.I * e.dm.K * draws * (e.dm.S / 4.0);
+  return units <= 4.0e7;
 }
 
 bool slot_matches(const Engine::GraphSlot& g, const Engine& e, int draws) {
@@ -304,7 +311,7 @@ bool slot_matches(const Engine::GraphSlot& g, const Engine& e, int draws) {
 // replayed.  The user's stream is ordered before and after with events.
 template <typename Body>
 int run_graphed(Engine& e, Engine::GraphSlot& slot, int draws, Body body) {
-  if (!graphs_enabled(e)) return body();
+  if (!graphs_enabled(e, draws)) return body();
   cudaStream_t user = e.stream;
   if (!slot_matches(slot, e, draws)) {
     if (slot.exec) cudaGraphExecDestroy(slot.exec);
@@ -795,7 +802,7 @@ int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branc
     const bool needQ = d_q != nullptr;
     if ((rc = run_backward_fused(e, grad_lnl, needQ, where))) return rc;
     if ((rc = small_fused_outputs(e, draws, needQ))) return rc;
-  } else if (e.preValid || !graphs_enabled(e) || !(e.spec4 || gmma_supported(e))) {
+  } else if (e.preValid || !graphs_enabled(e, draws) || !(e.spec4 || gmma_supported(e))) {
     if ((rc = ensure_eigen_grad_buffers(e))) return rc;
     if ((rc = run_backward(e, grad_lnl, where))) return rc;
     if ((rc = small_eigen_contract(e, draws))) return rc;

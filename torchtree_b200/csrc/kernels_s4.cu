@@ -29,6 +29,33 @@ struct __align__(32) V4 {
   double x, y, z, w;
 };
 
+// Programmatic dependent launch: a level kernel launched with the
+// programmaticStreamSerialization attribute may start (and run its prologue: tables,
+// matrix fragments, barrier setup -- nothing the previous level wrote) while the
+// previous level's last CTAs drain; pdl_wait() returns once that grid has completed
+// and its writes are visible.  The trigger follows the wait, so a kernel can only
+// overlap its immediate predecessor.
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_level(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem,
+                         cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ V4 ldg4(const double* p) {
   V4 v;
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -127,6 +154,7 @@ fwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
   build_child_table<K>(tabL, matsD + (size_t)op.left * K * 16, tipL, codeP, C);
   build_child_table<K>(tabR, matsD + (size_t)op.right * K * 16, tipR, codeP, C);
   __syncthreads();
+  pdl_wait_then_trigger();
 
   const size_t nodeStride = (size_t)K * Npad * 4;
   double* base = partials + (size_t)d * I * nodeStride;
@@ -560,6 +588,7 @@ fwd4_tips_kernel(const NodeOp* __restrict__ ops, int opBegin,
     pexp[pc] = eb - 1022;
   }
   __syncthreads();
+  pdl_wait_then_trigger();
 
   const size_t nodeStride = (size_t)K * Npad * 4;
   double* q = partials + ((size_t)d * I + (op.node - T)) * nodeStride;
@@ -1390,6 +1419,7 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  pdl_wait_then_trigger();   // everything above read only ops / mats / codeP
 #pragma unroll
   for (int blk = 0; blk < STAGES; ++blk) issue(blk);
 
@@ -1549,10 +1579,7 @@ bwd4_tips_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-#pragma unroll
-  for (int blk = 0; blk < STAGES; ++blk) issue(blk);
-
-  // transition tables while the first blocks are in flight
+  // transition tables (depend on mats / codeP only), then wait for the level above
   for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
     const int s = j & 3, code = j >> 2;
     const double* c = codeP + code * 4;
@@ -1562,6 +1589,9 @@ bwd4_tips_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
     tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
   }
   __syncthreads();
+  pdl_wait_then_trigger();
+#pragma unroll
+  for (int blk = 0; blk < STAGES; ++blk) issue(blk);
 
   double g[32];
 #pragma unroll
@@ -1820,6 +1850,11 @@ CherryArgs cherry_args(const Engine& e) {
   return ch;
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("TTB2_NO_PDL") == nullptr;
+  return on;
+}
+
 template <int K>
 void launch_fwdc(Engine& e, int draws, int opBegin, int count, int ppt) {
   const Dims& m = e.dm;
@@ -1834,7 +1869,7 @@ void launch_fwdc(Engine& e, int draws, int opBegin, int count, int ppt) {
 
 template <int K>
 void launch_fwd(Engine& e, int draws, int opBegin, int count, size_t smem, int ppt,
-                bool tipLevel) {
+                bool tipLevel, bool pdl) {
   const Dims& m = e.dm;
   const int per = FWD_THREADS * ppt;
   dim3 grid((m.Npad + per - 1) / per, count, draws);
@@ -1845,8 +1880,8 @@ void launch_fwd(Engine& e, int draws, int opBegin, int count, size_t smem, int p
         e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B, ppt);
     return;
   }
-  fwd4_kernel<K><<<grid, FWD_THREADS, smem, e.stream>>>(
-      e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B, ppt);
+  launch_level(fwd4_kernel<K>, grid, FWD_THREADS, smem, e.stream, pdl, e.ops, opBegin, e.mats,
+               e.tips, e.codeP, e.partials, e.expo, m.T, m.Npad, m.C, m.B, ppt);
 }
 
 }  // namespace
@@ -1925,17 +1960,18 @@ int s4_forward(Engine& e, int draws) {
       continue;
     }
     const bool tipLevel = (l == 0) && !(e.cfg.flags & TTB2_FLAG_NO_MMA);  // level 1: tip-tip nodes
+    const bool pdl = l > 0 && pdl_enabled();   // the first level follows pmatrix: ordinary launch
     // grid.y is limited to 65535
     for (int done = 0; done < count; done += 65535) {
       const int c = (count - done) < 65535 ? (count - done) : 65535;
       switch (m.K) {
-        case 1: launch_fwd<1>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
-        case 2: launch_fwd<2>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
-        case 3: launch_fwd<3>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
-        case 4: launch_fwd<4>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
-        case 5: launch_fwd<5>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
-        case 6: launch_fwd<6>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
-        case 8: launch_fwd<8>(e, draws, opBegin + done, c, smem, ppt, tipLevel); break;
+        case 1: launch_fwd<1>(e, draws, opBegin + done, c, smem, ppt, tipLevel, pdl); break;
+        case 2: launch_fwd<2>(e, draws, opBegin + done, c, smem, ppt, tipLevel, pdl); break;
+        case 3: launch_fwd<3>(e, draws, opBegin + done, c, smem, ppt, tipLevel, pdl); break;
+        case 4: launch_fwd<4>(e, draws, opBegin + done, c, smem, ppt, tipLevel, pdl); break;
+        case 5: launch_fwd<5>(e, draws, opBegin + done, c, smem, ppt, tipLevel, pdl); break;
+        case 6: launch_fwd<6>(e, draws, opBegin + done, c, smem, ppt, tipLevel, pdl); break;
+        case 8: launch_fwd<8>(e, draws, opBegin + done, c, smem, ppt, tipLevel, pdl); break;
         default: {
           dim3 grid((m.Npad + FWD_THREADS - 1) / FWD_THREADS, c, draws);
           fwd4_kernel_anyk<<<grid, FWD_THREADS, smem, e.stream>>>(
@@ -1992,6 +2028,7 @@ int s4_backward(Engine& e, int draws) {
     const int nChunk = e.levelChunks[l];
     int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
     chunkPatterns = (chunkPatterns + 31) / 32 * 32;
+    const bool pdl = l < nLevels - 1 && pdl_enabled();   // the top level follows root4_bwd
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
@@ -2009,9 +2046,10 @@ int s4_backward(Engine& e, int draws) {
                                (int)smemTips(256));
           attr = true;
         }
-        bwd4_tips_tma_kernel<ST><<<grid, BWD_THREADS, smemT, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre, e.gpart,
-            e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+        launch_level(bwd4_tips_tma_kernel<ST>, grid, BWD_THREADS, smemT, e.stream, pdl, e.ops,
+                     opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre,
+                     e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
+                     chunkPatterns, nChunk);
       } else if (useMma && l == 0 && e.codes01 && variant != 2 && !tipsViaTma) {
         const size_t smemT = (32 + 2 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
                              (size_t)m.C * sizeof(int);
@@ -2042,10 +2080,10 @@ int s4_backward(Engine& e, int draws) {
                                  (int)smemOf(ST, 256));                                          \
             attr = true;                                                                         \
           }                                                                                      \
-          bwd4_tma_kernel<ST, MB><<<grid, BWDF_THREADS, smemOf(ST, m.C), e.stream>>>(            \
-              e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,     \
-              e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,             \
-              chunkPatterns, nChunk);                                                            \
+          launch_level(bwd4_tma_kernel<ST, MB>, grid, BWDF_THREADS, smemOf(ST, m.C), e.stream,   \
+                       pdl, e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo,  \
+                       e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C,   \
+                       m.B, m.K, chunkPatterns, nChunk);                                         \
         } while (0)
         if (variant == 8) TTB2_LAUNCH_TMA(4, 4);
         else if (variant == 9) TTB2_LAUNCH_TMA(2, 6);
