@@ -934,8 +934,7 @@ constexpr int BWDM_THREADS = 128;
 constexpr int MMA_LD = 36;               // row stride (doubles) of the staging tiles
 constexpr int MMA_STAGE = 2 * 8 * MMA_LD;  // doubles per warp: X and Y tiles
 
-template <bool PREFETCH, int MINBLOCKS, bool PREG>
-__global__ void __launch_bounds__(BWDM_THREADS, MINBLOCKS)
+__global__ void __launch_bounds__(BWDM_THREADS, 4)
 bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
                 const double* __restrict__ codeP, const double* __restrict__ partials,
@@ -992,15 +991,8 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
   const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
 
-  // optional: both transition matrices in registers (no shared-memory broadcasts
-  // in the pattern loop)
-  double rPl[16], rPr[16];
-  if (PREG) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { rPl[j] = Pl[j]; rPr[j] = Pr[j]; }
-  }
-  const double* mPl = PREG ? rPl : Pl;
-  const double* mPr = PREG ? rPr : Pr;
+  const double* mPl = Pl;
+  const double* mPr = Pr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // staging tiles [8 rows][32 patterns], row stride 36 doubles: the per-pattern
   // stores (lane = pattern) and the MMA fragment loads (lane -> row lane>>2,
@@ -1037,7 +1029,7 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   for (int base = begin + warp * 32; base < end; base += BWDM_THREADS) {
     const int i = base + lane;
     Inputs nxt;
-    if (PREFETCH) fetch(i + BWDM_THREADS, nxt);
+    fetch(i + BWDM_THREADS, nxt);
     V4 xl{0.0, 0.0, 0.0, 0.0}, xr = xl, vl = xl, vr = xl;
     if (i < end) {
       V4 ul, ur;
@@ -1083,8 +1075,7 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < 8; ++t) dmma884(c0, c1, sX[t * 4 + fragOff], sY[t * 4 + fragOff]);
-    if (PREFETCH) cur = nxt;
-    else fetch(i + BWDM_THREADS, cur);
+    cur = nxt;
   }
   // accumulator fragment: row = lane>>2, cols = (lane&3)*2 + {0,1}
   red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = c0;
@@ -1121,151 +1112,16 @@ bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
 // Lanes c<2 therefore own the right child's outputs and lanes c>=2 the left
 // child's.  G = sum_i w m (x) p~ needs the child's whole p~ vector next to the
 // lane's two m values: a quad all-gather (three shuffles) and 8 FMAs per lane.
+//
+// Inputs: the three vectors of a 32-pattern block (q^_n, p~_l, p~_r: 1 KB each,
+// contiguous) are brought in by bulk asynchronous copies (cp.async.bulk -> SASS
+// UBLKCP) into a per-warp ring of shared-memory slots, completion tracked by one
+// mbarrier per slot; weights, scale exponents and tip codes ride along as 16-byte
+// cp.async.  Every warp is its own producer and consumer, so there is no CTA-wide
+// synchronisation in the pattern loop, and the loads in flight do not occupy
+// registers: STAGES-1 blocks (3 KB each) per warp.
 constexpr int BWDF_THREADS = 128;
 
-template <int MINBLOCKS>
-__global__ void __launch_bounds__(BWDF_THREADS, MINBLOCKS)
-bwd4_frag_kernel(const NodeOp* __restrict__ ops, int opBegin,
-                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
-                 const double* __restrict__ codeP, const double* __restrict__ partials,
-                 const int16_t* __restrict__ expo, const double* __restrict__ weights,
-                 double* __restrict__ pre, double* __restrict__ gpart,
-                 const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
-                 int C, int B, int K, int chunkPatterns, int nChunk) {
-  extern __shared__ __align__(16) double sm[];
-  // sm: cp[C][4] | red[warps][32]
-  constexpr int NW = BWDF_THREADS / 32;
-  double* cp = sm;
-  double* red = sm + C * 4;
-
-  const int nodeSlot = blockIdx.y / K;
-  const int k = blockIdx.y - nodeSlot * K;
-  const NodeOp op = ops[opBegin + nodeSlot];
-  const int d = blockIdx.z;
-  const int I = T - 1;
-  const bool tipL = op.left < T, tipR = op.right < T;
-  const double* matsD = mats + (size_t)d * B * K * 16;
-  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
-  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
-  if (tipL || tipR) {
-    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
-    __syncthreads();
-  }
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int p = lane >> 2, c = lane & 3;
-  const bool rside = c < 2;        // this lane produces m_r, q^_r, G_r
-  const int s0 = (c & 1) * 2;      // first of the two states it holds
-  // constant B fragments (lane holds B[k = c][n = p])
-  const double b1 = p < 4 ? gPl[p * 4 + c] : 0.0;          // [P_l^T | 0]
-  const double b2 = p >= 4 ? gPr[(p - 4) * 4 + c] : 0.0;   // [0 | P_r^T]
-  double ba, bb;                                           // W rows 2c, 2c+1
-  if (rside) {
-    ba = p < 4 ? gPr[(2 * c) * 4 + p] : 0.0;
-    bb = p < 4 ? gPr[(2 * c + 1) * 4 + p] : 0.0;
-  } else {
-    ba = p >= 4 ? gPl[(2 * c - 4) * 4 + (p - 4)] : 0.0;
-    bb = p >= 4 ? gPl[(2 * c - 3) * 4 + (p - 4)] : 0.0;
-  }
-
-  const size_t nodeStride = (size_t)K * Npad * 4;
-  const size_t drawBase = (size_t)d * I * nodeStride;
-  const size_t kOff = (size_t)k * Npad * 4;
-  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
-  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
-  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
-  const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
-  const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
-  // the child this lane writes to
-  const int mine = rside ? op.right : op.left;
-  const bool store = mine >= T;
-  double* qc = store ? pre + drawBase + (size_t)(mine - T) * nodeStride + kOff : nullptr;
-  const int16_t* ec = store ? expo + ((size_t)d * I + (mine - T)) * Npad : nullptr;
-
-  double g[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) g[i][j] = 0.0;
-
-  const int begin = blockIdx.x * chunkPatterns;
-  int end = begin + chunkPatterns;
-  end = end < Npad ? end : Npad;
-
-  // chunk boundaries and Npad are multiples of 32: a warp block is never ragged
-  for (int base = begin + warp * 32; base < end; base += BWDF_THREADS) {
-    double al[4], ar[4], w[4];
-    double2 q[4];
-    int ex[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int i = base + t * 8 + p;
-      al[t] = tipL ? cp[tl[i] * 4 + c] : __ldg(pl + (size_t)i * 4 + c);
-      ar[t] = tipR ? cp[tr[i] * 4 + c] : __ldg(prr + (size_t)i * 4 + c);
-      q[t] = __ldg(reinterpret_cast<const double2*>(qn + (size_t)i * 4 + s0));
-      w[t] = __ldg(weights + i);
-      ex[t] = store ? (int)ec[i] : 0;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int i = base + t * 8 + p;
-      double u0 = 0.0, u1 = 0.0;
-      dmma884(u0, u1, al[t], b1);
-      dmma884(u0, u1, ar[t], b2);
-      const double m0 = q[t].x * u0, m1 = q[t].y * u1;
-      double o0 = 0.0, o1 = 0.0;
-      dmma884(o0, o1, m0, ba);
-      dmma884(o0, o1, m1, bb);
-      if (store) {
-        const double f = __hiloint2double((1023 - ex[t]) << 20, 0);
-        *reinterpret_cast<double2*>(qc + (size_t)i * 4 + s0) = make_double2(o0 * f, o1 * f);
-      }
-      const bool live = w[t] != 0.0;
-      const double own = live ? (rside ? ar[t] : al[t]) : 0.0;
-      const double oth = live ? (rside ? al[t] : ar[t]) : 0.0;
-      const double wm0 = live ? w[t] * m0 : 0.0;
-      const double wm1 = live ? w[t] * m1 : 0.0;
-      // x[j] = p~_child[c ^ j]
-      const double x1 = __shfl_xor_sync(0xffffffffu, own, 1);
-      const double x2 = __shfl_xor_sync(0xffffffffu, oth, 2);
-      const double x3 = __shfl_xor_sync(0xffffffffu, oth, 3);
-      g[0][0] = fma(wm0, own, g[0][0]); g[1][0] = fma(wm1, own, g[1][0]);
-      g[0][1] = fma(wm0, x1, g[0][1]);  g[1][1] = fma(wm1, x1, g[1][1]);
-      g[0][2] = fma(wm0, x2, g[0][2]);  g[1][2] = fma(wm1, x2, g[1][2]);
-      g[0][3] = fma(wm0, x3, g[0][3]);  g[1][3] = fma(wm1, x3, g[1][3]);
-    }
-  }
-  // sum over the 8 pattern rows of the warp, then over warps (fixed order)
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double v = g[i][j];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      // G_child[s = s0 + i][s' = c ^ j]
-      if (p == 0) red[warp * 32 + (rside ? 16 : 0) + (s0 + i) * 4 + (c ^ j)] = v;
-    }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int child = threadIdx.x >> 4;
-    double t = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 32 + threadIdx.x];
-    const int branch = child ? op.right : op.left;
-    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
-          (threadIdx.x & 15)] = t;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Same arithmetic as bwd4_frag_kernel, with the three input vectors of a 32-pattern
-// block (q^_n, p~_l, p~_r: 1 KB each, contiguous) brought in by bulk asynchronous
-// copies (cp.async.bulk -> SASS UBLKCP) into a per-warp ring of shared-memory slots,
-// completion tracked by one mbarrier per slot.  Every warp is its own producer and
-// consumer, so there is no CTA-wide synchronisation in the pattern loop, and the
-// loads in flight do not occupy registers: STAGES-1 blocks (3 KB each) per warp.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -2014,9 +1870,8 @@ int s4_backward(Engine& e, int draws) {
     if (rc) return rc;
   }
   const bool useMma = !(e.cfg.flags & TTB2_FLAG_NO_MMA);
-  static const int variant = getenv("TTB2_BWD_VARIANT") ? atoi(getenv("TTB2_BWD_VARIANT")) : 0;
-  static const bool tipsViaTma = getenv("TTB2_BWD_TIPS_TMA") != nullptr;
-  static const int tipsVariant = getenv("TTB2_TIPS_VARIANT") ? atoi(getenv("TTB2_TIPS_VARIANT")) : 0;
+  // TTB2_BWD_LEGACY=1: the previous kernel generation (bwd4_mma_kernel / bwd4_tips_kernel), for A/B runs
+  static const bool legacy = getenv("TTB2_BWD_LEGACY") != nullptr;
   const size_t smem = useMma
       ? (32 + 3 * (size_t)m.C * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) * sizeof(double)
       : (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
@@ -2032,25 +1887,24 @@ int s4_backward(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      if (useMma && l == 0 && e.codes01 && variant != 2 && !tipsViaTma && tipsVariant != 1) {
+      if (useMma && l == 0 && e.codes01 && !legacy) {
         constexpr int ST = 4;
         auto smemTips = [&](int codes) {
           return (size_t)(BWD_THREADS / 32) * ST * BTT_SLOT +
                  (32 + 2 * (size_t)codes * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
                  (size_t)(BWD_THREADS / 32) * ST * sizeof(uint64_t) + (size_t)codes * sizeof(int);
         };
-        const size_t smemT = smemTips(m.C);
         static bool attr = false;
         if (!attr) {   // sized for the largest code table (uint8 codes)
           cudaFuncSetAttribute(bwd4_tips_tma_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smemTips(256));
           attr = true;
         }
-        launch_level(bwd4_tips_tma_kernel<ST>, grid, BWD_THREADS, smemT, e.stream, pdl, e.ops,
-                     opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre,
+        launch_level(bwd4_tips_tma_kernel<ST>, grid, BWD_THREADS, smemTips(m.C), e.stream, pdl,
+                     e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre,
                      e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
                      chunkPatterns, nChunk);
-      } else if (useMma && l == 0 && e.codes01 && variant != 2 && !tipsViaTma) {
+      } else if (useMma && l == 0 && e.codes01) {
         const size_t smemT = (32 + 2 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
                              (size_t)m.C * sizeof(int);
         bwd4_tips_kernel<<<grid, BWD_THREADS, smemT, e.stream>>>(
@@ -2065,63 +1919,31 @@ int s4_backward(Engine& e, int draws) {
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, ch, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns,
             nChunk);
-      } else if (useMma && (variant == 0 || (variant >= 7 && variant <= 9))) {
-        constexpr int NWF = BWDF_THREADS / 32;
-        auto smemOf = [&](int stages, int codes) {
-          return ((size_t)NWF * stages * BWDT_SLOT + NWF * 32 + (size_t)codes * 4) * sizeof(double) +
-                 (size_t)NWF * stages * sizeof(uint64_t);
+      } else if (useMma && !legacy) {
+        constexpr int ST = 3, MB = 5, NWF = BWDF_THREADS / 32;
+        auto smemOf = [&](int codes) {
+          return ((size_t)NWF * ST * BWDT_SLOT + NWF * 32 + (size_t)codes * 4) * sizeof(double) +
+                 (size_t)NWF * ST * sizeof(uint64_t);
         };
-#define TTB2_LAUNCH_TMA(ST, MB)                                                                  \
-        do {                                                                                     \
-          static bool attr = false;                                                              \
-          if (!attr) {                                                                           \
-            cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>,                                        \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
-                                 (int)smemOf(ST, 256));                                          \
-            attr = true;                                                                         \
-          }                                                                                      \
-          launch_level(bwd4_tma_kernel<ST, MB>, grid, BWDF_THREADS, smemOf(ST, m.C), e.stream,   \
-                       pdl, e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo,  \
-                       e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C,   \
-                       m.B, m.K, chunkPatterns, nChunk);                                         \
-        } while (0)
-        if (variant == 8) TTB2_LAUNCH_TMA(4, 4);
-        else if (variant == 9) TTB2_LAUNCH_TMA(2, 6);
-        else TTB2_LAUNCH_TMA(3, 5);
-#undef TTB2_LAUNCH_TMA
-      } else if (useMma && variant != 1 && (l > 0 || variant == 2)) {
-        const size_t smemF = ((size_t)m.C * 4 + (BWDF_THREADS / 32) * 32) * sizeof(double);
-        if (variant == 3)
-          bwd4_frag_kernel<8><<<grid, BWDF_THREADS, smemF, e.stream>>>(
-              e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
-              e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
-              chunkPatterns, nChunk);
-        else
-          bwd4_frag_kernel<6><<<grid, BWDF_THREADS, smemF, e.stream>>>(
-              e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
-              e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
-              chunkPatterns, nChunk);
-      } else if (useMma && variant == 4) {
-        bwd4_mma_kernel<false, 4, false><<<grid, BWDM_THREADS, smem, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
-            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      } else if (useMma && variant == 5) {
-        bwd4_mma_kernel<false, 3, true><<<grid, BWDM_THREADS, smem, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
-            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      } else if (useMma && variant == 6) {
-        bwd4_mma_kernel<true, 3, true><<<grid, BWDM_THREADS, smem, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
-            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+        static bool attr = false;
+        if (!attr) {
+          cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smemOf(256));
+          attr = true;
+        }
+        launch_level(bwd4_tma_kernel<ST, MB>, grid, BWDF_THREADS, smemOf(m.C), e.stream, pdl,
+                     e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
+                     e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
+                     chunkPatterns, nChunk);
       } else if (useMma) {
-        bwd4_mma_kernel<true, 4, false><<<grid, BWDM_THREADS, smem, e.stream>>>(
+        bwd4_mma_kernel<<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      }
-      else
+      } else {
         bwd4_kernel<<<grid, BWD_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
+      }
       ++e.launches;
     }
   }
