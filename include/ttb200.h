@@ -211,6 +211,28 @@ int ttb2_compress_patterns(const uint8_t* sequences, int32_t taxa, int64_t lengt
                            int32_t group, uint8_t* patterns, double* weights,
                            int64_t* pattern_count);
 
+/*
+ * Node-height reparameterisation of time trees on the device -- replaces the Python
+ * loop (and its autograd tape) of GeneralNodeHeightTransform._call,
+ * torchtree/evolution/tree_height_transform.py:58-66:
+ *     h[root] = x[root],  h[c] = b[c] + x[c] * (h[parent(c)] - b[c])
+ * for the T-1 internal nodes (index = node - T); b = the transform's lower bounds
+ * (`_bounds[taxa_count:]`, update_bounds :36-56).  One plan per topology.
+ *   postorder [T-1][3] (node, left, right), root last;  bounds [T-1]
+ *   x, heights, grad_heights, grad_x: [draws][T-1]; all host or all device (`where`)
+ * The calls return after the result is complete (they synchronise their own stream).
+ */
+typedef struct ttb2_heights ttb2_heights;
+int ttb2_heights_create(int32_t tip_count, const int32_t* postorder, const double* bounds,
+                        int32_t device, ttb2_heights** out);
+int ttb2_heights_destroy(ttb2_heights* plan);
+int ttb2_heights_forward(ttb2_heights* plan, int32_t draws, const double* x, double* heights,
+                         int32_t where);
+/* grad_x = (d heights / d x)^T grad_heights: the backward of the call above. */
+int ttb2_heights_backward(ttb2_heights* plan, int32_t draws, const double* x,
+                          const double* heights, const double* grad_heights, double* grad_x,
+                          int32_t where);
+
 /* Kernels launched by this engine since creation (bench `gpu_launches`). */
 int64_t ttb2_launch_count(const ttb2_engine* engine);
 /* Device bytes currently held by this engine. */

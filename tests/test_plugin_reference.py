@@ -263,3 +263,42 @@ def test_time_tree_with_strict_clock(patched):
     tree_model._internal_heights.tensor = tree_model._internal_heights.tensor.repeat(3, 68)
     like.lp_needs_update = True
     assert torch.allclose(torch.tensor([[-4618.2062529058] * 3]), like())
+
+
+def test_install_height_transform_rebinds_and_fails_loudly_without_gpu(patched):
+    """install(height_transform=True): ReparameterizedTimeTreeModel picks up the device
+    transform; without a GPU it must raise, not fall back to the Python loop."""
+    from torchtree.core.utils import REGISTERED_CLASSES
+    from torchtree.evolution.taxa import Taxa, Taxon
+
+    import torchtree.evolution.tree_height_transform as ref_transform
+    import torchtree.evolution.tree_likelihood as refmod
+    import torchtree.evolution.tree_model as ref_tree_model
+    from torchtree_b200._lib import EngineError
+    from torchtree_b200.height_transform import GeneralNodeHeightTransform
+
+    saved_reg = dict(REGISTERED_CLASSES)
+    saved = (refmod.TreeLikelihoodModel, ref_transform.GeneralNodeHeightTransform,
+             ref_tree_model.GeneralNodeHeightTransform)
+    try:
+        patched.install(override_reference=True, height_transform=True)
+        assert ref_tree_model.GeneralNodeHeightTransform is GeneralNodeHeightTransform
+        assert ref_transform.GeneralNodeHeightTransform is GeneralNodeHeightTransform
+        assert ref_tree_model.ReferenceGeneralNodeHeightTransform is saved[2]
+        taxa = Taxa("taxa", [Taxon(n, {"date": d}) for n, d in
+                             (("A", 0.0), ("B", 1.0), ("C", 2.0))])
+        build = lambda: ref_tree_model.ReparameterizedTimeTreeModel.from_json(  # noqa: E731
+            ref_tree_model.ReparameterizedTimeTreeModel.json_factory(
+                "tree", "((A:1,B:1):1,C:1);", "taxa", ratios=[0.5], root_height=[5.0]),
+            {"taxa": taxa})
+        if torch.cuda.is_available():
+            assert build().node_heights.shape[-1] == 5
+        else:
+            with pytest.raises(EngineError, match="no CUDA device"):
+                build().branch_lengths()
+    finally:
+        REGISTERED_CLASSES.clear()
+        REGISTERED_CLASSES.update(saved_reg)
+        refmod.TreeLikelihoodModel = saved[0]
+        ref_transform.GeneralNodeHeightTransform = saved[1]
+        ref_tree_model.GeneralNodeHeightTransform = saved[2]

@@ -56,6 +56,10 @@ EXPORTED_SYMBOLS = (
     "ttb2_enable_timing",
     "ttb2_phase_ms",
     "ttb2_compress_patterns",
+    "ttb2_heights_create",
+    "ttb2_heights_destroy",
+    "ttb2_heights_forward",
+    "ttb2_heights_backward",
     "ttb2_launch_count",
     "ttb2_device_bytes",
     "ttb2_last_error",
@@ -110,6 +114,14 @@ def load():
     lib.ttb2_phase_ms.restype = c_int32
     lib.ttb2_compress_patterns.argtypes = [vp, c_int32, c_int64, c_int32, vp, vp, vp]
     lib.ttb2_compress_patterns.restype = c_int32
+    lib.ttb2_heights_create.argtypes = [c_int32, vp, vp, c_int32, ctypes.POINTER(vp)]
+    lib.ttb2_heights_create.restype = c_int32
+    lib.ttb2_heights_destroy.argtypes = [vp]
+    lib.ttb2_heights_destroy.restype = c_int32
+    lib.ttb2_heights_forward.argtypes = [vp, c_int32, vp, vp, c_int32]
+    lib.ttb2_heights_forward.restype = c_int32
+    lib.ttb2_heights_backward.argtypes = [vp, c_int32, vp, vp, vp, vp, c_int32]
+    lib.ttb2_heights_backward.restype = c_int32
     lib.ttb2_launch_count.argtypes = [vp]
     lib.ttb2_launch_count.restype = c_int64
     lib.ttb2_device_bytes.argtypes = [vp]

@@ -37,9 +37,13 @@ def main(argv=None):
 
     from .tree_likelihood import install
 
-    install(override_reference=True)
     if argv is not None:
         sys.argv = [sys.argv[0]] + list(argv)
+    # --b200-heights: also run the ratio -> node-height transform of time trees on the GPU
+    heights = "--b200-heights" in sys.argv
+    if heights:
+        sys.argv.remove("--b200-heights")
+    install(override_reference=True, height_transform=heights)
     torchtree_main()
 
 

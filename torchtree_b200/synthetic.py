@@ -89,6 +89,17 @@ def postorder_from_children(children: dict, root: int, tip_count: int) -> np.nda
     return triples
 
 
+def random_postorder(tip_count: int, rng: np.random.Generator, topology: str = "random") -> np.ndarray:
+    """Post-order triples of a synthetic topology ("random", "caterpillar", "balanced")."""
+    if topology == "caterpillar":
+        children, root = caterpillar_topology(tip_count)
+    elif topology == "balanced":
+        children, root = balanced_topology(tip_count)
+    else:
+        children, root = random_join_topology(tip_count, rng)
+    return postorder_from_children(children, root, tip_count)
+
+
 @dataclass
 class Problem:
     """Flattened inputs of one tree-likelihood evaluation (what the engine,

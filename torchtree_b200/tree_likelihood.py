@@ -119,13 +119,16 @@ class TreeLikelihoodModel(CallableModel):
                    use_ambiguities, use_tip_states, device=data.get("device", 0))
 
 
-def install(override_reference: bool = True) -> None:
+def install(override_reference: bool = True, height_transform: bool = False) -> None:
     """Make existing configs resolve to this class (SURVEY 8(b) "Resolution"):
 
     * bare `"type": "TreeLikelihoodModel"` -> registry entry replaced;
     * dotted `torchtree.evolution.tree_likelihood.TreeLikelihoodModel` -> the
       module attribute is rebound;
-    * bare `"LG"` / `"WAG"` are registered (the reference forgets to).
+    * bare `"LG"` / `"WAG"` are registered (the reference forgets to, SURVEY F7);
+    * `height_transform=True` additionally rebinds `GeneralNodeHeightTransform`
+      where `ReparameterizedTimeTreeModel` looks it up (tree_model.py:539, :587), so
+      time trees map ratios to node heights on the GPU (height_transform.py).
     """
     import torchtree.evolution.tree_likelihood as ref_module
     from torchtree.evolution.substitution_model.amino_acid import LG, WAG
@@ -138,3 +141,12 @@ def install(override_reference: bool = True) -> None:
         ref_module.TreeLikelihoodModel = TreeLikelihoodModel
     register_class(LG, "LG")
     register_class(WAG, "WAG")
+    if height_transform:
+        import torchtree.evolution.tree_height_transform as ref_transform
+        import torchtree.evolution.tree_model as ref_tree_model
+
+        from .height_transform import GeneralNodeHeightTransform
+        for module in (ref_transform, ref_tree_model):
+            if not hasattr(module, "ReferenceGeneralNodeHeightTransform"):
+                module.ReferenceGeneralNodeHeightTransform = module.GeneralNodeHeightTransform
+            module.GeneralNodeHeightTransform = GeneralNodeHeightTransform
