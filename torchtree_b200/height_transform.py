@@ -144,8 +144,9 @@ class GeneralNodeHeightTransform(Transform):
 
     def _get_plan(self) -> NodeHeightPlan:
         if self._plan is None:
-            self._plan = NodeHeightPlan(self.taxa_count, self._postorder,
-                                        self._bounds[self.taxa_count:], self.device_index)
+            bounds = self._bounds[self.taxa_count:].detach().cpu().numpy()
+            self._plan = NodeHeightPlan(self.taxa_count, self._postorder, bounds,
+                                        self.device_index)
         return self._plan
 
     def _call(self, x: torch.Tensor) -> torch.Tensor:
