@@ -321,6 +321,51 @@ root4_kernel(const double* __restrict__ partials, const int16_t* __restrict__ ex
   if (threadIdx.x == 0) blockPart[(size_t)d * gridDim.x + blockIdx.x] = t;
 }
 
+// The same for small shards.  Block = 32 patterns x ROOT_SLICES node slices: the sum of
+// the I scale exponents of a pattern (I dependent-free loads per pattern, the long part)
+// is split over the slices so that a few thousand patterns still put enough loads in flight.
+constexpr int ROOT_SLICES = 8;
+
+__global__ void __launch_bounds__(32 * ROOT_SLICES)
+root4_small_kernel(const double* __restrict__ partials, const int16_t* __restrict__ expo,
+             const double* __restrict__ freqs, int freqDraws,
+             const double* __restrict__ props, int propDraws,
+             const double* __restrict__ weights, double* __restrict__ siteLnl,
+             double* __restrict__ blockPart, int T, int Npad, int K, int rootInode) {
+  __shared__ int esums[ROOT_SLICES][32];
+  const int d = blockIdx.y;
+  const int I = T - 1;
+  const int lane = threadIdx.x, slice = threadIdx.y;
+  const int i = blockIdx.x * 32 + lane;      // Npad is a multiple of 32
+  const double* fr = freqs + (freqDraws > 1 ? (size_t)d * 4 : 0);
+  const double* pr = props + (propDraws > 1 ? (size_t)d * K : 0);
+  int esum = 0;
+  const int16_t* e = expo + (size_t)d * I * Npad + i;
+#pragma unroll 4
+  for (int n = slice; n < I; n += ROOT_SLICES) esum += e[(size_t)n * Npad];
+  esums[slice][lane] = esum;
+  __syncthreads();
+  if (slice != 0) return;
+  esum = 0;
+#pragma unroll
+  for (int j = 0; j < ROOT_SLICES; ++j) esum += esums[j][lane];
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const double* p = partials + ((size_t)d * I + rootInode) * nodeStride + (size_t)i * 4;
+  double L = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const V4 v = ldg4(p + (size_t)k * Npad * 4);
+    const double dot = fma(fr[3], v.w, fma(fr[2], v.z, fma(fr[1], v.y, fr[0] * v.x)));
+    L = fma(pr[k], dot, L);
+  }
+  const double site = log(L) + (double)esum * 0.693147180559945309417232121458;
+  siteLnl[(size_t)d * Npad + i] = site;
+  const double w = weights[i];
+  double t = (w != 0.0) ? w * site : 0.0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+  if (lane == 0) blockPart[(size_t)d * gridDim.x + blockIdx.x] = t;
+}
+
 // ---------------------------------------------------------------------------
 // pre-order root: q^_root[k,s,i] = rho_k pi_s / (L~_i * 2^{e_root});
 // per-block partials of d lnL / d rho_k and the root term of d lnL / d pi_s
@@ -1844,9 +1889,19 @@ int s4_forward(Engine& e, int draws) {
 
 int s4_root(Engine& e, int draws) {
   const Dims& m = e.dm;
+  const int rootInode = e.hostOps.back().node - m.T;
+  if ((long)m.Npad * draws < 65536) {
+    const int nblocks = m.Npad / 32;   // <= redPartCap: (Npad/128) * (K + 4) entries per draw
+    dim3 grid(nblocks, draws);
+    root4_small_kernel<<<grid, dim3(32, ROOT_SLICES), 0, e.stream>>>(
+        e.partials, e.expo, e.freqs, e.freqDraws, e.props, e.propDraws, e.weights,
+        e.siteLnl, e.redPart, m.T, m.Npad, m.K, rootInode);
+    ++e.launches;
+    TTB2_CUDA_CHECK(cudaGetLastError());
+    return small_reduce_lnl(e, draws, nblocks);
+  }
   const int nblocks = (m.Npad + ROOT_THREADS - 1) / ROOT_THREADS;
   dim3 grid(nblocks, draws);
-  const int rootInode = e.hostOps.back().node - m.T;
   root4_kernel<<<grid, ROOT_THREADS, 0, e.stream>>>(
       e.partials, e.expo, e.freqs, e.freqDraws, e.props, e.propDraws, e.weights,
       e.siteLnl, e.redPart, m.T, m.Npad, m.K, rootInode);
@@ -1887,7 +1942,8 @@ int s4_backward(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      if (useMma && l == 0 && e.codes01 && !legacy) {
+      const bool tipTip = l == 0;   // level 1: both children are tips
+      if (useMma && tipTip && e.codes01 && !legacy) {
         constexpr int ST = 4;
         auto smemTips = [&](int codes) {
           return (size_t)(BWD_THREADS / 32) * ST * BTT_SLOT +
@@ -1895,7 +1951,7 @@ int s4_backward(Engine& e, int draws) {
                  (size_t)(BWD_THREADS / 32) * ST * sizeof(uint64_t) + (size_t)codes * sizeof(int);
         };
         static bool attr = false;
-        if (!attr) {   // sized for the largest code table (uint8 codes)
+        if (!attr) {
           cudaFuncSetAttribute(bwd4_tips_tma_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smemTips(256));
           attr = true;
