@@ -89,16 +89,18 @@ typedef struct ttb2_config {
 /* 4-state pre-order kernel: accumulate d lnL / d P with plain fp64 FMAs instead
  * of fp64 tensor-core MMAs (testing / comparison) */
 #define TTB2_FLAG_NO_MMA 8
-/* 4-state models: tabulate "cherries" (nodes whose two children are tips) by
- * tip-code pair instead of storing their vectors per pattern.  Removes a third
- * of the post-order HBM traffic on random trees (post-order sweep 4.2 -> 3.4 ms
- * on config 2) but the extra shared-memory lookups slow the L1-bound pre-order
- * kernel more than that (8.1 -> 10.0 ms), so it is opt-in. */
+/* accepted and ignored: cherry tabulation (below) used to be opt-in */
 #define TTB2_FLAG_CHERRY 16
 /* do not replay the per-evaluation kernel sequence from a CUDA graph (the default
  * captures the eigen-mode forward and backward sequences once per shape and
  * replays them: one graph launch instead of ~25-80 kernel launches) */
 #define TTB2_FLAG_NO_GRAPH 32
+/* 4-state models tabulate "cherries" (nodes whose two children are tips) by tip-code
+ * pair instead of storing their vectors per pattern whenever the pair alphabet is
+ * small (C*C <= 64): on a random tree a third of the internal nodes are cherries, so a
+ * third of the post-order traffic and a ninth of the pre-order reads never touch HBM
+ * (config 2: 10.8 -> 9.8 ms per evaluation).  This flag stores them like any other node. */
+#define TTB2_FLAG_NO_CHERRY 64
 
 /*
  * tip_codes      uint8 [T][N]: symbol code of tip t at pattern i

@@ -42,7 +42,7 @@ def _check(prob, flags=0, q_rtol=1e-7):
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [0, 4, 8, 16], ids=["levels", "fused", "levels-simt", "cherry"])
+@pytest.mark.parametrize("flags", [0, 4, 8, 64], ids=["levels", "fused", "levels-simt", "nocherry"])
 @pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_category_counts(K, flags):
     from torchtree_b200.synthetic import make_problem
@@ -50,7 +50,7 @@ def test_category_counts(K, flags):
     _check(make_problem(33, 257, 4, K, seed=100 + K, gap_fraction=0.05), flags=flags)
 
 
-@pytest.mark.parametrize("flags", [0, 4, 8, 16], ids=["levels", "fused", "levels-simt", "cherry"])
+@pytest.mark.parametrize("flags", [0, 4, 8, 64], ids=["levels", "fused", "levels-simt", "nocherry"])
 @pytest.mark.parametrize("topology", ["random", "caterpillar", "balanced"])
 def test_topologies_with_rescaling(topology, flags):
     from torchtree_b200.synthetic import make_problem

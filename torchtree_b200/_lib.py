@@ -19,6 +19,7 @@ TTB2_FLAG_FUSED = 4
 TTB2_FLAG_NO_MMA = 8
 TTB2_FLAG_CHERRY = 16
 TTB2_FLAG_NO_GRAPH = 32
+TTB2_FLAG_NO_CHERRY = 64
 
 
 class Ttb2Config(ctypes.Structure):

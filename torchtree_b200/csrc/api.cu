@@ -634,6 +634,7 @@ void ttb2_destroy(ttb2_engine* engine) {
   dev_free(e.streamF); dev_free(e.streamB);
   dev_free(e.chunkBase); dev_free(e.chunkCount);
   dev_free(e.cherryIdx); dev_free(e.cherryInfo); dev_free(e.cherryVec); dev_free(e.cherryExp);
+  dev_free(e.cherryCode);
   for (int j = 0; j < 8; ++j)
     if (e.ev[j]) cudaEventDestroy(e.ev[j]);
   drop_graphs(e);

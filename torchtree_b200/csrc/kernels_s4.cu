@@ -782,6 +782,7 @@ struct CherryArgs {
   const int* info;     // [n][3] (left tip, right tip, node)
   const double* vec;   // [D][n][K][CC][4]
   const int* exps;     // [D][n][CC]
+  const uint8_t* code; // [n][Npad] pair code of every pattern
   int n;               // number of cherries (0 = fusion off)
   int CC;              // C * C
 };
@@ -835,6 +836,18 @@ cherry_expo_kernel(const int* __restrict__ info, const int* __restrict__ exps,
   const int tipL = info[c * 3], tipR = info[c * 3 + 1], node = info[c * 3 + 2];
   const int pc = (int)tips[(size_t)tipL * Npad + i] * C + (int)tips[(size_t)tipR * Npad + i];
   expo[((size_t)d * (T - 1) + (node - T)) * Npad + i] = (int16_t)exps[((size_t)d * n + c) * (C * C) + pc];
+}
+
+// pair code of every pattern (static: built once per topology)
+__global__ void __launch_bounds__(256)
+cherry_code_kernel(const int* __restrict__ info, const uint8_t* __restrict__ tips,
+                   uint8_t* __restrict__ code, int C, int Npad) {
+  const int c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  const int tipL = info[c * 3], tipR = info[c * 3 + 1];
+  code[(size_t)c * Npad + i] =
+      (uint8_t)((int)tips[(size_t)tipL * Npad + i] * C + (int)tips[(size_t)tipR * Npad + i]);
 }
 
 // child kinds
@@ -904,19 +917,13 @@ fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restri
   build_child_table_c<K>(tabL, matsD + (size_t)op.left * K * 16, kindL, codeP, C, cvL, ch.CC, NC);
   build_child_table_c<K>(tabR, matsD + (size_t)op.right * K * 16, kindR, codeP, C, cvR, ch.CC, NC);
   __syncthreads();
-  // tip rows whose bytes form the child's symbol code
-  const uint8_t* l0 = nullptr; const uint8_t* l1 = nullptr;
-  const uint8_t* r0 = nullptr; const uint8_t* r1 = nullptr;
+  // byte row holding the child's symbol code (tip code, or pair code of a cherry)
+  const uint8_t* l0 = nullptr;
+  const uint8_t* r0 = nullptr;
   if (kindL == KIND_TIP) l0 = tips + (size_t)op.left * Npad;
-  if (kindL == KIND_CHERRY) {
-    l0 = tips + (size_t)ch.info[cidxL * 3] * Npad;
-    l1 = tips + (size_t)ch.info[cidxL * 3 + 1] * Npad;
-  }
+  if (kindL == KIND_CHERRY) l0 = ch.code + (size_t)cidxL * Npad;
   if (kindR == KIND_TIP) r0 = tips + (size_t)op.right * Npad;
-  if (kindR == KIND_CHERRY) {
-    r0 = tips + (size_t)ch.info[cidxR * 3] * Npad;
-    r1 = tips + (size_t)ch.info[cidxR * 3 + 1] * Npad;
-  }
+  if (kindR == KIND_CHERRY) r0 = ch.code + (size_t)cidxR * Npad;
 
   const size_t nodeStride = (size_t)K * Npad * 4;
   double* base = partials + (size_t)d * I * nodeStride;
@@ -933,7 +940,6 @@ fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restri
       for (int k = 0; k < K; ++k) a[k] = ldg4(p + (size_t)k * Npad * 4);
     } else {
       codeL = l0[i];
-      if (kindL == KIND_CHERRY) codeL = codeL * C + l1[i];
     }
     if (kindR == KIND_STORED) {
       const double* p = base + (size_t)(op.right - T) * nodeStride + (size_t)i * 4;
@@ -941,7 +947,6 @@ fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restri
       for (int k = 0; k < K; ++k) b[k] = ldg4(p + (size_t)k * Npad * 4);
     } else {
       codeR = r0[i];
-      if (kindR == KIND_CHERRY) codeR = codeR * C + r1[i];
     }
     V4 out[K];
     double m = 0.0;
@@ -1206,6 +1211,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// A child is STORED (its vector is bulk-copied), a TIP (vector = codeP[tip code]) or, with
+// cherry tabulation on, a CHERRY (vector = cherryVec[pair code]; it still receives q^ and
+// has its exponents in `expo`).
 template <int STAGES, int MINBLOCKS>
 __global__ void __launch_bounds__(BWDF_THREADS, MINBLOCKS)
 bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
@@ -1213,22 +1221,29 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
                 const double* __restrict__ codeP, const double* __restrict__ partials,
                 const int16_t* __restrict__ expo, const double* __restrict__ weights,
                 double* __restrict__ pre, double* __restrict__ gpart,
-                const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
-                int C, int B, int K, int chunkPatterns, int nChunk) {
+                const int* __restrict__ chunkBase, size_t chunkTotal, CherryArgs ch, int T,
+                int Npad, int C, int B, int K, int chunkPatterns, int nChunk) {
   extern __shared__ __align__(128) double sm[];
-  // sm: slots[warps][STAGES][448] | red[warps][32] | cp[C][4] | mbarriers[warps][STAGES]
+  // sm: slots[warps][STAGES][448] | red[warps][32] | cp[C][4] | vecL[CC][4] vecR[CC][4]
+  //     | mbarriers[warps][STAGES]
   constexpr int NW = BWDF_THREADS / 32;
   double* slots = sm;
   double* red = slots + NW * STAGES * BWDT_SLOT;
   double* cp = red + NW * 32;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cp + C * 4);
+  double* vecL = cp + C * 4;
+  double* vecR = vecL + ch.CC * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vecR + ch.CC * 4);
 
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
   const NodeOp op = ops[opBegin + nodeSlot];
   const int d = blockIdx.z;
   const int I = T - 1;
-  const bool tipL = op.left < T, tipR = op.right < T;
+  int cidxL, cidxR;
+  const int kindL = child_kind(op.left, T, ch, cidxL);
+  const int kindR = child_kind(op.right, T, ch, cidxR);
+  const bool storedL = kindL == KIND_STORED, storedR = kindR == KIND_STORED;
+  const bool tipL = kindL == KIND_TIP, tipR = kindR == KIND_TIP;
   const double* matsD = mats + (size_t)d * B * K * 16;
   const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
   const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
@@ -1241,6 +1256,14 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   }
   if (tipL || tipR)
     for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
+  if (kindL == KIND_CHERRY) {
+    const double* src = ch.vec + (((size_t)d * ch.n + cidxL) * K + k) * ch.CC * 4;
+    for (int j = threadIdx.x; j < ch.CC * 4; j += blockDim.x) vecL[j] = src[j];
+  }
+  if (kindR == KIND_CHERRY) {
+    const double* src = ch.vec + (((size_t)d * ch.n + cidxR) * K + k) * ch.CC * 4;
+    for (int j = threadIdx.x; j < ch.CC * 4; j += blockDim.x) vecR[j] = src[j];
+  }
   __syncthreads();
 
   const int p = lane >> 2, c = lane & 3;
@@ -1261,8 +1284,8 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   const size_t drawBase = (size_t)d * I * nodeStride;
   const size_t kOff = (size_t)k * Npad * 4;
   const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
-  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
-  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
+  const double* pl = storedL ? partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff : nullptr;
+  const double* prr = storedR ? partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff : nullptr;
   const int mine = rside ? op.right : op.left;
   const bool store = mine >= T;
   double* qc = store ? pre + drawBase + (size_t)(mine - T) * nodeStride + kOff : nullptr;
@@ -1270,6 +1293,12 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   // the one 16-byte piece of per-pattern side data this lane copies per block
   const char* sideSrc = nullptr;   // source at pattern 0
   int sideDst = 0, sideScale = 0;  // byte offset in the slot; source bytes per pattern
+  const uint8_t* rowL = tipL ? tips + (size_t)op.left * Npad
+                              : (storedL ? nullptr : ch.code + (size_t)cidxL * Npad);
+  const uint8_t* rowR = tipR ? tips + (size_t)op.right * Npad
+                              : (storedR ? nullptr : ch.code + (size_t)cidxR * Npad);
+  const double* tabL = tipL ? cp : vecL;   // coded child: vector of a code
+  const double* tabR = tipR ? cp : vecR;
   if (lane < 16) {
     sideSrc = reinterpret_cast<const char*>(weights) + lane * 16;
     sideDst = BWDT_W * 8 + lane * 16; sideScale = 8;
@@ -1280,10 +1309,10 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
     if (!tipR) sideSrc = reinterpret_cast<const char*>(expo + ((size_t)d * I + (op.right - T)) * Npad) + (lane - 20) * 16;
     sideDst = BWDT_ER + (lane - 20) * 16; sideScale = 2;
   } else if (lane < 26) {
-    if (tipL) sideSrc = reinterpret_cast<const char*>(tips + (size_t)op.left * Npad) + (lane - 24) * 16;
+    if (rowL) sideSrc = reinterpret_cast<const char*>(rowL) + (lane - 24) * 16;
     sideDst = BWDT_CL + (lane - 24) * 16; sideScale = 1;
   } else if (lane < 28) {
-    if (tipR) sideSrc = reinterpret_cast<const char*>(tips + (size_t)op.right * Npad) + (lane - 26) * 16;
+    if (rowR) sideSrc = reinterpret_cast<const char*>(rowR) + (lane - 26) * 16;
     sideDst = BWDT_CR + (lane - 26) * 16; sideScale = 1;
   }
 
@@ -1300,7 +1329,7 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   const int nb = first < end ? (end - first + BWDF_THREADS - 1) / BWDF_THREADS : 0;
   double* mySlots = slots + warp * STAGES * BWDT_SLOT;
   const uint32_t myBars = smem_u32(bars + warp * STAGES);
-  const uint32_t txBytes = 1024u + (tipL ? 0u : 1024u) + (tipR ? 0u : 1024u);
+  const uint32_t txBytes = 1024u + (storedL ? 1024u : 0u) + (storedR ? 1024u : 0u);
 
   // all lanes; exactly one cp.async group is committed per call (possibly empty)
   auto issue = [&](int blk) {
@@ -1314,8 +1343,8 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
         const uint32_t bar = myBars + st * 8;
         mbar_expect_tx(bar, txBytes);
         bulk_g2s(dst, qn + off, 1024u, bar);
-        if (!tipL) bulk_g2s(dst + 1024u, pl + off, 1024u, bar);
-        if (!tipR) bulk_g2s(dst + 2048u, prr + off, 1024u, bar);
+        if (storedL) bulk_g2s(dst + 1024u, pl + off, 1024u, bar);
+        if (storedR) bulk_g2s(dst + 2048u, prr + off, 1024u, bar);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1337,10 +1366,10 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
       const int j = t * 8 + p;
       const int i = base + j;
       const double2 q = *reinterpret_cast<const double2*>(slot + j * 4 + s0);
-      const double al = tipL ? cp[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CL)[j] * 4 + c]
-                             : slot[128 + t * 32 + lane];
-      const double ar = tipR ? cp[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CR)[j] * 4 + c]
-                             : slot[256 + t * 32 + lane];
+      const double al = storedL ? slot[128 + t * 32 + lane]
+                                : tabL[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CL)[j] * 4 + c];
+      const double ar = storedR ? slot[256 + t * 32 + lane]
+                                : tabR[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CR)[j] * 4 + c];
       const double w = slot[BWDT_W + j];
       double u0 = 0.0, u1 = 0.0;
       dmma884(u0, u1, al, b1);
@@ -1746,6 +1775,7 @@ CherryArgs cherry_args(const Engine& e) {
   ch.info = e.cherryInfo;
   ch.vec = e.cherryVec;
   ch.exps = e.cherryExp;
+  ch.code = e.cherryCode;
   ch.n = e.cherryOn ? e.nCherry : 0;
   ch.CC = e.cherryOn ? e.dm.C * e.dm.C : 0;
   return ch;
@@ -1793,7 +1823,7 @@ int s4_build_cherries(Engine& e) {
   const Dims& m = e.dm;
   e.cherryOn = false;
   e.nCherry = 0;
-  const bool allowed = e.spec4 && (e.cfg.flags & TTB2_FLAG_CHERRY) &&
+  const bool allowed = e.spec4 && !(e.cfg.flags & TTB2_FLAG_NO_CHERRY) &&
                        !(e.cfg.flags & TTB2_FLAG_NO_MMA) && m.C * m.C <= 64 &&
                        m.T > 2 && (m.K <= 6 || m.K == 8);
   if (!allowed) return TTB2_OK;
@@ -1821,6 +1851,14 @@ int s4_build_cherries(Engine& e) {
   TTB2_CUDA_CHECK(cudaMemcpy(e.cherryIdx, idx.data(), m.I * sizeof(int), cudaMemcpyHostToDevice));
   TTB2_CUDA_CHECK(cudaMemcpy(e.cherryInfo, info.data(), info.size() * sizeof(int),
                              cudaMemcpyHostToDevice));
+  if (e.cherryCode) { cudaFree(e.cherryCode); e.cherryCode = nullptr; }
+  TTB2_CUDA_CHECK(cudaMalloc((void**)&e.cherryCode, (size_t)e.nCherry * m.Npad));
+  {
+    dim3 grid((m.Npad + 255) / 256, e.nCherry);
+    cherry_code_kernel<<<grid, 256, 0, e.stream>>>(e.cherryInfo, e.tips, e.cherryCode, m.C, m.Npad);
+    TTB2_CUDA_CHECK(cudaGetLastError());
+    TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  }
   e.cherryOn = true;
   return TTB2_OK;
 }
@@ -1966,7 +2004,7 @@ int s4_backward(Engine& e, int draws) {
         bwd4_tips_kernel<<<grid, BWD_THREADS, smemT, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre, e.gpart,
             e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      } else if (useMma && e.cherryOn) {
+      } else if (useMma && e.cherryOn && legacy) {
         const CherryArgs ch = cherry_args(e);
         const int NC = ch.CC > m.C ? ch.CC : m.C;
         const size_t smemC = (32 + 4 * (size_t)NC * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) *
@@ -1977,19 +2015,21 @@ int s4_backward(Engine& e, int draws) {
             nChunk);
       } else if (useMma && !legacy) {
         constexpr int ST = 3, MB = 5, NWF = BWDF_THREADS / 32;
-        auto smemOf = [&](int codes) {
-          return ((size_t)NWF * ST * BWDT_SLOT + NWF * 32 + (size_t)codes * 4) * sizeof(double) +
+        const CherryArgs ch = cherry_args(e);
+        auto smemOf = [&](int codes, int pairCodes) {
+          return ((size_t)NWF * ST * BWDT_SLOT + NWF * 32 + (size_t)codes * 4 +
+                  2 * (size_t)pairCodes * 4) * sizeof(double) +
                  (size_t)NWF * ST * sizeof(uint64_t);
         };
         static bool attr = false;
-        if (!attr) {
+        if (!attr) {   // largest code table (uint8 codes); cherries need C * C <= 64
           cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smemOf(256));
+                               (int)smemOf(256, 64));
           attr = true;
         }
-        launch_level(bwd4_tma_kernel<ST, MB>, grid, BWDF_THREADS, smemOf(m.C), e.stream, pdl,
+        launch_level(bwd4_tma_kernel<ST, MB>, grid, BWDF_THREADS, smemOf(m.C, ch.CC), e.stream, pdl,
                      e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
-                     e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
+                     e.pre, e.gpart, e.chunkBase, e.chunkTotal, ch, m.T, m.Npad, m.C, m.B, m.K,
                      chunkPatterns, nChunk);
       } else if (useMma) {
         bwd4_mma_kernel<<<grid, BWDM_THREADS, smem, e.stream>>>(
