@@ -825,17 +825,28 @@ cherry_table_kernel(const int* __restrict__ info, const double* __restrict__ mat
 }
 
 // per-pattern scale exponents of the cherries (2 bytes per pattern; the only
-// per-pattern data a cherry keeps -- read by the root sum and the pre-order pass)
-__global__ void __launch_bounds__(256)
+// per-pattern data a cherry keeps -- read by the root sum and the pre-order pass).
+// A thread translates 16 consecutive pair codes (one 16-byte load, 32 bytes stored).
+__global__ void __launch_bounds__(128)
 cherry_expo_kernel(const int* __restrict__ info, const int* __restrict__ exps,
-                   const uint8_t* __restrict__ tips, int16_t* __restrict__ expo, int n, int C,
+                   const uint8_t* __restrict__ code, int16_t* __restrict__ expo, int n, int CC,
                    int T, int Npad) {
+  __shared__ int16_t tab[256];
   const int c = blockIdx.y, d = blockIdx.z;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = threadIdx.x; j < CC; j += blockDim.x)
+    tab[j] = (int16_t)exps[((size_t)d * n + c) * CC + j];
+  __syncthreads();
+  const int node = info[c * 3 + 2];
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16;   // Npad is a multiple of 32
   if (i >= Npad) return;
-  const int tipL = info[c * 3], tipR = info[c * 3 + 1], node = info[c * 3 + 2];
-  const int pc = (int)tips[(size_t)tipL * Npad + i] * C + (int)tips[(size_t)tipR * Npad + i];
-  expo[((size_t)d * (T - 1) + (node - T)) * Npad + i] = (int16_t)exps[((size_t)d * n + c) * (C * C) + pc];
+  const uint4 in = *reinterpret_cast<const uint4*>(code + (size_t)c * Npad + i);
+  const unsigned words[4] = {in.x, in.y, in.z, in.w};
+  __align__(16) int16_t out[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = tab[(words[j >> 2] >> ((j & 3) * 8)) & 0xff];
+  int16_t* dst = expo + ((size_t)d * (T - 1) + (node - T)) * Npad + i;
+  reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(out)[0];
+  reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(out)[1];
 }
 
 // pair code of every pattern (static: built once per topology)
@@ -917,6 +928,7 @@ fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restri
   build_child_table_c<K>(tabL, matsD + (size_t)op.left * K * 16, kindL, codeP, C, cvL, ch.CC, NC);
   build_child_table_c<K>(tabR, matsD + (size_t)op.right * K * 16, kindR, codeP, C, cvR, ch.CC, NC);
   __syncthreads();
+  pdl_wait_then_trigger();
   // byte row holding the child's symbol code (tip code, or pair code of a cherry)
   const uint8_t* l0 = nullptr;
   const uint8_t* r0 = nullptr;
@@ -1787,15 +1799,15 @@ bool pdl_enabled() {
 }
 
 template <int K>
-void launch_fwdc(Engine& e, int draws, int opBegin, int count, int ppt) {
+void launch_fwdc(Engine& e, int draws, int opBegin, int count, int ppt, bool pdl) {
   const Dims& m = e.dm;
   const CherryArgs ch = cherry_args(e);
   const int NC = ch.CC > m.C ? ch.CC : m.C;
   const size_t smem = 2 * (size_t)K * (NC > 4 ? NC : 4) * 4 * sizeof(double);
   const int per = FWD_THREADS * ppt;
   dim3 grid((m.Npad + per - 1) / per, count, draws);
-  fwd4c_kernel<K><<<grid, FWD_THREADS, smem, e.stream>>>(
-      e.ops, opBegin, e.mats, e.tips, e.codeP, e.partials, e.expo, ch, m.T, m.Npad, m.C, m.B, ppt);
+  launch_level(fwd4c_kernel<K>, grid, FWD_THREADS, smem, e.stream, pdl, e.ops, opBegin, e.mats,
+               e.tips, e.codeP, e.partials, e.expo, ch, m.T, m.Npad, m.C, m.B, ppt);
 }
 
 template <int K>
@@ -1873,9 +1885,9 @@ int s4_forward(Engine& e, int draws) {
     cherry_table_kernel<<<grid, 128, 2 * (size_t)m.K * m.C * 4 * sizeof(double), e.stream>>>(
         e.cherryInfo, e.mats, e.codeP, e.cherryVec, e.cherryExp, e.nCherry, m.C, m.B, m.K);
     ++e.launches;
-    dim3 grid2((m.Npad + 255) / 256, e.nCherry, draws);
-    cherry_expo_kernel<<<grid2, 256, 0, e.stream>>>(e.cherryInfo, e.cherryExp, e.tips, e.expo,
-                                                    e.nCherry, m.C, m.T, m.Npad);
+    dim3 grid2((m.Npad / 16 + 127) / 128, e.nCherry, draws);
+    cherry_expo_kernel<<<grid2, 128, 0, e.stream>>>(e.cherryInfo, e.cherryExp, e.cherryCode, e.expo,
+                                                    e.nCherry, m.C * m.C, m.T, m.Npad);
     ++e.launches;
   }
   for (int l = e.cherryOn ? 1 : 0; l < nLevels; ++l) {
@@ -1883,16 +1895,17 @@ int s4_forward(Engine& e, int draws) {
     const int count = e.levelOff[l + 1] - opBegin;
     const int ppt = fwd_patterns_per_thread(e, draws, count);
     if (e.cherryOn && (m.K <= 6 || m.K == 8)) {
+      const bool pdlc = l > 1 && pdl_enabled();   // the first level follows the cherry tables
       for (int done = 0; done < count; done += 65535) {
         const int c = (count - done) < 65535 ? (count - done) : 65535;
         switch (m.K) {
-          case 1: launch_fwdc<1>(e, draws, opBegin + done, c, ppt); break;
-          case 2: launch_fwdc<2>(e, draws, opBegin + done, c, ppt); break;
-          case 3: launch_fwdc<3>(e, draws, opBegin + done, c, ppt); break;
-          case 4: launch_fwdc<4>(e, draws, opBegin + done, c, ppt); break;
-          case 5: launch_fwdc<5>(e, draws, opBegin + done, c, ppt); break;
-          case 6: launch_fwdc<6>(e, draws, opBegin + done, c, ppt); break;
-          default: launch_fwdc<8>(e, draws, opBegin + done, c, ppt); break;
+          case 1: launch_fwdc<1>(e, draws, opBegin + done, c, ppt, pdlc); break;
+          case 2: launch_fwdc<2>(e, draws, opBegin + done, c, ppt, pdlc); break;
+          case 3: launch_fwdc<3>(e, draws, opBegin + done, c, ppt, pdlc); break;
+          case 4: launch_fwdc<4>(e, draws, opBegin + done, c, ppt, pdlc); break;
+          case 5: launch_fwdc<5>(e, draws, opBegin + done, c, ppt, pdlc); break;
+          case 6: launch_fwdc<6>(e, draws, opBegin + done, c, ppt, pdlc); break;
+          default: launch_fwdc<8>(e, draws, opBegin + done, c, ppt, pdlc); break;
         }
         ++e.launches;
       }
