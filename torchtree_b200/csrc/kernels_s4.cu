@@ -1215,7 +1215,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // slot (bytes): q^_n 1024 | p~_l 1024 | p~_r 1024 | w 256 | e_l 64 | e_r 64 | code_l 32 | code_r 32
-constexpr int BWDT_SLOT = 448;      // doubles per slot (3584 bytes)
+constexpr int BWDT_SLOT = 440;      // doubles per slot (3520 bytes)
 constexpr int BWDT_W = 384;         // double offset of the weights
 constexpr int BWDT_EL = 3328, BWDT_ER = 3392, BWDT_CL = 3456, BWDT_CR = 3488;  // byte offsets
 
@@ -1236,12 +1236,11 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
                 const int* __restrict__ chunkBase, size_t chunkTotal, CherryArgs ch, int T,
                 int Npad, int C, int B, int K, int chunkPatterns, int nChunk) {
   extern __shared__ __align__(128) double sm[];
-  // sm: slots[warps][STAGES][448] | red[warps][32] | cp[C][4] | vecL[CC][4] vecR[CC][4]
-  //     | mbarriers[warps][STAGES]
+  // sm: slots[warps][STAGES][440] | cp[C][4] | vecL[CC][4] vecR[CC][4] | mbarriers[warps][STAGES]
+  // (5 CTAs/SM need <= 45 KB each; the final reduction reuses the head of each warp's ring)
   constexpr int NW = BWDF_THREADS / 32;
   double* slots = sm;
-  double* red = slots + NW * STAGES * BWDT_SLOT;
-  double* cp = red + NW * 32;
+  double* cp = slots + NW * STAGES * BWDT_SLOT;
   double* vecL = cp + C * 4;
   double* vecR = vecL + ch.CC * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(vecR + ch.CC * 4);
@@ -1420,14 +1419,14 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (p == 0) red[warp * 32 + (rside ? 16 : 0) + (s0 + i) * 4 + (c ^ j)] = v;
+      if (p == 0) mySlots[(rside ? 16 : 0) + (s0 + i) * 4 + (c ^ j)] = v;
     }
   __syncthreads();
   if (threadIdx.x < 32) {
     const int child = threadIdx.x >> 4;
     double t = 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 32 + threadIdx.x];
+    for (int w2 = 0; w2 < NW; ++w2) t += slots[w2 * STAGES * BWDT_SLOT + threadIdx.x];
     const int branch = child ? op.right : op.left;
     gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
           (threadIdx.x & 15)] = t;
@@ -2030,7 +2029,7 @@ int s4_backward(Engine& e, int draws) {
         constexpr int ST = 3, MB = 5, NWF = BWDF_THREADS / 32;
         const CherryArgs ch = cherry_args(e);
         auto smemOf = [&](int codes, int pairCodes) {
-          return ((size_t)NWF * ST * BWDT_SLOT + NWF * 32 + (size_t)codes * 4 +
+          return ((size_t)NWF * ST * BWDT_SLOT + (size_t)codes * 4 +
                   2 * (size_t)pairCodes * 4) * sizeof(double) +
                  (size_t)NWF * ST * sizeof(uint64_t);
         };
