@@ -72,23 +72,39 @@ reduce_rows_kernel(const double* __restrict__ part, double* __restrict__ out, in
 }
 
 // dmat[d][b][k][e] = sum_chunk gpart[d][chunkBase[b] + k * chunkCount[b] + chunk][e]
-__global__ void gpart_reduce_kernel(const double* __restrict__ gpart,
-                                    const int* __restrict__ chunkBase,
-                                    const int* __restrict__ chunkCount,
-                                    double* __restrict__ dmat, size_t chunkTotal, int B, int K,
-                                    int SS, int draws) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)draws * B * K * SS) return;
-  const size_t item = idx / SS;
-  const int e = (int)(idx - item * SS);
+// One block per (d, b, k): GR_ROWS row groups stride over the chunks (the few branches
+// near the root have hundreds of chunks), then a fixed-order sum over the groups.
+constexpr int GR_THREADS = 256;
+
+__global__ void __launch_bounds__(GR_THREADS)
+gpart_reduce_kernel(const double* __restrict__ gpart, const int* __restrict__ chunkBase,
+                    const int* __restrict__ chunkCount, double* __restrict__ dmat,
+                    size_t chunkTotal, int B, int K, int SS) {
+  extern __shared__ double part[];   // [groups][SS]
+  const size_t item = blockIdx.x;
   const int k = (int)(item % K);
   const int b = (int)((item / K) % B);
   const size_t d = item / ((size_t)K * B);
   const int n = chunkCount[b];
-  const double* p = gpart + (d * chunkTotal + chunkBase[b] + (size_t)k * n) * SS + e;
-  double acc = 0.0;
-  for (int c = 0; c < n; ++c) acc += p[(size_t)c * SS];
-  dmat[idx] = acc;
+  const double* p = gpart + (d * chunkTotal + chunkBase[b] + (size_t)k * n) * SS;
+  // thread -> (element e, row group r); SS <= GR_THREADS uses GR_THREADS / SS groups
+  const int per = SS < GR_THREADS ? SS : GR_THREADS;
+  const int groups = SS < GR_THREADS ? GR_THREADS / SS : 1;
+  for (int e0 = 0; e0 < SS; e0 += per) {
+    const int e = e0 + (int)(threadIdx.x % per);
+    const int r = (int)(threadIdx.x / per);
+    double acc = 0.0;
+    if (r < groups && e < SS)
+      for (int c = r; c < n; c += groups) acc += p[(size_t)c * SS + e];
+    if (r < groups && e < SS) part[r * per + (e - e0)] = acc;
+    __syncthreads();
+    if (r == 0 && e < SS) {
+      double t = 0.0;
+      for (int g = 0; g < groups; ++g) t += part[g * per + (e - e0)];
+      dmat[item * SS + e] = t;
+    }
+    __syncthreads();
+  }
 }
 
 // out[d][j] = g[d] * in[d][j]
@@ -363,11 +379,8 @@ int small_gpart_reduce(Engine& e, int draws) {
   const Dims& m = e.dm;
   const size_t items = (size_t)draws * m.B * m.K;
   const int SS = m.S * m.S;
-  const size_t total = items * SS;
-  const int threads = 256;
-  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  gpart_reduce_kernel<<<blocks, threads, 0, e.stream>>>(e.gpart, e.chunkBase, e.chunkCount, e.dmat,
-                                                       e.chunkTotal, m.B, m.K, SS, draws);
+  gpart_reduce_kernel<<<(unsigned)items, GR_THREADS, GR_THREADS * sizeof(double), e.stream>>>(
+      e.gpart, e.chunkBase, e.chunkCount, e.dmat, e.chunkTotal, m.B, m.K, SS);
   ++e.launches;
   TTB2_CUDA_CHECK(cudaGetLastError());
   return TTB2_OK;
