@@ -102,6 +102,7 @@ struct Engine {
   int* cherryInfo = nullptr;    // [nCherry][3] (left tip, right tip, node)
   double* cherryVec = nullptr;  // [D][nCherry][K][C*C][4]
   int* cherryExp = nullptr;     // [D][nCherry][C*C]
+  bool smemAttrTma = false, smemAttrTips = false;  // opt-in shared-memory sizes set on this device
   uint8_t* cherryCode = nullptr;  // [nCherry][Npad] pair code = code(left tip) * C + code(right tip)
 
   // fused-traversal path (S = 4, eigen mode)

@@ -2000,11 +2000,11 @@ int s4_backward(Engine& e, int draws) {
                  (32 + 2 * (size_t)codes * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
                  (size_t)(BWD_THREADS / 32) * ST * sizeof(uint64_t) + (size_t)codes * sizeof(int);
         };
-        static bool attr = false;
-        if (!attr) {
-          cudaFuncSetAttribute(bwd4_tips_tma_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smemTips(256));
-          attr = true;
+        if (!e.smemAttrTips) {   // sized for the largest code table (uint8 codes)
+          TTB2_CUDA_CHECK(cudaFuncSetAttribute(bwd4_tips_tma_kernel<ST>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smemTips(256)));
+          e.smemAttrTips = true;
         }
         launch_level(bwd4_tips_tma_kernel<ST>, grid, BWD_THREADS, smemTips(m.C), e.stream, pdl,
                      e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre,
@@ -2033,11 +2033,11 @@ int s4_backward(Engine& e, int draws) {
                   2 * (size_t)pairCodes * 4) * sizeof(double) +
                  (size_t)NWF * ST * sizeof(uint64_t);
         };
-        static bool attr = false;
-        if (!attr) {   // largest code table (uint8 codes); cherries need C * C <= 64
-          cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smemOf(256, 64));
-          attr = true;
+        if (!e.smemAttrTma) {   // largest code table (uint8 codes); cherries need C * C <= 64
+          TTB2_CUDA_CHECK(cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smemOf(256, 64)));
+          e.smemAttrTma = true;
         }
         launch_level(bwd4_tma_kernel<ST, MB>, grid, BWDF_THREADS, smemOf(m.C, ch.CC), e.stream, pdl,
                      e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
