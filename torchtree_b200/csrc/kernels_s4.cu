@@ -398,7 +398,9 @@ root4_bwd_kernel(const double* __restrict__ partials, const int16_t* __restrict_
     invL = 1.0 / L;
     w = weights[i];
     const int e = expo[((size_t)d * I + rootInode) * Npad + i];
-    const double scale = invL * __hiloint2double((1023 - e) << 20, 0);
+    // zero-weight patterns (padding, or masked by the caller) get q^ = 0 here, so every
+    // pre-order quantity below the root is exactly 0 for them without further tests
+    const double scale = (w != 0.0) ? invL * __hiloint2double((1023 - e) << 20, 0) : 0.0;
     double* q = pre + ((size_t)d * I + rootInode) * nodeStride + (size_t)i * 4;
     for (int k = 0; k < K; ++k) {
       const double c = pr[k] * scale;
@@ -1394,11 +1396,10 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
         const double f = __hiloint2double((1023 - ex) << 20, 0);
         *reinterpret_cast<double2*>(qc + (size_t)i * 4 + s0) = make_double2(o0 * f, o1 * f);
       }
-      const bool live = w != 0.0;
-      const double own = live ? (rside ? ar : al) : 0.0;
-      const double oth = live ? (rside ? al : ar) : 0.0;
-      const double wm0 = live ? w * m0 : 0.0;
-      const double wm1 = live ? w * m1 : 0.0;
+      // (q^_n, hence m, is exactly 0 where w == 0: see root4_bwd_kernel)
+      const double own = rside ? ar : al;
+      const double oth = rside ? al : ar;
+      const double wm0 = w * m0, wm1 = w * m1;
       const double x1 = __shfl_xor_sync(0xffffffffu, own, 1);
       const double x2 = __shfl_xor_sync(0xffffffffu, oth, 2);
       const double x3 = __shfl_xor_sync(0xffffffffu, oth, 3);
