@@ -13,6 +13,7 @@
 // Layout in HBM is the generic one ([draw][inode][k][s][pattern], kernels_gen.cu)
 // and the root / reduction kernels are shared with it.
 #include <climits>
+#include <cstdlib>
 
 #include "engine.cuh"
 
@@ -531,9 +532,13 @@ int gmma_forward2(Engine& e, int draws) {
   const size_t smem = gm_fwd2_smem(m);
   const int MT = gm_shape(m.S).Sp / 8;
   const int ntg = MT >= 8 ? 4 : (MT >= 4 ? 2 : 1);
-  const int nw = MT >= 5 ? 8 : 4;  // small state spaces: fewer, busier warps per CTA
+  int nw = MT >= 5 ? 8 : 4;
+  // 20 states: 8 warps x 2 pattern tiles per A fragment measured best on config 4
+  // (<1,4>: 26.6 ms, <1,8>: 22.5, <2,4>: 26.8, <2,8>: 21.6 per evaluation)
+  if (m.S == 20) nw = 8;
+  // 61 states: <2,8>, <4,16>, <2,16> all measured within 2 % of <4,8> on config 5
   auto kern = m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
-              : m.S == 20 ? gm_fwd2_kernel<1, 4, 20>
+              : m.S == 20 ? gm_fwd2_kernel<2, 8, 20>
               : ntg == 4  ? gm_fwd2_kernel<4, 8, 0>
               : nw == 8   ? gm_fwd2_kernel<2, 8, 0>
               : ntg == 2  ? gm_fwd2_kernel<2, 4, 0>
@@ -591,9 +596,13 @@ int gmma_backward2(Engine& e, int draws) {
   const size_t smem = gm_bwd2_smem(m);
   const int MT = gm_shape(m.S).Sp / 8;
   const int ntg = MT >= 8 ? 4 : (MT >= 4 ? 2 : 1);
-  const int nw = MT >= 5 ? 8 : 4;
+  int nw = MT >= 5 ? 8 : 4;
+  // 20 states: 8 warps x 2 pattern tiles per A fragment measured best on config 4
+  // (<1,4>: 26.6 ms, <1,8>: 22.5, <2,4>: 26.8, <2,8>: 21.6 per evaluation)
+  if (m.S == 20) nw = 8;
+  // 61 states: <2,8>, <4,16>, <2,16> all measured within 2 % of <4,8> on config 5
   auto kern = m.S == 61 ? gm_bwd2_kernel<4, 8, 61>
-              : m.S == 20 ? gm_bwd2_kernel<1, 4, 20>
+              : m.S == 20 ? gm_bwd2_kernel<2, 8, 20>
               : ntg == 4  ? gm_bwd2_kernel<4, 8, 0>
               : nw == 8   ? gm_bwd2_kernel<2, 8, 0>
               : ntg == 2  ? gm_bwd2_kernel<2, 4, 0>
