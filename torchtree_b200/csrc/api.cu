@@ -132,7 +132,7 @@ int ensure_grad_buffers(Engine& e, int draws) {
   if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)e.cfg.max_draws * (m.K + m.S))))
     return rc;
   const int planBefore = e.chunkPlanDraws;
-  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, e.spec4 ? 32 : 8))) return rc;
+  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, (e.spec4 || e.dm.S <= 32) ? 32 : 16))) return rc;
   if (planBefore != e.chunkPlanDraws) drop_graphs(e);
   const size_t need = planned_gpart_doubles(e, draws);
   if (need > e.gpartCap) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -218,5 +219,39 @@ int fused_root(Engine& e, int draws);
 int fused_backward(Engine& e, int draws, bool needQ);
 size_t fused_gspart_doubles(const Engine& e, int draws);
 int small_fused_outputs(Engine& e, int draws, bool needQ);
+
+// Programmatic dependent launch: a level kernel launched with the
+// programmaticStreamSerialization attribute may start (and run its prologue: tables,
+// matrix fragments, barrier setup -- nothing the previous level wrote) while the
+// previous level's last CTAs drain; pdl_wait() returns once that grid has completed
+// and its writes are visible.  The trigger follows the wait, so a kernel can only
+// overlap its immediate predecessor.
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_level(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem,
+                         cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+
+// TTB2_NO_PDL=1 launches every level kernel with ordinary stream ordering (A/B runs)
+inline bool pdl_enabled() {
+  static const bool on = getenv("TTB2_NO_PDL") == nullptr;
+  return on;
+}
 
 }  // namespace ttb2

@@ -165,6 +165,7 @@ gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
 
   gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
   gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+  pdl_wait_then_trigger();   // the matrices come from pmatrix; the tiles below from the previous level
 
   const int begin = blockIdx.x * chunkPatterns;
   int end = begin + chunkPatterns;
@@ -358,6 +359,7 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   const int MT = g.Sp / 8, KT = g.Kp / 4, KTr = g.Sp / 4;
   gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
   gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+  pdl_wait_then_trigger();
 
   // persistent G accumulators: items (child, mt, mt2) dealt round-robin to the warps
   double acc[GM_MAXACC][2];
@@ -518,7 +520,9 @@ size_t gmma_expo_elems(const Engine& e) {
 // chunk of patterns per post-order CTA (enough CTAs to fill the GPU, long-lived otherwise)
 static int gm_fwd_chunk(const Engine& e, int draws, int count) {
   const Dims& m = e.dm;
-  const long target = (long)e.smCount * 8;
+  // staging the two S x S matrices is the per-CTA fixed cost: many short CTAs for small
+  // alphabets (config 4, S=20: 32/SM best), few long ones for large (config 5, S=61: 8/SM)
+  const long target = (long)e.smCount * (m.S <= 32 ? 32 : 8);
   long chunks = (target + (long)count * m.K * draws - 1) / ((long)count * m.K * draws);
   const long maxChunks = m.Npad / GM_TP;
   if (chunks > maxChunks) chunks = maxChunks;
@@ -556,9 +560,9 @@ int gmma_forward2(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      kern<<<grid, nw * 32, smem, e.stream>>>(e.ops, opBegin + done, e.mats, e.tips, e.codeP,
-                                              e.partials, e.expoK, m.T, m.Npad, m.B, m.K, m.S,
-                                              chunkPatterns);
+      launch_level(kern, grid, nw * 32, smem, e.stream, l > 0 && pdl_enabled(), e.ops,
+                   opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad, m.B,
+                   m.K, m.S, chunkPatterns);
       ++e.launches;
     }
   }
@@ -621,9 +625,10 @@ int gmma_backward2(Engine& e, int draws) {
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      kern<<<grid, nw * 32, smem, e.stream>>>(
-          e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, e.weights, e.pre,
-          e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B, m.K, m.S, chunkPatterns, nChunk);
+      launch_level(kern, grid, nw * 32, smem, e.stream, l < nLevels - 1 && pdl_enabled(), e.ops,
+                   opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, e.weights, e.pre,
+                   e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B, m.K, m.S, chunkPatterns,
+                   nChunk);
       ++e.launches;
     }
   }

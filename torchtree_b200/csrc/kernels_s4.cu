@@ -29,33 +29,6 @@ struct __align__(32) V4 {
   double x, y, z, w;
 };
 
-// Programmatic dependent launch: a level kernel launched with the
-// programmaticStreamSerialization attribute may start (and run its prologue: tables,
-// matrix fragments, barrier setup -- nothing the previous level wrote) while the
-// previous level's last CTAs drain; pdl_wait() returns once that grid has completed
-// and its writes are visible.  The trigger follows the wait, so a kernel can only
-// overlap its immediate predecessor.
-__device__ __forceinline__ void pdl_wait_then_trigger() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
-template <typename... KArgs, typename... Args>
-cudaError_t launch_level(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem,
-                         cudaStream_t stream, bool pdl, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 __device__ __forceinline__ V4 ldg4(const double* p) {
   V4 v;
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -1791,11 +1764,6 @@ CherryArgs cherry_args(const Engine& e) {
   ch.n = e.cherryOn ? e.nCherry : 0;
   ch.CC = e.cherryOn ? e.dm.C * e.dm.C : 0;
   return ch;
-}
-
-bool pdl_enabled() {
-  static const bool on = getenv("TTB2_NO_PDL") == nullptr;
-  return on;
 }
 
 template <int K>
