@@ -132,7 +132,12 @@ int ensure_grad_buffers(Engine& e, int draws) {
   if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)e.cfg.max_draws * (m.K + m.S))))
     return rc;
   const int planBefore = e.chunkPlanDraws;
-  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, (e.spec4 || e.dm.S <= 32) ? 32 : 16))) return rc;
+  // CTAs per SM aimed at per pre-order launch: many short CTAs shorten the last wave of the
+  // big levels, but a CTA needs a few hundred patterns to amortise its prologue -- measured
+  // optimum on the 1000-taxon problem: 8 at 12.5k patterns, 16 at 25k, 32 from 50k up
+  int perSm = e.dm.S <= 32 ? 32 : 16;
+  if (e.spec4) perSm = e.dm.Npad < 20000 ? 8 : (e.dm.Npad < 40000 ? 16 : 32);
+  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, perSm))) return rc;
   if (planBefore != e.chunkPlanDraws) drop_graphs(e);
   const size_t need = planned_gpart_doubles(e, draws);
   if (need > e.gpartCap) {
