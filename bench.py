@@ -135,7 +135,34 @@ def build_problem(args, lo=0, hi=None, patterns=None):
     return prob
 
 
-def cpu_baseline(args, threads=None):
+def engine_vs_oracle(prob, ref, device):
+    """Parity gate of the run: the engine on the CPU baseline's own sample
+    against the oracle's result -- lnL rel <= 1e-10, gradients rel <= 1e-8."""
+    from torchtree_b200 import Engine, reversible_eigensystem
+
+    eng = Engine(prob.tip_states, prob.weights, prob.postorder, 4, prob.category_count,
+                 max_draws=1, device=device)
+    q, f = torch.tensor(prob.q_matrix), torch.tensor(prob.freqs)
+    evec, ivec, evals = reversible_eigensystem(q, f)
+    lnl = eng.loglik_eigen(torch.tensor(prob.branch_lengths), torch.tensor(prob.site_rates),
+                           torch.tensor(prob.site_props), evec, ivec, evals, f)
+    g = eng.grad_eigen()
+    eng.close()
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    out = {"lnL_rel_err": rel(lnl.cpu().numpy(), ref["lnL"]),
+           "branch_grad_rel_err": rel(g["branch_lengths"].cpu().numpy(), ref["branch_lengths"]),
+           "site_rate_grad_rel_err": rel(g["site_rates"].cpu().numpy(), ref["site_rates"]),
+           "root_freq_grad_rel_err": rel(g["freqs"].cpu().numpy(), ref["freqs"])}
+    out["ok"] = bool(out["lnL_rel_err"] <= 1e-10 and all(
+        v <= 1e-8 for k, v in out.items() if k.endswith("grad_rel_err")))
+    return out
+
+
+def cpu_baseline(args, threads=None, check_device=None):
     """The oracle port (torch CPU ops + autograd, like the reference) on a bounded
     sample of the same workload: same tree and model, fewer patterns."""
     from oracle import treelik as orc
@@ -143,14 +170,16 @@ def cpu_baseline(args, threads=None):
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     prob = build_problem(args, patterns=args.cpu_patterns)
-    orc.evaluate(prob, want_grad=True)  # warm-up
+    ref = orc.evaluate(prob, want_grad=True)  # warm-up
     times = []
     for _ in range(2):
         t0 = time.perf_counter()
         orc.evaluate(prob, want_grad=True)
         times.append(time.perf_counter() - t0)
     best = min(times)
+    parity = engine_vs_oracle(prob, ref, check_device) if check_device is not None else None
     return {
+        "parity_on_sample": parity,
         "value": prob.units / best,
         "unit": UNIT,
         "cores": threads,
@@ -392,7 +421,10 @@ def main():
             "device_bytes": eng.device_bytes,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+            line["cpu_baseline"] = cpu_baseline(args, check_device=local_rank)
+            if not line["cpu_baseline"]["parity_on_sample"]["ok"]:
+                raise SystemExit("bench.py: engine and oracle disagree on the baseline sample: %r"
+                                 % (line["cpu_baseline"]["parity_on_sample"],))
         print(json.dumps(line))
     eng.close()
     if world > 1:
