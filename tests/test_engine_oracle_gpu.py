@@ -309,3 +309,90 @@ def test_many_categories(S, K):
     from torchtree_b200.synthetic import make_problem
 
     _check(make_problem(9, 70, S, K, seed=61, weibull_shape=1.5), q_rtol=1e-6)
+
+
+def _with_code_table(prob, C, rng):
+    """Give the tips an ambiguity alphabet of C codes: unit vectors, all-ones, then random
+    0/1 masks (as `use_ambiguities` produces, datatype.py:78-97)."""
+    S = prob.state_count
+    table = [np.eye(S)[s] for s in range(S)] + [np.ones(S)]
+    while len(table) < C:
+        m = (rng.random(S) < 0.5).astype(np.float64)
+        if m.sum() >= 2 and not any(np.array_equal(m, t) for t in table):
+            table.append(m)
+    prob.code_partials = np.array(table)
+    extra = rng.integers(S, C, size=prob.tip_states.shape)
+    use = rng.random(prob.tip_states.shape) < 0.15
+    prob.tip_states = np.where(use, extra, prob.tip_states).astype(np.uint8)
+    return prob
+
+
+@pytest.mark.parametrize("flags", [0, 64], ids=["levels", "nocherry"])
+@pytest.mark.parametrize("C", [6, 8, 9, 15])   # 15 = every 0/1 mask with >= 2 states + the unit vectors
+def test_ambiguity_code_tables(C, flags):
+    """Pair alphabets on both sides of the cherry-tabulation limit (C*C <= 64)."""
+    from torchtree_b200.synthetic import make_problem
+
+    rng = np.random.default_rng(C)
+    prob = _with_code_table(make_problem(41, 200, 4, 4, seed=40 + C), C, rng)
+    _check(prob, flags=flags)
+
+
+def test_zero_weight_patterns_do_not_contribute():
+    """Patterns masked with weight 0 (SRD06-style partitions, padding) drop out of lnL and
+    of every gradient."""
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(24, 160, 4, 4, seed=77)
+    masked = np.arange(0, 160, 7)
+    prob.weights[masked] = 0.0
+    eng, got = _run(prob)
+    eng.close()
+    keep = np.setdiff1d(np.arange(160), masked)
+    sub = make_problem(24, 160, 4, 4, seed=77)
+    sub.tip_states = np.ascontiguousarray(sub.tip_states[:, keep])
+    sub.weights = np.ascontiguousarray(sub.weights[keep])
+    sub.pattern_count = len(keep)
+    eng2, want = _run(sub)
+    eng2.close()
+    assert_lnl_close(got["lnL"], want["lnL"])
+    for k in ("branch_lengths", "site_rates", "props", "freqs", "q"):
+        assert_grad_close(got[k], want[k], what=k)
+    # a masked pattern the tree can hardly explain (one tip differs from all others on very
+    # short branches) leaves everything finite
+    prob.branch_lengths[:] = 1e-6
+    prob.tip_states[0, masked[0]] = 0
+    prob.tip_states[1:, masked[0]] = 1
+    eng3, out = _run(prob)
+    eng3.close()
+    assert np.all(np.isfinite(out["lnL"]))
+    assert all(np.all(np.isfinite(out[k])) for k in ("branch_lengths", "site_rates", "props", "freqs"))
+
+
+def test_two_engines_interleaved():
+    """Engines own their buffers: interleaving forward / backward calls of two engines (the
+    two SRD06 partitions of one model) gives what each gives alone."""
+    from torchtree_b200 import Engine, reversible_eigensystem
+    from torchtree_b200.synthetic import make_problem
+
+    probs = [make_problem(30, 150, 4, 4, seed=5), make_problem(30, 90, 4, 2, seed=6)]
+    alone = []
+    for p in probs:
+        e, out = _run(p)
+        e.close()
+        alone.append(out)
+    engines, args = [], []
+    for p in probs:
+        engines.append(Engine(p.tip_states, p.weights, p.postorder, 4, p.category_count,
+                              code_partials=p.code_partials, max_draws=1))
+        evec, ivec, evals = reversible_eigensystem(torch.tensor(p.q_matrix), torch.tensor(p.freqs))
+        args.append((p.branch_lengths, p.site_rates, p.site_props, evec, ivec, evals, p.freqs))
+    l0 = engines[0].loglik_eigen(*args[0])
+    l1 = engines[1].loglik_eigen(*args[1])
+    g1 = engines[1].grad_eigen()
+    g0 = engines[0].grad_eigen()
+    for lnl, g, want in ((l0, g0, alone[0]), (l1, g1, alone[1])):
+        assert np.array_equal(lnl.numpy(), want["lnL"])
+        assert np.array_equal(g["branch_lengths"].numpy(), want["branch_lengths"])
+    for e in engines:
+        e.close()
