@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--cpu-patterns", type=int, default=8000,
                     help="patterns of the bounded CPU-baseline sample")
+    ap.add_argument("--topology", default="random", choices=["random", "caterpillar", "balanced"],
+                    help="tree shape (the headline workload is the random-join tree)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine-flags", type=int, default=0,
                     help="extra TTB2_FLAG_* bits for experiments (32 = no CUDA graphs)")
@@ -127,7 +129,7 @@ def build_problem(args, lo=0, hi=None, patterns=None):
     from torchtree_b200.synthetic import make_problem
 
     prob = make_problem(args.taxa, patterns or args.patterns, 4, args.categories,
-                        seed=args.seed)
+                        seed=args.seed, topology=args.topology)
     if hi is not None:
         prob.tip_states = np.ascontiguousarray(prob.tip_states[:, lo:hi])
         prob.weights = np.ascontiguousarray(prob.weights[lo:hi])

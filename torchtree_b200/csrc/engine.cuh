@@ -248,6 +248,40 @@ inline cudaError_t launch_level(void (*kernel)(KArgs...), dim3 grid, int threads
 }
 
 
+// Chain runs: maximal runs of >= 2 consecutive levels (above level 1) that hold at most
+// TTB2_CHAIN_MAX (default 4) nodes each -- the top of any tree, all of a ladder-like one.
+// The 4-state path walks such a run in ONE launch per sweep (every CTA walks the run's
+// nodes for its own pattern slice) instead of one small launch per level.
+// first[l] = last level of the run starting at l (else -1); last[l] = its first level.
+struct ChainRuns {
+  std::vector<int> endOfStart, startOfEnd;
+};
+inline ChainRuns chain_runs(const Engine& e) {
+  static const int mx = getenv("TTB2_CHAIN_MAX") ? atoi(getenv("TTB2_CHAIN_MAX")) : 4;
+  const int nLevels = (int)e.levelOff.size() - 1;
+  ChainRuns r;
+  r.endOfStart.assign(nLevels, -1);
+  r.startOfEnd.assign(nLevels, -1);
+  const bool kOk = e.dm.K <= 6 || e.dm.K == 8;   // template instances of the chain kernels
+  // a chain trades node-level parallelism for fewer launches: only when the pattern axis alone
+  // fills the GPU (measured: a gain from ~40k patterns per GPU, a small loss at 12.5k)
+  const bool wide = (long)e.dm.Npad * e.cfg.max_draws >= 40000;
+  if (mx <= 0 || !e.spec4 || !kOk || !wide || (e.cfg.flags & TTB2_FLAG_NO_MMA)) return r;
+  int l = 1;
+  while (l < nLevels) {
+    int j = l;
+    while (j < nLevels && e.levelOff[j + 1] - e.levelOff[j] <= mx) ++j;
+    if (j - l >= 2) {
+      r.endOfStart[l] = j - 1;
+      r.startOfEnd[j - 1] = l;
+      l = j;
+    } else {
+      l = j > l ? j : l + 1;
+    }
+  }
+  return r;
+}
+
 // TTB2_NO_PDL=1 launches every level kernel with ordinary stream ordering (A/B runs)
 inline bool pdl_enabled() {
   static const bool on = getenv("TTB2_NO_PDL") == nullptr;

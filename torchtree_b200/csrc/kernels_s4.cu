@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace ttb2 {
@@ -34,6 +36,16 @@ __device__ __forceinline__ V4 ldg4(const double* p) {
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
                : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
                : "l"(p));
+  return v;
+}
+
+// coherent variant: for vectors this thread wrote earlier in the same kernel (chain mode)
+__device__ __forceinline__ V4 ldg4_coherent(const double* p) {
+  V4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p)
+               : "memory");
   return v;
 }
 
@@ -879,15 +891,18 @@ __device__ __forceinline__ V4 lds4_planes(const double* tab, int k, int NC, int 
   return V4{lo.x, lo.y, hi.x, hi.y};
 }
 
-// post-order level kernel, cherry-aware (levels >= 2 when fusion is on)
-template <int K>
+// post-order level kernel, cherry-aware (levels >= 2 when fusion is on).
+// CHAIN: one launch walks `chainOps` consecutive ops (a run of levels with very few nodes,
+// e.g. the top of the tree, or all of a ladder-like tree) for its own pattern slice:
+// a pattern only depends on itself, so a thread re-reads what it wrote one op earlier
+// (coherent loads, mostly L2 hits) and no grid-wide barrier is needed between levels.
+template <int K, bool CHAIN>
 __global__ void __launch_bounds__(FWD_THREADS, (K <= 4 ? 4 : 2))
 fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
              const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
              double* __restrict__ partials, int16_t* __restrict__ expo, CherryArgs ch, int T,
-             int Npad, int C, int B, int ppt) {
+             int Npad, int C, int B, int ppt, int chainOps) {
   extern __shared__ double sm[];
-  const NodeOp op = ops[opBegin + blockIdx.y];
   const int d = blockIdx.z;
   const int I = T - 1;
   const int NC = ch.CC > C ? ch.CC : C;
@@ -895,62 +910,69 @@ fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restri
   double* tabL = sm;
   double* tabR = sm + tabN;
   const double* matsD = mats + (size_t)d * B * K * 16;
-  int cidxL, cidxR;
-  const int kindL = child_kind(op.left, T, ch, cidxL);
-  const int kindR = child_kind(op.right, T, ch, cidxR);
-  const double* cvL = kindL == KIND_CHERRY ? ch.vec + ((size_t)d * ch.n + cidxL) * K * ch.CC * 4 : nullptr;
-  const double* cvR = kindR == KIND_CHERRY ? ch.vec + ((size_t)d * ch.n + cidxR) * K * ch.CC * 4 : nullptr;
-  build_child_table_c<K>(tabL, matsD + (size_t)op.left * K * 16, kindL, codeP, C, cvL, ch.CC, NC);
-  build_child_table_c<K>(tabR, matsD + (size_t)op.right * K * 16, kindR, codeP, C, cvR, ch.CC, NC);
-  __syncthreads();
-  pdl_wait_then_trigger();
-  // byte row holding the child's symbol code (tip code, or pair code of a cherry)
-  const uint8_t* l0 = nullptr;
-  const uint8_t* r0 = nullptr;
-  if (kindL == KIND_TIP) l0 = tips + (size_t)op.left * Npad;
-  if (kindL == KIND_CHERRY) l0 = ch.code + (size_t)cidxL * Npad;
-  if (kindR == KIND_TIP) r0 = tips + (size_t)op.right * Npad;
-  if (kindR == KIND_CHERRY) r0 = ch.code + (size_t)cidxR * Npad;
-
   const size_t nodeStride = (size_t)K * Npad * 4;
   double* base = partials + (size_t)d * I * nodeStride;
   const int i0 = blockIdx.x * (FWD_THREADS * ppt) + threadIdx.x;
+  const int nOps = CHAIN ? chainOps : 1;
+  for (int j = 0; j < nOps; ++j) {
+    const NodeOp op = ops[opBegin + (CHAIN ? j : (int)blockIdx.y)];
+    int cidxL, cidxR;
+    const int kindL = child_kind(op.left, T, ch, cidxL);
+    const int kindR = child_kind(op.right, T, ch, cidxR);
+    const double* cvL = kindL == KIND_CHERRY ? ch.vec + ((size_t)d * ch.n + cidxL) * K * ch.CC * 4 : nullptr;
+    const double* cvR = kindR == KIND_CHERRY ? ch.vec + ((size_t)d * ch.n + cidxR) * K * ch.CC * 4 : nullptr;
+    if (CHAIN && j > 0) __syncthreads();   // the previous op's tables are no longer read
+    build_child_table_c<K>(tabL, matsD + (size_t)op.left * K * 16, kindL, codeP, C, cvL, ch.CC, NC);
+    build_child_table_c<K>(tabR, matsD + (size_t)op.right * K * 16, kindR, codeP, C, cvR, ch.CC, NC);
+    __syncthreads();
+    if (j == 0) pdl_wait_then_trigger();
+    // byte row holding the child's symbol code (tip code, or pair code of a cherry)
+    const uint8_t* l0 = nullptr;
+    const uint8_t* r0 = nullptr;
+    if (kindL == KIND_TIP) l0 = tips + (size_t)op.left * Npad;
+    if (kindL == KIND_CHERRY) l0 = ch.code + (size_t)cidxL * Npad;
+    if (kindR == KIND_TIP) r0 = tips + (size_t)op.right * Npad;
+    if (kindR == KIND_CHERRY) r0 = ch.code + (size_t)cidxR * Npad;
+
 #pragma unroll 1
-  for (int it = 0; it < ppt; ++it) {
-    const int i = i0 + it * FWD_THREADS;
-    if (i >= Npad) break;
-    V4 a[K], b[K];
-    int codeL = 0, codeR = 0;
-    if (kindL == KIND_STORED) {
-      const double* p = base + (size_t)(op.left - T) * nodeStride + (size_t)i * 4;
+    for (int it = 0; it < ppt; ++it) {
+      const int i = i0 + it * FWD_THREADS;
+      if (i >= Npad) break;
+      V4 a[K], b[K];
+      int codeL = 0, codeR = 0;
+      if (kindL == KIND_STORED) {
+        const double* p = base + (size_t)(op.left - T) * nodeStride + (size_t)i * 4;
 #pragma unroll
-      for (int k = 0; k < K; ++k) a[k] = ldg4(p + (size_t)k * Npad * 4);
-    } else {
-      codeL = l0[i];
+        for (int k = 0; k < K; ++k)
+          a[k] = CHAIN ? ldg4_coherent(p + (size_t)k * Npad * 4) : ldg4(p + (size_t)k * Npad * 4);
+      } else {
+        codeL = l0[i];
+      }
+      if (kindR == KIND_STORED) {
+        const double* p = base + (size_t)(op.right - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          b[k] = CHAIN ? ldg4_coherent(p + (size_t)k * Npad * 4) : ldg4(p + (size_t)k * Npad * 4);
+      } else {
+        codeR = r0[i];
+      }
+      V4 out[K];
+      double m = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const V4 ul = kindL != KIND_STORED ? lds4_planes(tabL, k, NC, codeL) : matvec(tabL + k * 16, a[k]);
+        const V4 ur = kindR != KIND_STORED ? lds4_planes(tabR, k, NC, codeR) : matvec(tabR + k * 16, b[k]);
+        out[k] = mul4(ul, ur);
+        m = fmax(m, max4(out[k]));
+      }
+      int eb = (__double2hiint(m) >> 20) & 0x7ff;
+      eb = eb > 2044 ? 2044 : eb;
+      const double f = __hiloint2double((2045 - eb) << 20, 0);
+      double* q = base + (size_t)(op.node - T) * nodeStride + (size_t)i * 4;
+#pragma unroll
+      for (int k = 0; k < K; ++k) stg4(q + (size_t)k * Npad * 4, scale4(out[k], f));
+      expo[((size_t)d * I + (op.node - T)) * Npad + i] = (int16_t)(eb - 1022);
     }
-    if (kindR == KIND_STORED) {
-      const double* p = base + (size_t)(op.right - T) * nodeStride + (size_t)i * 4;
-#pragma unroll
-      for (int k = 0; k < K; ++k) b[k] = ldg4(p + (size_t)k * Npad * 4);
-    } else {
-      codeR = r0[i];
-    }
-    V4 out[K];
-    double m = 0.0;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const V4 ul = kindL != KIND_STORED ? lds4_planes(tabL, k, NC, codeL) : matvec(tabL + k * 16, a[k]);
-      const V4 ur = kindR != KIND_STORED ? lds4_planes(tabR, k, NC, codeR) : matvec(tabR + k * 16, b[k]);
-      out[k] = mul4(ul, ur);
-      m = fmax(m, max4(out[k]));
-    }
-    int eb = (__double2hiint(m) >> 20) & 0x7ff;
-    eb = eb > 2044 ? 2044 : eb;
-    const double f = __hiloint2double((2045 - eb) << 20, 0);
-    double* q = base + (size_t)(op.node - T) * nodeStride + (size_t)i * 4;
-#pragma unroll
-    for (int k = 0; k < K; ++k) stg4(q + (size_t)k * Npad * 4, scale4(out[k], f));
-    expo[((size_t)d * I + (op.node - T)) * Npad + i] = (int16_t)(eb - 1022);
   }
 }
 
@@ -1201,7 +1223,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 // A child is STORED (its vector is bulk-copied), a TIP (vector = codeP[tip code]) or, with
 // cherry tabulation on, a CHERRY (vector = cherryVec[pair code]; it still receives q^ and
 // has its exponents in `expo`).
-template <int STAGES, int MINBLOCKS>
+// CHAIN: the launch covers a run of levels with very few nodes (see chain_runs): grid
+// (chunks, K, draws), and every CTA walks the run's ops from the top level down for its own
+// (pattern chunk, category).  What a child reads (q^ written while its parent was processed)
+// was written by the same warp of the same CTA, so levels need no grid-wide barrier -- only
+// a generic->async proxy fence, because the reads are bulk copies.
+template <int STAGES, int MINBLOCKS, bool CHAIN>
 __global__ void __launch_bounds__(BWDF_THREADS, MINBLOCKS)
 bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
@@ -1209,7 +1236,7 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
                 const int16_t* __restrict__ expo, const double* __restrict__ weights,
                 double* __restrict__ pre, double* __restrict__ gpart,
                 const int* __restrict__ chunkBase, size_t chunkTotal, CherryArgs ch, int T,
-                int Npad, int C, int B, int K, int chunkPatterns, int nChunk) {
+                int Npad, int C, int B, int K, int chunkPatterns, int nChunk, int chainOps) {
   extern __shared__ __align__(128) double sm[];
   // sm: slots[warps][STAGES][440] | cp[C][4] | vecL[CC][4] vecR[CC][4] | mbarriers[warps][STAGES]
   // (5 CTAs/SM need <= 45 KB each; the final reduction reuses the head of each warp's ring)
@@ -1220,94 +1247,18 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   double* vecR = vecL + ch.CC * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(vecR + ch.CC * 4);
 
-  const int nodeSlot = blockIdx.y / K;
-  const int k = blockIdx.y - nodeSlot * K;
-  const NodeOp op = ops[opBegin + nodeSlot];
   const int d = blockIdx.z;
   const int I = T - 1;
-  int cidxL, cidxR;
-  const int kindL = child_kind(op.left, T, ch, cidxL);
-  const int kindR = child_kind(op.right, T, ch, cidxR);
-  const bool storedL = kindL == KIND_STORED, storedR = kindR == KIND_STORED;
-  const bool tipL = kindL == KIND_TIP, tipR = kindR == KIND_TIP;
-  const double* matsD = mats + (size_t)d * B * K * 16;
-  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
-  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = lane >> 2, c = lane & 3;
+  const bool rside = c < 2;
+  const int s0 = (c & 1) * 2;
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < STAGES; ++st) mbar_init(smem_u32(bars + warp * STAGES + st), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (tipL || tipR)
-    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
-  if (kindL == KIND_CHERRY) {
-    const double* src = ch.vec + (((size_t)d * ch.n + cidxL) * K + k) * ch.CC * 4;
-    for (int j = threadIdx.x; j < ch.CC * 4; j += blockDim.x) vecL[j] = src[j];
-  }
-  if (kindR == KIND_CHERRY) {
-    const double* src = ch.vec + (((size_t)d * ch.n + cidxR) * K + k) * ch.CC * 4;
-    for (int j = threadIdx.x; j < ch.CC * 4; j += blockDim.x) vecR[j] = src[j];
-  }
-  __syncthreads();
-
-  const int p = lane >> 2, c = lane & 3;
-  const bool rside = c < 2;
-  const int s0 = (c & 1) * 2;
-  const double b1 = p < 4 ? gPl[p * 4 + c] : 0.0;
-  const double b2 = p >= 4 ? gPr[(p - 4) * 4 + c] : 0.0;
-  double ba, bb;
-  if (rside) {
-    ba = p < 4 ? gPr[(2 * c) * 4 + p] : 0.0;
-    bb = p < 4 ? gPr[(2 * c + 1) * 4 + p] : 0.0;
-  } else {
-    ba = p >= 4 ? gPl[(2 * c - 4) * 4 + (p - 4)] : 0.0;
-    bb = p >= 4 ? gPl[(2 * c - 3) * 4 + (p - 4)] : 0.0;
-  }
-
-  const size_t nodeStride = (size_t)K * Npad * 4;
-  const size_t drawBase = (size_t)d * I * nodeStride;
-  const size_t kOff = (size_t)k * Npad * 4;
-  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
-  const double* pl = storedL ? partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff : nullptr;
-  const double* prr = storedR ? partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff : nullptr;
-  const int mine = rside ? op.right : op.left;
-  const bool store = mine >= T;
-  double* qc = store ? pre + drawBase + (size_t)(mine - T) * nodeStride + kOff : nullptr;
-
-  // the one 16-byte piece of per-pattern side data this lane copies per block
-  const char* sideSrc = nullptr;   // source at pattern 0
-  int sideDst = 0, sideScale = 0;  // byte offset in the slot; source bytes per pattern
-  const uint8_t* rowL = tipL ? tips + (size_t)op.left * Npad
-                              : (storedL ? nullptr : ch.code + (size_t)cidxL * Npad);
-  const uint8_t* rowR = tipR ? tips + (size_t)op.right * Npad
-                              : (storedR ? nullptr : ch.code + (size_t)cidxR * Npad);
-  const double* tabL = tipL ? cp : vecL;   // coded child: vector of a code
-  const double* tabR = tipR ? cp : vecR;
-  if (lane < 16) {
-    sideSrc = reinterpret_cast<const char*>(weights) + lane * 16;
-    sideDst = BWDT_W * 8 + lane * 16; sideScale = 8;
-  } else if (lane < 20) {
-    if (!tipL) sideSrc = reinterpret_cast<const char*>(expo + ((size_t)d * I + (op.left - T)) * Npad) + (lane - 16) * 16;
-    sideDst = BWDT_EL + (lane - 16) * 16; sideScale = 2;
-  } else if (lane < 24) {
-    if (!tipR) sideSrc = reinterpret_cast<const char*>(expo + ((size_t)d * I + (op.right - T)) * Npad) + (lane - 20) * 16;
-    sideDst = BWDT_ER + (lane - 20) * 16; sideScale = 2;
-  } else if (lane < 26) {
-    if (rowL) sideSrc = reinterpret_cast<const char*>(rowL) + (lane - 24) * 16;
-    sideDst = BWDT_CL + (lane - 24) * 16; sideScale = 1;
-  } else if (lane < 28) {
-    if (rowR) sideSrc = reinterpret_cast<const char*>(rowR) + (lane - 26) * 16;
-    sideDst = BWDT_CR + (lane - 26) * 16; sideScale = 1;
-  }
-
-  double g[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) g[i][j] = 0.0;
-
   const int begin = blockIdx.x * chunkPatterns;
   int end = begin + chunkPatterns;
   end = end < Npad ? end : Npad;
@@ -1315,97 +1266,192 @@ bwd4_tma_kernel(const NodeOp* __restrict__ ops, int opBegin,
   const int nb = first < end ? (end - first + BWDF_THREADS - 1) / BWDF_THREADS : 0;
   double* mySlots = slots + warp * STAGES * BWDT_SLOT;
   const uint32_t myBars = smem_u32(bars + warp * STAGES);
-  const uint32_t txBytes = 1024u + (storedL ? 1024u : 0u) + (storedR ? 1024u : 0u);
+  const size_t nodeStride = (size_t)K * Npad * 4;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const double* matsD = mats + (size_t)d * B * K * 16;
+  int ring = 0;   // blocks this warp has pushed through its ring so far (all ops)
+  bool cpLoaded = false;
 
-  // all lanes; exactly one cp.async group is committed per call (possibly empty)
-  auto issue = [&](int blk) {
-    if (blk < nb) {
-      const int st = blk % STAGES;
-      const int i0 = first + blk * BWDF_THREADS;
-      const uint32_t dst = smem_u32(mySlots + st * BWDT_SLOT);
-      if (sideSrc) cp_async16(dst + sideDst, sideSrc + (size_t)i0 * sideScale);
-      if (lane == 0) {
-        const size_t off = (size_t)i0 * 4;
-        const uint32_t bar = myBars + st * 8;
-        mbar_expect_tx(bar, txBytes);
-        bulk_g2s(dst, qn + off, 1024u, bar);
-        if (storedL) bulk_g2s(dst + 1024u, pl + off, 1024u, bar);
-        if (storedR) bulk_g2s(dst + 2048u, prr + off, 1024u, bar);
-      }
+  const int nOps = CHAIN ? chainOps : 1;
+  for (int jop = 0; jop < nOps; ++jop) {
+    int k;
+    NodeOp op;
+    if (CHAIN) {
+      k = blockIdx.y;
+      op = ops[opBegin + chainOps - 1 - jop];   // ops are sorted by level: walk downwards
+    } else {
+      const int nodeSlot = blockIdx.y / K;
+      k = blockIdx.y - nodeSlot * K;
+      op = ops[opBegin + nodeSlot];
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  pdl_wait_then_trigger();   // everything above read only ops / mats / codeP
-#pragma unroll
-  for (int blk = 0; blk < STAGES; ++blk) issue(blk);
+    int cidxL, cidxR;
+    const int kindL = child_kind(op.left, T, ch, cidxL);
+    const int kindR = child_kind(op.right, T, ch, cidxR);
+    const bool storedL = kindL == KIND_STORED, storedR = kindR == KIND_STORED;
+    const bool tipL = kindL == KIND_TIP, tipR = kindR == KIND_TIP;
+    const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
+    const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
+    if ((tipL || tipR) && !cpLoaded) {
+      for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
+      cpLoaded = true;   // block-uniform
+    }
+    if (kindL == KIND_CHERRY) {
+      const double* src = ch.vec + (((size_t)d * ch.n + cidxL) * K + k) * ch.CC * 4;
+      for (int j = threadIdx.x; j < ch.CC * 4; j += blockDim.x) vecL[j] = src[j];
+    }
+    if (kindR == KIND_CHERRY) {
+      const double* src = ch.vec + (((size_t)d * ch.n + cidxR) * K + k) * ch.CC * 4;
+      for (int j = threadIdx.x; j < ch.CC * 4; j += blockDim.x) vecR[j] = src[j];
+    }
+    __syncthreads();
 
-  for (int blk = 0; blk < nb; ++blk) {
-    const int base = first + blk * BWDF_THREADS;
-    const int st = blk % STAGES;
-    const double* slot = mySlots + st * BWDT_SLOT;
-    const char* slotB = reinterpret_cast<const char*>(slot);
-    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
-    __syncwarp();
-    mbar_wait(myBars + st * 8, (uint32_t)((blk / STAGES) & 1));
+    const double b1 = p < 4 ? gPl[p * 4 + c] : 0.0;
+    const double b2 = p >= 4 ? gPr[(p - 4) * 4 + c] : 0.0;
+    double ba, bb;
+    if (rside) {
+      ba = p < 4 ? gPr[(2 * c) * 4 + p] : 0.0;
+      bb = p < 4 ? gPr[(2 * c + 1) * 4 + p] : 0.0;
+    } else {
+      ba = p >= 4 ? gPl[(2 * c - 4) * 4 + (p - 4)] : 0.0;
+      bb = p >= 4 ? gPl[(2 * c - 3) * 4 + (p - 4)] : 0.0;
+    }
+
+    const size_t kOff = (size_t)k * Npad * 4;
+    const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
+    const double* pl = storedL ? partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff : nullptr;
+    const double* prr = storedR ? partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff : nullptr;
+    const int mine = rside ? op.right : op.left;
+    const bool store = mine >= T;
+    double* qc = store ? pre + drawBase + (size_t)(mine - T) * nodeStride + kOff : nullptr;
+
+    // the one 16-byte piece of per-pattern side data this lane copies per block
+    const char* sideSrc = nullptr;   // source at pattern 0
+    int sideDst = 0, sideScale = 0;  // byte offset in the slot; source bytes per pattern
+    const uint8_t* rowL = tipL ? tips + (size_t)op.left * Npad
+                                : (storedL ? nullptr : ch.code + (size_t)cidxL * Npad);
+    const uint8_t* rowR = tipR ? tips + (size_t)op.right * Npad
+                                : (storedR ? nullptr : ch.code + (size_t)cidxR * Npad);
+    const double* tabL = tipL ? cp : vecL;   // coded child: vector of a code
+    const double* tabR = tipR ? cp : vecR;
+    if (lane < 16) {
+      sideSrc = reinterpret_cast<const char*>(weights) + lane * 16;
+      sideDst = BWDT_W * 8 + lane * 16; sideScale = 8;
+    } else if (lane < 20) {
+      if (!tipL) sideSrc = reinterpret_cast<const char*>(expo + ((size_t)d * I + (op.left - T)) * Npad) + (lane - 16) * 16;
+      sideDst = BWDT_EL + (lane - 16) * 16; sideScale = 2;
+    } else if (lane < 24) {
+      if (!tipR) sideSrc = reinterpret_cast<const char*>(expo + ((size_t)d * I + (op.right - T)) * Npad) + (lane - 20) * 16;
+      sideDst = BWDT_ER + (lane - 20) * 16; sideScale = 2;
+    } else if (lane < 26) {
+      if (rowL) sideSrc = reinterpret_cast<const char*>(rowL) + (lane - 24) * 16;
+      sideDst = BWDT_CL + (lane - 24) * 16; sideScale = 1;
+    } else if (lane < 28) {
+      if (rowR) sideSrc = reinterpret_cast<const char*>(rowR) + (lane - 26) * 16;
+      sideDst = BWDT_CR + (lane - 26) * 16; sideScale = 1;
+    }
+
+    double g[2][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int j = t * 8 + p;
-      const int i = base + j;
-      const double2 q = *reinterpret_cast<const double2*>(slot + j * 4 + s0);
-      const double al = storedL ? slot[128 + t * 32 + lane]
-                                : tabL[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CL)[j] * 4 + c];
-      const double ar = storedR ? slot[256 + t * 32 + lane]
-                                : tabR[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CR)[j] * 4 + c];
-      const double w = slot[BWDT_W + j];
-      double u0 = 0.0, u1 = 0.0;
-      dmma884(u0, u1, al, b1);
-      dmma884(u0, u1, ar, b2);
-      const double m0 = q.x * u0, m1 = q.y * u1;
-      double o0 = 0.0, o1 = 0.0;
-      dmma884(o0, o1, m0, ba);
-      dmma884(o0, o1, m1, bb);
-      if (store) {
-        const int ex = reinterpret_cast<const int16_t*>(slotB + (rside ? BWDT_ER : BWDT_EL))[j];
-        const double f = __hiloint2double((1023 - ex) << 20, 0);
-        *reinterpret_cast<double2*>(qc + (size_t)i * 4 + s0) = make_double2(o0 * f, o1 * f);
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[i][j] = 0.0;
+
+    const uint32_t txBytes = 1024u + (storedL ? 1024u : 0u) + (storedR ? 1024u : 0u);
+
+    // all lanes; exactly one cp.async group is committed per call (possibly empty)
+    auto issue = [&](int blk) {
+      if (blk < nb) {
+        const int st = (ring + blk) % STAGES;
+        const int i0 = first + blk * BWDF_THREADS;
+        const uint32_t dst = smem_u32(mySlots + st * BWDT_SLOT);
+        if (sideSrc) cp_async16(dst + sideDst, sideSrc + (size_t)i0 * sideScale);
+        if (lane == 0) {
+          const size_t off = (size_t)i0 * 4;
+          const uint32_t bar = myBars + st * 8;
+          mbar_expect_tx(bar, txBytes);
+          bulk_g2s(dst, qn + off, 1024u, bar);
+          if (storedL) bulk_g2s(dst + 1024u, pl + off, 1024u, bar);
+          if (storedR) bulk_g2s(dst + 2048u, prr + off, 1024u, bar);
+        }
       }
-      // (q^_n, hence m, is exactly 0 where w == 0: see root4_bwd_kernel)
-      const double own = rside ? ar : al;
-      const double oth = rside ? al : ar;
-      const double wm0 = w * m0, wm1 = w * m1;
-      const double x1 = __shfl_xor_sync(0xffffffffu, own, 1);
-      const double x2 = __shfl_xor_sync(0xffffffffu, oth, 2);
-      const double x3 = __shfl_xor_sync(0xffffffffu, oth, 3);
-      g[0][0] = fma(wm0, own, g[0][0]); g[1][0] = fma(wm1, own, g[1][0]);
-      g[0][1] = fma(wm0, x1, g[0][1]);  g[1][1] = fma(wm1, x1, g[1][1]);
-      g[0][2] = fma(wm0, x2, g[0][2]);  g[1][2] = fma(wm1, x2, g[1][2]);
-      g[0][3] = fma(wm0, x3, g[0][3]);  g[1][3] = fma(wm1, x3, g[1][3]);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (jop == 0) pdl_wait_then_trigger();   // everything above read only ops / mats / codeP / cherry tables
+#pragma unroll
+    for (int blk = 0; blk < STAGES; ++blk) issue(blk);
+
+    for (int blk = 0; blk < nb; ++blk) {
+      const int base = first + blk * BWDF_THREADS;
+      const int st = (ring + blk) % STAGES;
+      const double* slot = mySlots + st * BWDT_SLOT;
+      const char* slotB = reinterpret_cast<const char*>(slot);
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+      __syncwarp();
+      mbar_wait(myBars + st * 8, (uint32_t)(((ring + blk) / STAGES) & 1));
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = t * 8 + p;
+        const int i = base + j;
+        const double2 q = *reinterpret_cast<const double2*>(slot + j * 4 + s0);
+        const double al = storedL ? slot[128 + t * 32 + lane]
+                                  : tabL[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CL)[j] * 4 + c];
+        const double ar = storedR ? slot[256 + t * 32 + lane]
+                                  : tabR[(int)reinterpret_cast<const uint8_t*>(slotB + BWDT_CR)[j] * 4 + c];
+        const double w = slot[BWDT_W + j];
+        double u0 = 0.0, u1 = 0.0;
+        dmma884(u0, u1, al, b1);
+        dmma884(u0, u1, ar, b2);
+        const double m0 = q.x * u0, m1 = q.y * u1;
+        double o0 = 0.0, o1 = 0.0;
+        dmma884(o0, o1, m0, ba);
+        dmma884(o0, o1, m1, bb);
+        if (store) {
+          const int ex = reinterpret_cast<const int16_t*>(slotB + (rside ? BWDT_ER : BWDT_EL))[j];
+          const double f = __hiloint2double((1023 - ex) << 20, 0);
+          *reinterpret_cast<double2*>(qc + (size_t)i * 4 + s0) = make_double2(o0 * f, o1 * f);
+        }
+        // (q^_n, hence m, is exactly 0 where w == 0: see root4_bwd_kernel)
+        const double own = rside ? ar : al;
+        const double oth = rside ? al : ar;
+        const double wm0 = w * m0, wm1 = w * m1;
+        const double x1 = __shfl_xor_sync(0xffffffffu, own, 1);
+        const double x2 = __shfl_xor_sync(0xffffffffu, oth, 2);
+        const double x3 = __shfl_xor_sync(0xffffffffu, oth, 3);
+        g[0][0] = fma(wm0, own, g[0][0]); g[1][0] = fma(wm1, own, g[1][0]);
+        g[0][1] = fma(wm0, x1, g[0][1]);  g[1][1] = fma(wm1, x1, g[1][1]);
+        g[0][2] = fma(wm0, x2, g[0][2]);  g[1][2] = fma(wm1, x2, g[1][2]);
+        g[0][3] = fma(wm0, x3, g[0][3]);  g[1][3] = fma(wm1, x3, g[1][3]);
+      }
+      __syncwarp();   // every lane has read the slot: it can be refilled
+      issue(blk + STAGES);
     }
-    __syncwarp();   // every lane has read the slot: it can be refilled
-    issue(blk + STAGES);
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    ring += nb;
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double v = g[i][j];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (p == 0) mySlots[(rside ? 16 : 0) + (s0 + i) * 4 + (c ^ j)] = v;
+      for (int j = 0; j < 4; ++j) {
+        double v = g[i][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (p == 0) mySlots[(rside ? 16 : 0) + (s0 + i) * 4 + (c ^ j)] = v;
+      }
+    if (CHAIN) asm volatile("fence.proxy.async;" ::: "memory");   // q^ stores -> later bulk reads
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int child = threadIdx.x >> 4;
+      double t = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) t += slots[w2 * STAGES * BWDT_SLOT + threadIdx.x];
+      const int branch = child ? op.right : op.left;
+      gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
+            (threadIdx.x & 15)] = t;
     }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int child = threadIdx.x >> 4;
-    double t = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) t += slots[w2 * STAGES * BWDT_SLOT + threadIdx.x];
-    const int branch = child ? op.right : op.left;
-    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
-          (threadIdx.x & 15)] = t;
+    if (CHAIN) __syncthreads();   // ring heads and code tables are reused by the next op
   }
 }
+
 
 // ---------------------------------------------------------------------------
 // Pre-order kernel for nodes whose two children are tips (level 1), bulk-copy
@@ -1767,15 +1813,21 @@ CherryArgs cherry_args(const Engine& e) {
 }
 
 template <int K>
-void launch_fwdc(Engine& e, int draws, int opBegin, int count, int ppt, bool pdl) {
+void launch_fwdc(Engine& e, int draws, int opBegin, int count, int ppt, bool pdl, bool chain) {
   const Dims& m = e.dm;
   const CherryArgs ch = cherry_args(e);
   const int NC = ch.CC > m.C ? ch.CC : m.C;
   const size_t smem = 2 * (size_t)K * (NC > 4 ? NC : 4) * 4 * sizeof(double);
   const int per = FWD_THREADS * ppt;
+  if (chain) {   // `count` consecutive ops walked by every CTA for its own patterns
+    dim3 grid((m.Npad + per - 1) / per, 1, draws);
+    launch_level(fwd4c_kernel<K, true>, grid, FWD_THREADS, smem, e.stream, pdl, e.ops, opBegin,
+                 e.mats, e.tips, e.codeP, e.partials, e.expo, ch, m.T, m.Npad, m.C, m.B, ppt, count);
+    return;
+  }
   dim3 grid((m.Npad + per - 1) / per, count, draws);
-  launch_level(fwd4c_kernel<K>, grid, FWD_THREADS, smem, e.stream, pdl, e.ops, opBegin, e.mats,
-               e.tips, e.codeP, e.partials, e.expo, ch, m.T, m.Npad, m.C, m.B, ppt);
+  launch_level(fwd4c_kernel<K, false>, grid, FWD_THREADS, smem, e.stream, pdl, e.ops, opBegin,
+               e.mats, e.tips, e.codeP, e.partials, e.expo, ch, m.T, m.Npad, m.C, m.B, ppt, 0);
 }
 
 template <int K>
@@ -1858,25 +1910,35 @@ int s4_forward(Engine& e, int draws) {
                                                     e.nCherry, m.C * m.C, m.T, m.Npad);
     ++e.launches;
   }
+  const ChainRuns runs = chain_runs(e);
   for (int l = e.cherryOn ? 1 : 0; l < nLevels; ++l) {
-    const int opBegin = e.levelOff[l];
-    const int count = e.levelOff[l + 1] - opBegin;
-    const int ppt = fwd_patterns_per_thread(e, draws, count);
-    if (e.cherryOn && (m.K <= 6 || m.K == 8)) {
+    int opBegin = e.levelOff[l];
+    int count = e.levelOff[l + 1] - opBegin;
+    const bool chain = l >= 1 && runs.endOfStart[l] >= 0;
+    if (chain) count = e.levelOff[runs.endOfStart[l] + 1] - opBegin;   // all ops of the run
+    int ppt = fwd_patterns_per_thread(e, draws, count);
+    if (chain) {   // one wave: every CTA is resident from the first op to the last
+      const long slots = std::max(1L, (long)e.smCount * (m.K <= 4 ? 4 : 2) / draws);
+      ppt = (int)((m.Npad + (long)FWD_THREADS * slots - 1) / ((long)FWD_THREADS * slots));
+      if (ppt < 1) ppt = 1;
+    }
+    if (chain || (e.cherryOn && (m.K <= 6 || m.K == 8))) {
       const bool pdlc = l > 1 && pdl_enabled();   // the first level follows the cherry tables
       for (int done = 0; done < count; done += 65535) {
-        const int c = (count - done) < 65535 ? (count - done) : 65535;
+        const int c = chain ? count : ((count - done) < 65535 ? (count - done) : 65535);
         switch (m.K) {
-          case 1: launch_fwdc<1>(e, draws, opBegin + done, c, ppt, pdlc); break;
-          case 2: launch_fwdc<2>(e, draws, opBegin + done, c, ppt, pdlc); break;
-          case 3: launch_fwdc<3>(e, draws, opBegin + done, c, ppt, pdlc); break;
-          case 4: launch_fwdc<4>(e, draws, opBegin + done, c, ppt, pdlc); break;
-          case 5: launch_fwdc<5>(e, draws, opBegin + done, c, ppt, pdlc); break;
-          case 6: launch_fwdc<6>(e, draws, opBegin + done, c, ppt, pdlc); break;
-          default: launch_fwdc<8>(e, draws, opBegin + done, c, ppt, pdlc); break;
+          case 1: launch_fwdc<1>(e, draws, opBegin + done, c, ppt, pdlc, chain); break;
+          case 2: launch_fwdc<2>(e, draws, opBegin + done, c, ppt, pdlc, chain); break;
+          case 3: launch_fwdc<3>(e, draws, opBegin + done, c, ppt, pdlc, chain); break;
+          case 4: launch_fwdc<4>(e, draws, opBegin + done, c, ppt, pdlc, chain); break;
+          case 5: launch_fwdc<5>(e, draws, opBegin + done, c, ppt, pdlc, chain); break;
+          case 6: launch_fwdc<6>(e, draws, opBegin + done, c, ppt, pdlc, chain); break;
+          default: launch_fwdc<8>(e, draws, opBegin + done, c, ppt, pdlc, chain); break;
         }
         ++e.launches;
+        if (chain) break;
       }
+      if (chain) l = runs.endOfStart[l];
       continue;
     }
     const bool tipLevel = (l == 0) && !(e.cfg.flags & TTB2_FLAG_NO_MMA);  // level 1: tip-tip nodes
@@ -1951,6 +2013,7 @@ int s4_backward(Engine& e, int draws) {
       : (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
   const int nLevels = (int)e.levelOff.size() - 1;
   const int maxNodes = 65535 / m.K;
+  const ChainRuns runs = chain_runs(e);
   for (int l = nLevels - 1; l >= 0; --l) {
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
@@ -1958,6 +2021,12 @@ int s4_backward(Engine& e, int draws) {
     int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
     chunkPatterns = (chunkPatterns + 31) / 32 * 32;
     const bool pdl = l < nLevels - 1 && pdl_enabled();   // the top level follows root4_bwd
+    // a run of sparse levels ending here (we walk downwards) goes out as one chain launch
+    int chainBegin = 0, chainCount = 0;
+    if (useMma && !legacy && runs.startOfEnd[l] >= 0) {
+      chainBegin = e.levelOff[runs.startOfEnd[l]];
+      chainCount = e.levelOff[l + 1] - chainBegin;
+    }
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
@@ -2003,15 +2072,26 @@ int s4_backward(Engine& e, int draws) {
                  (size_t)NWF * ST * sizeof(uint64_t);
         };
         if (!e.smemAttrTma) {   // largest code table (uint8 codes); cherries need C * C <= 64
-          TTB2_CUDA_CHECK(cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB>,
+          TTB2_CUDA_CHECK(cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB, false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smemOf(256, 64)));
+          TTB2_CUDA_CHECK(cudaFuncSetAttribute(bwd4_tma_kernel<ST, MB, true>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smemOf(256, 64)));
           e.smemAttrTma = true;
         }
-        launch_level(bwd4_tma_kernel<ST, MB>, grid, BWDF_THREADS, smemOf(m.C, ch.CC), e.stream, pdl,
-                     e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights,
-                     e.pre, e.gpart, e.chunkBase, e.chunkTotal, ch, m.T, m.Npad, m.C, m.B, m.K,
-                     chunkPatterns, nChunk);
+        if (chainCount > 0) {   // the whole run of levels in one launch
+          dim3 cgrid(nChunk, m.K, draws);
+          launch_level(bwd4_tma_kernel<ST, MB, true>, cgrid, BWDF_THREADS, smemOf(m.C, ch.CC),
+                       e.stream, pdl, e.ops, chainBegin, e.mats, e.tips, e.codeP, e.partials,
+                       e.expo, e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, ch, m.T,
+                       m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk, chainCount);
+        } else {
+          launch_level(bwd4_tma_kernel<ST, MB, false>, grid, BWDF_THREADS, smemOf(m.C, ch.CC),
+                       e.stream, pdl, e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials,
+                       e.expo, e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, ch, m.T,
+                       m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk, 0);
+        }
       } else if (useMma) {
         bwd4_mma_kernel<<<grid, BWDM_THREADS, smem, e.stream>>>(
             e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
@@ -2022,7 +2102,9 @@ int s4_backward(Engine& e, int draws) {
             e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
       }
       ++e.launches;
+      if (chainCount > 0) break;
     }
+    if (chainCount > 0) l = runs.startOfEnd[l];   // the run is done; continue below it
   }
   TTB2_CUDA_CHECK(cudaGetLastError());
   return small_gpart_reduce(e, draws);

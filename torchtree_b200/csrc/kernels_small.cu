@@ -311,9 +311,17 @@ int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm) {
   e.levelChunks.assign(nLevels, 1);
   e.hostChunkBase.assign(m.B + 1, 0);
   e.hostChunkCount.assign(m.B + 1, 0);
+  // levels of a chain run share one chunk count: the run is one launch of (chunks x K x draws)
+  // CTAs, each walking all of the run's nodes -- one wave of 5 CTAs per SM
+  const ChainRuns runs = chain_runs(e);
+  std::vector<char> inRun(nLevels, 0);
+  for (int l = 0; l < nLevels; ++l)
+    if (runs.endOfStart[l] >= 0)
+      for (int j = l; j <= runs.endOfStart[l]; ++j) inRun[j] = 1;
   for (int l = 0; l < nLevels; ++l) {
     const long count = e.levelOff[l + 1] - e.levelOff[l];
     long want = (target + count * m.K * draws - 1) / (count * m.K * draws);
+    if (inRun[l]) want = ((long)e.smCount * 5 + (long)m.K * draws - 1) / ((long)m.K * draws);
     if (want > maxChunks) want = maxChunks;
     if (want < 1) want = 1;
     e.levelChunks[l] = (int)want;
