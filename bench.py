@@ -396,7 +396,7 @@ def main():
                 "peak_kind": peak_kind,
                 "traffic": (NCU_PREORDER_SWEEP_BYTES / max(1, ph["preorder_launches"])
                             if world == 1 and args.taxa == 1000 and args.patterns == 100_000
-                            and args.categories == 4 else None),
+                            and args.categories == 4 and args.topology == "random" else None),
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read+write summed over the "
                                 "pre-order sweep / launches, profiles/r01_cherry_dram_bytes.csv); below "
                                 "the algorithmic bytes because cherry vectors are tabulated, not read",

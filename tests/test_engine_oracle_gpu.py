@@ -396,3 +396,46 @@ def test_two_engines_interleaved():
         assert np.array_equal(g["branch_lengths"].numpy(), want["branch_lengths"])
     for e in engines:
         e.close()
+
+
+@pytest.fixture
+def chain_mode_for_small_problems(monkeypatch):
+    """Chain launches (runs of sparse levels walked by one launch per sweep) are reserved for
+    wide pattern axes; switch them on for test-sized problems."""
+    monkeypatch.setenv("TTB2_CHAIN_MIN_PATTERNS", "0")
+    yield
+    monkeypatch.delenv("TTB2_CHAIN_MIN_PATTERNS")
+
+
+@pytest.mark.parametrize("flags", [0, 64], ids=["levels", "nocherry"])
+@pytest.mark.parametrize("topology,T", [("caterpillar", 120), ("random", 200), ("balanced", 64)])
+@pytest.mark.parametrize("K", [1, 4])
+def test_chain_launches(chain_mode_for_small_problems, topology, T, K, flags):
+    from torchtree_b200.synthetic import make_problem
+
+    _check(make_problem(T, 300, 4, K, seed=T + K, topology=topology, gap_fraction=0.03), flags=flags)
+
+
+def test_chain_launches_draws_and_set_postorder(chain_mode_for_small_problems):
+    from torchtree_b200 import Engine, reversible_eigensystem
+    from torchtree_b200.synthetic import make_problem
+
+    _check(make_problem(60, 130, 4, 4, draws=3, seed=9, topology="caterpillar", per_draw_model=True))
+    # a topology change re-plans the runs
+    a = make_problem(50, 200, 4, 4, seed=21, topology="caterpillar")
+    b = make_problem(50, 200, 4, 4, seed=21, topology="random")
+    b.tip_states, b.weights = a.tip_states, a.weights
+    eng = Engine(a.tip_states, a.weights, a.postorder, 4, 4, max_draws=1)
+    out = []
+    for prob in (a, b, a):
+        eng.set_postorder(prob.postorder)
+        evec, ivec, evals = reversible_eigensystem(torch.tensor(prob.q_matrix), torch.tensor(prob.freqs))
+        lnl = eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props, evec, ivec,
+                               evals, prob.freqs)
+        out.append((lnl.numpy().copy(), eng.grad_eigen()["branch_lengths"].numpy().copy()))
+    eng.close()
+    assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
+    from oracle import treelik as orc
+    want = orc.evaluate(b, want_grad=True)
+    assert_lnl_close(out[1][0], want["lnL"])
+    assert_grad_close(out[1][1], want["branch_lengths"], what="d_bl after set_postorder")

@@ -257,7 +257,10 @@ struct ChainRuns {
   std::vector<int> endOfStart, startOfEnd;
 };
 inline ChainRuns chain_runs(const Engine& e) {
-  static const int mx = getenv("TTB2_CHAIN_MAX") ? atoi(getenv("TTB2_CHAIN_MAX")) : 4;
+  // (read at every call: the tests switch chain mode on for small problems)
+  const int mx = getenv("TTB2_CHAIN_MAX") ? atoi(getenv("TTB2_CHAIN_MAX")) : 4;
+  const long minPatterns =
+      getenv("TTB2_CHAIN_MIN_PATTERNS") ? atol(getenv("TTB2_CHAIN_MIN_PATTERNS")) : 40000;
   const int nLevels = (int)e.levelOff.size() - 1;
   ChainRuns r;
   r.endOfStart.assign(nLevels, -1);
@@ -265,7 +268,7 @@ inline ChainRuns chain_runs(const Engine& e) {
   const bool kOk = e.dm.K <= 6 || e.dm.K == 8;   // template instances of the chain kernels
   // a chain trades node-level parallelism for fewer launches: only when the pattern axis alone
   // fills the GPU (measured: a gain from ~40k patterns per GPU, a small loss at 12.5k)
-  const bool wide = (long)e.dm.Npad * e.cfg.max_draws >= 40000;
+  const bool wide = (long)e.dm.Npad * e.cfg.max_draws >= minPatterns;
   if (mx <= 0 || !e.spec4 || !kOk || !wide || (e.cfg.flags & TTB2_FLAG_NO_MMA)) return r;
   int l = 1;
   while (l < nLevels) {
