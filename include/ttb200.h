@@ -239,6 +239,13 @@ int ttb2_heights_backward(ttb2_heights* plan, int32_t draws, const double* x,
 int64_t ttb2_launch_count(const ttb2_engine* engine);
 /* Device bytes currently held by this engine. */
 int64_t ttb2_device_bytes(const ttb2_engine* engine);
+/* Number of ttb2_loglik_* calls this engine has served.  A gradient call always refers to
+ * the latest one: a binding that defers the gradient (autograd) compares this serial with
+ * the one it saw after its own forward and re-runs the forward if another one intervened
+ * (SURVEY 8(b) autograd contract). */
+int64_t ttb2_eval_serial(const ttb2_engine* engine);
+/* The configuration the engine was created with (shapes for argument checks in bindings). */
+int ttb2_get_config(const ttb2_engine* engine, ttb2_config* out);
 
 const char* ttb2_last_error(void);
 int ttb2_version(void);

@@ -32,6 +32,35 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert lib.ttb2_version() == 100
 
 
+def test_torch_extension_builds_loads_and_links_the_cabi():
+    """The autograd Functions are a torch C++ extension over the C ABI (north_star);
+    no GPU here, so only loading, linkage and argument errors can be checked."""
+    import subprocess
+
+    from torchtree_b200 import _lib, build
+
+    ext = build.build_torch_extension()
+    assert os.path.exists(ext)
+    from torchtree_b200 import _ttb200_torch
+
+    assert _ttb200_torch.abi_version() == _lib.load().ttb2_version()
+    needed = subprocess.run(["readelf", "-d", ext], capture_output=True, text=True).stdout
+    assert "libttb200.so" in needed and "$ORIGIN/lib" in needed
+    x = torch.zeros(1, 4, dtype=torch.float64)
+    with pytest.raises(RuntimeError, match="null engine handle"):
+        _ttb200_torch.log_likelihood_eigen(0, x, x, x, x, x)
+    with pytest.raises(RuntimeError, match="null node-height plan"):
+        _ttb200_torch.node_heights(0, 0, x)
+
+
+def test_function_module_has_no_python_autograd_function():
+    """function.py / height_transform.py must route through the extension, not keep a
+    Python torch.autograd.Function beside it."""
+    for name in ("function.py", "height_transform.py"):
+        text = open(os.path.join(REPO, "torchtree_b200", name)).read()
+        assert "autograd.Function)" not in text, name
+
+
 def test_library_is_sm100a_only():
     import subprocess
 

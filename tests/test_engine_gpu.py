@@ -227,3 +227,79 @@ def test_fused_without_q_gradient():
     want = orc.evaluate(prob, want_grad=True, route="expm")["q_matrix"]
     assert_grad_close(g["q"].numpy(), want, rtol=1e-7, what="d_q")
     eng.close()
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("per_draw_model", [False, True])
+def test_torch_extension_autograd_matches_engine_calls(where, per_draw_model):
+    """The torch C++ extension's Functions (csrc/torch_ext.cpp) hand back exactly what the
+    raw C-ABI calls produce: batched draws, shared or per-draw models, host or device
+    tensors, a weighted sum over draws as the loss (grad_lnl != 1)."""
+    from torchtree_b200 import log_likelihood_eigen, log_likelihood_mats
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(24, 333, 4, 3, draws=3, seed=77, per_draw_model=per_draw_model,
+                        gap_fraction=0.05)
+    eng = _engine(prob)
+    evec, ivec, evals = _eig(prob)
+    wts = torch.tensor([0.5, -2.0, 1.25])
+    host_args = [torch.tensor(a) for a in (prob.branch_lengths, prob.site_rates,
+                                           prob.site_props, prob.q_matrix, prob.freqs)]
+    lnl_ref = eng.loglik_eigen(host_args[0], host_args[1], host_args[2], evec, ivec, evals,
+                               host_args[4]).clone()
+    g_ref = {k: v.clone() for k, v in eng.grad_eigen(wts).items()}
+    mats_ref = eng.get_mats().clone()
+
+    dev = "cuda" if where == "device" else "cpu"
+    args = [a.to(dev).requires_grad_(True) for a in host_args]
+    lnl = log_likelihood_eigen(eng, *args)
+    assert lnl.device.type == dev and lnl.shape == (3,)
+    if where == "host":
+        assert torch.equal(lnl.detach(), lnl_ref)
+    else:
+        assert_lnl_close(lnl.detach().cpu().numpy(), lnl_ref.numpy())
+    (lnl * wts.to(dev)).sum().backward()
+    for a, key in zip(args, ("branch_lengths", "site_rates", "props", "q", "freqs")):
+        assert a.grad.shape == a.shape, key
+        # eigh on the device (cusolver) differs from LAPACK in the last bits
+        tol = 0 if where == "host" else 1e-9
+        assert_grad_close(a.grad.cpu().numpy(), g_ref[key].numpy(), rtol=max(tol, 1e-13), what=key)
+
+    # matrices route, mats not requiring grad: d_mats is skipped, the rest still flows
+    freqs = host_args[4].to(dev).requires_grad_(True)
+    props = host_args[2].to(dev).requires_grad_(True)
+    lnl_m = log_likelihood_mats(eng, mats_ref.to(dev), freqs, props)
+    assert_lnl_close(lnl_m.detach().cpu().numpy(), lnl_ref.numpy())
+    (lnl_m * wts.to(dev)).sum().backward()
+    assert_grad_close(props.grad.cpu().numpy(), g_ref["props"].numpy(), what="mats route d_props")
+    assert_grad_close(freqs.grad.cpu().numpy(), g_ref["freqs"].numpy(), what="mats route d_freqs")
+    mats = mats_ref.to(dev).requires_grad_(True)
+    lnl_m = log_likelihood_mats(eng, mats, freqs.detach(), props.detach())
+    lnl_m.sum().backward()
+    assert mats.grad.shape == mats.shape and torch.isfinite(mats.grad).all()
+    eng.close()
+
+
+def test_torch_extension_frequency_draws_broadcast_the_generator():
+    """One generator, per-draw frequencies: the extension decomposes one system per draw and
+    sums d lnL/dQ back onto the shared generator."""
+    from torchtree_b200 import log_likelihood_eigen
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(12, 100, 4, 2, draws=2, seed=5)
+    eng = _engine(prob)
+    q = torch.tensor(prob.q_matrix)[:1].clone().requires_grad_(True)
+    f0 = torch.tensor(prob.freqs)[:1]
+    freqs = torch.cat((f0, f0)).clone().requires_grad_(True)
+    bls = torch.tensor(prob.branch_lengths)
+    rates, props = torch.tensor(prob.site_rates)[:1], torch.tensor(prob.site_props)[:1]
+    lnl = log_likelihood_eigen(eng, bls, rates, props, q, freqs)
+    lnl.sum().backward()
+    assert q.grad.shape == (1, 4, 4) and freqs.grad.shape == (2, 4)
+    # same thing with the generator expanded by the caller
+    q2 = q.detach().expand(2, -1, -1).clone().requires_grad_(True)
+    lnl2 = log_likelihood_eigen(eng, bls, rates, props, q2, freqs.detach())
+    lnl2.sum().backward()
+    assert torch.equal(lnl2.detach(), lnl.detach())
+    assert_grad_close(q.grad.numpy(), q2.grad.sum(0, keepdim=True).numpy(), rtol=1e-12, what="d_q")
+    eng.close()

@@ -63,6 +63,8 @@ EXPORTED_SYMBOLS = (
     "ttb2_heights_backward",
     "ttb2_launch_count",
     "ttb2_device_bytes",
+    "ttb2_eval_serial",
+    "ttb2_get_config",
     "ttb2_last_error",
     "ttb2_version",
 )
@@ -127,6 +129,10 @@ def load():
     lib.ttb2_launch_count.restype = c_int64
     lib.ttb2_device_bytes.argtypes = [vp]
     lib.ttb2_device_bytes.restype = c_int64
+    lib.ttb2_eval_serial.argtypes = [vp]
+    lib.ttb2_eval_serial.restype = c_int64
+    lib.ttb2_get_config.argtypes = [vp, POINTER(Ttb2Config)]
+    lib.ttb2_get_config.restype = c_int32
     _lib = lib
     return lib
 

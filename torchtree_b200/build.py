@@ -84,6 +84,54 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TORCH_EXT = os.path.join(PKG, "_ttb200_torch.so")
+TORCH_EXT_SRC = os.path.join(CSRC, "torch_ext.cpp")
+
+
+def build_torch_extension(force: bool = False) -> str:
+    """Compile csrc/torch_ext.cpp (the torch C++ autograd Functions over the C ABI) into
+    torchtree_b200/_ttb200_torch.so with an explicit g++ command: host code only, linked
+    against lib/libttb200.so through an $ORIGIN-relative rpath."""
+    import torch
+    from torch.utils import cpp_extension
+
+    build()
+    h = hashlib.sha256()
+    for path in (TORCH_EXT_SRC, HEADERS[1]):
+        with open(path, "rb") as fp:
+            h.update(fp.read())
+    h.update(torch.__version__.encode())
+    digest = h.hexdigest()
+    stamp = os.path.join(LIBDIR, "_ttb200_torch.stamp")
+    if not force and os.path.exists(TORCH_EXT) and os.path.exists(stamp):
+        with open(stamp) as fp:
+            if fp.read().strip() == digest:
+                return TORCH_EXT
+    import sysconfig
+
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+    if not cxx:
+        raise RuntimeError("g++ not found; cannot build the torch extension")
+    incs = cpp_extension.include_paths() + [sysconfig.get_paths()["include"],
+                                            os.path.join(PKG, "..", "include")]
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+           "-DTORCH_EXTENSION_NAME=_ttb200_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    cmd += ["-isystem" + i for i in incs]
+    cmd += [TORCH_EXT_SRC, "-o", TORCH_EXT,
+            "-L" + LIBDIR, "-lttb200", "-Wl,-rpath,$ORIGIN/lib",
+            "-L" + torch_lib, "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+            "-Wl,-rpath," + torch_lib]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the torch extension failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(stamp, "w") as fp:
+        fp.write(digest)
+    return TORCH_EXT
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)
+    print(build_torch_extension(force="--force" in sys.argv))

@@ -697,6 +697,7 @@ int ttb2_loglik_mats(ttb2_engine* engine, int32_t draws, const double* mats,
   e.propDraws = prop_draws;
   e.rateDraws = e.eigDraws = 1;
   e.mode = MODE_MATS;
+  ++e.evalSerial;
   return run_forward(e, draws, lnl, where);
 }
 
@@ -733,6 +734,7 @@ int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws, const double* branch_l
   e.rateDraws = rate_draws;
   e.eigDraws = eig_draws;
   e.mode = MODE_EIGEN;
+  ++e.evalSerial;
   e.draws = draws;
   if (e.fusedOK || !e.spec4 && !gmma_supported(e)) {
     if ((rc = small_pmatrix(e, draws))) return rc;
@@ -918,6 +920,19 @@ int64_t ttb2_launch_count(const ttb2_engine* engine) {
 
 int64_t ttb2_device_bytes(const ttb2_engine* engine) {
   return engine ? reinterpret_cast<const Engine*>(engine)->deviceBytes : 0;
+}
+
+int64_t ttb2_eval_serial(const ttb2_engine* engine) {
+  return engine ? reinterpret_cast<const Engine*>(engine)->evalSerial : 0;
+}
+
+int ttb2_get_config(const ttb2_engine* engine, ttb2_config* out) {
+  if (!engine || !out) {
+    set_error("ttb2_get_config: null argument");
+    return TTB2_E_INVALID;
+  }
+  *out = reinterpret_cast<const Engine*>(engine)->cfg;
+  return TTB2_OK;
 }
 
 }  // extern "C"

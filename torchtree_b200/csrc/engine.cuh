@@ -133,6 +133,7 @@ struct Engine {
   bool preValid = false;
 
   int64_t launches = 0;
+  int64_t evalSerial = 0;  // loglik calls so far (ttb2_eval_serial)
   int64_t deviceBytes = 0;
 
   // CUDA-graph replay of the eigen-mode kernel sequences (api.cu)

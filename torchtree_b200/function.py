@@ -1,4 +1,6 @@
-"""Differentiable entry points: custom autograd Functions over the engine.
+"""Differentiable entry points: the custom autograd Functions live in the torch C++
+extension (csrc/torch_ext.cpp, `torch::autograd::Function` over the C ABI); this module
+only normalises shapes and hands tensors over.
 
 The reference differentiates the peeling loop with the autograd tape
 (SURVEY 3.4); here `backward` calls the engine's analytic pre-order pass, so no
@@ -10,6 +12,7 @@ from __future__ import annotations
 
 import torch
 
+from ._lib import EngineError
 from .engine import Engine
 
 
@@ -28,52 +31,24 @@ def reversible_eigensystem(q_norm: torch.Tensor, freqs: torch.Tensor):
     return evec, ivec, evals
 
 
-class _EigenLikelihood(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, engine: Engine, bls, rates, props, q_norm, freqs):
-        with torch.no_grad():
-            evec, ivec, evals = reversible_eigensystem(q_norm, freqs)
-            lnl = engine.loglik_eigen(bls, rates, props, evec, ivec, evals, freqs)
-        ctx.engine = engine
-        ctx.stamp = engine._stamp = getattr(engine, "_stamp", 0) + 1
-        ctx.save_for_backward(bls, rates, props, evec, ivec, evals, freqs)
-        return lnl
-
-    @staticmethod
-    def backward(ctx, grad_lnl):
-        engine = ctx.engine
-        bls, rates, props, evec, ivec, evals, freqs = ctx.saved_tensors
-        if engine._stamp != ctx.stamp:
-            # another forward ran on this engine since ours: its buffers were
-            # overwritten, recompute (SURVEY 8(b) autograd contract)
-            engine.loglik_eigen(bls, rates, props, evec, ivec, evals, freqs)
-            engine._stamp += 1
-            ctx.stamp = engine._stamp
-        g = engine.grad_eigen(grad_lnl.contiguous())
-        return None, g["branch_lengths"], g["site_rates"], g["props"], g["q"], g["freqs"]
+def _ext():
+    """The torch C++ extension (csrc/torch_ext.cpp -> _ttb200_torch.so) that holds the
+    autograd Functions; it must have been built (`python -m torchtree_b200.build`)."""
+    try:
+        from . import _ttb200_torch
+    except ImportError as exc:  # no fallback: say how to get the product path
+        raise EngineError(
+            "torchtree_b200: the torch extension _ttb200_torch.so is missing or cannot be "
+            "loaded (%s). Build it with `python -m torchtree_b200.build`. There is no "
+            "Python or CPU fallback." % exc) from exc
+    return _ttb200_torch
 
 
-class _MatsLikelihood(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, engine: Engine, mats, freqs, props):
-        with torch.no_grad():
-            lnl = engine.loglik_mats(mats, freqs, props)
-        ctx.engine = engine
-        ctx.stamp = engine._stamp = getattr(engine, "_stamp", 0) + 1
-        ctx.save_for_backward(mats, freqs, props)
-        return lnl
-
-    @staticmethod
-    def backward(ctx, grad_lnl):
-        engine = ctx.engine
-        mats, freqs, props = ctx.saved_tensors
-        if engine._stamp != ctx.stamp:
-            engine.loglik_mats(mats, freqs, props)
-            engine._stamp += 1
-            ctx.stamp = engine._stamp
-        d_mats, d_freqs, d_props = engine.grad_mats(
-            grad_lnl.contiguous(), want_mats=ctx.needs_input_grad[1])
-        return None, d_mats, d_freqs, d_props
+def _handle(engine: Engine) -> int:
+    h = getattr(engine, "_h", None)
+    if h is None or not h.value:
+        raise EngineError("engine is closed")
+    return int(h.value)
 
 
 def _lead(x: torch.Tensor, tail: int) -> torch.Tensor:
@@ -98,12 +73,13 @@ def log_likelihood_eigen(engine: Engine, branch_lengths, site_rates, site_props,
     if freqs.shape[0] > q_norm.shape[0]:
         # one eigen-system per frequency draw: give Q the same leading dimension
         q_norm = q_norm.expand(freqs.shape[0], -1, -1)
-    return _EigenLikelihood.apply(
-        engine, _lead(branch_lengths, 1), _lead(site_rates, 1), _lead(site_props, 1),
+    return _ext().log_likelihood_eigen(
+        _handle(engine), _lead(branch_lengths, 1), _lead(site_rates, 1), _lead(site_props, 1),
         q_norm, freqs)
 
 
 def log_likelihood_mats(engine: Engine, mats, freqs, site_props):
     """lnL [D] from transition matrices [D,B,K,S,S] computed by the caller
     (any SubstitutionModel.p_t); differentiable w.r.t. mats, freqs, site_props."""
-    return _MatsLikelihood.apply(engine, _lead(mats, 4), _lead(freqs, 1), _lead(site_props, 1))
+    return _ext().log_likelihood_mats(
+        _handle(engine), _lead(mats, 4), _lead(freqs, 1), _lead(site_props, 1))

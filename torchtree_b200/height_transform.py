@@ -85,23 +85,16 @@ class NodeHeightPlan:
         return out.reshape(x.shape)
 
 
-class _Heights(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, plan):
-        heights = plan.forward(x)
-        ctx.plan = plan
-        ctx.save_for_backward(x.detach(), heights)
-        return heights.to(x.dtype)
-
-    @staticmethod
-    def backward(ctx, grad):
-        x, heights = ctx.saved_tensors
-        return ctx.plan.backward(x, heights, grad.contiguous()).to(grad.dtype), None
-
-
 def node_heights(x: torch.Tensor, plan: NodeHeightPlan) -> torch.Tensor:
-    """Differentiable ratios/root-height -> internal node heights."""
-    return _Heights.apply(x, plan)
+    """Differentiable ratios/root-height -> internal node heights: the autograd Function
+    is `NodeHeights` in the torch C++ extension (csrc/torch_ext.cpp)."""
+    from .function import _ext
+
+    if not getattr(plan, "_h", None):
+        raise EngineError("node-height plan is closed")
+    if x.shape[-1] != plan.I:
+        raise EngineError("node_heights: last dimension must be tip_count - 1")
+    return _ext().node_heights(int(plan._h.value), plan.device, x)
 
 
 class GeneralNodeHeightTransform(Transform):
