@@ -166,7 +166,28 @@ int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws,
                       int32_t freq_draws, double* lnl, int32_t where);
 
 /*
- * Gradient for the latest ttb2_loglik_eigen call.
+ * The same evaluation from the normalised generator itself: the eigen-system of every draw is
+ * computed on the device (one CTA per generator, parallel cyclic Jacobi on the sqrt(pi)
+ * symmetrisation, csrc/eigen.cu) -- replaces the host torch.linalg.eigh round trip of
+ * SymmetricSubstitutionModel.p_t, substitution_model/abstract.py:57-66.
+ *   q_norm [q_draws][S][S]  reversible generator, already normalised (abstract.py:49-50);
+ *                           only the lower triangle of its symmetrisation is read, as eigh does
+ *   freqs  [freq_draws][S]  its stationary frequencies (also the root frequencies)
+ * One eigen-system per max(q_draws, freq_draws).  S <= 64.  ttb2_grad_eigen follows it exactly
+ * as it follows ttb2_loglik_eigen (d_q then has max(q_draws, freq_draws) leading entries).
+ */
+int ttb2_loglik_q(ttb2_engine* engine, int32_t draws, const double* branch_lengths,
+                  const double* site_rates, int32_t rate_draws, const double* props,
+                  int32_t prop_draws, const double* q_norm, int32_t q_draws,
+                  const double* freqs, int32_t freq_draws, double* lnl, int32_t where);
+
+/* The eigen-system used by the latest eigen-mode call: evec / ivec [eig_draws][S][S],
+ * eval [eig_draws][S] (ascending); any pointer may be NULL. */
+int ttb2_get_eigen(ttb2_engine* engine, double* evec, double* ivec, double* eval,
+                   int32_t where);
+
+/*
+ * Gradient for the latest ttb2_loglik_eigen / ttb2_loglik_q call.
  *   d_branch_lengths [D][B]; d_site_rates [rate_draws][K];
  *   d_props [prop_draws][K]; d_freqs [freq_draws][S] (root term only);
  *   d_q [eig_draws][S][S] = d lnL / d Q for the generator Q = V L V^-1 with all

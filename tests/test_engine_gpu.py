@@ -254,20 +254,17 @@ def test_torch_extension_autograd_matches_engine_calls(where, per_draw_model):
     args = [a.to(dev).requires_grad_(True) for a in host_args]
     lnl = log_likelihood_eigen(eng, *args)
     assert lnl.device.type == dev and lnl.shape == (3,)
-    if where == "host":
-        assert torch.equal(lnl.detach(), lnl_ref)
-    else:
-        assert_lnl_close(lnl.detach().cpu().numpy(), lnl_ref.numpy())
+    # (the extension decomposes the generator on the device, lnl_ref used LAPACK)
+    assert_lnl_close(lnl.detach().cpu().numpy(), lnl_ref.numpy(), rtol=1e-12)
     (lnl * wts.to(dev)).sum().backward()
     for a, key in zip(args, ("branch_lengths", "site_rates", "props", "q", "freqs")):
         assert a.grad.shape == a.shape, key
-        # eigh on the device (cusolver) differs from LAPACK in the last bits
-        tol = 0 if where == "host" else 1e-9
-        assert_grad_close(a.grad.cpu().numpy(), g_ref[key].numpy(), rtol=max(tol, 1e-13), what=key)
+        assert_grad_close(a.grad.cpu().numpy(), g_ref[key].numpy(),
+                          rtol=1e-7 if key == "q" else 1e-9, what=key)
 
     # matrices route, mats not requiring grad: d_mats is skipped, the rest still flows
-    freqs = host_args[4].to(dev).requires_grad_(True)
-    props = host_args[2].to(dev).requires_grad_(True)
+    freqs = host_args[4].clone().to(dev).requires_grad_(True)
+    props = host_args[2].clone().to(dev).requires_grad_(True)
     lnl_m = log_likelihood_mats(eng, mats_ref.to(dev), freqs, props)
     assert_lnl_close(lnl_m.detach().cpu().numpy(), lnl_ref.numpy())
     (lnl_m * wts.to(dev)).sum().backward()

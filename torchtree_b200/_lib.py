@@ -52,6 +52,8 @@ EXPORTED_SYMBOLS = (
     "ttb2_grad_mats",
     "ttb2_loglik_eigen",
     "ttb2_grad_eigen",
+    "ttb2_loglik_q",
+    "ttb2_get_eigen",
     "ttb2_site_loglik",
     "ttb2_get_mats",
     "ttb2_enable_timing",
@@ -105,6 +107,11 @@ def load():
     lib.ttb2_loglik_eigen.argtypes = [
         vp, c_int32, vp, vp, c_int32, vp, c_int32, vp, vp, vp, c_int32, vp, c_int32, vp, c_int32]
     lib.ttb2_loglik_eigen.restype = c_int32
+    lib.ttb2_loglik_q.argtypes = [
+        vp, c_int32, vp, vp, c_int32, vp, c_int32, vp, c_int32, vp, c_int32, vp, c_int32]
+    lib.ttb2_loglik_q.restype = c_int32
+    lib.ttb2_get_eigen.argtypes = [vp, vp, vp, vp, c_int32]
+    lib.ttb2_get_eigen.restype = c_int32
     lib.ttb2_grad_eigen.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int32]
     lib.ttb2_grad_eigen.restype = c_int32
     lib.ttb2_site_loglik.argtypes = [vp, vp, c_int32]

@@ -308,7 +308,7 @@ bool graphs_enabled(const Engine& e, int draws) {
 
 bool slot_matches(const Engine::GraphSlot& g, const Engine& e, int draws) {
   return g.exec && g.draws == draws && g.fd == e.freqDraws && g.pd == e.propDraws &&
-         g.rd == e.rateDraws && g.ed == e.eigDraws;
+         g.rd == e.rateDraws && g.ed == e.eigDraws && g.qd == e.qDraws;
 }
 
 // Runs `body` (a sequence of kernel launches on e.stream) through a cached CUDA
@@ -347,6 +347,7 @@ int run_graphed(Engine& e, Engine::GraphSlot& slot, int draws, Body body) {
     e.launches = before;  // counted per replay below
     slot.draws = draws;
     slot.fd = e.freqDraws; slot.pd = e.propDraws; slot.rd = e.rateDraws; slot.ed = e.eigDraws;
+    slot.qd = e.qDraws;
   }
   TTB2_CUDA_CHECK(cudaEventRecord(e.evIn, user));
   TTB2_CUDA_CHECK(cudaStreamWaitEvent(e.ownStream, e.evIn, 0));
@@ -532,6 +533,7 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
   TRY(dev_alloc(e, &e.evec, (size_t)D * m.S * m.S));
   TRY(dev_alloc(e, &e.ivec, (size_t)D * m.S * m.S));
   TRY(dev_alloc(e, &e.eval, (size_t)D * m.S));
+  TRY(dev_alloc(e, &e.qnorm, (size_t)D * m.S * m.S));
   TRY(dev_alloc(e, &e.gradLnl, (size_t)D));
   TRY(dev_alloc(e, &e.ones, (size_t)D));
   {
@@ -630,7 +632,7 @@ void ttb2_destroy(ttb2_engine* engine) {
   dev_free(e.dmat); dev_free(e.gpart); dev_free(e.siteLnl); dev_free(e.redPart);
   dev_free(e.lnl); dev_free(e.rootGrad); dev_free(e.hpart); dev_free(e.gscal);
   dev_free(e.freqs); dev_free(e.props); dev_free(e.bl); dev_free(e.rates);
-  dev_free(e.evec); dev_free(e.ivec); dev_free(e.eval); dev_free(e.gradLnl); dev_free(e.ones);
+  dev_free(e.evec); dev_free(e.ivec); dev_free(e.eval); dev_free(e.qnorm); dev_free(e.gradLnl); dev_free(e.ones);
   dev_free(e.outBl); dev_free(e.outRates); dev_free(e.outProps); dev_free(e.outFreqs);
   dev_free(e.outQ);
   dev_free(e.fwdProg); dev_free(e.bwdProg); dev_free(e.expoK); dev_free(e.esum);
@@ -701,6 +703,33 @@ int ttb2_loglik_mats(ttb2_engine* engine, int32_t draws, const double* mats,
   return run_forward(e, draws, lnl, where);
 }
 
+// Shared tail of the two eigen-mode entry points: inputs are staged; `qDraws` > 0 asks for
+// the eigen-system to be computed on the device from e.qnorm / e.freqs first.
+static int run_eigen_mode(Engine& e, int draws, int qDraws, double* lnl, int where) {
+  int rc;
+  e.mode = MODE_EIGEN;
+  ++e.evalSerial;
+  e.draws = draws;
+  e.qDraws = qDraws;
+  if (e.fusedOK || !e.spec4 && !gmma_supported(e)) {
+    if (qDraws && (rc = small_sym_eigh(e, qDraws, e.eigDraws))) return rc;
+    if ((rc = small_pmatrix(e, draws))) return rc;
+    return run_forward(e, draws, lnl, where);
+  }
+  if (!e.spec4 && !e.expoK && (rc = dev_alloc(e, &e.expoK, gmma_expo_elems(e)))) return rc;
+  rc = run_graphed(e, e.gFwd, draws, [&]() -> int {
+    int r;
+    if (qDraws && (r = small_sym_eigh(e, qDraws, e.eigDraws))) return r;
+    if ((r = small_pmatrix(e, draws))) return r;
+    return run_forward(e, draws, nullptr, TTB2_DEVICE);
+  });
+  if (rc) return rc;
+  e.draws = draws;
+  e.preValid = false;
+  if ((rc = copy_out(e, lnl, e.lnl, (size_t)draws * sizeof(double), where))) return rc;
+  return finish(e, where);
+}
+
 int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws, const double* branch_lengths,
                       const double* site_rates, int32_t rate_draws, const double* props,
                       int32_t prop_draws, const double* evec, const double* ivec,
@@ -733,23 +762,64 @@ int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws, const double* branch_l
   e.propDraws = prop_draws;
   e.rateDraws = rate_draws;
   e.eigDraws = eig_draws;
-  e.mode = MODE_EIGEN;
-  ++e.evalSerial;
-  e.draws = draws;
-  if (e.fusedOK || !e.spec4 && !gmma_supported(e)) {
-    if ((rc = small_pmatrix(e, draws))) return rc;
-    return run_forward(e, draws, lnl, where);
+  return run_eigen_mode(e, draws, 0, lnl, where);
+}
+
+int ttb2_loglik_q(ttb2_engine* engine, int32_t draws, const double* branch_lengths,
+                  const double* site_rates, int32_t rate_draws, const double* props,
+                  int32_t prop_draws, const double* q_norm, int32_t q_draws, const double* freqs,
+                  int32_t freq_draws, double* lnl, int32_t where) {
+  if (!engine || !branch_lengths || !site_rates || !props || !q_norm || !freqs) {
+    set_error("ttb2_loglik_q: null argument");
+    return TTB2_E_INVALID;
   }
-  if (!e.spec4 && !e.expoK && (rc = dev_alloc(e, &e.expoK, gmma_expo_elems(e)))) return rc;
-  rc = run_graphed(e, e.gFwd, draws, [&]() -> int {
-    int r = small_pmatrix(e, draws);
-    if (r) return r;
-    return run_forward(e, draws, nullptr, TTB2_DEVICE);
-  });
-  if (rc) return rc;
-  e.draws = draws;
-  e.preValid = false;
-  if ((rc = copy_out(e, lnl, e.lnl, (size_t)draws * sizeof(double), where))) return rc;
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  const Dims& m = e.dm;
+  if (draws < 1 || draws > e.cfg.max_draws || bad_draws(freq_draws, draws) ||
+      bad_draws(prop_draws, draws) || bad_draws(rate_draws, draws) || bad_draws(q_draws, draws)) {
+    set_error("ttb2_loglik_q: draws out of range (or a *_draws that is neither 1 nor draws)");
+    return TTB2_E_INVALID;
+  }
+  if (m.S > 64) {
+    set_error("ttb2_loglik_q: the device eigen-decomposition supports at most 64 states; "
+              "decompose on the host and call ttb2_loglik_eigen");
+    return TTB2_E_INVALID;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  mark(e, 0);
+  const size_t SS = (size_t)m.S * m.S;
+  if ((rc = copy_in(e, e.bl, branch_lengths, (size_t)draws * m.B * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.rates, site_rates, (size_t)rate_draws * m.K * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.props, props, (size_t)prop_draws * m.K * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.qnorm, q_norm, q_draws * SS * sizeof(double), where))) return rc;
+  if ((rc = copy_in(e, e.freqs, freqs, (size_t)freq_draws * m.S * sizeof(double), where))) return rc;
+  e.freqDraws = freq_draws;
+  e.propDraws = prop_draws;
+  e.rateDraws = rate_draws;
+  // one eigen-system per generator draw or per frequency draw, whichever varies
+  e.eigDraws = q_draws > freq_draws ? q_draws : freq_draws;
+  return run_eigen_mode(e, draws, q_draws, lnl, where);
+}
+
+int ttb2_get_eigen(ttb2_engine* engine, double* evec, double* ivec, double* eval, int32_t where) {
+  if (!engine) {
+    set_error("ttb2_get_eigen: null engine");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  if (e.mode != MODE_EIGEN) {
+    set_error("ttb2_get_eigen: no eigen-mode evaluation yet");
+    return TTB2_E_STATE;
+  }
+  const Dims& m = e.dm;
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  const size_t SS = (size_t)m.S * m.S;
+  if (evec && (rc = copy_out(e, evec, e.evec, e.eigDraws * SS * sizeof(double), where))) return rc;
+  if (ivec && (rc = copy_out(e, ivec, e.ivec, e.eigDraws * SS * sizeof(double), where))) return rc;
+  if (eval && (rc = copy_out(e, eval, e.eval, (size_t)e.eigDraws * m.S * sizeof(double), where)))
+    return rc;
   return finish(e, where);
 }
 

@@ -87,6 +87,7 @@ struct Engine {
   double* evec = nullptr;       // [Dmax][S][S]
   double* ivec = nullptr;
   double* eval = nullptr;       // [Dmax][S]
+  double* qnorm = nullptr;      // [Dmax][S][S] generator staged for the device eigen-decomposition
   double* gradLnl = nullptr;    // [Dmax]
   double* ones = nullptr;       // [Dmax] default grad_lnl
   // staged outputs (small)
@@ -133,13 +134,14 @@ struct Engine {
   bool preValid = false;
 
   int64_t launches = 0;
+  int qDraws = 0;  // generator draws of the latest ttb2_loglik_q call (0: eigen-system supplied)
   int64_t evalSerial = 0;  // loglik calls so far (ttb2_eval_serial)
   int64_t deviceBytes = 0;
 
   // CUDA-graph replay of the eigen-mode kernel sequences (api.cu)
   struct GraphSlot {
     cudaGraphExec_t exec = nullptr;
-    int draws = -1, fd = -1, pd = -1, rd = -1, ed = -1;
+    int draws = -1, fd = -1, pd = -1, rd = -1, ed = -1, qd = -1;
     int64_t kernels = 0;
   };
   GraphSlot gFwd, gBwd;
@@ -196,6 +198,8 @@ int gmma_backward2(Engine& e, int draws);
 
 // small kernels (kernels_small.cu)
 int small_pmatrix(Engine& e, int draws);
+// batched Jacobi eigen-decomposition of the staged generators (eigen.cu)
+int small_sym_eigh(Engine& e, int qDraws, int eigDraws);
 int small_reduce_lnl(Engine& e, int draws, int nblocks);
 int small_root_grad_reduce(Engine& e, int draws, int nblocks);
 int small_gpart_reduce(Engine& e, int draws);

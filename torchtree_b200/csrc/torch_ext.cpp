@@ -7,15 +7,16 @@
 // `forward` calls ttb2_loglik_* and `backward` calls the engine's analytic pre-order
 // pass (ttb2_grad_*), so no tape over the tree exists.  Everything below only marshals
 // tensors into the plain-pointer C ABI of include/ttb200.h -- no arithmetic on the path
-// happens here except the S x S symmetric eigen-decomposition of the generator
-// (at::linalg_eigh on the host, as SymmetricSubstitutionModel.p_t does at
-// substitution_model/abstract.py:57-66).
+// happens here (the eigen-decomposition of the generator runs on the device inside
+// ttb2_loglik_q; only state spaces beyond 64 states use at::linalg_eigh on the host, as
+// SymmetricSubstitutionModel.p_t does at substitution_model/abstract.py:57-66).
 //
 // Built by torchtree_b200/build.py into torchtree_b200/_ttb200_torch.so, linked against
 // lib/libttb200.so (rpath $ORIGIN/lib).  There is no fallback: without a CUDA device the
 // C ABI calls fail and the error is raised.
 #include <torch/extension.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -85,11 +86,28 @@ double* dptr(const Tensor& t) { return t.defined() ? t.data_ptr<double>() : null
 // ---------------------------------------------------------------------------------------
 // reversible models: P = V exp(L r t) V^-1 on the device (ttb2_loglik_eigen / ttb2_grad_eigen)
 struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
+  // S <= 64: the generator goes to the device as it is and ttb2_loglik_q decomposes it there
+  // (csrc/eigen.cu); larger state spaces decompose on the host and use ttb2_loglik_eigen.
   static void run_forward(int64_t handle, const ttb2_config& cfg, const Tensor& bls,
-                          const Tensor& rates, const Tensor& props, const Tensor& evec,
-                          const Tensor& ivec, const Tensor& evals, const Tensor& freqs,
-                          Tensor& lnl) {
-    const int where = where_of({bls, rates, props, evec, ivec, evals, freqs}, cfg.device);
+                          const Tensor& rates, const Tensor& props, const Tensor& q,
+                          const Tensor& freqs, Tensor& lnl) {
+    const int where = where_of({bls, rates, props, q, freqs}, cfg.device);
+    if (cfg.state_count <= 64) {
+      check(ttb2_loglik_q(as_engine(handle), (int32_t)bls.size(0), dptr(bls), dptr(rates),
+                          (int32_t)rates.size(0), dptr(props), (int32_t)props.size(0), dptr(q),
+                          (int32_t)q.size(0), dptr(freqs), (int32_t)freqs.size(0), dptr(lnl),
+                          where),
+            "ttb2_loglik_q");
+      return;
+    }
+    // eigen-system through the sqrt(pi) symmetrisation (abstract.py:57-66), no graph
+    Tensor root = freqs.sqrt();
+    Tensor sym = root.unsqueeze(-1) * q / root.unsqueeze(-2);
+    auto eig = at::linalg_eigh(sym, "L");
+    Tensor evals = std::get<0>(eig).contiguous();
+    Tensor u = std::get<1>(eig);
+    Tensor evec = (u / root.unsqueeze(-1)).contiguous();
+    Tensor ivec = (u.transpose(-1, -2) * root.unsqueeze(-2)).contiguous();
     check(ttb2_loglik_eigen(as_engine(handle), (int32_t)bls.size(0), dptr(bls), dptr(rates),
                             (int32_t)rates.size(0), dptr(props), (int32_t)props.size(0),
                             dptr(evec), dptr(ivec), dptr(evals), (int32_t)evec.size(0),
@@ -107,20 +125,11 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     Tensor props = prep(site_props, {K}, "site_props");
     Tensor q = prep(q_norm, {S, S}, "q_norm");
     Tensor freqs = prep(frequencies, {S}, "freqs");
-    // eigen-system through the sqrt(pi) symmetrisation (abstract.py:57-66), no graph
-    Tensor root = freqs.sqrt();
-    Tensor sym = root.unsqueeze(-1) * q / root.unsqueeze(-2);
-    auto eig = at::linalg_eigh(sym, "L");
-    Tensor evals = std::get<0>(eig).contiguous();
-    Tensor u = std::get<1>(eig);
-    Tensor evec = (u / root.unsqueeze(-1)).contiguous();
-    Tensor ivec = (u.transpose(-1, -2) * root.unsqueeze(-2)).contiguous();
     Tensor lnl = at::empty({bls.size(0)}, bls.options());
-    run_forward(handle, cfg, bls, rates, props, evec, ivec, evals, freqs, lnl);
+    run_forward(handle, cfg, bls, rates, props, q, freqs, lnl);
     ctx->saved_data["handle"] = handle;
     ctx->saved_data["serial"] = ttb2_eval_serial(as_engine(handle));
-    ctx->saved_data["q_draws"] = q.size(0);
-    ctx->save_for_backward({bls, rates, props, evec, ivec, evals, freqs});
+    ctx->save_for_backward({bls, rates, props, q, freqs});
     return lnl;
   }
 
@@ -128,13 +137,13 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     const int64_t handle = ctx->saved_data["handle"].toInt();
     const ttb2_config cfg = config_of(handle);
     auto saved = ctx->get_saved_variables();
-    const Tensor &bls = saved[0], &rates = saved[1], &props = saved[2], &evec = saved[3],
-                 &ivec = saved[4], &evals = saved[5], &freqs = saved[6];
+    const Tensor &bls = saved[0], &rates = saved[1], &props = saved[2], &q = saved[3],
+                 &freqs = saved[4];
     if (ttb2_eval_serial(as_engine(handle)) != ctx->saved_data["serial"].toInt()) {
       // another forward ran on this engine since ours and overwrote its buffers:
       // recompute (SURVEY 8(b) autograd contract)
       Tensor lnl = at::empty({bls.size(0)}, bls.options());
-      run_forward(handle, cfg, bls, rates, props, evec, ivec, evals, freqs, lnl);
+      run_forward(handle, cfg, bls, rates, props, q, freqs, lnl);
       ctx->saved_data["serial"] = ttb2_eval_serial(as_engine(handle));
     }
     const int64_t S = cfg.state_count;
@@ -144,16 +153,16 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     TORCH_CHECK(!g.defined() || g.numel() == bls.size(0), "ttb200: grad_lnl must have one entry per draw");
     Tensor d_bl = at::empty_like(bls), d_rates = at::empty_like(rates),
            d_props = at::empty_like(props), d_freqs = at::empty_like(freqs);
-    // the saved eigen-system may have been broadcast over frequency draws; d_q has its
-    // leading extent and is summed back to q_norm's below
+    // one eigen-system per generator draw or frequency draw, whichever varies; d_q has that
+    // leading extent and is summed back onto a shared generator below
     // (needs_input_grad indexes the tensor arguments only: bls 0, rates 1, props 2, q 3, freqs 4)
-    Tensor d_q = ctx->needs_input_grad(3) ? at::empty({evec.size(0), S, S}, bls.options()) : Tensor();
+    const int64_t eig_draws = std::max(q.size(0), freqs.size(0));
+    Tensor d_q = ctx->needs_input_grad(3) ? at::empty({eig_draws, S, S}, bls.options()) : Tensor();
     const int where = where_of({bls, g}, cfg.device);
     check(ttb2_grad_eigen(as_engine(handle), dptr(g), dptr(d_bl), dptr(d_rates), dptr(d_props),
                           dptr(d_q), dptr(d_freqs), where),
           "ttb2_grad_eigen");
-    const int64_t q_draws = ctx->saved_data["q_draws"].toInt();
-    if (d_q.defined() && d_q.size(0) != q_draws) d_q = d_q.sum(0, /*keepdim=*/true);
+    if (d_q.defined() && d_q.size(0) != q.size(0)) d_q = d_q.sum(0, /*keepdim=*/true);
     return {Tensor(), d_bl, d_rates, d_props, d_q, d_freqs};
   }
 };

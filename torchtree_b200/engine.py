@@ -237,6 +237,39 @@ class Engine:
                             rd=rates.shape[0], ed=evec.shape[0])
         return lnl
 
+    def loglik_q(self, branch_lengths, site_rates, props, q_norm, freqs, out=None) -> torch.Tensor:
+        """lnL [D] from the normalised reversible generator; its eigen-system is computed on
+        the device (ttb2_loglik_q, csrc/eigen.cu).  `grad_eigen` follows as usual."""
+        S, K, B = self.S, self.K, self.B
+        bl = self._prep(branch_lengths, (B,), "branch_lengths")
+        rates = self._prep(site_rates, (K,), "site_rates")
+        props = self._prep(props, (K,), "props")
+        q = self._prep(q_norm, (S, S), "q_norm")
+        freqs = self._prep(freqs, (S,), "freqs")
+        D = bl.shape[0]
+        where, dev = self._where([bl, rates, props, q, freqs])
+        lnl = out if out is not None else torch.empty(D, dtype=torch.float64, device=dev)
+        _lib.check(self._lib.ttb2_loglik_q(
+            self._h, D, _ptr(bl), _ptr(rates), rates.shape[0], _ptr(props), props.shape[0],
+            _ptr(q), q.shape[0], _ptr(freqs), freqs.shape[0], _ptr(lnl), where), "ttb2_loglik_q")
+        self._draws = D
+        self._shapes = dict(where=where, dev=dev, D=D, fd=freqs.shape[0], pd=props.shape[0],
+                            rd=rates.shape[0], ed=max(q.shape[0], freqs.shape[0]))
+        return lnl
+
+    def get_eigen(self):
+        """(evec, ivec, evals) of the latest eigen-mode call, as the engine holds them."""
+        sh = self._shapes
+        if sh is None or "ed" not in sh:
+            raise EngineError("get_eigen before an eigen-mode loglik call")
+        S, ed, dev = self.S, sh["ed"], sh["dev"]
+        evec = torch.empty((ed, S, S), dtype=torch.float64, device=dev)
+        ivec = torch.empty((ed, S, S), dtype=torch.float64, device=dev)
+        evals = torch.empty((ed, S), dtype=torch.float64, device=dev)
+        _lib.check(self._lib.ttb2_get_eigen(self._h, _ptr(evec), _ptr(ivec), _ptr(evals),
+                                            sh["where"]), "ttb2_get_eigen")
+        return evec, ivec, evals
+
     def grad_eigen(self, grad_lnl=None, out=None):
         sh = self._shapes
         if sh is None or "ed" not in sh:
