@@ -263,8 +263,8 @@ def test_torch_extension_autograd_matches_engine_calls(where, per_draw_model):
                           rtol=1e-7 if key == "q" else 1e-9, what=key)
 
     # matrices route, mats not requiring grad: d_mats is skipped, the rest still flows
-    freqs = host_args[4].clone().to(dev).requires_grad_(True)
-    props = host_args[2].clone().to(dev).requires_grad_(True)
+    freqs = host_args[4].detach().clone().to(dev).requires_grad_(True)
+    props = host_args[2].detach().clone().to(dev).requires_grad_(True)
     lnl_m = log_likelihood_mats(eng, mats_ref.to(dev), freqs, props)
     assert_lnl_close(lnl_m.detach().cpu().numpy(), lnl_ref.numpy())
     (lnl_m * wts.to(dev)).sum().backward()
