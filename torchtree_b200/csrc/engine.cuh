@@ -195,6 +195,11 @@ size_t gmma_expo_elems(const Engine& e);
 int gmma_forward2(Engine& e, int draws);
 int gmma_root2(Engine& e, int draws);
 int gmma_backward2(Engine& e, int draws);
+// warp-autonomous DMMA level kernels for 20 states (kernels_gwarp.cu); TTB2_GM_LEGACY=1 keeps
+// the shared-memory tile kernels of kernels_gmma.cu
+bool gwarp_supported(const Engine& e, bool backward);
+int gwarp_forward(Engine& e, int draws);
+int gwarp_backward_levels(Engine& e, int draws);
 
 // small kernels (kernels_small.cu)
 int small_pmatrix(Engine& e, int draws);

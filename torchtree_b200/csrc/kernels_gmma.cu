@@ -532,6 +532,7 @@ static int gm_fwd_chunk(const Engine& e, int draws, int count) {
 }
 
 int gmma_forward2(Engine& e, int draws) {
+  if (gwarp_supported(e, false)) return gwarp_forward(e, draws);
   const Dims& m = e.dm;
   const size_t smem = gm_fwd2_smem(m);
   const int MT = gm_shape(m.S).Sp / 8;
@@ -596,6 +597,10 @@ int gmma_backward2(Engine& e, int draws) {
     TTB2_CUDA_CHECK(cudaGetLastError());
     int rc = small_root_grad_reduce(e, draws, nblocks);
     if (rc) return rc;
+  }
+  if (gwarp_supported(e, true)) {
+    const int rc = gwarp_backward_levels(e, draws);
+    return rc ? rc : small_gpart_reduce(e, draws);
   }
   const size_t smem = gm_bwd2_smem(m);
   const int MT = gm_shape(m.S).Sp / 8;
