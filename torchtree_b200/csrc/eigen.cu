@@ -6,7 +6,8 @@
 //     sym = sqrt(pi) Q sqrt(pi)^-1;  e, U = eigh(sym);  V = sqrt(pi)^-1 U;  V^-1 = U^T sqrt(pi)
 // with one CTA per generator running a parallel cyclic Jacobi iteration in shared memory:
 // every step rotates n/2 disjoint index pairs (round-robin tournament ordering, n-1 steps
-// per sweep), rows first, then columns of A and of the accumulated U.  Jacobi converges
+// per sweep); A <- J^T A J is applied block-wise in one pass (each 2 x 2 block of a row pair x
+// column pair is rotated from both sides by one thread), U <- U J alongside: two barriers per step.  Jacobi converges
 // quadratically and delivers eigenvalues / vectors at least as accurately as LAPACK's
 // syevd (which the reference calls through torch.linalg.eigh); 6-9 sweeps for S = 4..64.
 // Like eigh's default, only the lower triangle of `sym` is read.  Eigenvalues come out in
@@ -45,6 +46,7 @@ sym_eigh_kernel(const double* __restrict__ q, int qDraws, const double* __restri
   double* root = rot + n;     // [n] sqrt(pi)
   double* red = root + n;     // [2 * 8] block reduction scratch
   __shared__ int rank[64];
+  __shared__ int pairs[64];  // (p, q) of every pair of the current step
   __shared__ int done;
 
   const int d = blockIdx.x;
@@ -66,17 +68,18 @@ sym_eigh_kernel(const double* __restrict__ q, int qDraws, const double* __restri
   }
   __syncthreads();
 
-  const int half = n / 2;
+  const int half = n / 2;  // <= 32: one lane per pair
   const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NWARP = EIGH_THREADS / 32;
   for (int sweep = 0; sweep < EIGH_MAX_SWEEPS; ++sweep) {
     // off-diagonal and total Frobenius norms, summed directly (no cancellation)
     double off = 0.0, tot = 0.0;
-    for (int e = tid; e < n * n; e += EIGH_THREADS) {
-      const int i = e / n, j = e % n;
-      const double a = A[i * ld + j];
-      tot += a * a;
-      if (i != j) off += a * a;
-    }
+    for (int i = warp; i < n; i += NWARP)
+      for (int j = lane; j < n; j += 32) {
+        const double a = A[i * ld + j];
+        tot += a * a;
+        if (i != j) off += a * a;
+      }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       off += __shfl_xor_sync(0xffffffffu, off, o);
@@ -89,7 +92,7 @@ sym_eigh_kernel(const double* __restrict__ q, int qDraws, const double* __restri
     __syncthreads();
     if (tid == 0) {
       double o = 0.0, t = 0.0;
-      for (int w = 0; w < EIGH_THREADS / 32; ++w) {
+      for (int w = 0; w < NWARP; ++w) {
         o += red[w];
         t += red[8 + w];
       }
@@ -101,6 +104,7 @@ sym_eigh_kernel(const double* __restrict__ q, int qDraws, const double* __restri
     if (done) break;
 
     for (int r = 0; r < n - 1; ++r) {
+      // rotation of every pair of this step, from the current A
       if (tid < half) {
         int p, qq;
         rr_pair(n, r, tid, p, qq);
@@ -118,34 +122,38 @@ sym_eigh_kernel(const double* __restrict__ q, int qDraws, const double* __restri
         }
         rot[2 * tid] = c;
         rot[2 * tid + 1] = s;
+        pairs[2 * tid] = p;
+        pairs[2 * tid + 1] = qq;
       }
       __syncthreads();
-      // rows: A <- J^T A
-      for (int e = tid; e < half * n; e += EIGH_THREADS) {
-        const int k = e / n, j = e % n;
-        const double c = rot[2 * k], s = rot[2 * k + 1];
-        if (s != 0.0) {
-          int p, qq;
-          rr_pair(n, r, k, p, qq);
-          const double ap = A[p * ld + j], aq = A[qq * ld + j];
-          A[p * ld + j] = c * ap - s * aq;
-          A[qq * ld + j] = s * ap + c * aq;
+      // A <- J^T A J in one pass: the 2 x 2 block (pair ki, pair kj) is read once, rotated from
+      // both sides and written once; every element belongs to exactly one block.
+      // Lane = column pair, warps stride over the row pairs.
+      if (lane < half) {
+        const int pj = pairs[2 * lane], qj = pairs[2 * lane + 1];
+        const double cj = rot[2 * lane], sj = rot[2 * lane + 1];
+        for (int ki = warp; ki < half; ki += NWARP) {
+          const int pi = pairs[2 * ki], qi = pairs[2 * ki + 1];
+          const double ci = rot[2 * ki], si = rot[2 * ki + 1];
+          if (si != 0.0 || sj != 0.0) {
+            const double a = A[pi * ld + pj], b = A[pi * ld + qj];
+            const double cc = A[qi * ld + pj], d = A[qi * ld + qj];
+            const double a1 = ci * a - si * cc, c1 = si * a + ci * cc;
+            const double b1 = ci * b - si * d, d1 = si * b + ci * d;
+            const bool diag = ki == lane;  // the annihilated pair is set to exactly zero
+            A[pi * ld + pj] = cj * a1 - sj * b1;
+            A[pi * ld + qj] = diag ? 0.0 : sj * a1 + cj * b1;
+            A[qi * ld + pj] = diag ? 0.0 : cj * c1 - sj * d1;
+            A[qi * ld + qj] = sj * c1 + cj * d1;
+          }
         }
-      }
-      __syncthreads();
-      // columns: A <- A J, U <- U J; the annihilated pair is set to exactly zero
-      for (int e = tid; e < half * n; e += EIGH_THREADS) {
-        const int k = e / n, i = e % n;
-        const double c = rot[2 * k], s = rot[2 * k + 1];
-        if (s != 0.0) {
-          int p, qq;
-          rr_pair(n, r, k, p, qq);
-          const double ap = A[i * ld + p], aq = A[i * ld + qq];
-          A[i * ld + p] = i == qq ? 0.0 : c * ap - s * aq;
-          A[i * ld + qq] = i == p ? 0.0 : s * ap + c * aq;
-          const double up = U[i * ld + p], uq = U[i * ld + qq];
-          U[i * ld + p] = c * up - s * uq;
-          U[i * ld + qq] = s * up + c * uq;
+        // U <- U J: lane = column pair, warps stride over the rows
+        if (sj != 0.0) {
+          for (int i = warp; i < n; i += NWARP) {
+            const double up = U[i * ld + pj], uq = U[i * ld + qj];
+            U[i * ld + pj] = cj * up - sj * uq;
+            U[i * ld + qj] = sj * up + cj * uq;
+          }
         }
       }
       __syncthreads();

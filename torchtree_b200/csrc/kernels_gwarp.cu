@@ -105,22 +105,32 @@ __device__ __forceinline__ void gw_issue_tile(double* tile, const double* plane,
   }
 }
 
-// A fragments of one child from its staged tile / from the tip code table
+// A fragments of one child from its staged tile / from the tip code table (`code` = this
+// lane's tip code for pattern i0 + r, prefetched one group ahead)
 template <int S>
-__device__ __forceinline__ void gw_frag_child(double (&a)[GwShape<S>::KT], bool tip,
-                                              const uint8_t* tipRow, const double* codeP,
-                                              const double* tile, int i0, int lane) {
+__device__ __forceinline__ void gw_frag_child(double (&a)[GwShape<S>::KT], bool tip, int code,
+                                              const double* table, const double* tile, int lane) {
   using G = GwShape<S>;
   static_assert(S % 4 == 0, "state rows beyond S are not staged");
   const int r = lane >> 2, c = lane & 3;
   if (tip) {
-    const double* cp = codeP + (size_t)tipRow[i0 + r] * S;
+    const double* cp = table + code * S + c;
 #pragma unroll
-    for (int kt = 0; kt < G::KT; ++kt) a[kt] = __ldg(cp + 4 * kt + c);
+    for (int kt = 0; kt < G::KT; ++kt) a[kt] = cp[4 * kt];
   } else {
 #pragma unroll
     for (int kt = 0; kt < G::KT; ++kt) a[kt] = tile[(4 * kt + c) * GW_LD + r];
   }
+}
+
+// the tip code table in shared memory when it is small (it always is for real alphabets)
+constexpr int GW_MAX_CODES = 64;
+template <int S>
+__device__ __forceinline__ const double* gw_stage_codes(double* dst, const double* codeP,
+                                                        int codeCount, int nthreads) {
+  if (codeCount > GW_MAX_CODES) return codeP;
+  for (int idx = threadIdx.x; idx < codeCount * S; idx += nthreads) dst[idx] = codeP[idx];
+  return dst;
 }
 
 // acc[nt] += A . B over all k-steps (C fragment: pattern r, states 8 nt + 2 c + {0, 1})
@@ -145,12 +155,14 @@ __global__ void __launch_bounds__(NW * 32, 2)
 gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
               const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
               double* __restrict__ partials, int16_t* __restrict__ expoK, int T, int Npad, int B,
-              int K, int chunkPatterns) {
+              int K, int chunkPatterns, int codeCount) {
   using G = GwShape<S>;
   extern __shared__ double sm[];
   double* fragU = sm;  // [2][KT][NT][32]
   constexpr int SS = S * S;
   constexpr int TILE = S * GW_LD;
+  const double* table = gw_stage_codes<S>(sm + G::UF * 32 + NW * STAGES * 2 * TILE, codeP,
+                                          codeCount, NW * 32);
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
   const NodeOp op = ops[opBegin + nodeSlot];
@@ -191,14 +203,20 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
 #pragma unroll
   for (int j = 0; j < STAGES - 1; ++j) issue(j);
   int j = 0;
+  int codeL = (tipL && first < end) ? tl[first + r] : 0, codeR = (tipR && first < end) ? tr[first + r] : 0;
   for (int i0 = first; i0 < end; i0 += NW * 8, ++j) {
     issue(j + STAGES - 1);
+    const int inext = i0 + NW * 8;
+    const int nextL = (tipL && inext < end) ? tl[inext + r] : 0;
+    const int nextR = (tipR && inext < end) ? tr[inext + r] : 0;
     cp_wait<STAGES - 1>();
     __syncwarp();
     const double* slot = ring + (j % STAGES) * 2 * TILE;
     double aL[G::KT], aR[G::KT];
-    gw_frag_child<S>(aL, tipL, tl, codeP, slot, i0, lane);
-    gw_frag_child<S>(aR, tipR, tr, codeP, slot + TILE, i0, lane);
+    gw_frag_child<S>(aL, tipL, codeL, table, slot, lane);
+    gw_frag_child<S>(aR, tipR, codeR, table, slot + TILE, lane);
+    codeL = nextL;
+    codeR = nextR;
     double accL[G::NT][2], accR[G::NT][2];
 #pragma unroll
     for (int nt = 0; nt < G::NT; ++nt) accL[nt][0] = accL[nt][1] = accR[nt][0] = accR[nt][1] = 0.0;
@@ -241,7 +259,7 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
               const double* __restrict__ partials, const int16_t* __restrict__ expoK,
               const double* __restrict__ weights, double* __restrict__ pre,
               double* __restrict__ gpart, const int* __restrict__ chunkBase, size_t chunkTotal,
-              int T, int Npad, int B, int K, int chunkPatterns, int nChunk) {
+              int T, int Npad, int B, int K, int chunkPatterns, int nChunk, int codeCount) {
   using G = GwShape<S>;
   extern __shared__ double sm[];
   double* fragU = sm;
@@ -250,6 +268,8 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   constexpr int SS = S * S;
   constexpr int NT = G::NT;
   constexpr int TILE = S * GW_LD;
+  const double* table = gw_stage_codes<S>(ringAll + NW * STAGES * 3 * TILE, codeP, codeCount,
+                                          NW * 32);
   static_assert(STAGES * 3 * TILE >= 2 * SS, "the ring doubles as the G staging area");
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
@@ -307,8 +327,12 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
 #pragma unroll
   for (int j = 0; j < STAGES - 1; ++j) issue(j);
   int j = 0;
+  int codeL = (tipL && first < end) ? tl[first + r] : 0, codeR = (tipR && first < end) ? tr[first + r] : 0;
   for (int i0 = first; i0 < end; i0 += NW * 8, ++j) {
     issue(j + STAGES - 1);
+    const int inext = i0 + NW * 8;
+    const int nextL = (tipL && inext < end) ? tl[inext + r] : 0;
+    const int nextR = (tipR && inext < end) ? tr[inext + r] : 0;
     const double w = weights[i0 + r];
     const int el = tipL ? 0 : (int)elp[i0 + r];
     const int er = tipR ? 0 : (int)erp[i0 + r];
@@ -316,8 +340,8 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     __syncwarp();
     const double* slot = ring + (j % STAGES) * 3 * TILE;
     double aL[G::KT], aR[G::KT];
-    gw_frag_child<S>(aL, tipL, tl, codeP, slot + TILE, i0, lane);
-    gw_frag_child<S>(aR, tipR, tr, codeP, slot + 2 * TILE, i0, lane);
+    gw_frag_child<S>(aL, tipL, codeL, table, slot + TILE, lane);
+    gw_frag_child<S>(aR, tipR, codeR, table, slot + 2 * TILE, lane);
     double uL[NT][2], uR[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) uL[nt][0] = uL[nt][1] = uR[nt][0] = uR[nt][1] = 0.0;
@@ -364,15 +388,17 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
       }
       // G phase: G_c[s][t] += sum_p (w_p m_c[s][p]) v_c[t][p], contraction over the 8 patterns
       const double* vt = slot + (1 + side) * TILE;
-      const uint8_t* trow = side ? tr : tl;
+      const int mycode = side ? codeR : codeL;
 #pragma unroll
       for (int kp = 0; kp < 2; ++kp) {
         // B[k = pattern 4 kp + c][n = child state 8 nt + r]
         double bv[NT];
         if (tip) {
-          const double* cp = codeP + (size_t)trow[i0 + 4 * kp + c] * S;
+          // the code of pattern 4 kp + c is held by the lanes of row 4 kp + c
+          const int code = __shfl_sync(0xffffffffu, mycode, (4 * kp + c) << 2);
+          const double* cp = table + code * S + r;
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) bv[nt] = (8 * nt + r < S) ? __ldg(cp + 8 * nt + r) : 0.0;
+          for (int nt = 0; nt < NT; ++nt) bv[nt] = (8 * nt + r < S) ? cp[8 * nt] : 0.0;
         } else {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt)
@@ -394,6 +420,8 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
         }
       }
     }
+    codeL = nextL;
+    codeR = nextR;
     __syncwarp();  // the slot is free for the copy issued in the next trip
   }
   cp_wait<0>();
@@ -431,12 +459,13 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
 
 template <int S, int NW, int STAGES>
 size_t gw_fwd_smem() {
-  return ((size_t)GwShape<S>::UF * 32 + (size_t)NW * STAGES * 2 * S * GW_LD) * sizeof(double);
+  return ((size_t)GwShape<S>::UF * 32 + (size_t)NW * STAGES * 2 * S * GW_LD +
+          (size_t)GW_MAX_CODES * S) * sizeof(double);
 }
 template <int S, int NW, int STAGES>
 size_t gw_bwd_smem() {
-  return ((size_t)(GwShape<S>::UF + GwShape<S>::QF) * 32 + (size_t)NW * STAGES * 3 * S * GW_LD) *
-         sizeof(double);
+  return ((size_t)(GwShape<S>::UF + GwShape<S>::QF) * 32 + (size_t)NW * STAGES * 3 * S * GW_LD +
+          (size_t)GW_MAX_CODES * S) * sizeof(double);
 }
 
 constexpr int GW_GRANULE = 64;  // chunk sizes are multiples of 8 patterns x 8 warps
@@ -468,7 +497,7 @@ int gw_launch_fwd(Engine& e, int draws, int ctas) {
       dim3 grid(nChunk, cnt * m.K, draws);
       launch_level(kern, grid, NW * 32, smem, e.stream, l > 0 && pdl_enabled(), e.ops,
                    opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad, m.B,
-                   m.K, chunkPatterns);
+                   m.K, chunkPatterns, e.cfg.code_count);
       ++e.launches;
     }
   }
@@ -498,7 +527,7 @@ int gw_launch_bwd(Engine& e, int draws) {
       launch_level(kern, grid, NW * 32, smem, e.stream, l < nLevels - 1 && pdl_enabled(), e.ops,
                    opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, e.weights, e.pre,
                    e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B, m.K, chunkPatterns,
-                   nChunk);
+                   nChunk, e.cfg.code_count);
       ++e.launches;
     }
   }
@@ -531,12 +560,12 @@ int gwarp_forward(Engine& e, int draws) {
 
 // the pre-order level sweep (the root kernel and the gpart reduction stay with the caller)
 int gwarp_backward_levels(Engine& e, int draws) {
-  static const int variant = getenv("TTB2_GW_BWD") ? atoi(getenv("TTB2_GW_BWD")) : 83;
+  static const int variant = getenv("TTB2_GW_BWD") ? atoi(getenv("TTB2_GW_BWD")) : 43;
   switch (variant) {
     case 82: return gw_launch_bwd<8, 2>(e, draws);
-    case 43: return gw_launch_bwd<4, 3>(e, draws);
+    case 83: return gw_launch_bwd<8, 3>(e, draws);
     case 44: return gw_launch_bwd<4, 4>(e, draws);
-    default: return gw_launch_bwd<8, 3>(e, draws);
+    default: return gw_launch_bwd<4, 3>(e, draws);
   }
 }
 

@@ -86,13 +86,21 @@ double* dptr(const Tensor& t) { return t.defined() ? t.data_ptr<double>() : null
 // ---------------------------------------------------------------------------------------
 // reversible models: P = V exp(L r t) V^-1 on the device (ttb2_loglik_eigen / ttb2_grad_eigen)
 struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
-  // S <= 64: the generator goes to the device as it is and ttb2_loglik_q decomposes it there
-  // (csrc/eigen.cu); larger state spaces decompose on the host and use ttb2_loglik_eigen.
+  // Where the S x S eigen-system is computed.  The device Jacobi kernel (csrc/eigen.cu, one
+  // CTA per generator) takes a flat ~0.02 / 0.13 / 0.85 ms for S = 4 / 20 / 61 however many
+  // draws there are (up to one per SM); LAPACK on the host takes 0.02 / 0.03 / 0.18 ms PER
+  // generator (profiles/r01_eigen_device.jsonl).  So: small alphabets and batches of draws
+  // decompose on the device (ttb2_loglik_q), a single large generator on the host
+  // (at::linalg_eigh + ttb2_loglik_eigen), as does anything beyond the kernel's 64 states.
+  static bool device_eigh(int64_t S, int64_t eig_draws) {
+    return S <= 64 && (S <= 8 || eig_draws >= 6);
+  }
+
   static void run_forward(int64_t handle, const ttb2_config& cfg, const Tensor& bls,
                           const Tensor& rates, const Tensor& props, const Tensor& q,
                           const Tensor& freqs, Tensor& lnl) {
     const int where = where_of({bls, rates, props, q, freqs}, cfg.device);
-    if (cfg.state_count <= 64) {
+    if (device_eigh(cfg.state_count, std::max(q.size(0), freqs.size(0)))) {
       check(ttb2_loglik_q(as_engine(handle), (int32_t)bls.size(0), dptr(bls), dptr(rates),
                           (int32_t)rates.size(0), dptr(props), (int32_t)props.size(0), dptr(q),
                           (int32_t)q.size(0), dptr(freqs), (int32_t)freqs.size(0), dptr(lnl),
