@@ -8,7 +8,7 @@ for l in sys.stdin:
 " "$@"; }
 run TTB2_GM_LEGACY=1
 run X=default
-for v in 82 43 44; do run TTB2_GW_BWD=$v; done
-for c in 8 16; do run TTB2_CHUNK_TARGET=$c; run TTB2_CHUNK_TARGET=$c TTB2_GW_BWD=82; done
-for v in 84 44 43; do run TTB2_GW_FWD=$v; done
+for v in 83 43 45; do run TTB2_GW_FWD=$v; done
 for c in 8 32; do run TTB2_GW_FWD_CTAS=$c; done
+for v in 42 44 83; do run TTB2_GW_BWD=$v; done
+for c in 8 16; do run TTB2_CHUNK_TARGET=$c; run TTB2_CHUNK_TARGET=$c TTB2_GW_BWD=42; done

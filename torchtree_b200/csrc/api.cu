@@ -136,6 +136,7 @@ int ensure_grad_buffers(Engine& e, int draws) {
   // big levels, but a CTA needs a few hundred patterns to amortise its prologue -- measured
   // optimum on the 1000-taxon problem: 8 at 12.5k patterns, 16 at 25k, 32 from 50k up
   int perSm = e.dm.S <= 32 ? 32 : 16;
+  if (gwarp_supported(e, true)) perSm = 16;   // warp-autonomous 20-state kernels: 9.8 ms vs 10.0 at 32
   if (e.spec4) perSm = e.dm.Npad < 20000 ? 8 : (e.dm.Npad < 40000 ? 16 : 32);
   if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, perSm))) return rc;
   if (planBefore != e.chunkPlanDraws) drop_graphs(e);

@@ -124,7 +124,7 @@ __device__ __forceinline__ void gw_frag_child(double (&a)[GwShape<S>::KT], bool 
 }
 
 // the tip code table in shared memory when it is small (it always is for real alphabets)
-constexpr int GW_MAX_CODES = 64;
+constexpr int GW_MAX_CODES = 32;
 template <int S>
 __device__ __forceinline__ const double* gw_stage_codes(double* dst, const double* codeP,
                                                         int codeCount, int nthreads) {
@@ -151,7 +151,7 @@ __device__ __forceinline__ void gw_u(double (&acc)[GwShape<S>::NT][2],
 // shared: fragU [UF][32] | ring [NW][STAGES][2][S][GW_LD]
 // ---------------------------------------------------------------------------------------
 template <int S, int NW, int STAGES>
-__global__ void __launch_bounds__(NW * 32, 2)
+__global__ void __launch_bounds__(NW * 32)
 gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
               const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
               double* __restrict__ partials, int16_t* __restrict__ expoK, int T, int Npad, int B,
@@ -200,29 +200,28 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     }
     cp_commit();
   };
+  static_assert(STAGES >= 3, "two groups are being consumed while the next ones travel");
 #pragma unroll
   for (int j = 0; j < STAGES - 1; ++j) issue(j);
-  int j = 0;
-  int codeL = (tipL && first < end) ? tl[first + r] : 0, codeR = (tipR && first < end) ? tr[first + r] : 0;
-  for (int i0 = first; i0 < end; i0 += NW * 8, ++j) {
-    issue(j + STAGES - 1);
-    const int inext = i0 + NW * 8;
-    const int nextL = (tipL && inext < end) ? tl[inext + r] : 0;
-    const int nextR = (tipR && inext < end) ? tr[inext + r] : 0;
-    cp_wait<STAGES - 1>();
-    __syncwarp();
-    const double* slot = ring + (j % STAGES) * 2 * TILE;
+  if (first >= end) {
+    cp_wait<0>();
+    return;
+  }
+  // Software pipeline over the warp's groups: the DMMAs of group j + 1 are issued BEFORE the
+  // epilogue (product, rescaling, stores) of group j, so the tensor pipe never drains while a
+  // warp finishes a group.  Two accumulator sets alternate (the loop is unrolled by two).
+  auto start_group = [&](double (&accL)[G::NT][2], double (&accR)[G::NT][2], int jj, int codeL,
+                         int codeR) {
+    const double* slot = ring + (jj % STAGES) * 2 * TILE;
     double aL[G::KT], aR[G::KT];
     gw_frag_child<S>(aL, tipL, codeL, table, slot, lane);
     gw_frag_child<S>(aR, tipR, codeR, table, slot + TILE, lane);
-    codeL = nextL;
-    codeR = nextR;
-    double accL[G::NT][2], accR[G::NT][2];
 #pragma unroll
     for (int nt = 0; nt < G::NT; ++nt) accL[nt][0] = accL[nt][1] = accR[nt][0] = accR[nt][1] = 0.0;
     gw_u<S>(accL, aL, fragU, lane);
     gw_u<S>(accR, aR, fragU + G::KT * G::NT * 32, lane);
-    __syncwarp();  // the slot is free for the copy issued in the next trip
+  };
+  auto finish_group = [&](double (&accL)[G::NT][2], double (&accR)[G::NT][2], int i0) {
     double m = 0.0;
 #pragma unroll
     for (int nt = 0; nt < G::NT; ++nt) {
@@ -243,6 +242,37 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
       if (s0 + 1 < S) o[(size_t)(s0 + 1) * Npad] = accL[nt][1] * f;
     }
     if (c == 0) en[i0 + r] = (int16_t)e;
+  };
+  // one trip: start group j + 1 (if any) with `nxt`, finish group j held in `cur`
+  auto trip = [&](double (&curL)[G::NT][2], double (&curR)[G::NT][2], double (&nxtL)[G::NT][2],
+                  double (&nxtR)[G::NT][2], int jj, int i0, int& codeL, int& codeR) {
+    issue(jj + STAGES - 1);  // into the slot of group j - 1, read one trip ago
+    const int i1 = i0 + NW * 8, i2 = i0 + 2 * NW * 8;
+    const int nextL = (tipL && i2 < end) ? tl[i2 + r] : 0;   // codes of group j + 2
+    const int nextR = (tipR && i2 < end) ? tr[i2 + r] : 0;
+    if (i1 < end) {
+      cp_wait<STAGES - 2>();  // group j + 1 has landed
+      __syncwarp();
+      start_group(nxtL, nxtR, jj + 1, codeL, codeR);
+    }
+    finish_group(curL, curR, i0);
+    __syncwarp();  // every lane has read slot j + 1 before the next trip overwrites slot j
+    codeL = nextL;
+    codeR = nextR;
+  };
+  double a0L[G::NT][2], a0R[G::NT][2], a1L[G::NT][2], a1R[G::NT][2];
+  {
+    cp_wait<STAGES - 2>();  // group 0
+    __syncwarp();
+    start_group(a0L, a0R, 0, tipL ? tl[first + r] : 0, tipR ? tr[first + r] : 0);
+  }
+  // codes of group 1, then the trips hand over the codes of group j + 2
+  int codeL = (tipL && first + NW * 8 < end) ? tl[first + NW * 8 + r] : 0;
+  int codeR = (tipR && first + NW * 8 < end) ? tr[first + NW * 8 + r] : 0;
+  int j = 0;
+  for (int i0 = first; i0 < end; i0 += 2 * NW * 8, j += 2) {
+    trip(a0L, a0R, a1L, a1R, j, i0, codeL, codeR);
+    if (i0 + NW * 8 < end) trip(a1L, a1R, a0L, a0R, j + 1, i0 + NW * 8, codeL, codeR);
   }
   cp_wait<0>();
 }
@@ -549,23 +579,26 @@ bool gwarp_supported(const Engine& e, bool backward) {
 
 int gwarp_forward(Engine& e, int draws) {
   static const int ctas = getenv("TTB2_GW_FWD_CTAS") ? atoi(getenv("TTB2_GW_FWD_CTAS")) : 16;
-  static const int variant = getenv("TTB2_GW_FWD") ? atoi(getenv("TTB2_GW_FWD")) : 83;
+  static const int variant = getenv("TTB2_GW_FWD") ? atoi(getenv("TTB2_GW_FWD")) : 44;
   switch (variant) {
-    case 84: return gw_launch_fwd<8, 4>(e, draws, ctas);
-    case 44: return gw_launch_fwd<4, 4>(e, draws, ctas);
+    case 83: return gw_launch_fwd<8, 3>(e, draws, ctas);
     case 43: return gw_launch_fwd<4, 3>(e, draws, ctas);
-    default: return gw_launch_fwd<8, 3>(e, draws, ctas);
+    case 45: return gw_launch_fwd<4, 5>(e, draws, ctas);
+    default: return gw_launch_fwd<4, 4>(e, draws, ctas);
   }
 }
 
 // the pre-order level sweep (the root kernel and the gpart reduction stay with the caller)
 int gwarp_backward_levels(Engine& e, int draws) {
-  static const int variant = getenv("TTB2_GW_BWD") ? atoi(getenv("TTB2_GW_BWD")) : 43;
+  static const int variant = getenv("TTB2_GW_BWD") ? atoi(getenv("TTB2_GW_BWD")) : 42;
   switch (variant) {
     case 82: return gw_launch_bwd<8, 2>(e, draws);
+    // 4 warps x 2 stages: 68 KB of shared memory per CTA -> 3 CTAs (12 warps) per SM; measured on
+    // config 4: <4,2> 10.0 ms, <4,3> 12.5, <4,4> 12.6, <8,3> 13.6 (profiles/r01_config4_gwarp_tuning.log)
     case 83: return gw_launch_bwd<8, 3>(e, draws);
+    case 43: return gw_launch_bwd<4, 3>(e, draws);
     case 44: return gw_launch_bwd<4, 4>(e, draws);
-    default: return gw_launch_bwd<4, 3>(e, draws);
+    default: return gw_launch_bwd<4, 2>(e, draws);
   }
 }
 
