@@ -91,6 +91,10 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -124,7 +128,45 @@ __device__ __forceinline__ void gw_frag_child(double (&a)[GwShape<S>::KT], bool 
 }
 
 // the tip code table in shared memory when it is small (it always is for real alphabets)
-constexpr int GW_MAX_CODES = 32;
+constexpr int GW_MAX_CODES = 24;
+
+// Tip children need no GEMM: u = P_c . codeP[code] is one of C vectors, tabulated per CTA
+// (UT[side][code][parent state]) and read in C-fragment layout with one LDS.128 per tile.
+// On a random tree half of all child slots are tips: half of the U-phase DMMAs disappear.
+template <int S>
+__device__ __forceinline__ void gw_stage_utab(double* ut, const double* Pl, const double* Pr,
+                                              bool tipL, bool tipR, const double* codeP,
+                                              int codeCount, int nthreads) {
+  for (int idx = threadIdx.x; idx < 2 * codeCount * S; idx += nthreads) {
+    const int side = idx / (codeCount * S), rem = idx - side * codeCount * S;
+    if (!(side ? tipR : tipL)) continue;
+    const int code = rem / S, s = rem - code * S;
+    const double* P = (side ? Pr : Pl) + s * S;
+    const double* v = codeP + code * S;
+    double acc = 0.0;
+    for (int j = 0; j < S; ++j) acc = fma(P[j], v[j], acc);
+    ut[(side * GW_MAX_CODES + code) * S + s] = acc;
+  }
+}
+
+// u^T of a tip child in C-fragment layout: pattern r, states 8 nt + 2 c + {0, 1}
+template <int S>
+__device__ __forceinline__ void gw_u_tip(double (&acc)[GwShape<S>::NT][2], const double* ut,
+                                         int side, int code, int lane) {
+  static_assert(S % 2 == 0, "pairs of states are read as double2");
+  const int c = lane & 3;
+  const double* row = ut + (side * GW_MAX_CODES + code) * S + 2 * c;
+#pragma unroll
+  for (int nt = 0; nt < GwShape<S>::NT; ++nt) {
+    if (8 * nt + 2 * c < S) {
+      const double2 v = *reinterpret_cast<const double2*>(row + 8 * nt);
+      acc[nt][0] = v.x;
+      acc[nt][1] = v.y;
+    } else {
+      acc[nt][0] = acc[nt][1] = 0.0;
+    }
+  }
+}
 template <int S>
 __device__ __forceinline__ const double* gw_stage_codes(double* dst, const double* codeP,
                                                         int codeCount, int nthreads) {
@@ -161,8 +203,10 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   double* fragU = sm;  // [2][KT][NT][32]
   constexpr int SS = S * S;
   constexpr int TILE = S * GW_LD;
-  const double* table = gw_stage_codes<S>(sm + G::UF * 32 + NW * STAGES * 2 * TILE, codeP,
-                                          codeCount, NW * 32);
+  double* smTable = sm + G::UF * 32 + NW * STAGES * 2 * TILE;
+  const double* table = gw_stage_codes<S>(smTable, codeP, codeCount, NW * 32);
+  const double* utab = smTable + GW_MAX_CODES * S;
+  const bool useUtab = codeCount <= GW_MAX_CODES;
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
   const NodeOp op = ops[opBegin + nodeSlot];
@@ -170,7 +214,8 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   const int I = T - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, c = lane & 3;
-  double* ring = fragU + G::UF * 32 + (size_t)warp * STAGES * 2 * TILE;
+  constexpr int SLOT = 2 * TILE;  // a stage: the two child tiles of a group
+  double* ring = fragU + G::UF * 32 + (size_t)warp * STAGES * SLOT;
   const bool tipL = op.left < T, tipR = op.right < T;
   const size_t plane = (size_t)S * Npad;
   const size_t nodeStride = (size_t)K * plane;
@@ -178,6 +223,9 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   const double* matsD = mats + (size_t)d * B * K * SS;
   gw_stage_u<S>(fragU, matsD + ((size_t)op.left * K + k) * SS,
                 matsD + ((size_t)op.right * K + k) * SS, NW * 32);
+  if (useUtab)
+    gw_stage_utab<S>(smTable + GW_MAX_CODES * S, matsD + ((size_t)op.left * K + k) * SS,
+                     matsD + ((size_t)op.right * K + k) * SS, tipL, tipR, codeP, codeCount, NW * 32);
   pdl_wait_then_trigger();  // the matrices come from pmatrix; the child vectors from the previous level
   __syncthreads();
   const uint8_t* tl = tips + (size_t)(tipL ? op.left : 0) * Npad;
@@ -194,7 +242,7 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   auto issue = [&](int j) {
     const int i0 = first + j * (NW * 8);
     if (i0 < end) {
-      double* slot = ring + (j % STAGES) * 2 * TILE;
+      double* slot = ring + (j % STAGES) * SLOT;
       if (!tipL) gw_issue_tile<S>(slot, pl, Npad, i0, lane);
       if (!tipR) gw_issue_tile<S>(slot + TILE, pr, Npad, i0, lane);
     }
@@ -212,14 +260,25 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   // warp finishes a group.  Two accumulator sets alternate (the loop is unrolled by two).
   auto start_group = [&](double (&accL)[G::NT][2], double (&accR)[G::NT][2], int jj, int codeL,
                          int codeR) {
-    const double* slot = ring + (jj % STAGES) * 2 * TILE;
-    double aL[G::KT], aR[G::KT];
-    gw_frag_child<S>(aL, tipL, codeL, table, slot, lane);
-    gw_frag_child<S>(aR, tipR, codeR, table, slot + TILE, lane);
+    const double* slot = ring + (jj % STAGES) * SLOT;
+    if (tipL && useUtab) {
+      gw_u_tip<S>(accL, utab, 0, codeL, lane);
+    } else {
+      double aL[G::KT];
+      gw_frag_child<S>(aL, tipL, codeL, table, slot, lane);
 #pragma unroll
-    for (int nt = 0; nt < G::NT; ++nt) accL[nt][0] = accL[nt][1] = accR[nt][0] = accR[nt][1] = 0.0;
-    gw_u<S>(accL, aL, fragU, lane);
-    gw_u<S>(accR, aR, fragU + G::KT * G::NT * 32, lane);
+      for (int nt = 0; nt < G::NT; ++nt) accL[nt][0] = accL[nt][1] = 0.0;
+      gw_u<S>(accL, aL, fragU, lane);
+    }
+    if (tipR && useUtab) {
+      gw_u_tip<S>(accR, utab, 1, codeR, lane);
+    } else {
+      double aR[G::KT];
+      gw_frag_child<S>(aR, tipR, codeR, table, slot + TILE, lane);
+#pragma unroll
+      for (int nt = 0; nt < G::NT; ++nt) accR[nt][0] = accR[nt][1] = 0.0;
+      gw_u<S>(accR, aR, fragU + G::KT * G::NT * 32, lane);
+    }
   };
   auto finish_group = [&](double (&accL)[G::NT][2], double (&accR)[G::NT][2], int i0) {
     double m = 0.0;
@@ -243,22 +302,32 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     }
     if (c == 0) en[i0 + r] = (int16_t)e;
   };
+  auto code_at = [&](const uint8_t* row, bool tip, int g) {
+    const int i = first + g * (NW * 8);
+    return (tip && i < end) ? (int)row[i + r] : 0;
+  };
+  int code1L = code_at(tl, tipL, 1), code1R = code_at(tr, tipR, 1);
+  int code2L = code_at(tl, tipL, 2), code2R = code_at(tr, tipR, 2);
   // one trip: start group j + 1 (if any) with `nxt`, finish group j held in `cur`
   auto trip = [&](double (&curL)[G::NT][2], double (&curR)[G::NT][2], double (&nxtL)[G::NT][2],
-                  double (&nxtR)[G::NT][2], int jj, int i0, int& codeL, int& codeR) {
+                  double (&nxtR)[G::NT][2], int jj, int i0) {
     issue(jj + STAGES - 1);  // into the slot of group j - 1, read one trip ago
-    const int i1 = i0 + NW * 8, i2 = i0 + 2 * NW * 8;
-    const int nextL = (tipL && i2 < end) ? tl[i2 + r] : 0;   // codes of group j + 2
-    const int nextR = (tipR && i2 < end) ? tr[i2 + r] : 0;
+    const int i1 = i0 + NW * 8, i3 = i0 + 3 * NW * 8;
+    // tip codes travel in registers, two trips ahead of their use (an L2 round trip is longer
+    // than one trip): code1 = group j + 1, code2 = group j + 2, loaded here: group j + 3
+    const int c3L = (tipL && i3 < end) ? tl[i3 + r] : 0;
+    const int c3R = (tipR && i3 < end) ? tr[i3 + r] : 0;
     if (i1 < end) {
       cp_wait<STAGES - 2>();  // group j + 1 has landed
       __syncwarp();
-      start_group(nxtL, nxtR, jj + 1, codeL, codeR);
+      start_group(nxtL, nxtR, jj + 1, code1L, code1R);
     }
     finish_group(curL, curR, i0);
     __syncwarp();  // every lane has read slot j + 1 before the next trip overwrites slot j
-    codeL = nextL;
-    codeR = nextR;
+    code1L = code2L;
+    code1R = code2R;
+    code2L = c3L;
+    code2R = c3R;
   };
   double a0L[G::NT][2], a0R[G::NT][2], a1L[G::NT][2], a1R[G::NT][2];
   {
@@ -266,13 +335,10 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     __syncwarp();
     start_group(a0L, a0R, 0, tipL ? tl[first + r] : 0, tipR ? tr[first + r] : 0);
   }
-  // codes of group 1, then the trips hand over the codes of group j + 2
-  int codeL = (tipL && first + NW * 8 < end) ? tl[first + NW * 8 + r] : 0;
-  int codeR = (tipR && first + NW * 8 < end) ? tr[first + NW * 8 + r] : 0;
   int j = 0;
   for (int i0 = first; i0 < end; i0 += 2 * NW * 8, j += 2) {
-    trip(a0L, a0R, a1L, a1R, j, i0, codeL, codeR);
-    if (i0 + NW * 8 < end) trip(a1L, a1R, a0L, a0R, j + 1, i0 + NW * 8, codeL, codeR);
+    trip(a0L, a0R, a1L, a1R, j, i0);
+    if (i0 + NW * 8 < end) trip(a1L, a1R, a0L, a0R, j + 1, i0 + NW * 8);
   }
   cp_wait<0>();
 }
@@ -298,9 +364,12 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   constexpr int SS = S * S;
   constexpr int NT = G::NT;
   constexpr int TILE = S * GW_LD;
-  const double* table = gw_stage_codes<S>(ringAll + NW * STAGES * 3 * TILE, codeP, codeCount,
-                                          NW * 32);
-  static_assert(STAGES * 3 * TILE >= 2 * SS, "the ring doubles as the G staging area");
+  double* smTable = ringAll + NW * STAGES * (3 * TILE + 2);
+  const double* table = gw_stage_codes<S>(smTable, codeP, codeCount, NW * 32);
+  const double* utab = smTable + GW_MAX_CODES * S;
+  const bool useUtab = codeCount <= GW_MAX_CODES;
+  constexpr int SLOT = 3 * TILE + 2;  // q^_n, v_l, v_r tiles + the 8 + 8 tip codes of the group
+  static_assert(STAGES * SLOT >= 2 * SS, "the ring doubles as the G staging area");
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
   const NodeOp op = ops[opBegin + nodeSlot];
@@ -308,7 +377,7 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   const int I = T - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, c = lane & 3;
-  double* ring = ringAll + (size_t)warp * STAGES * 3 * TILE;
+  double* ring = ringAll + (size_t)warp * STAGES * SLOT;
   const bool tipL = op.left < T, tipR = op.right < T;
   const size_t plane = (size_t)S * Npad;
   const size_t nodeStride = (size_t)K * plane;
@@ -319,6 +388,8 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     const double* Pr = matsD + ((size_t)op.right * K + k) * SS;
     gw_stage_u<S>(fragU, Pl, Pr, NW * 32);
     gw_stage_q<S>(fragQ, Pl, Pr, NW * 32);
+    if (useUtab)
+      gw_stage_utab<S>(smTable + GW_MAX_CODES * S, Pl, Pr, tipL, tipR, codeP, codeCount, NW * 32);
   }
   pdl_wait_then_trigger();
   __syncthreads();
@@ -347,36 +418,47 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   auto issue = [&](int j) {
     const int i0 = first + j * (NW * 8);
     if (i0 < end) {
-      double* slot = ring + (j % STAGES) * 3 * TILE;
+      double* slot = ring + (j % STAGES) * SLOT;
       gw_issue_tile<S>(slot, qsrc, Npad, i0, lane);
       if (!tipL) gw_issue_tile<S>(slot + TILE, lsrc, Npad, i0, lane);
+      else if (lane == 0) cp_async8(slot + 3 * TILE, tl + i0);
       if (!tipR) gw_issue_tile<S>(slot + 2 * TILE, rsrc, Npad, i0, lane);
+      else if (lane == 1) cp_async8(slot + 3 * TILE + 1, tr + i0);
     }
     cp_commit();
   };
 #pragma unroll
   for (int j = 0; j < STAGES - 1; ++j) issue(j);
   int j = 0;
-  int codeL = (tipL && first < end) ? tl[first + r] : 0, codeR = (tipR && first < end) ? tr[first + r] : 0;
   for (int i0 = first; i0 < end; i0 += NW * 8, ++j) {
     issue(j + STAGES - 1);
-    const int inext = i0 + NW * 8;
-    const int nextL = (tipL && inext < end) ? tl[inext + r] : 0;
-    const int nextR = (tipR && inext < end) ? tr[inext + r] : 0;
     const double w = weights[i0 + r];
     const int el = tipL ? 0 : (int)elp[i0 + r];
     const int er = tipR ? 0 : (int)erp[i0 + r];
     cp_wait<STAGES - 1>();
     __syncwarp();
-    const double* slot = ring + (j % STAGES) * 3 * TILE;
-    double aL[G::KT], aR[G::KT];
-    gw_frag_child<S>(aL, tipL, codeL, table, slot + TILE, lane);
-    gw_frag_child<S>(aR, tipR, codeR, table, slot + 2 * TILE, lane);
+    const double* slot = ring + (j % STAGES) * SLOT;
+    const uint8_t* codes = reinterpret_cast<const uint8_t*>(slot + 3 * TILE);
+    const int codeL = tipL ? codes[r] : 0, codeR = tipR ? codes[8 + r] : 0;
     double uL[NT][2], uR[NT][2];
+    if (tipL && useUtab) {
+      gw_u_tip<S>(uL, utab, 0, codeL, lane);
+    } else {
+      double aL[G::KT];
+      gw_frag_child<S>(aL, tipL, codeL, table, slot + TILE, lane);
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) uL[nt][0] = uL[nt][1] = uR[nt][0] = uR[nt][1] = 0.0;
-    gw_u<S>(uL, aL, fragU, lane);
-    gw_u<S>(uR, aR, fragU + G::KT * NT * 32, lane);
+      for (int nt = 0; nt < NT; ++nt) uL[nt][0] = uL[nt][1] = 0.0;
+      gw_u<S>(uL, aL, fragU, lane);
+    }
+    if (tipR && useUtab) {
+      gw_u_tip<S>(uR, utab, 1, codeR, lane);
+    } else {
+      double aR[G::KT];
+      gw_frag_child<S>(aR, tipR, codeR, table, slot + 2 * TILE, lane);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) uR[nt][0] = uR[nt][1] = 0.0;
+      gw_u<S>(uR, aR, fragU + G::KT * NT * 32, lane);
+    }
     // m_l = q^ o u_r, m_r = q^ o u_l with q^_n^T read in C-fragment layout
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -418,15 +500,12 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
       }
       // G phase: G_c[s][t] += sum_p (w_p m_c[s][p]) v_c[t][p], contraction over the 8 patterns
       const double* vt = slot + (1 + side) * TILE;
-      const int mycode = side ? codeR : codeL;
 #pragma unroll
       for (int kp = 0; kp < 2; ++kp) {
         // B[k = pattern 4 kp + c][n = child state 8 nt + r]
         double bv[NT];
         if (tip) {
-          // the code of pattern 4 kp + c is held by the lanes of row 4 kp + c
-          const int code = __shfl_sync(0xffffffffu, mycode, (4 * kp + c) << 2);
-          const double* cp = table + code * S + r;
+          const double* cp = table + (int)codes[side * 8 + 4 * kp + c] * S + r;
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) bv[nt] = (8 * nt + r < S) ? cp[8 * nt] : 0.0;
         } else {
@@ -450,8 +529,6 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
         }
       }
     }
-    codeL = nextL;
-    codeR = nextR;
     __syncwarp();  // the slot is free for the copy issued in the next trip
   }
   cp_wait<0>();
@@ -481,7 +558,7 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   for (int idx = threadIdx.x; idx < 2 * SS; idx += NW * 32) {
     double t = 0.0;
 #pragma unroll
-    for (int wv = 0; wv < NW; ++wv) t += ringAll[(size_t)wv * STAGES * 3 * TILE + idx];
+    for (int wv = 0; wv < NW; ++wv) t += ringAll[(size_t)wv * STAGES * SLOT + idx];
     if (idx < SS) oL[idx] = t;
     else oR[idx - SS] = t;
   }
@@ -490,12 +567,12 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
 template <int S, int NW, int STAGES>
 size_t gw_fwd_smem() {
   return ((size_t)GwShape<S>::UF * 32 + (size_t)NW * STAGES * 2 * S * GW_LD +
-          (size_t)GW_MAX_CODES * S) * sizeof(double);
+          (size_t)3 * GW_MAX_CODES * S) * sizeof(double);
 }
 template <int S, int NW, int STAGES>
 size_t gw_bwd_smem() {
-  return ((size_t)(GwShape<S>::UF + GwShape<S>::QF) * 32 + (size_t)NW * STAGES * 3 * S * GW_LD +
-          (size_t)GW_MAX_CODES * S) * sizeof(double);
+  return ((size_t)(GwShape<S>::UF + GwShape<S>::QF) * 32 + (size_t)NW * STAGES * (3 * S * GW_LD + 2) +
+          (size_t)3 * GW_MAX_CODES * S) * sizeof(double);
 }
 
 constexpr int GW_GRANULE = 64;  // chunk sizes are multiples of 8 patterns x 8 warps
@@ -579,12 +656,12 @@ bool gwarp_supported(const Engine& e, bool backward) {
 
 int gwarp_forward(Engine& e, int draws) {
   static const int ctas = getenv("TTB2_GW_FWD_CTAS") ? atoi(getenv("TTB2_GW_FWD_CTAS")) : 16;
-  static const int variant = getenv("TTB2_GW_FWD") ? atoi(getenv("TTB2_GW_FWD")) : 44;
+  static const int variant = getenv("TTB2_GW_FWD") ? atoi(getenv("TTB2_GW_FWD")) : 83;
   switch (variant) {
-    case 83: return gw_launch_fwd<8, 3>(e, draws, ctas);
+    case 44: return gw_launch_fwd<4, 4>(e, draws, ctas);
     case 43: return gw_launch_fwd<4, 3>(e, draws, ctas);
     case 45: return gw_launch_fwd<4, 5>(e, draws, ctas);
-    default: return gw_launch_fwd<4, 4>(e, draws, ctas);
+    default: return gw_launch_fwd<8, 3>(e, draws, ctas);
   }
 }
 
