@@ -301,11 +301,21 @@ def main():
             pack(lnl_d, out_d)
             dist.all_reduce(packed)
 
+    # the call a user makes: the differentiable op of the torch extension (csrc/torch_ext.cpp),
+    # host tensors in (pinned), generator decomposed on the device, .backward() hands the
+    # gradients back as host tensors, lnL read on the host
+    from torchtree_b200 import log_likelihood_eigen
+
+    user_in = [t.clone().pin_memory().requires_grad_(True) for t in
+               (host[0], host[1], host[2], q.contiguous(), host[6])]
+
     def step_e2e():
         if world == 1:
-            eng.loglik_eigen(*host, out=lnl_h)
-            eng.grad_eigen(out=out_h)
-            return lnl_h
+            for t in user_in:
+                t.grad = None
+            lnl = log_likelihood_eigen(eng, *user_in)
+            lnl.sum().backward()
+            return lnl.detach()
         d_in = [t.to(dev, non_blocking=True) for t in host]
         eng.loglik_eigen(*d_in, out=lnl_d)
         eng.grad_eigen(out=out_d)
@@ -374,7 +384,7 @@ def main():
         ach_pre = units_rank * BYTES_PER_UNIT_PRE / (ph_pre * 1e-3) / 1e9
         ach_post = units_rank * BYTES_PER_UNIT_POST / (ph_post * 1e-3) / 1e9
         ach_step = units_rank * BYTES_PER_UNIT / (ms_dev * 1e-3) / 1e9
-        h2d = sum(t.numel() * 8 for t in host)
+        h2d = sum(t.numel() * 8 for t in (user_in if world == 1 else host))
         d2h = packed_n * 8
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
@@ -385,7 +395,11 @@ def main():
             "evals_per_s": 1e3 / ms_dev, "lnL": lnl_value,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": wall_e2e * 1e3,
-                    "api": "Engine.loglik_eigen + Engine.grad_eigen (C ABI, pinned host buffers)"},
+                    "api": ("torchtree_b200.log_likelihood_eigen(...).backward(): torch C++ extension "
+                            "autograd Function -> ttb2_loglik_q / ttb2_grad_eigen, pinned host tensors "
+                            "in, host gradients out") if world == 1 else
+                           "Engine.loglik_eigen + Engine.grad_eigen on device buffers + NCCL all-reduce "
+                           "+ copy of the packed result to pinned host memory"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
