@@ -61,6 +61,46 @@ __device__ __forceinline__ void gm_stage_matrix(double* dst, const double* src, 
   }
 }
 
+// Tip children need no GEMM: u = P . codeP[code] is one of C vectors.  The table UT[code][s]
+// (leading dimension Sp + 1: rows of different codes fall into different banks) takes the place
+// of the tip side's staged P, which nothing else reads (the Q phase skips tip children, the
+// G phase reads the code vectors from the pattern tile).  Codes below S are unit vectors by
+// the C ABI's contract, so their rows are columns of P; only gap / ambiguity codes are summed.
+__host__ __device__ inline bool gm_utab_fits(const GmShape g, int codeCount) {
+  return (long)codeCount * (g.Sp + 1) <= (long)g.Sp * g.PLD;
+}
+
+__device__ __forceinline__ void gm_stage_utab(double* dst, const double* P, const double* codeP,
+                                              int codeCount, const GmShape g) {
+  const int uld = g.Sp + 1;
+  for (int j = threadIdx.x; j < codeCount * g.Sp; j += blockDim.x) {
+    const int code = j / g.Sp, s2 = j - code * g.Sp;
+    double v = 0.0;
+    if (s2 < g.S) {
+      if (code < g.S) {
+        v = P[s2 * g.S + code];
+      } else {
+        const double* cp = codeP + (size_t)code * g.S;
+        for (int t = 0; t < g.S; ++t) v = fma(P[s2 * g.S + t], cp[t], v);
+      }
+    }
+    dst[code * uld + s2] = v;
+  }
+}
+
+// C fragments of a tip child's u for row tile mt, pattern tiles nt0 .. nt0 + NTG
+template <int NTG>
+__device__ __forceinline__ void gm_u_tip(double (&c)[NTG][2], const double* ut, int uld,
+                                         const uint8_t* codes, int mt, int nt0, int lane) {
+  const int row = mt * 8 + (lane >> 2);
+#pragma unroll
+  for (int n = 0; n < NTG; ++n) {
+    const int col = (nt0 + n) * 8 + (lane & 3) * 2;
+    c[n][0] = ut[(int)codes[col] * uld + row];
+    c[n][1] = ut[(int)codes[col + 1] * uld + row];
+  }
+}
+
 // D[mt][nt0..nt0+NTG) += A[mt rows][.] . B[.][cols]: A row-major with leading dimension
 // lda, B a [contraction][32 patterns] tile.  One A fragment feeds NTG pattern tiles
 // (NTG independent accumulator chains, 1 + NTG shared-memory loads per NTG MMAs).
@@ -131,7 +171,7 @@ __global__ void __launch_bounds__(NW * 32)
 gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
                const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
                double* __restrict__ partials, int16_t* __restrict__ expoK, int T, int Npad, int B,
-               int K, int Srt, int chunkPatterns) {
+               int K, int Srt, int chunkPatterns, int codeCount) {
   extern __shared__ double sm[];
   const int S = CS ? CS : Srt;  // compile-time state count for the common alphabets
   const GmShape g = gm_shape(S);
@@ -143,6 +183,9 @@ gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   double* cr = cl + 2 * tileN;      // two buffers
   double* out = cr + 2 * tileN;
   double* wmax = out + tileN;
+  uint8_t* codesS = reinterpret_cast<uint8_t*>(wmax + NW * 32);  // [2 buffers][2 sides][32]
+  const bool utab = gm_utab_fits(g, codeCount);
+  const int uld = g.Sp + 1;
 
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
@@ -163,37 +206,44 @@ gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   double* qn = base + (size_t)(op.node - T) * nodeStride;
   int16_t* en = expoK + (((size_t)d * I + (op.node - T)) * K + k) * Npad;
 
-  gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
-  gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+  const bool tabL = tipL && utab, tabR = tipR && utab;
+  if (tabL) gm_stage_utab(Pl, matsD + ((size_t)op.left * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
+  if (tabR) gm_stage_utab(Pr, matsD + ((size_t)op.right * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
   pdl_wait_then_trigger();   // the matrices come from pmatrix; the tiles below from the previous level
 
   const int begin = blockIdx.x * chunkPatterns;
   int end = begin + chunkPatterns;
   end = end < Npad ? end : Npad;
-  if (begin < end) {
-    gm_stage_tile_async<NW>(cl, tipL, tl, codeP, pl, begin, Npad, g);
-    gm_stage_tile_async<NW>(cr, tipR, tr, codeP, pr, begin, Npad, g);
-  }
+  // a tabulated tip child stages its 32 codes instead of a tile of code vectors
+  auto stage = [&](int b, int i0) {
+    if (tabL) { if (warp == 0) codesS[b * 64 + lane] = tl[i0 + lane]; }
+    else gm_stage_tile_async<NW>(cl + b * tileN, tipL, tl, codeP, pl, i0, Npad, g);
+    if (tabR) { if (warp == 1 % NW) codesS[b * 64 + 32 + lane] = tr[i0 + lane]; }
+    else gm_stage_tile_async<NW>(cr + b * tileN, tipR, tr, codeP, pr, i0, Npad, g);
+  };
+  if (begin < end) stage(0, begin);
   cp_async_commit();
   int buf = 0;
   for (int i0 = begin; i0 < end; i0 += GM_TP, buf ^= 1) {
     cp_async_wait_all();
     __syncthreads();  // tile `buf` (and P on the first trip) visible; `out` free
-    if (i0 + GM_TP < end) {
-      gm_stage_tile_async<NW>(cl + (buf ^ 1) * tileN, tipL, tl, codeP, pl, i0 + GM_TP, Npad, g);
-      gm_stage_tile_async<NW>(cr + (buf ^ 1) * tileN, tipR, tr, codeP, pr, i0 + GM_TP, Npad, g);
-    }
+    if (i0 + GM_TP < end) stage(buf ^ 1, i0 + GM_TP);
     cp_async_commit();
     const double* tcl = cl + buf * tileN;
     const double* tcr = cr + buf * tileN;
+    const uint8_t* cds = codesS + buf * 64;
     constexpr int NG = 4 / NTG;
     for (int item = warp; item < MT * NG; item += NW) {
       const int mt = item / NG, nt0 = (item - mt * NG) * NTG;
       double accL[NTG][2], accR[NTG][2];
 #pragma unroll
       for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
-      gm_mma_ab_g<NTG>(accL, Pl, g.PLD, tcl, mt, nt0, KT, lane);
-      gm_mma_ab_g<NTG>(accR, Pr, g.PLD, tcr, mt, nt0, KT, lane);
+      if (tabL) gm_u_tip<NTG>(accL, Pl, uld, cds, mt, nt0, lane);
+      else gm_mma_ab_g<NTG>(accL, Pl, g.PLD, tcl, mt, nt0, KT, lane);
+      if (tabR) gm_u_tip<NTG>(accR, Pr, uld, cds + 32, mt, nt0, lane);
+      else gm_mma_ab_g<NTG>(accR, Pr, g.PLD, tcr, mt, nt0, KT, lane);
       double* o = out + (mt * 8 + (lane >> 2)) * GM_LDT + nt0 * 8 + (lane & 3) * 2;
 #pragma unroll
       for (int n = 0; n < NTG; ++n) {
@@ -329,11 +379,14 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
               const double* __restrict__ partials, const int16_t* __restrict__ expoK,
               const double* __restrict__ weights, double* __restrict__ pre,
               double* __restrict__ gpart, const int* __restrict__ chunkBase, size_t chunkTotal,
-              int T, int Npad, int B, int K, int Srt, int chunkPatterns, int nChunk) {
+              int T, int Npad, int B, int K, int Srt, int chunkPatterns, int nChunk,
+              int codeCount) {
   extern __shared__ double sm[];
   const int S = CS ? CS : Srt;
   const GmShape g = gm_shape(S);
   const int SS = S * S;
+  const bool utab = gm_utab_fits(g, codeCount);
+  const int uld = g.Sp + 1;
   double* Pl = sm;
   double* Pr = Pl + g.Sp * g.PLD;
   const int tileN = g.R * GM_LDT;
@@ -344,6 +397,7 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   double* mr = ml + tileN;
   double* wsB = mr + tileN;          // [2][32]
   int* seB = reinterpret_cast<int*>(wsB + 64);  // [2][el[32], er[32]]
+  uint8_t* codesS = reinterpret_cast<uint8_t*>(seB + 128);  // [2 buffers][2 sides][32]
 
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
@@ -357,8 +411,12 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   const size_t drawBase = (size_t)d * I * nodeStride;
   const double* matsD = mats + (size_t)d * B * K * SS;
   const int MT = g.Sp / 8, KT = g.Kp / 4, KTr = g.Sp / 4;
-  gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
-  gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+  // tabulated tip children: UT takes the place of P (the Q phase skips tips, G reads the tiles)
+  const bool tabL = tipL && utab, tabR = tipR && utab;
+  if (tabL) gm_stage_utab(Pl, matsD + ((size_t)op.left * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
+  if (tabR) gm_stage_utab(Pr, matsD + ((size_t)op.right * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
   pdl_wait_then_trigger();
 
   // persistent G accumulators: items (child, mt, mt2) dealt round-robin to the warps
@@ -385,6 +443,8 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       wsB[b * 32 + lane] = weights[i];
       seB[b * 64 + lane] = tipL ? 0 : (int)elp[i];
       seB[b * 64 + 32 + lane] = tipR ? 0 : (int)erp[i];
+      if (tabL) codesS[b * 64 + lane] = tl[i];
+      if (tabR) codesS[b * 64 + 32 + lane] = tr[i];
     }
   };
   if (begin < end) stage(0, begin);
@@ -407,8 +467,10 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       double accL[NTG][2], accR[NTG][2];
 #pragma unroll
       for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
-      gm_mma_ab_g<NTG>(accL, Pl, g.PLD, vl, mt, nt0, KT, lane);
-      gm_mma_ab_g<NTG>(accR, Pr, g.PLD, vr, mt, nt0, KT, lane);
+      if (tabL) gm_u_tip<NTG>(accL, Pl, uld, codesS + buf * 64, mt, nt0, lane);
+      else gm_mma_ab_g<NTG>(accL, Pl, g.PLD, vl, mt, nt0, KT, lane);
+      if (tabR) gm_u_tip<NTG>(accR, Pr, uld, codesS + buf * 64 + 32, mt, nt0, lane);
+      else gm_mma_ab_g<NTG>(accR, Pr, g.PLD, vr, mt, nt0, KT, lane);
 #pragma unroll
       for (int n = 0; n < NTG; ++n) {
         const int off = (mt * 8 + (lane >> 2)) * GM_LDT + (nt0 + n) * 8 + (lane & 3) * 2;
@@ -494,13 +556,13 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
 
 size_t gm_fwd2_smem(const Dims& m) {
   const GmShape g = gm_shape(m.S);
-  return (2 * (size_t)g.Sp * g.PLD + 5 * (size_t)g.R * GM_LDT + GM_WARPS * 32) * sizeof(double);
+  return (2 * (size_t)g.Sp * g.PLD + 5 * (size_t)g.R * GM_LDT + 16 * 32) * sizeof(double) + 128;
 }
 
 size_t gm_bwd2_smem(const Dims& m) {
   const GmShape g = gm_shape(m.S);
   return (2 * (size_t)g.Sp * g.PLD + 8 * (size_t)g.R * GM_LDT + 64) * sizeof(double) +
-         128 * sizeof(int);
+         128 * sizeof(int) + 128;
 }
 
 }  // namespace
@@ -563,7 +625,7 @@ int gmma_forward2(Engine& e, int draws) {
       dim3 grid(nChunk, c * m.K, draws);
       launch_level(kern, grid, nw * 32, smem, e.stream, l > 0 && pdl_enabled(), e.ops,
                    opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad, m.B,
-                   m.K, m.S, chunkPatterns);
+                   m.K, m.S, chunkPatterns, e.cfg.code_count);
       ++e.launches;
     }
   }
@@ -633,7 +695,7 @@ int gmma_backward2(Engine& e, int draws) {
       launch_level(kern, grid, nw * 32, smem, e.stream, l < nLevels - 1 && pdl_enabled(), e.ops,
                    opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, e.weights, e.pre,
                    e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B, m.K, m.S, chunkPatterns,
-                   nChunk);
+                   nChunk, e.cfg.code_count);
       ++e.launches;
     }
   }
