@@ -646,7 +646,7 @@ int gw_launch_bwd(Engine& e, int draws) {
 
 // TTB2_GM_LEGACY=1: shared-memory tile kernels for both sweeps; =fwd / =bwd: for that sweep only
 bool gwarp_supported(const Engine& e, bool backward) {
-  static const char* legacy = getenv("TTB2_GM_LEGACY");
+  const char* legacy = getenv("TTB2_GM_LEGACY");  // read per call: the tests switch it
   if (e.dm.S != 20) return false;
   if (!legacy) return true;
   if (legacy[0] == 'f') return backward;
