@@ -36,7 +36,9 @@ namespace ttb2 {
 namespace {
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  // not volatile: a pure function of its operands, so the compiler may interleave the
+  // independent accumulator chains of different phases
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
@@ -364,12 +366,15 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   constexpr int SS = S * S;
   constexpr int NT = G::NT;
   constexpr int TILE = S * GW_LD;
-  double* smTable = ringAll + NW * STAGES * (3 * TILE + 2);
+  // a stage: q^_n, v_l, v_r tiles | 8 + 8 tip codes (2 doubles) | 8 + 8 int16 scale exponents
+  // of the children (4 doubles) | 8 pattern weights: everything a group reads rides the ring --
+  // a plain load of the exponents at the top of the trip was 20 % of all stall samples
+  constexpr int SLOT = 3 * TILE + 14;
+  static_assert(STAGES * SLOT >= 2 * SS, "the ring doubles as the G staging area");
+  double* smTable = ringAll + NW * STAGES * SLOT;
   const double* table = gw_stage_codes<S>(smTable, codeP, codeCount, NW * 32);
   const double* utab = smTable + GW_MAX_CODES * S;
   const bool useUtab = codeCount <= GW_MAX_CODES;
-  constexpr int SLOT = 3 * TILE + 2;  // q^_n, v_l, v_r tiles + the 8 + 8 tip codes of the group
-  static_assert(STAGES * SLOT >= 2 * SS, "the ring doubles as the G staging area");
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
   const NodeOp op = ops[opBegin + nodeSlot];
@@ -424,6 +429,10 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
       else if (lane == 0) cp_async8(slot + 3 * TILE, tl + i0);
       if (!tipR) gw_issue_tile<S>(slot + 2 * TILE, rsrc, Npad, i0, lane);
       else if (lane == 1) cp_async8(slot + 3 * TILE + 1, tr + i0);
+      if (!tipL && lane == 2) cp_async16(slot + 3 * TILE + 2, reinterpret_cast<const double*>(elp + i0));
+      if (!tipR && lane == 3) cp_async16(slot + 3 * TILE + 4, reinterpret_cast<const double*>(erp + i0));
+      if (lane >= 4 && lane < 8)
+        cp_async16(slot + 3 * TILE + 6 + 2 * (lane - 4), weights + i0 + 2 * (lane - 4));
     }
     cp_commit();
   };
@@ -432,13 +441,14 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   int j = 0;
   for (int i0 = first; i0 < end; i0 += NW * 8, ++j) {
     issue(j + STAGES - 1);
-    const double w = weights[i0 + r];
-    const int el = tipL ? 0 : (int)elp[i0 + r];
-    const int er = tipR ? 0 : (int)erp[i0 + r];
     cp_wait<STAGES - 1>();
     __syncwarp();
     const double* slot = ring + (j % STAGES) * SLOT;
     const uint8_t* codes = reinterpret_cast<const uint8_t*>(slot + 3 * TILE);
+    const int16_t* expo = reinterpret_cast<const int16_t*>(slot + 3 * TILE + 2);
+    const double w = slot[3 * TILE + 6 + r];
+    const int el = tipL ? 0 : (int)expo[r];
+    const int er = tipR ? 0 : (int)expo[8 + r];
     const int codeL = tipL ? codes[r] : 0, codeR = tipR ? codes[8 + r] : 0;
     double uL[NT][2], uR[NT][2];
     if (tipL && useUtab) {
@@ -571,7 +581,7 @@ size_t gw_fwd_smem() {
 }
 template <int S, int NW, int STAGES>
 size_t gw_bwd_smem() {
-  return ((size_t)(GwShape<S>::UF + GwShape<S>::QF) * 32 + (size_t)NW * STAGES * (3 * S * GW_LD + 2) +
+  return ((size_t)(GwShape<S>::UF + GwShape<S>::QF) * 32 + (size_t)NW * STAGES * (3 * S * GW_LD + 14) +
           (size_t)3 * GW_MAX_CODES * S) * sizeof(double);
 }
 
