@@ -131,6 +131,7 @@ __device__ __forceinline__ void gw_frag_child(double (&a)[GwShape<S>::KT], bool 
 
 // the tip code table in shared memory when it is small (it always is for real alphabets)
 constexpr int GW_MAX_CODES = 24;
+constexpr int GW_CODE_AHEAD = 5;  // post-order: tip codes are copied this many groups ahead of the tiles
 
 // Tip children need no GEMM: u = P_c . codeP[code] is one of C vectors, tabulated per CTA
 // (UT[side][code][parent state]) and read in C-fragment layout with one LDS.128 per tile.
@@ -205,7 +206,7 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   double* fragU = sm;  // [2][KT][NT][32]
   constexpr int SS = S * S;
   constexpr int TILE = S * GW_LD;
-  double* smTable = sm + G::UF * 32 + NW * STAGES * 2 * TILE;
+  double* smTable = sm + G::UF * 32 + NW * STAGES * 2 * TILE + NW * (GW_CODE_AHEAD + STAGES) * 2;
   const double* table = gw_stage_codes<S>(smTable, codeP, codeCount, NW * 32);
   const double* utab = smTable + GW_MAX_CODES * S;
   const bool useUtab = codeCount <= GW_MAX_CODES;
@@ -218,6 +219,13 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   const int r = lane >> 2, c = lane & 3;
   constexpr int SLOT = 2 * TILE;  // a stage: the two child tiles of a group
   double* ring = fragU + G::UF * 32 + (size_t)warp * STAGES * SLOT;
+  // Tip codes travel in their own small ring (8 + 8 bytes per group), CODE_AHEAD groups ahead of
+  // the tiles: a group of two tip children has nothing else to wait for, and its trip is far
+  // shorter than an L2 round trip (the dependent code -> table address chain was 13 % of all
+  // stall samples with codes prefetched two trips ahead in registers).
+  // (a code slot is rewritten CODE_AHEAD + STAGES groups later: after its group has started)
+  constexpr int CODE_AHEAD = GW_CODE_AHEAD, CSTAGES = GW_CODE_AHEAD + STAGES;
+  double* cring = fragU + G::UF * 32 + (size_t)NW * STAGES * SLOT + (size_t)warp * CSTAGES * 2;
   const bool tipL = op.left < T, tipR = op.right < T;
   const size_t plane = (size_t)S * Npad;
   const size_t nodeStride = (size_t)K * plane;
@@ -241,6 +249,13 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   int end = begin + chunkPatterns;
   end = end < Npad ? end : Npad;
   const int first = begin + warp * 8;
+  auto issue_codes = [&](int g) {
+    const int i0 = first + g * (NW * 8);
+    if (i0 < end) {
+      if (tipL && lane == 0) cp_async8(cring + (g % CSTAGES) * 2, tl + i0);
+      if (tipR && lane == 1) cp_async8(cring + (g % CSTAGES) * 2 + 1, tr + i0);
+    }
+  };
   auto issue = [&](int j) {
     const int i0 = first + j * (NW * 8);
     if (i0 < end) {
@@ -248,9 +263,12 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
       if (!tipL) gw_issue_tile<S>(slot, pl, Npad, i0, lane);
       if (!tipR) gw_issue_tile<S>(slot + TILE, pr, Npad, i0, lane);
     }
+    issue_codes(j + CODE_AHEAD);
     cp_commit();
   };
   static_assert(STAGES >= 3, "two groups are being consumed while the next ones travel");
+#pragma unroll
+  for (int g = 0; g < CODE_AHEAD; ++g) issue_codes(g);  // joins the first commit group below
 #pragma unroll
   for (int j = 0; j < STAGES - 1; ++j) issue(j);
   if (first >= end) {
@@ -260,9 +278,10 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
   // Software pipeline over the warp's groups: the DMMAs of group j + 1 are issued BEFORE the
   // epilogue (product, rescaling, stores) of group j, so the tensor pipe never drains while a
   // warp finishes a group.  Two accumulator sets alternate (the loop is unrolled by two).
-  auto start_group = [&](double (&accL)[G::NT][2], double (&accR)[G::NT][2], int jj, int codeL,
-                         int codeR) {
+  auto start_group = [&](double (&accL)[G::NT][2], double (&accR)[G::NT][2], int jj) {
     const double* slot = ring + (jj % STAGES) * SLOT;
+    const uint8_t* codes = reinterpret_cast<const uint8_t*>(cring + (jj % CSTAGES) * 2);
+    const int codeL = tipL ? codes[r] : 0, codeR = tipR ? codes[8 + r] : 0;
     if (tipL && useUtab) {
       gw_u_tip<S>(accL, utab, 0, codeL, lane);
     } else {
@@ -304,38 +323,24 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     }
     if (c == 0) en[i0 + r] = (int16_t)e;
   };
-  auto code_at = [&](const uint8_t* row, bool tip, int g) {
-    const int i = first + g * (NW * 8);
-    return (tip && i < end) ? (int)row[i + r] : 0;
-  };
-  int code1L = code_at(tl, tipL, 1), code1R = code_at(tr, tipR, 1);
-  int code2L = code_at(tl, tipL, 2), code2R = code_at(tr, tipR, 2);
   // one trip: start group j + 1 (if any) with `nxt`, finish group j held in `cur`
   auto trip = [&](double (&curL)[G::NT][2], double (&curR)[G::NT][2], double (&nxtL)[G::NT][2],
                   double (&nxtR)[G::NT][2], int jj, int i0) {
     issue(jj + STAGES - 1);  // into the slot of group j - 1, read one trip ago
-    const int i1 = i0 + NW * 8, i3 = i0 + 3 * NW * 8;
-    // tip codes travel in registers, two trips ahead of their use (an L2 round trip is longer
-    // than one trip): code1 = group j + 1, code2 = group j + 2, loaded here: group j + 3
-    const int c3L = (tipL && i3 < end) ? tl[i3 + r] : 0;
-    const int c3R = (tipR && i3 < end) ? tr[i3 + r] : 0;
+    const int i1 = i0 + NW * 8;
     if (i1 < end) {
       cp_wait<STAGES - 2>();  // group j + 1 has landed
       __syncwarp();
-      start_group(nxtL, nxtR, jj + 1, code1L, code1R);
+      start_group(nxtL, nxtR, jj + 1);
     }
     finish_group(curL, curR, i0);
     __syncwarp();  // every lane has read slot j + 1 before the next trip overwrites slot j
-    code1L = code2L;
-    code1R = code2R;
-    code2L = c3L;
-    code2R = c3R;
   };
   double a0L[G::NT][2], a0R[G::NT][2], a1L[G::NT][2], a1R[G::NT][2];
   {
     cp_wait<STAGES - 2>();  // group 0
     __syncwarp();
-    start_group(a0L, a0R, 0, tipL ? tl[first + r] : 0, tipR ? tr[first + r] : 0);
+    start_group(a0L, a0R, 0);
   }
   int j = 0;
   for (int i0 = first; i0 < end; i0 += 2 * NW * 8, j += 2) {
@@ -577,7 +582,7 @@ gw_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
 template <int S, int NW, int STAGES>
 size_t gw_fwd_smem() {
   return ((size_t)GwShape<S>::UF * 32 + (size_t)NW * STAGES * 2 * S * GW_LD +
-          (size_t)3 * GW_MAX_CODES * S) * sizeof(double);
+          (size_t)NW * (GW_CODE_AHEAD + STAGES) * 2 + (size_t)3 * GW_MAX_CODES * S) * sizeof(double);
 }
 template <int S, int NW, int STAGES>
 size_t gw_bwd_smem() {
