@@ -143,6 +143,10 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -218,9 +222,11 @@ gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   end = end < Npad ? end : Npad;
   // a tabulated tip child stages its 32 codes instead of a tile of code vectors
   auto stage = [&](int b, int i0) {
-    if (tabL) { if (warp == 0) codesS[b * 64 + lane] = tl[i0 + lane]; }
+    // (the small per-tile arrays are copied asynchronously as well: a plain load + shared store
+    // would park the staging warp on the load while the other warps wait for it at the barrier)
+    if (tabL) { if (warp == 0 && lane < 8) cp_async4(codesS + b * 64 + 4 * lane, tl + i0 + 4 * lane); }
     else gm_stage_tile_async<NW>(cl + b * tileN, tipL, tl, codeP, pl, i0, Npad, g);
-    if (tabR) { if (warp == 1 % NW) codesS[b * 64 + 32 + lane] = tr[i0 + lane]; }
+    if (tabR) { if (warp == 1 && lane < 8) cp_async4(codesS + b * 64 + 32 + 4 * lane, tr + i0 + 4 * lane); }
     else gm_stage_tile_async<NW>(cr + b * tileN, tipR, tr, codeP, pr, i0, Npad, g);
   };
   if (begin < end) stage(0, begin);
@@ -396,8 +402,8 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   double* ml = vrB + 2 * tileN;
   double* mr = ml + tileN;
   double* wsB = mr + tileN;          // [2][32]
-  int* seB = reinterpret_cast<int*>(wsB + 64);  // [2][el[32], er[32]]
-  uint8_t* codesS = reinterpret_cast<uint8_t*>(seB + 128);  // [2 buffers][2 sides][32]
+  int16_t* seB = reinterpret_cast<int16_t*>(wsB + 64);  // [2][el[32], er[32]] (512 bytes reserved)
+  uint8_t* codesS = reinterpret_cast<uint8_t*>(wsB + 64) + 512;  // [2 buffers][2 sides][32]
 
   const int nodeSlot = blockIdx.y / K;
   const int k = blockIdx.y - nodeSlot * K;
@@ -438,13 +444,18 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     gm_stage_tile_async<NW>(tqB + b * tileN, false, nullptr, codeP, qsrc, i0, Npad, g);
     gm_stage_tile_async<NW>(vlB + b * tileN, tipL, tl, codeP, lsrc, i0, Npad, g);
     gm_stage_tile_async<NW>(vrB + b * tileN, tipR, tr, codeP, rsrc, i0, Npad, g);
+    // weights, child exponents and tip codes: asynchronous copies too -- a plain load + shared
+    // store would park warp 0 on the load while the other warps wait for it at the barrier
     if (warp == 0) {
-      const int i = i0 + lane;
-      wsB[b * 32 + lane] = weights[i];
-      seB[b * 64 + lane] = tipL ? 0 : (int)elp[i];
-      seB[b * 64 + 32 + lane] = tipR ? 0 : (int)erp[i];
-      if (tabL) codesS[b * 64 + lane] = tl[i];
-      if (tabR) codesS[b * 64 + 32 + lane] = tr[i];
+      cp_async8(wsB + b * 32 + lane, weights + i0 + lane);
+      if (lane < 16) {
+        if (!tipL) cp_async4(seB + b * 64 + 2 * lane, elp + i0 + 2 * lane);
+        if (!tipR) cp_async4(seB + b * 64 + 32 + 2 * lane, erp + i0 + 2 * lane);
+      } else if (lane < 24) {
+        if (tabL) cp_async4(codesS + b * 64 + 4 * (lane - 16), tl + i0 + 4 * (lane - 16));
+      } else {
+        if (tabR) cp_async4(codesS + b * 64 + 32 + 4 * (lane - 24), tr + i0 + 4 * (lane - 24));
+      }
     }
   };
   if (begin < end) stage(0, begin);
@@ -459,7 +470,7 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     const double* vl = vlB + buf * tileN;
     const double* vr = vrB + buf * tileN;
     const double* ws = wsB + buf * 32;
-    const int* se = seB + buf * 64;
+    const int16_t* se = seB + buf * 64;
     // U phase: u_l = P_l v_l, u_r = P_r v_r;  m_l = q^ o u_r, m_r = q^ o u_l
     constexpr int NG = 4 / NTG;
     for (int item = warp; item < MT * NG; item += NW) {
@@ -500,8 +511,8 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
 #pragma unroll
           for (int n = 0; n < NTG; ++n) {
             const int col = (nt0 + n) * 8 + (lane & 3) * 2;
-            const double f0 = __hiloint2double((1023 - se[side * 32 + col]) << 20, 0);
-            const double f1 = __hiloint2double((1023 - se[side * 32 + col + 1]) << 20, 0);
+            const double f0 = __hiloint2double((1023 - (int)se[side * 32 + col]) << 20, 0);
+            const double f1 = __hiloint2double((1023 - (int)se[side * 32 + col + 1]) << 20, 0);
             *reinterpret_cast<double2*>(qout + (size_t)row * Npad + col) =
                 make_double2(c[n][0] * f0, c[n][1] * f1);
           }
