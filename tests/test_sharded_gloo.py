@@ -76,3 +76,65 @@ def test_shard_range_covers_everything():
             for a, b in zip(spans, spans[1:]):
                 assert a[1] == b[0]
             assert all(hi >= lo for lo, hi in spans)
+
+
+def _draw_worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import treelik as orc
+    from torchtree_b200.sharded import draw_sharded_log_likelihood
+    from torchtree_b200.synthetic import make_problem
+
+    # 5 draws on 2 ranks (3 + 2): per-draw branch lengths / generator / frequencies, shared site model
+    prob = make_problem(12, 40, 4, 3, draws=5, seed=21, per_draw_model=True)
+    tips = orc.tip_partials_from_states(prob.tip_states, 4)
+    w = torch.tensor(prob.weights)
+
+    def local(bl, rates, props, q, freqs):
+        d = bl.shape[0]
+        t = bl.unsqueeze(-1) * rates.reshape(-1, 1, rates.shape[-1])
+        mats = orc.p_t_expm(q, t)
+        return orc.log_likelihood(tips, w, prob.postorder, mats, freqs.expand(d, -1).unsqueeze(-2),
+                                  props.expand(d, -1)[..., None, None]).squeeze(-1)
+
+    names = ("branch_lengths", "site_rates", "site_props", "q_matrix", "freqs")
+    vals = [getattr(prob, n) for n in names]
+    vals[1], vals[2] = vals[1][:1], vals[2][:1]          # the site model is shared by all draws
+    tensors = [torch.tensor(np.ascontiguousarray(v), requires_grad=True) for v in vals]
+    lnl = draw_sharded_log_likelihood(local, tensors, draws=5)
+    wts = torch.tensor([1.0, -0.5, 2.0, 0.25, 1.5])
+    (lnl * wts).sum().backward()
+    np.savez(os.path.join(out_dir, "draw_rank%d.npz" % rank), lnL=lnl.detach().numpy(),
+             **{n: t.grad.numpy() for n, t in zip(names, tensors)})
+    dist.destroy_process_group()
+
+
+def test_draw_sharding_two_ranks(tmp_path):
+    """Config 3's sharding: draws split 3 + 2 over two ranks; every rank ends with lnL of all draws
+    and the full gradients (per-draw tensors assembled, shared tensors summed)."""
+    from oracle import treelik as orc
+    from torchtree_b200.synthetic import make_problem
+
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_draw_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    prob = make_problem(12, 40, 4, 3, draws=5, seed=21, per_draw_model=True)
+    tips = orc.tip_partials_from_states(prob.tip_states, 4)
+    names = ("branch_lengths", "site_rates", "site_props", "q_matrix", "freqs")
+    vals = [getattr(prob, n) for n in names]
+    vals[1], vals[2] = vals[1][:1], vals[2][:1]
+    tensors = [torch.tensor(np.ascontiguousarray(v), requires_grad=True) for v in vals]
+    bl, rates, props, q, freqs = tensors
+    t = bl.unsqueeze(-1) * rates.reshape(-1, 1, rates.shape[-1])
+    lnl = orc.log_likelihood(tips, torch.tensor(prob.weights), prob.postorder, orc.p_t_expm(q, t),
+                             freqs.unsqueeze(-2), props.expand(5, -1)[..., None, None]).squeeze(-1)
+    (lnl * torch.tensor([1.0, -0.5, 2.0, 0.25, 1.5])).sum().backward()
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), "draw_rank%d.npz" % rank))
+        np.testing.assert_allclose(got["lnL"], lnl.detach().numpy(), rtol=1e-12)
+        for n, tt in zip(names, tensors):
+            want = tt.grad.numpy()
+            assert got[n].shape == want.shape, n
+            np.testing.assert_allclose(got[n], want, rtol=1e-10, atol=1e-10 * np.abs(want).max(),
+                                       err_msg=n)

@@ -73,3 +73,81 @@ def sharded_log_likelihood(local_fn, tensors, group=None):
     """
     copies = _CopyToShards.apply(group, *tensors)
     return _SumOverShards.apply(group, local_fn(*copies))
+
+
+# ---- draw sharding (BASELINE config 3: a batch of ADVI / HMC draws per step) -------------------
+# Draws are independent evaluations of the same data with different parameters: rank g owns the
+# draws [g*D/G, (g+1)*D/G) of every per-draw tensor (leading extent D) and the whole of every
+# shared tensor (leading extent 1).  The exchanges are, per step, one all-reduce of the
+# zero-padded lnL vector (D doubles) and one of the packed gradients (SURVEY 8(e) "Draw sharding").
+
+class _ScatterDraws(torch.autograd.Function):
+    """Forward: this rank's slice of the per-draw tensors, shared tensors untouched.
+    Backward: the full gradients on every rank (slices placed into zeros, shared ones as they
+    are, then one sum all-reduce of everything)."""
+
+    @staticmethod
+    def forward(ctx, group, lo, hi, draws, *tensors):
+        ctx.group, ctx.lo, ctx.hi = group, lo, hi
+        ctx.shapes = [tuple(t.shape) for t in tensors]
+        ctx.per_draw = [t.shape[0] == draws and draws > 1 for t in tensors]
+        return tuple(t[lo:hi] if p else t.view_as(t) for t, p in zip(tensors, ctx.per_draw))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        full = []
+        for g, shape, per_draw in zip(grads, ctx.shapes, ctx.per_draw):
+            if g is None:
+                full.append(None)
+            elif per_draw:
+                z = g.new_zeros(shape)
+                z[ctx.lo:ctx.hi] = g
+                full.append(z)
+            else:
+                full.append(g.contiguous())
+        live = [g for g in full if g is not None]
+        if live and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            flat = torch.cat([g.reshape(-1) for g in live])
+            dist.all_reduce(flat, group=ctx.group)
+            off = 0
+            for i, g in enumerate(full):
+                if g is not None:
+                    full[i] = flat[off:off + g.numel()].view_as(g)
+                    off += g.numel()
+        return (None, None, None, None) + tuple(full)
+
+
+class _GatherDraws(torch.autograd.Function):
+    """Forward: lnL of all draws on every rank.  Backward: this rank's slice of the gradient."""
+
+    @staticmethod
+    def forward(ctx, group, lo, hi, draws, lnl):
+        ctx.lo, ctx.hi = lo, hi
+        out = lnl.new_zeros((draws,) + tuple(lnl.shape[1:]))
+        out[lo:hi] = lnl
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(out, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return None, None, None, None, grad[ctx.lo:ctx.hi]
+
+
+def draw_sharded_log_likelihood(local_fn, tensors, draws, group=None):
+    """lnL [D] of a batch of draws evaluated `D / world_size` draws per rank.
+
+    `tensors`: every tensor has leading extent D (per-draw) or 1 (shared by all draws);
+    `local_fn(*local_tensors) -> lnL[d_local]` evaluates this rank's draws with an engine that
+    holds the whole alignment (`max_draws >= ceil(D / world_size)`).  Every rank receives lnL of
+    all draws and, after `.backward()`, the full gradient of every tensor.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_range(draws, rank, world)
+    local = _ScatterDraws.apply(group, lo, hi, draws, *tensors)
+    if hi > lo:
+        lnl_local = local_fn(*local)
+    else:  # more ranks than draws: this rank contributes nothing but still joins the collectives
+        lnl_local = sum((t.sum() * 0.0 for t in local), torch.zeros(0, dtype=tensors[0].dtype))
+    return _GatherDraws.apply(group, lo, hi, draws, lnl_local)
