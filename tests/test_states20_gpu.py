@@ -79,3 +79,25 @@ def test_bitwise_reproducible_and_kernel_families_agree(monkeypatch):
         assert_grad_close(a[k], c[k], rtol=1e-10, what=k)
     for e in (e1, e2, e3):
         e.close()
+
+
+@pytest.mark.parametrize("S,extra", [(8, 12), (20, 16)])
+def test_tile_kernels_with_untabulated_tips(monkeypatch, S, extra):
+    """More tip codes than the table that replaces the tip side's staged P can hold
+    (gm_utab_fits): the tile kernels multiply tip children like any other child."""
+    from torchtree_b200.synthetic import make_problem
+
+    monkeypatch.setenv("TTB2_GM_LEGACY", "1")
+    prob = make_problem(14, 500, S, 2, seed=S + extra, gap_fraction=0.02)
+    rng = np.random.default_rng(extra)
+    rows = []
+    for _ in range(extra):
+        m = np.zeros(S)
+        m[rng.choice(S, size=rng.integers(2, 4), replace=False)] = 1.0
+        rows.append(m)
+    table = np.concatenate([np.eye(S), np.ones((1, S)), np.array(rows)], 0)
+    tips = prob.tip_states.copy()
+    hit = rng.random(tips.shape) < 0.15
+    tips[hit] = rng.integers(S + 1, S + 1 + extra, size=int(hit.sum()))
+    prob = dataclasses.replace(prob, tip_states=tips.astype(np.uint8), code_partials=table)
+    _check(prob, q_rtol=1e-6)
