@@ -302,3 +302,117 @@ def test_install_height_transform_rebinds_and_fails_loudly_without_gpu(patched):
         refmod.TreeLikelihoodModel = saved[0]
         ref_transform.GeneralNodeHeightTransform = saved[1]
         ref_tree_model.GeneralNodeHeightTransform = saved[2]
+
+
+# ---- the variants existing configs contain (SURVEY 8(b) "Variants the drop-in will meet") -------
+_P = lambda id_, v: {"id": id_, "type": "Parameter", "tensor": v}  # noqa: E731
+_SUBST = {
+    "HKY": {"id": "hky", "type": "HKY", "kappa": _P("kappa", [3.2]),
+            "frequencies": _P("freqs", [0.3, 0.2, 0.24, 0.26])},
+    "GTR": {"id": "gtr", "type": "GTR", "rates": _P("rates", [0.9, 3.1, 0.6, 1.3, 4.2, 1.0]),
+            "frequencies": _P("freqs", [0.33, 0.19, 0.22, 0.26])},
+    # matrix_exp route: the model's own p_t supplies the matrices (abstract.py:89-94)
+    "NONSYM": {"id": "ns", "type": "GeneralNonSymmetricSubstitutionModel",
+               "data_type": {"id": "dt", "type": "NucleotideDataType"},
+               "mapping": list(range(12)),
+               "rates": _P("rates", [0.5, 1.7, 0.8, 1.1, 2.3, 0.4, 0.9, 1.4, 0.7, 1.9, 0.6, 1.2]),
+               "frequencies": _P("freqs", [0.28, 0.22, 0.24, 0.26])},
+}
+_SITE = {
+    "constant": ({"id": "sm", "type": "ConstantSiteModel"}, []),
+    "constant_mu": ({"id": "sm", "type": "ConstantSiteModel", "mu": _P("mu", [1.7])}, ["mu"]),
+    "invariant": ({"id": "sm", "type": "InvariantSiteModel", "invariant": _P("pinv", [0.23])},
+                  ["pinv"]),
+    "weibull_inv_mu": ({"id": "sm", "type": "WeibullSiteModel", "categories": 3,
+                        "shape": _P("shape", [0.8]), "invariant": _P("pinv", [0.15]),
+                        "mu": _P("mu", [0.6])}, ["shape", "pinv", "mu"]),
+}
+
+
+@pytest.mark.parametrize("subst,site", [("HKY", "constant"), ("GTR", "invariant"),
+                                        ("GTR", "weibull_inv_mu"), ("HKY", "constant_mu"),
+                                        ("NONSYM", "weibull_inv_mu")])
+def test_model_variants_match_reference(patched, subst, site):
+    objs, like = _flu_json()
+    like = dict(like, substitution_model=_SUBST[subst], site_model=_SITE[site][0])
+    ref = _build(objs, like, "torchtree.evolution.tree_likelihood.TreeLikelihoodModel")
+    new = _build(objs, like, "torchtree_b200.TreeLikelihoodModel")
+    names = ["blens", "freqs"] + _SITE[site][1] + (["kappa"] if subst == "HKY" else ["rates"])
+    v_ref, g_ref = _grads(ref, names)
+    v_new, g_new = _grads(new, names)
+    assert v_new.shape == v_ref.shape
+    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0), (v_new, v_ref)
+    for n in names:
+        assert g_new[n].shape == g_ref[n].shape, n
+        assert torch.allclose(g_new[n], g_ref[n], rtol=1e-7, atol=1e-7 * g_ref[n].abs().max()), n
+
+
+def test_srd06_two_likelihoods_share_a_tree(patched):
+    """SRD06 (cli/evolution.py:630-671): codon positions 1+2 and 3 as two TreeLikelihoodModels
+    over `SitePattern.indices`, one tree -> two engines."""
+    objs, like = _flu_json()
+    totals = {}
+    for kind in ("torchtree.evolution.tree_likelihood.TreeLikelihoodModel",
+                 "torchtree_b200.TreeLikelihoodModel"):
+        dic = _build(objs, dict(like, id="like12",
+                                site_pattern=dict(like["site_pattern"], id="sp12",
+                                                  indices="::3,1::3")), kind)
+        from torchtree.core.utils import process_objects
+
+        second = json.loads(json.dumps(dict(
+            like, id="like3", tree_model="tree", site_model="sm", substitution_model="gtr",
+            site_pattern=dict(like["site_pattern"], id="sp3", indices="2::3"))))
+        second["type"] = kind
+        process_objects(second, dic)
+        dic["blens"].requires_grad = True
+        total = dic["like12"]() + dic["like3"]()
+        total.sum().backward()
+        totals[kind] = (total.detach().clone(), dic["blens"].grad.clone(),
+                        dic["like12"].weights.sum().item() + dic["like3"].weights.sum().item())
+    (v_ref, g_ref, n_ref), (v_new, g_new, n_new) = totals.values()
+    assert n_ref == n_new == 987  # every site of fluA lands in exactly one partition
+    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0)
+    assert torch.allclose(g_new, g_ref, rtol=1e-7, atol=1e-7 * g_ref.abs().max())
+
+
+def test_amino_acid_lg_weibull(patched):
+    """Empirical 20-state model (LG, amino_acid.py:12-57) on an inline protein alignment with
+    gaps and ambiguity letters: the eigen route through `normalised_generator`."""
+    rng = np.random.default_rng(12)
+    names = ["t%d" % i for i in range(6)]
+    letters = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
+    base = rng.integers(0, 20, 60)
+    seqs = []
+    for _ in names:
+        s = base.copy()
+        flip = rng.random(60) < 0.25
+        s[flip] = rng.integers(0, 20, int(flip.sum()))
+        chars = letters[s]
+        chars[rng.random(60) < 0.05] = "-"
+        chars[rng.random(60) < 0.03] = "X"
+        seqs.append("".join(chars))
+    objs = [
+        {"id": "taxa", "type": "Taxa", "taxa": [{"id": n, "type": "Taxon"} for n in names]},
+        {"id": "alignment", "type": "Alignment",
+         "datatype": {"id": "aa", "type": "AminoAcidDataType"}, "taxa": "taxa",
+         "sequences": [{"taxon": n, "sequence": s} for n, s in zip(names, seqs)]},
+    ]
+    like = {
+        "id": "like", "type": "TreeLikelihoodModel",
+        "tree_model": {"id": "tree", "type": "UnRootedTreeModel",
+                       "newick": "((t0:0.1,t1:0.2):0.05,(t2:0.1,t3:0.3):0.1,(t4:0.2,t5:0.1):0.1);",
+                       "taxa": "taxa",
+                       "branch_lengths": _P("blens", rng.uniform(0.05, 0.4, 9).tolist())},
+        "site_model": {"id": "sm", "type": "WeibullSiteModel", "categories": 4,
+                       "shape": _P("shape", [0.6])},
+        "substitution_model": {"id": "lg", "type": "torchtree.evolution.substitution_model.amino_acid.LG"},
+        "site_pattern": {"id": "sp", "type": "SitePattern", "alignment": "alignment"},
+    }
+    ref = _build(objs, like, "torchtree.evolution.tree_likelihood.TreeLikelihoodModel")
+    new = _build(objs, like, "torchtree_b200.TreeLikelihoodModel")
+    assert new["like"]._state_count == 20
+    v_ref, g_ref = _grads(ref, ["blens", "shape"])
+    v_new, g_new = _grads(new, ["blens", "shape"])
+    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0), (v_new, v_ref)
+    for n in ("blens", "shape"):
+        assert torch.allclose(g_new[n], g_ref[n], rtol=1e-7, atol=1e-7 * g_ref[n].abs().max()), n
