@@ -416,3 +416,60 @@ def test_amino_acid_lg_weibull(patched):
     assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0), (v_new, v_ref)
     for n in ("blens", "shape"):
         assert torch.allclose(g_new[n], g_ref[n], rtol=1e-7, atol=1e-7 * g_ref[n].abs().max()), n
+
+
+def _run_cli(argv, capsys):
+    from torchtree.cli.cli import main as cli_main
+
+    old = sys.argv
+    sys.argv = ["torchtree-cli"] + argv
+    try:
+        capsys.readouterr()
+        cli_main()
+        return capsys.readouterr().out
+    finally:
+        sys.argv = old
+
+
+def _run_torchtree(path, capsys, seed=1):
+    from torchtree.torchtree import main as torchtree_main
+
+    old = sys.argv
+    sys.argv = ["torchtree", path, "-s", str(seed)]
+    try:
+        capsys.readouterr()
+        torchtree_main()
+        return capsys.readouterr().out
+    finally:
+        sys.argv = old
+
+
+def test_cli_generated_advi_config_runs_unchanged(patched, tmp_path, capsys):
+    """BASELINE config 1 end to end on the host side: `torchtree-cli advi -m GTR -C 4` writes the
+    JSON, `--b200` only swaps the likelihood's type, and the stock runner optimises both with the
+    same seed -- the ELBO traces must agree (the engine is the pinned oracle here; the CUDA engine
+    meets the same oracle in the -m gpu tests)."""
+    import re
+
+    sys.path.insert(0, REPO)
+    base = ["advi", "-i", DATA + "/fluA.fa", "-t", DATA + "/fluA.tree", "-m", "GTR", "-C", "4",
+            "--iter", "6", "--elbo_samples", "3", "--grad_samples", "1", "--convergence_every", "2",
+            "--stem", str(tmp_path / "run")]
+    traces = {}
+    for tag, extra in (("reference", []), ("b200", ["--b200"])):
+        cfg = _run_cli(base + extra, capsys)
+        data = json.loads(cfg)
+        types = re.findall(r'"type": "([A-Za-z_.0-9]*TreeLikelihoodModel)"', cfg)
+        assert types == (["torchtree_b200.TreeLikelihoodModel"] if extra else ["TreeLikelihoodModel"])
+        path = tmp_path / (tag + ".json")
+        path.write_text(json.dumps(data))
+        out = _run_torchtree(str(path), capsys)
+        # the runner prints a table: iter, ELBO, delta_ELBO_mean, delta_ELBO_med
+        elbos = [float(m.group(1)) for m in
+                 re.finditer(r"^\s*\d+\s+(-?\d+\.\d+)\s+\d+\.\d+\s+\d+\.\d+", out, flags=re.M)]
+        assert len(elbos) >= 3, out[-2000:]
+        traces[tag] = elbos
+    ref, new = np.array(traces["reference"]), np.array(traces["b200"])
+    assert ref.shape == new.shape
+    # same seed, same draws: the traces agree to the accumulated round-off of six Adam steps
+    np.testing.assert_allclose(new, ref, rtol=1e-7)
