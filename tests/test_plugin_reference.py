@@ -473,3 +473,30 @@ def test_cli_generated_advi_config_runs_unchanged(patched, tmp_path, capsys):
     assert ref.shape == new.shape
     # same seed, same draws: the traces agree to the accumulated round-off of six Adam steps
     np.testing.assert_allclose(new, ref, rtol=1e-7)
+
+
+@pytest.mark.parametrize("command,extra", [
+    ("map", ["--max_iter", "3"]),
+    ("hmc", ["--iter", "4", "--steps", "3"]),
+    ("mcmc", ["--iter", "20"]),
+])
+def test_other_cli_drivers_run_unchanged(patched, tmp_path, capsys, command, extra):
+    """`torchtree-cli map / hmc / mcmc ... [--b200]` + the stock runner: the drivers see the same
+    log-posterior values, accept the same proposals and print the same numbers."""
+    import re
+
+    sys.path.insert(0, REPO)
+    outs = {}
+    for tag, flag in (("reference", []), ("b200", ["--b200"])):
+        argv = [command, "-i", DATA + "/fluA.fa", "-t", DATA + "/fluA.tree", "-m", "JC69",
+                "--stem", str(tmp_path / (tag + "_run"))] + extra + flag
+        cfg = _run_cli(argv, capsys)
+        assert ("torchtree_b200.TreeLikelihoodModel" in cfg) == bool(flag)
+        path = tmp_path / (tag + ".json")
+        path.write_text(cfg)
+        outs[tag] = _run_torchtree(str(path), capsys)
+    num = re.compile(r"-?\d+\.\d+(?:e[-+]?\d+)?|nan")
+    ref = [float(x) for x in num.findall(outs["reference"])]
+    new = [float(x) for x in num.findall(outs["b200"])]
+    assert len(ref) == len(new) and len(ref) >= 2, (outs["reference"][-800:], outs["b200"][-800:])
+    np.testing.assert_allclose(new, ref, rtol=1e-6, equal_nan=True)
