@@ -256,6 +256,23 @@ int ttb2_heights_backward(ttb2_heights* plan, int32_t draws, const double* x,
                           const double* heights, const double* grad_heights, double* grad_x,
                           int32_t where);
 
+/*
+ * Constant-population coalescent log-density of a batch of time trees on the device -- replaces
+ * ConstantCoalescent.log_prob, torchtree/evolution/coalescent.py:112-134 (argsort of the 2T-1 node
+ * heights, lineage counts by cumulative sum, sum of C(k,2) x interval / theta) and its autograd
+ * backward (closed form once the order is known).  One CTA per draw; 2 <= T <= 4096.
+ *   node_heights [draws][2T-1]  tips first (sampling times), then the T-1 internal nodes
+ *   theta        [theta_draws]  population size, theta_draws = 1 (shared) or draws
+ *   log_prob     [draws]
+ *   d_heights    [draws][2T-1]  d log_prob[d] / d node_heights[d][.]   (may be NULL)
+ *   d_theta      [draws]        d log_prob[d] / d theta (per draw; sum them for a shared theta; may be NULL)
+ * Stateless; all pointers host or all device (`where`); returns after the result is complete.
+ */
+int ttb2_coalescent_constant(int32_t device, int32_t draws, int32_t tip_count,
+                             const double* node_heights, const double* theta,
+                             int32_t theta_draws, double* log_prob, double* d_heights,
+                             double* d_theta, int32_t where);
+
 /* Kernels launched by this engine since creation (bench `gpu_launches`). */
 int64_t ttb2_launch_count(const ttb2_engine* engine);
 /* Device bytes currently held by this engine. */

@@ -500,3 +500,58 @@ def test_other_cli_drivers_run_unchanged(patched, tmp_path, capsys, command, ext
     new = [float(x) for x in num.findall(outs["b200"])]
     assert len(ref) == len(new) and len(ref) >= 2, (outs["reference"][-800:], outs["b200"][-800:])
     np.testing.assert_allclose(new, ref, rtol=1e-6, equal_nan=True)
+
+
+def test_device_coalescent_class_is_a_dropin(patched, monkeypatch):
+    """`ConstantCoalescentModel` with the device log-density (coalescent.py): same JSON, same value
+    and gradients as the reference class (the kernel is replaced by the pinned oracle here), bare /
+    dotted type names rebound by install(coalescent=True), loud failure without a GPU."""
+    from torchtree.core.utils import REGISTERED_CLASSES, get_class, process_objects
+
+    import torchtree.evolution.coalescent as refmod
+
+    import torchtree_b200.coalescent as cmod
+    from oracle.coalescent import constant_log_prob
+
+    rng = np.random.default_rng(3)
+    T = 7
+    tips = rng.uniform(0, 3, T)
+    inner = tips.max() + np.cumsum(rng.exponential(0.5, T - 1))
+    heights = np.concatenate([tips, inner])
+
+    def build(type_name, batch):
+        dic = {}
+        data = {"id": "coal", "type": type_name,
+                "theta": _P("theta", [4.0] if batch is None else [[4.0], [2.5], [7.0]]),
+                "times": heights.tolist(), "events": [1] * T + [0] * (T - 1)}
+        process_objects(json.loads(json.dumps(data)), dic)
+        return dic
+
+    saved_reg, saved_cls = dict(REGISTERED_CLASSES), refmod.ConstantCoalescentModel
+    try:
+        for batch in (None, 3):
+            ref = build("torchtree.evolution.coalescent.ConstantCoalescentModel", batch)
+            new = build("torchtree_b200.coalescent.ConstantCoalescentModel", batch)
+            assert type(new["coal"]).__module__ == "torchtree_b200.coalescent"
+            assert isinstance(new["coal"], refmod.ConstantCoalescentModel)
+            if not torch.cuda.is_available():
+                with pytest.raises(RuntimeError, match="no CUDA device"):
+                    new["coal"]()
+            monkeypatch.setattr(cmod, "constant_coalescent_log_prob",
+                                lambda h, th, device=0: constant_log_prob(h, th))
+            new["coal"].lp_needs_update = True
+            for dic in (ref, new):
+                dic["theta"].requires_grad = True
+                dic["coal"]().sum().backward()
+            assert new["coal"]().shape == ref["coal"]().shape
+            assert torch.allclose(new["coal"](), ref["coal"](), rtol=1e-12, atol=0)
+            assert torch.allclose(new["theta"].grad, ref["theta"].grad, rtol=1e-10, atol=0)
+            monkeypatch.undo()
+        patched.install(override_reference=False, coalescent=True)
+        assert get_class("ConstantCoalescentModel") is cmod.ConstantCoalescentModel
+        assert get_class("torchtree.evolution.coalescent.ConstantCoalescentModel") \
+            is cmod.ConstantCoalescentModel
+    finally:
+        REGISTERED_CLASSES.clear()
+        REGISTERED_CLASSES.update(saved_reg)
+        refmod.ConstantCoalescentModel = saved_cls

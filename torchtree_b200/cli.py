@@ -21,8 +21,17 @@ class B200Plugin(Plugin):
                     "--b200", action="store_true",
                     help="compute the tree likelihood with the torchtree_b200 CUDA engine")
                 parser.add_argument(
+                    "--b200_coalescent", action="store_true",
+                    help="compute the constant-population coalescent on the GPU as well")
+                parser.add_argument(
                     "--b200_device", type=int, default=0,
                     help="CUDA device ordinal used by the torchtree_b200 engine")
+
+    def process_coalescent(self, arg, data):
+        # constant-population coalescent on the device (coalescent.py); other demographic models
+        # keep the reference class
+        if getattr(arg, "b200_coalescent", False) and data.get("type") == "ConstantCoalescentModel":
+            data["type"] = "torchtree_b200.coalescent.ConstantCoalescentModel"
 
     def process_tree_likelihood(self, arg, data):
         if getattr(arg, "b200", False):
@@ -43,7 +52,11 @@ def main(argv=None):
     heights = "--b200-heights" in sys.argv
     if heights:
         sys.argv.remove("--b200-heights")
-    install(override_reference=True, height_transform=heights)
+    # --b200-coalescent: ConstantCoalescentModel on the GPU as well
+    coalescent = "--b200-coalescent" in sys.argv
+    if coalescent:
+        sys.argv.remove("--b200-coalescent")
+    install(override_reference=True, height_transform=heights, coalescent=coalescent)
     torchtree_main()
 
 

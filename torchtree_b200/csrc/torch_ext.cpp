@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -32,7 +33,11 @@ using torch::autograd::variable_list;
 void check(int status, const char* what) {
   if (status != 0) {
     const char* msg = ttb2_last_error();
-    TORCH_CHECK(false, what, " failed (status ", status, "): ", msg ? msg : "?");
+    // a plain std::runtime_error (pybind11 raises it as RuntimeError): building a c10::Error here,
+    // right after a failed CUDA runtime call inside libttb200's static runtime, crashed while it
+    // captured its backtrace
+    throw std::runtime_error(std::string(what) + " failed (status " + std::to_string(status) +
+                             "): " + (msg ? msg : "?"));
   }
 }
 
@@ -265,6 +270,50 @@ struct NodeHeights : public torch::autograd::Function<NodeHeights> {
   }
 };
 
+// ---------------------------------------------------------------------------------------
+// constant-population coalescent (ttb2_coalescent_constant), replacing the argsort / gather /
+// cumsum graph of ConstantCoalescent.log_prob (coalescent.py:112-134).  The kernel returns the
+// partial derivatives with the value; backward only scales them.
+struct ConstantCoalescent : public torch::autograd::Function<ConstantCoalescent> {
+  static Tensor forward(AutogradContext* ctx, int64_t device, const Tensor& node_heights,
+                        const Tensor& theta) {
+    TORCH_CHECK(node_heights.dim() == 2, "ttb200: node_heights must be [draws, 2T-1]");
+    TORCH_CHECK(theta.dim() == 1, "ttb200: theta must be [1] or [draws]");
+    Tensor h = node_heights.detach();
+    if (h.scalar_type() != at::kDouble) h = h.to(at::kDouble);
+    h = h.contiguous();
+    Tensor th = theta.detach();
+    if (th.scalar_type() != at::kDouble) th = th.to(at::kDouble);
+    th = th.contiguous();
+    const int64_t D = h.size(0), n = h.size(1);
+    TORCH_CHECK(n % 2 == 1 && n >= 3, "ttb200: node_heights needs 2T-1 columns");
+    TORCH_CHECK(th.size(0) == 1 || th.size(0) == D, "ttb200: theta must have 1 or `draws` entries");
+    Tensor lp = at::empty({D}, h.options()), dh = at::empty_like(h), dth = at::empty({D}, h.options());
+    const int where = where_of({h, th}, (int)device);
+    check(ttb2_coalescent_constant((int32_t)device, (int32_t)D, (int32_t)((n + 1) / 2), dptr(h),
+                                   dptr(th), (int32_t)th.size(0), dptr(lp), dptr(dh), dptr(dth),
+                                   where),
+          "ttb2_coalescent_constant");
+    ctx->saved_data["theta_draws"] = th.size(0);
+    ctx->save_for_backward({dh, dth});
+    return lp;
+  }
+
+  static variable_list backward(AutogradContext* ctx, variable_list grad_out) {
+    auto saved = ctx->get_saved_variables();
+    const Tensor &dh = saved[0], &dth = saved[1];
+    Tensor g = grad_out[0].to(dh.device(), at::kDouble).reshape({-1});
+    Tensor gh = dh * g.unsqueeze(1);
+    Tensor gt = dth * g;
+    if (ctx->saved_data["theta_draws"].toInt() == 1) gt = gt.sum(0, /*keepdim=*/true);
+    return {Tensor(), gh, gt};
+  }
+};
+
+Tensor constant_coalescent(int64_t device, const Tensor& node_heights, const Tensor& theta) {
+  return ConstantCoalescent::apply(device, node_heights, theta);
+}
+
 Tensor log_likelihood_eigen(int64_t handle, const Tensor& branch_lengths, const Tensor& site_rates,
                             const Tensor& site_props, const Tensor& q_norm, const Tensor& freqs) {
   return EigenLikelihood::apply(handle, branch_lengths, site_rates, site_props, q_norm, freqs);
@@ -292,5 +341,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("mats"), py::arg("freqs"), py::arg("site_props"));
   m.def("node_heights", &node_heights, "ratios / root height -> internal node heights",
         py::arg("plan_handle"), py::arg("device"), py::arg("x"));
+  m.def("constant_coalescent", &constant_coalescent,
+        "log-density [D] of the constant-population coalescent for node heights [D, 2T-1]",
+        py::arg("device"), py::arg("node_heights"), py::arg("theta"));
   m.def("abi_version", []() { return ttb2_version(); });
 }

@@ -119,7 +119,8 @@ class TreeLikelihoodModel(CallableModel):
                    use_ambiguities, use_tip_states, device=data.get("device", 0))
 
 
-def install(override_reference: bool = True, height_transform: bool = False) -> None:
+def install(override_reference: bool = True, height_transform: bool = False,
+            coalescent: bool = False) -> None:
     """Make existing configs resolve to this class (SURVEY 8(b) "Resolution"):
 
     * bare `"type": "TreeLikelihoodModel"` -> registry entry replaced;
@@ -128,7 +129,9 @@ def install(override_reference: bool = True, height_transform: bool = False) -> 
     * bare `"LG"` / `"WAG"` are registered (the reference forgets to, SURVEY F7);
     * `height_transform=True` additionally rebinds `GeneralNodeHeightTransform`
       where `ReparameterizedTimeTreeModel` looks it up (tree_model.py:539, :587), so
-      time trees map ratios to node heights on the GPU (height_transform.py).
+      time trees map ratios to node heights on the GPU (height_transform.py);
+    * `coalescent=True` makes `ConstantCoalescentModel` (bare and dotted) resolve to the device
+      version (coalescent.py).
     """
     import torchtree.evolution.tree_likelihood as ref_module
     from torchtree.evolution.substitution_model.amino_acid import LG, WAG
@@ -141,6 +144,16 @@ def install(override_reference: bool = True, height_transform: bool = False) -> 
         ref_module.TreeLikelihoodModel = TreeLikelihoodModel
     register_class(LG, "LG")
     register_class(WAG, "WAG")
+    if coalescent:
+        import torchtree.evolution.coalescent as ref_coalescent
+
+        from . import coalescent as b200_coalescent
+        cls = b200_coalescent.ConstantCoalescentModel
+        register_class(cls, "torchtree_b200.ConstantCoalescentModel")
+        register_class(cls, "ConstantCoalescentModel")
+        if not hasattr(ref_coalescent, "ReferenceConstantCoalescentModel"):
+            ref_coalescent.ReferenceConstantCoalescentModel = ref_coalescent.ConstantCoalescentModel
+        ref_coalescent.ConstantCoalescentModel = cls
     if height_transform:
         import torchtree.evolution.tree_height_transform as ref_transform
         import torchtree.evolution.tree_model as ref_tree_model
