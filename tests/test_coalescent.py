@@ -100,7 +100,7 @@ def test_unbatched_heights_with_batched_theta_and_limits():
 
     rec = np.load(GOLDEN[0])
     h = torch.tensor(rec["heights"][0], requires_grad=True)          # [2T-1]
-    theta = torch.tensor([[2.0], [3.5], [7.0]], requires_grad=True)  # [3,1]
+    theta = torch.tensor([[2.0], [3.5], [7.0]], dtype=torch.float64, requires_grad=True)  # [3,1]
     lp = constant_coalescent_log_prob(h, theta)
     assert lp.shape == (3, 1)
     lp.sum().backward()
