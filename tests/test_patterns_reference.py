@@ -129,3 +129,26 @@ def test_argument_validation():
         compress_sequences(["ACGT", "ACGT"], group=3)
     p, w = compress_sequences(["AAAA", "CCCC"])
     assert p.shape == (2, 1, 1) and w.tolist() == [4.0]
+
+
+@pytest.mark.reference
+def test_fuzz_small_alignments(ref):
+    """Edge shapes against the reference's `compress`: one site, one / two taxa, identical
+    columns, all-distinct columns, low-entropy alphabets (many repeated columns)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    dt = ref["datatype"].NucleotideDataType("nuc")
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.integers(1, 5), st.integers(1, 40), st.sampled_from(["AC", "ACGT", "ACGT-RN", "A"]),
+           st.integers(0, 2 ** 31 - 1))
+    def run(taxa, length, alphabet, seed):
+        rng = random.Random(seed)
+        names = [f"t{i}" for i in range(taxa)]
+        seqs = ["".join(rng.choice(alphabet) for _ in range(length)) for _ in names]
+        aln = _alignment(ref, names, seqs, dt)
+        n = _check(ref, aln, True)
+        assert 1 <= n <= length
+
+    run()
