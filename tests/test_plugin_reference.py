@@ -555,3 +555,57 @@ def test_device_coalescent_class_is_a_dropin(patched, monkeypatch):
         REGISTERED_CLASSES.clear()
         REGISTERED_CLASSES.update(saved_reg)
         refmod.ConstantCoalescentModel = saved_cls
+
+
+def test_time_tree_with_per_branch_clock_rates(patched):
+    """Relaxed clock (`SimpleClockModel`: one rate per branch, branch_model.py:58-80) on the
+    reparameterised fluA time tree: value and gradients w.r.t. ratios, root height and rates equal the
+    reference class's (the scaled branch lengths reach the engine through
+    flatten.scaled_branch_lengths, tree_likelihood.py:323-344)."""
+    from torchtree import Parameter
+    from torchtree.evolution.branch_model import SimpleClockModel
+    from torchtree.evolution.site_model import ConstantSiteModel
+    from torchtree.evolution.site_pattern import SitePattern
+    from torchtree.evolution.substitution_model import JC69
+    from torchtree.evolution.taxa import Taxa, Taxon
+    from torchtree.evolution.tree_likelihood import TreeLikelihoodModel as Reference
+    from torchtree.evolution.tree_model import ReparameterizedTimeTreeModel
+
+    taxa_list = []
+    with open(DATA + "/fluA.fa") as fp:
+        for line in fp:
+            if line.startswith(">"):
+                t = line[1:].strip()
+                taxa_list.append(Taxon(t, {"date": float(t.split("_")[-1])}))
+    with open(DATA + "/fluA.tree") as fp:
+        newick = fp.read().strip()
+    rng = np.random.default_rng(8)
+    rates0 = rng.uniform(5e-4, 3e-3, 136)
+    results = []
+    for cls in (Reference, patched.TreeLikelihoodModel):
+        dic = {"taxa": Taxa("taxa", taxa_list)}
+        tree_model = ReparameterizedTimeTreeModel.from_json(
+            ReparameterizedTimeTreeModel.json_factory(
+                "tree_model", newick, "taxa", ratios=[0.5] * 67, root_height=[20.0],
+                **{"keep_branch_lengths": True}), dic)
+        sp = SitePattern.from_json({
+            "id": "sp", "type": "SitePattern",
+            "alignment": {"id": "a", "type": "Alignment", "datatype": "nucleotide",
+                          "file": DATA + "/fluA.fa", "taxa": "taxa"}}, dic)
+        rates = Parameter("rates", torch.tensor(rates0))
+        clock = SimpleClockModel("clock", rates, tree_model)
+        like = cls("like", sp, tree_model, JC69("jc"), ConstantSiteModel("sm"), clock)
+        # ratios and root height are the two members of the CatParameter behind the tree
+        leaves = [rates] + list(tree_model._internal_heights._parameter_container.parameters())
+        assert len(leaves) == 3
+        for p in leaves:
+            p.requires_grad = True
+        value = like()
+        value.sum().backward()
+        results.append((value.detach().clone(), [p.grad.clone() for p in leaves]))
+    (v_ref, g_ref), (v_new, g_new) = results
+    assert v_new.shape == v_ref.shape
+    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0), (v_new, v_ref)
+    for a, b in zip(g_new, g_ref):
+        assert a.shape == b.shape
+        assert torch.allclose(a, b, rtol=1e-7, atol=1e-7 * b.abs().max())
