@@ -15,6 +15,7 @@ from .function import (  # noqa: F401
     reversible_eigensystem,
 )
 from ._lib import EngineError  # noqa: F401
+from .coalescent import constant_coalescent_log_prob  # noqa: F401
 
 
 def __getattr__(name):
@@ -25,6 +26,10 @@ def __getattr__(name):
         from .tree_likelihood import TreeLikelihoodModel
 
         return TreeLikelihoodModel
+    if name == "ConstantCoalescentModel":
+        from .coalescent import ConstantCoalescentModel
+
+        return ConstantCoalescentModel
     if name == "install":
         from .tree_likelihood import install
 
