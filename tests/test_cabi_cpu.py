@@ -140,3 +140,15 @@ def test_synthetic_postorder_convention():
         assert post[-1, 0] == 2 * T - 2
         assert 2 * T - 3 in post[-1, 1:]  # node 2T-3 is a child of the root
         assert prob.branch_lengths[0, -1] == 0.0
+
+
+def test_every_entry_point_is_documented_with_its_reference_counterpart():
+    """include/ttb200.h is the drop-in boundary: INTEGRATION.md must name every symbol it declares,
+    and the header must cite reference files (file:line) for what the entry points replace."""
+    declared = _declared_symbols()
+    integration = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    missing = [s for s in declared if s not in integration]
+    assert not missing, missing
+    header = open(os.path.join(REPO, "include", "ttb200.h")).read()
+    cites = re.findall(r"[a-z_/]+\.py:\d+", header)
+    assert len(cites) >= 15, cites
