@@ -138,3 +138,38 @@ def test_draw_sharding_two_ranks(tmp_path):
             assert got[n].shape == want.shape, n
             np.testing.assert_allclose(got[n], want, rtol=1e-10, atol=1e-10 * np.abs(want).max(),
                                        err_msg=n)
+
+
+def _idle_rank_worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from torchtree_b200.sharded import draw_sharded_log_likelihood
+
+    x = torch.tensor([[1.5, 2.0]], dtype=torch.float64, requires_grad=True)   # one draw only
+    shared = torch.tensor([[3.0]], dtype=torch.float64, requires_grad=True)
+    calls = []
+
+    def local(xl, sl):
+        calls.append(xl.shape[0])
+        return (xl ** 2).sum(-1) * sl.reshape(-1)
+
+    out = draw_sharded_log_likelihood(local, [x, shared], draws=1)
+    out.sum().backward()
+    np.savez(os.path.join(out_dir, "idle_rank%d.npz" % rank), out=out.detach().numpy(),
+             gx=x.grad.numpy(), gs=shared.grad.numpy(), calls=np.array(calls))
+    dist.destroy_process_group()
+
+
+def test_draw_sharding_with_more_ranks_than_draws(tmp_path):
+    """One draw on two ranks: the idle rank evaluates nothing but joins both collectives and ends
+    with the same value and gradients."""
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_idle_rank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), "idle_rank%d.npz" % rank))
+        np.testing.assert_allclose(got["out"], [(1.5 ** 2 + 2.0 ** 2) * 3.0])
+        np.testing.assert_allclose(got["gx"], [[2 * 1.5 * 3.0, 2 * 2.0 * 3.0]])
+        np.testing.assert_allclose(got["gs"], [[1.5 ** 2 + 2.0 ** 2]])
+        assert got["calls"].tolist() == ([1] if rank == 0 else [])
