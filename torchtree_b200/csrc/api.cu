@@ -296,8 +296,9 @@ void drop_graphs(Engine& e) {
   e.gBwd = Engine::GraphSlot();
 }
 
-// (threshold re-measured with bench.py --patterns 12500 / 25000, profiles/r01_small_shard.log:
-// replay still gains 3 % / 1.6 % there, i.e. on the 4- and 8-GPU shards of the headline problem)
+// (bench.py --patterns 12500 / 25000, profiles/r01_small_shard.log: replay would still gain 3 % /
+// 1.6 % there, i.e. on the 8- / 4-GPU shards of the headline problem; TTB2_GRAPH_MAX_UNITS=1.2e8
+// enables it -- not the default until replay has been run next to the NCCL all-reduce on 4-8 GPUs)
 // Graph replay pays when an evaluation is launch-bound (fluA: 79 launches of a few
 // microseconds each, 0.53 -> 0.37 ms).  When the level kernels run for milliseconds the
 // host is far ahead of the device anyway and replay only adds its own launch and
@@ -307,7 +308,7 @@ bool graphs_enabled(const Engine& e, int draws) {
   if ((e.cfg.flags & TTB2_FLAG_NO_GRAPH) || e.timing || e.ownStream == nullptr) return false;
   const double units = (double)e.dm.Npad * e.dm.I * e.dm.K * draws * (e.dm.S / 4.0);
   static const double maxUnits =
-      getenv("TTB2_GRAPH_MAX_UNITS") ? atof(getenv("TTB2_GRAPH_MAX_UNITS")) : 1.2e8;
+      getenv("TTB2_GRAPH_MAX_UNITS") ? atof(getenv("TTB2_GRAPH_MAX_UNITS")) : 4.0e7;
   return units <= maxUnits;
 }
 
