@@ -131,9 +131,11 @@ CONFIGS = {
                                     seed=3, note="500-taxon tree, K=1, 128 draws per step "
                                     "(draw batch; tree prior and height transform stay in torch)"),
     "config4_aa_LG_like": dict(T=200, N=50_000, S=20, K=4, D=1, D_parity=1, N_parity=200, seed=4,
-                               note="20-state reversible model + 4 categories (generic-S kernels)"),
+                               note="20-state reversible model + 4 categories (warp-autonomous DMMA kernels, "
+                               "csrc/kernels_gwarp.cu)"),
     "config5_codon_61": dict(T=100, N=20_000, S=61, K=4, D=1, D_parity=1, N_parity=64, seed=5,
-                             note="61-state reversible model + 4 categories (generic-S kernels)"),
+                             note="61-state reversible model + 4 categories (DMMA tile kernels, "
+                             "csrc/kernels_gmma.cu)"),
 }
 
 if __name__ == "__main__":
