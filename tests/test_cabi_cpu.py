@@ -152,3 +152,46 @@ def test_every_entry_point_is_documented_with_its_reference_counterpart():
     header = open(os.path.join(REPO, "include", "ttb200.h")).read()
     cites = re.findall(r"[a-z_/]+\.py:\d+", header)
     assert len(cites) >= 15, cites
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/ttb200.h must compile as C99 and a C program must link
+    against libttb200.so and get error codes (not crashes) for bad arguments."""
+    import shutil
+    import subprocess
+
+    from torchtree_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc unavailable")
+    src = tmp_path / "cabi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "ttb200.h"
+int main(void) {
+  ttb2_engine* e = NULL;
+  ttb2_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  if (ttb2_version() != TTB2_VERSION) return 1;
+  if (ttb2_create(NULL, NULL, NULL, NULL, NULL, &e) == TTB2_OK) return 2;
+  if (ttb2_last_error() == NULL || strlen(ttb2_last_error()) == 0) return 3;
+  if (ttb2_loglik_q(NULL, 1, NULL, NULL, 1, NULL, 1, NULL, 1, NULL, 1, NULL, TTB2_HOST) != TTB2_E_INVALID) return 4;
+  if (ttb2_coalescent_constant(0, 0, 1, NULL, NULL, 1, NULL, NULL, NULL, TTB2_HOST) != TTB2_E_INVALID) return 5;
+  if (ttb2_get_config(NULL, &cfg) != TTB2_E_INVALID) return 6;
+  if (ttb2_eval_serial(NULL) != 0 || ttb2_launch_count(NULL) != 0) return 7;
+  ttb2_destroy(NULL);
+  puts("c-abi ok");
+  return 0;
+}
+''')
+    exe = tmp_path / "cabi"
+    libdir = os.path.dirname(_lib.lib_path())
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic",
+                        "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lttb200", "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "c-abi ok" in run.stdout, (run.returncode, run.stdout, run.stderr)
