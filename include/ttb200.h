@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define TTB2_VERSION 100
+#define TTB2_VERSION 200
 
 #define TTB2_HOST 0
 #define TTB2_DEVICE 1
@@ -80,14 +80,13 @@ typedef struct ttb2_config {
 /* keep per-(node,pattern) data for the gradient pass resident from create()
  * (otherwise allocated at the first ttb2_grad_* call) */
 #define TTB2_FLAG_PREALLOC_GRAD 1
-/* force the generic-S kernels even when a specialised path exists (testing) */
+/* force the generic-S SIMT kernels even when a specialised path exists (testing: an
+ * independent implementation of the same sweeps) */
 #define TTB2_FLAG_FORCE_GENERIC 2
-/* 4-state models, eigen mode: use the experimental fused whole-tree traversal
- * kernels (one persistent launch per sweep, 2 instead of 5 vectors of HBM
- * traffic per node) instead of the per-level kernels */
+/* accepted and ignored (round 1 had an experimental fused whole-tree traversal behind it) */
 #define TTB2_FLAG_FUSED 4
-/* 4-state pre-order kernel: accumulate d lnL / d P with plain fp64 FMAs instead
- * of fp64 tensor-core MMAs (testing / comparison) */
+/* 8..64 states: plain fp64 FMA kernels instead of the fp64 tensor-core (DMMA) kernels
+ * (testing / comparison); ignored by the 4-state path */
 #define TTB2_FLAG_NO_MMA 8
 /* accepted and ignored: cherry tabulation (below) used to be opt-in */
 #define TTB2_FLAG_CHERRY 16
@@ -124,7 +123,8 @@ int ttb2_set_postorder(ttb2_engine* engine, const int32_t* postorder);
 void ttb2_destroy(ttb2_engine* engine);
 
 /* Use `cuda_stream` (a cudaStream_t) for all subsequent work; NULL = the
- * legacy default stream. */
+ * legacy default stream.  The new stream is ordered behind the work already queued on
+ * the previous one (event wait, no host synchronisation); a no-op if unchanged. */
 int ttb2_set_stream(ttb2_engine* engine, void* cuda_stream);
 int ttb2_synchronize(ttb2_engine* engine);
 
@@ -199,6 +199,19 @@ int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl,
                     double* d_branch_lengths, double* d_site_rates,
                     double* d_props, double* d_q, double* d_freqs,
                     int32_t where);
+
+/*
+ * The same gradient as ONE contiguous vector, for callers that reduce it across pattern shards
+ * (one NCCL all-reduce over NVLink) or move it to the host in one copy:
+ *   packed = [ lnL[D] | d_branch_lengths[D][B] | d_site_rates[rate_draws][K] |
+ *              d_props[prop_draws][K] | d_q[eig_draws][S][S] | d_freqs[freq_draws][S] ]
+ * with the draw counts of the latest ttb2_loglik_eigen / ttb2_loglik_q call;
+ * ttb2_packed_count returns its length in doubles, `capacity` is the length of `packed`.
+ * The output kernels write this layout directly (no gather step).
+ */
+int ttb2_grad_eigen_packed(ttb2_engine* engine, const double* grad_lnl, double* packed,
+                           int64_t capacity, int32_t where);
+int64_t ttb2_packed_count(const ttb2_engine* engine);
 
 /* Per-pattern log-likelihoods of the latest loglik call: out [D][N]. */
 int ttb2_site_loglik(ttb2_engine* engine, double* out, int32_t where);

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
-    assert lib.ttb2_version() == 100
+    assert lib.ttb2_version() == 200
 
 
 def test_torch_extension_builds_loads_and_links_the_cabi():
@@ -47,8 +47,13 @@ def test_torch_extension_builds_loads_and_links_the_cabi():
     needed = subprocess.run(["readelf", "-d", ext], capture_output=True, text=True).stdout
     assert "libttb200.so" in needed and "$ORIGIN/lib" in needed
     x = torch.zeros(1, 4, dtype=torch.float64)
-    with pytest.raises(RuntimeError, match="null engine handle"):
-        _ttb200_torch.log_likelihood_eigen(0, x, x, x, x, x)
+    # a closed (here: never created) engine raises instead of dereferencing its handle
+    ref = _ttb200_torch.EngineRef(0)
+    assert ref.closed
+    with pytest.raises(RuntimeError, match="has been closed"):
+        _ttb200_torch.log_likelihood_eigen(ref, x, x, x, x, x)
+    with pytest.raises(TypeError):
+        _ttb200_torch.log_likelihood_eigen(0, x, x, x, x, x)   # raw handles are not accepted
     with pytest.raises(RuntimeError, match="null node-height plan"):
         _ttb200_torch.node_heights(0, 0, x)
 

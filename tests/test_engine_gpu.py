@@ -42,7 +42,7 @@ def _reduce(ref, like_rows):
     return ref
 
 
-@pytest.mark.parametrize("flags", [0, 2, 8, 64], ids=["levels", "generic", "levels-simt", "nocherry"])
+@pytest.mark.parametrize("flags", [0, 2, 64], ids=["levels", "generic", "nocherry"])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_mats_mode(name, flags):
     """ttb2_loglik_mats / ttb2_grad_mats with the reference's own matrices."""
@@ -64,7 +64,7 @@ def test_golden_mats_mode(name, flags):
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [0, 2, 4, 8, 64, 32], ids=["levels", "generic", "fused", "levels-simt", "nocherry", "nograph"])
+@pytest.mark.parametrize("flags", [0, 2, 64, 32], ids=["levels", "generic", "nocherry", "nograph"])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_eigen_mode(name, flags):
     """ttb2_loglik_eigen / ttb2_grad_eigen: P(t) on the device, gradients w.r.t.
@@ -114,7 +114,7 @@ def _gtr_chain(rec, eng_grads, prob):
 @pytest.mark.parametrize("name", ["fluA_gtr_w4_generic", "fluA_gtr_w4_ambig", "syn40_gtr_w4",
                                   "syn400_gtr_w4_caterpillar", "syn17_gtr_w3",
                                   "fluA_gtr_w4_batch3"])
-@pytest.mark.parametrize("flags", [0, 4, 8, 64], ids=["levels", "fused", "levels-simt", "nocherry"])
+@pytest.mark.parametrize("flags", [0, 64], ids=["levels", "nocherry"])
 def test_gtr_parameter_gradients_match_reference(name, flags):
     """End of the chain: d lnL / d (GTR rates, GTR freqs, Weibull shape, branch
     lengths) as torchtree's own `like().backward()` produced them."""
@@ -189,11 +189,11 @@ def test_device_resident_inputs_match_host_inputs():
     eng.close()
 
 
-def test_grad_mats_after_fused_eigen_forward():
-    """d lnL / d P requested after an eigen-mode (fused) forward: the engine
-    falls back to the per-level sweeps for that call."""
+def test_grad_mats_after_eigen_forward():
+    """d lnL / d P requested after an eigen-mode forward: both gradient entry points serve
+    the same pre-order sweep."""
     prob, rec = load_golden("syn40_gtr_w4")
-    eng = _engine(prob, flags=4)
+    eng = _engine(prob)
     evec, ivec, evals = _eig(prob)
     eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props, evec, ivec, evals,
                      prob.freqs)
@@ -204,14 +204,14 @@ def test_grad_mats_after_fused_eigen_forward():
     eng.close()
 
 
-def test_fused_without_q_gradient():
+def test_grad_eigen_without_q_gradient():
     """grad_eigen with d_q skipped (models without free substitution parameters)."""
     import ctypes
 
     from torchtree_b200 import _lib
 
     prob, rec = load_golden("fluA_gtr_w4_generic")
-    eng = _engine(prob, flags=4)
+    eng = _engine(prob)
     evec, ivec, evals = _eig(prob)
     eng.loglik_eigen(prob.branch_lengths, prob.site_rates, prob.site_props, evec, ivec, evals,
                      prob.freqs)

@@ -1,6 +1,7 @@
 """Native site-pattern compression == the reference's `compress` family
 (torchtree/evolution/site_pattern.py:69-151).  Host code: runs without a GPU.
-Needs the reference importable (this container); skipped on the GPU box."""
+Needs the reference importable: `baseline/_ref` (tools/vendor_reference.py; travels to the GPU box,
+where the "box" variants run under `-m gpu`) or /root/reference (authoring container)."""
 import os
 import random
 import sys
@@ -9,16 +10,16 @@ import numpy as np
 import pytest
 import torch
 
-REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refenv  # noqa: E402
+
+REF = os.path.dirname(refenv.data_dir() or "/root/reference/data")
 
 
-@pytest.fixture(scope="module")
-def ref():
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "dendropy_shim"))
-    sys.path.insert(0, REF)
+@pytest.fixture(scope="module", params=["host", pytest.param("box", marks=pytest.mark.gpu)])
+def ref(request):
+    refenv.activate()
     import torchtree  # noqa: F401
     from torchtree.evolution import alignment, datatype, site_pattern, taxa
     return dict(alignment=alignment, datatype=datatype, site_pattern=site_pattern, taxa=taxa)

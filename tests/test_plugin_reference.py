@@ -1,10 +1,17 @@
-"""The torchtree plug-in class against the REAL reference (authoring container
-only: needs /root/reference).  There is no GPU here, so the two engine entry
-points the glue calls are replaced by the pinned CPU oracle (test-only
-injection); what is verified is everything *around* the engine: JSON parsing,
-class registration / type resolution, tip-code extraction, the flattening of
-torchtree's sub-models, batch shapes, the output contract and the gradient
-hand-back to torchtree Parameters."""
+"""The torchtree plug-in class against the REAL reference, in two set-ups:
+
+* `backend = "cuda"` (`-m gpu`, the B200 box): `torchtree_b200.TreeLikelihoodModel` + the real
+  CUDA engine (libttb200.so through the torch extension) + the real torchtree, vendored into
+  `baseline/_ref` by tools/vendor_reference.py -- the product as a user runs it.  Every test
+  builds the same JSON twice (reference class / drop-in class) and compares lnL at 1e-10 and every
+  `Parameter.grad` at 1e-8 (substitution parameters whose reference gradient goes through the
+  `eigh` backward: 1e-7; tests/test_truth_mpmath_gpu.py attributes that slack to the
+  reference), and runs `torchtree-cli advi|hmc|map|mcmc ... --b200` + the stock runner.
+* `backend = "oracle"` (`-m "not gpu"`, the authoring container, no GPU): the two engine entry
+  points the glue calls are replaced by the pinned CPU oracle (test-only injection); what is
+  verified is everything *around* the engine: JSON parsing, class registration / type
+  resolution, tip-code extraction, the flattening of torchtree's sub-models, batch shapes, the
+  output contract and the gradient hand-back to torchtree Parameters."""
 import json
 import os
 import sys
@@ -16,19 +23,23 @@ import torch
 pytestmark = pytest.mark.reference
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DATA = "/root/reference/data"
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refenv  # noqa: E402
+
+DATA = refenv.data_dir() or "/root/reference/data"
+BACKENDS = ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)]
 
 
 @pytest.fixture(scope="module")
 def torchtree_env():
-    sys.path.insert(0, os.path.join(REPO, "oracle", "dendropy_shim"))
-    sys.path.insert(0, "/root/reference")
+    added = refenv.activate()
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     yield
     torch.set_default_dtype(old)
-    sys.path.remove("/root/reference")
-    sys.path.remove(os.path.join(REPO, "oracle", "dendropy_shim"))
+    for p in added:
+        if p != REPO:
+            sys.path.remove(p)
 
 
 class FakeEngine:
@@ -47,6 +58,9 @@ class FakeEngine:
         self.postorder = postorder
 
     def close(self):
+        pass
+
+    def release(self):
         pass
 
 
@@ -78,15 +92,37 @@ def fake_mats(engine, mats, freqs, props):
         freqs.expand(D, -1).unsqueeze(-2), props.expand(D, -1)[..., None, None]).squeeze(-1)
 
 
-@pytest.fixture
-def patched(torchtree_env, monkeypatch):
+@pytest.fixture(params=BACKENDS)
+def patched(request, torchtree_env, monkeypatch):
+    """The drop-in module, backed by the CUDA engine ("cuda") or by the oracle ("oracle")."""
     import torchtree_b200.flatten as flatten
     import torchtree_b200.tree_likelihood as tlmod
 
-    monkeypatch.setattr(flatten, "log_likelihood_eigen", fake_eigen)
-    monkeypatch.setattr(flatten, "log_likelihood_mats", fake_mats)
-    monkeypatch.setattr(tlmod, "Engine", FakeEngine)
+    monkeypatch.setattr(tlmod, "BACKEND", request.param, raising=False)
+    if request.param == "oracle":
+        monkeypatch.setattr(flatten, "log_likelihood_eigen", fake_eigen)
+        monkeypatch.setattr(flatten, "log_likelihood_mats", fake_mats)
+        monkeypatch.setattr(tlmod, "Engine", FakeEngine)
+    else:
+        assert torch.cuda.is_available(), "the cuda backend needs a GPU"
+        from torchtree_b200 import _lib
+
+        _lib.load()  # the product path: fail loudly when the CUDA library is missing
     return tlmod
+
+
+def _grad_tol(name):
+    """north_star: gradients at 1e-8; parameters whose *reference* gradient flows through the
+    eigh backward (1/eigen-gap error amplification) at 1e-7."""
+    return 1e-7 if name in ("rates", "freqs", "kappa") else 1e-8
+
+
+def _assert_grads(g_new, g_ref, names):
+    for n in names:
+        assert g_new[n].shape == g_ref[n].shape, n
+        tol = _grad_tol(n)
+        assert torch.allclose(g_new[n], g_ref[n], rtol=tol, atol=tol * g_ref[n].abs().max()), \
+            (n, (g_new[n] - g_ref[n]).abs().max().item(), g_ref[n].abs().max().item())
 
 
 def _flu_json(tree_type="unrooted", model="GTR", batch=None):
@@ -160,10 +196,8 @@ def test_dropin_equals_reference_on_fluA_gtr(patched, batch):
     v_ref, g_ref = _grads(ref, names)
     v_new, g_new = _grads(new, names)
     assert v_new.shape == v_ref.shape  # sample_shape + (1,)
-    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0)
-    for n in names:
-        assert g_new[n].shape == g_ref[n].shape
-        assert torch.allclose(g_new[n], g_ref[n], rtol=1e-7, atol=1e-7 * g_ref[n].abs().max()), n
+    assert torch.allclose(v_new, v_ref, rtol=1e-10, atol=0)
+    _assert_grads(g_new, g_ref, names)
 
 
 def test_tip_states_and_ambiguities_flags(patched):
@@ -172,7 +206,7 @@ def test_tip_states_and_ambiguities_flags(patched):
         cfg = dict(like, **extra)
         ref = _build(objs, cfg, "torchtree.evolution.tree_likelihood.TreeLikelihoodModel")
         new = _build(objs, cfg, "torchtree_b200.TreeLikelihoodModel")
-        assert torch.allclose(new["like"](), ref["like"](), rtol=1e-11, atol=0), extra
+        assert torch.allclose(new["like"](), ref["like"](), rtol=1e-10, atol=0), extra
 
 
 def test_install_overrides_bare_and_dotted_type_names(patched):
@@ -341,10 +375,8 @@ def test_model_variants_match_reference(patched, subst, site):
     v_ref, g_ref = _grads(ref, names)
     v_new, g_new = _grads(new, names)
     assert v_new.shape == v_ref.shape
-    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0), (v_new, v_ref)
-    for n in names:
-        assert g_new[n].shape == g_ref[n].shape, n
-        assert torch.allclose(g_new[n], g_ref[n], rtol=1e-7, atol=1e-7 * g_ref[n].abs().max()), n
+    assert torch.allclose(v_new, v_ref, rtol=1e-10, atol=0), (v_new, v_ref)
+    _assert_grads(g_new, g_ref, names)
 
 
 def test_srd06_two_likelihoods_share_a_tree(patched):
@@ -371,8 +403,8 @@ def test_srd06_two_likelihoods_share_a_tree(patched):
                         dic["like12"].weights.sum().item() + dic["like3"].weights.sum().item())
     (v_ref, g_ref, n_ref), (v_new, g_new, n_new) = totals.values()
     assert n_ref == n_new == 987  # every site of fluA lands in exactly one partition
-    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0)
-    assert torch.allclose(g_new, g_ref, rtol=1e-7, atol=1e-7 * g_ref.abs().max())
+    assert torch.allclose(v_new, v_ref, rtol=1e-10, atol=0)
+    assert torch.allclose(g_new, g_ref, rtol=1e-8, atol=1e-8 * g_ref.abs().max())
 
 
 def test_amino_acid_lg_weibull(patched):
@@ -413,9 +445,8 @@ def test_amino_acid_lg_weibull(patched):
     assert new["like"]._state_count == 20
     v_ref, g_ref = _grads(ref, ["blens", "shape"])
     v_new, g_new = _grads(new, ["blens", "shape"])
-    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0), (v_new, v_ref)
-    for n in ("blens", "shape"):
-        assert torch.allclose(g_new[n], g_ref[n], rtol=1e-7, atol=1e-7 * g_ref[n].abs().max()), n
+    assert torch.allclose(v_new, v_ref, rtol=1e-10, atol=0), (v_new, v_ref)
+    _assert_grads(g_new, g_ref, ["blens", "shape"])
 
 
 def _run_cli(argv, capsys):
@@ -528,26 +559,29 @@ def test_device_coalescent_class_is_a_dropin(patched, monkeypatch):
         return dic
 
     saved_reg, saved_cls = dict(REGISTERED_CLASSES), refmod.ConstantCoalescentModel
+    backend, install = patched.BACKEND, patched.install
     try:
         for batch in (None, 3):
             ref = build("torchtree.evolution.coalescent.ConstantCoalescentModel", batch)
             new = build("torchtree_b200.coalescent.ConstantCoalescentModel", batch)
             assert type(new["coal"]).__module__ == "torchtree_b200.coalescent"
             assert isinstance(new["coal"], refmod.ConstantCoalescentModel)
-            if not torch.cuda.is_available():
-                with pytest.raises(RuntimeError, match="no CUDA device"):
-                    new["coal"]()
-            monkeypatch.setattr(cmod, "constant_coalescent_log_prob",
-                                lambda h, th, device=0: constant_log_prob(h, th))
-            new["coal"].lp_needs_update = True
+            if backend == "oracle":
+                if not torch.cuda.is_available():
+                    with pytest.raises(RuntimeError, match="no CUDA device"):
+                        new["coal"]()
+                monkeypatch.setattr(cmod, "constant_coalescent_log_prob",
+                                    lambda h, th, device=0: constant_log_prob(h, th))
+                new["coal"].lp_needs_update = True
             for dic in (ref, new):
                 dic["theta"].requires_grad = True
                 dic["coal"]().sum().backward()
             assert new["coal"]().shape == ref["coal"]().shape
             assert torch.allclose(new["coal"](), ref["coal"](), rtol=1e-12, atol=0)
             assert torch.allclose(new["theta"].grad, ref["theta"].grad, rtol=1e-10, atol=0)
-            monkeypatch.undo()
-        patched.install(override_reference=False, coalescent=True)
+            if backend == "oracle":
+                monkeypatch.undo()
+        install(override_reference=False, coalescent=True)
         assert get_class("ConstantCoalescentModel") is cmod.ConstantCoalescentModel
         assert get_class("torchtree.evolution.coalescent.ConstantCoalescentModel") \
             is cmod.ConstantCoalescentModel
@@ -605,7 +639,7 @@ def test_time_tree_with_per_branch_clock_rates(patched):
         results.append((value.detach().clone(), [p.grad.clone() for p in leaves]))
     (v_ref, g_ref), (v_new, g_new) = results
     assert v_new.shape == v_ref.shape
-    assert torch.allclose(v_new, v_ref, rtol=1e-11, atol=0), (v_new, v_ref)
+    assert torch.allclose(v_new, v_ref, rtol=1e-10, atol=0), (v_new, v_ref)
     for a, b in zip(g_new, g_ref):
         assert a.shape == b.shape
-        assert torch.allclose(a, b, rtol=1e-7, atol=1e-7 * b.abs().max())
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-8 * b.abs().max())

@@ -52,6 +52,8 @@ EXPORTED_SYMBOLS = (
     "ttb2_grad_mats",
     "ttb2_loglik_eigen",
     "ttb2_grad_eigen",
+    "ttb2_grad_eigen_packed",
+    "ttb2_packed_count",
     "ttb2_loglik_q",
     "ttb2_get_eigen",
     "ttb2_site_loglik",
@@ -115,6 +117,10 @@ def load():
     lib.ttb2_get_eigen.restype = c_int32
     lib.ttb2_grad_eigen.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int32]
     lib.ttb2_grad_eigen.restype = c_int32
+    lib.ttb2_grad_eigen_packed.argtypes = [vp, vp, vp, c_int64, c_int32]
+    lib.ttb2_grad_eigen_packed.restype = c_int32
+    lib.ttb2_packed_count.argtypes = [vp]
+    lib.ttb2_packed_count.restype = c_int64
     lib.ttb2_site_loglik.argtypes = [vp, vp, c_int32]
     lib.ttb2_site_loglik.restype = c_int32
     lib.ttb2_get_mats.argtypes = [vp, vp, c_int32]

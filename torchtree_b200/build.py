@@ -21,7 +21,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 BUILD = os.path.join(PKG, "_obj")
 LIB = os.path.join(LIBDIR, "libttb200.so")
-SOURCES = ["api.cu", "kernels_s4.cu", "kernels_small.cu", "kernels_gen.cu", "kernels_fused.cu",
+SOURCES = ["api.cu", "kernels_s4.cu", "kernels_small.cu", "kernels_gen.cu",
            "kernels_gmma.cu", "patterns.cu", "heights.cu", "eigen.cu", "kernels_gwarp.cu", "coalescent.cu"]
 HEADERS = [os.path.join(CSRC, "engine.cuh"), os.path.join(PKG, "..", "include", "ttb200.h")]
 NVCC_FLAGS = [
@@ -112,8 +112,10 @@ def build_torch_extension(force: bool = False) -> str:
     cxx = os.environ.get("CXX") or shutil.which("g++")
     if not cxx:
         raise RuntimeError("g++ not found; cannot build the torch extension")
+    cuda_home = os.environ.get("CUDA_HOME") or os.path.dirname(os.path.dirname(_nvcc()))
     incs = cpp_extension.include_paths() + [sysconfig.get_paths()["include"],
-                                            os.path.join(PKG, "..", "include")]
+                                            os.path.join(PKG, "..", "include"),
+                                            os.path.join(cuda_home, "include")]
     torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
     cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
            "-DTORCH_EXTENSION_NAME=_ttb200_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
@@ -121,7 +123,7 @@ def build_torch_extension(force: bool = False) -> str:
     cmd += ["-isystem" + i for i in incs]
     cmd += [TORCH_EXT_SRC, "-o", TORCH_EXT,
             "-L" + LIBDIR, "-lttb200", "-Wl,-rpath,$ORIGIN/lib",
-            "-L" + torch_lib, "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+            "-L" + torch_lib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python",
             "-Wl,-rpath," + torch_lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -131,7 +133,11 @@ def build_torch_extension(force: bool = False) -> str:
     return TORCH_EXT
 
 
-if __name__ == "__main__":
+def main():
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)
     print(build_torch_extension(force="--force" in sys.argv))
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,26 @@ import sys
 
 from torchtree.cli.plugin import Plugin
 
+MAX_STATES = 64  # ttb2_create's limit
+
+
+def engine_supports(data: dict):
+    """(ok, why) for one generated tree-likelihood block (SURVEY 8(b) policy: rewrite the type only
+    for what the engine implements; anything else stays on the reference class -- there is no CPU
+    fallback to hide behind).  The engine serves every reversible model through its eigen route and
+    every other SubstitutionModel through the model's own p_t (matrices route), any site model and
+    any clock; what it cannot hold is a state space beyond 64 states."""
+    subst = data.get("substitution_model")
+    states = None
+    if isinstance(subst, dict):
+        states = subst.get("state_count")
+        data_type = subst.get("data_type")
+        if states is None and isinstance(data_type, dict) and "codes" in data_type:
+            states = len(data_type["codes"])
+    if states is not None and int(states) > MAX_STATES:
+        return False, "%d states > %d" % (int(states), MAX_STATES)
+    return True, ""
+
 
 class B200Plugin(Plugin):
     def load_arguments(self, subparsers):
@@ -26,6 +46,10 @@ class B200Plugin(Plugin):
                 parser.add_argument(
                     "--b200_device", type=int, default=0,
                     help="CUDA device ordinal used by the torchtree_b200 engine")
+                parser.add_argument(
+                    "--b200_shard", choices=["patterns", "draws"], default=None,
+                    help="multi-GPU runs (one process per GPU, e.g. torchrun): shard the site "
+                         "patterns or the batch of draws across the ranks")
 
     def process_coalescent(self, arg, data):
         # constant-population coalescent on the device (coalescent.py); other demographic models
@@ -34,10 +58,18 @@ class B200Plugin(Plugin):
             data["type"] = "torchtree_b200.coalescent.ConstantCoalescentModel"
 
     def process_tree_likelihood(self, arg, data):
-        if getattr(arg, "b200", False):
-            data["type"] = "torchtree_b200.TreeLikelihoodModel"
-            if getattr(arg, "b200_device", 0):
-                data["device"] = arg.b200_device
+        if not getattr(arg, "b200", False):
+            return
+        ok, why = engine_supports(data)
+        if not ok:
+            sys.stderr.write("torchtree_b200: %s keeps the reference TreeLikelihoodModel (%s)\n"
+                             % (data.get("id"), why))
+            return
+        data["type"] = "torchtree_b200.TreeLikelihoodModel"
+        if getattr(arg, "b200_device", 0):
+            data["device"] = arg.b200_device
+        if getattr(arg, "b200_shard", None):
+            data["shard"] = arg.b200_shard
 
 
 def main(argv=None):

@@ -4,9 +4,18 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "engine.cuh"
 
 namespace ttb2 {
+
+// NVTX ranges around the phases of an evaluation (visible in Nsight Systems / Compute; a no-op
+// without an attached tool): ttb2:loglik {pmatrix, postorder, root}, ttb2:grad {preorder, contract}
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_last_error;
 
@@ -118,6 +127,22 @@ int finish(Engine& e, int where) {
 
 bool bad_draws(int d, int draws) { return !(d == 1 || d == draws); }
 
+// The small outputs of a gradient call live back to back in one buffer,
+//   [ lnL[D] | d_bl[D][B] | d_rates[rd][K] | d_props[pd][K] | d_q[ed][S][S] | d_freqs[fd][S] ],
+// so that a caller that reduces them across shards (NCCL all-reduce over NVLink) or copies them
+// to the host moves ONE contiguous vector (ttb2_grad_eigen_packed).  The layout is a function
+// of the draw counts of the latest loglik call (the key of the captured CUDA graphs as well).
+void layout_outputs(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  size_t off = (size_t)draws;
+  e.outBl = e.outPacked + off;     off += (size_t)draws * m.B;
+  e.outRates = e.outPacked + off;  off += (size_t)e.rateDraws * m.K;
+  e.outProps = e.outPacked + off;  off += (size_t)e.propDraws * m.K;
+  e.outQ = e.outPacked + off;      off += (size_t)e.eigDraws * m.S * m.S;
+  e.outFreqs = e.outPacked + off;  off += (size_t)e.freqDraws * m.S;
+  e.packedCount = (int64_t)off;
+}
+
 void drop_graphs(Engine& e);
 
 int ensure_grad_buffers(Engine& e, int draws) {
@@ -165,105 +190,12 @@ int ensure_eigen_grad_buffers(Engine& e) {
   return TTB2_OK;
 }
 
-int upload_fused_programs(Engine& e) {
-  const Dims& m = e.dm;
-  e.fusedOK = false;
-  {
-    int rc0 = s4_build_cherries(e);
-    if (rc0) return rc0;
-  }
-  if (!e.spec4 || !(e.cfg.flags & TTB2_FLAG_FUSED)) return TTB2_OK;
-  int rc = fused_build_programs(e);
-  if (rc) return rc;
-  if (!fused_supported(e)) return TTB2_OK;
-  if (!e.fwdProg) {
-    const int D = e.cfg.max_draws;
-    if ((rc = dev_alloc(e, &e.fwdProg, (size_t)m.I))) return rc;
-    if ((rc = dev_alloc(e, &e.bwdProg, (size_t)m.I))) return rc;
-    if ((rc = dev_alloc(e, &e.expoK, (size_t)D * m.I * m.K * m.Npad))) return rc;
-    if ((rc = dev_alloc(e, &e.esum, (size_t)D * m.K * m.Npad))) return rc;
-    if ((rc = dev_alloc(e, &e.fusedCounter, (size_t)1))) return rc;
-    const size_t tipWords = (size_t)fused_tip_groups(e) * m.Npad;
-    if ((rc = dev_alloc(e, &e.tipsF4, tipWords))) return rc;
-    if ((rc = dev_alloc(e, &e.tipsB4, tipWords))) return rc;
-    if ((rc = dev_alloc(e, &e.tipOrder, (size_t)m.T))) return rc;
-    if ((rc = dev_alloc(e, &e.streamF, (size_t)D * m.K * m.I * 32))) return rc;
-  }
-  TTB2_CUDA_CHECK(cudaMemcpy(e.fwdProg, e.hostFwdProg.data(), m.I * sizeof(FusedRec),
-                             cudaMemcpyHostToDevice));
-  TTB2_CUDA_CHECK(cudaMemcpy(e.bwdProg, e.hostBwdProg.data(), m.I * sizeof(FusedRec),
-                             cudaMemcpyHostToDevice));
-  if ((rc = fused_pack_tips(e))) return rc;
-  e.fusedOK = true;
-  return TTB2_OK;
-}
-
-int ensure_fused_grad_buffers(Engine& e, int draws) {
-  const Dims& m = e.dm;
-  const int D = e.cfg.max_draws;
-  int rc;
-  if (!e.qroot && (rc = dev_alloc(e, &e.qroot, (size_t)D * m.K * m.Npad * 4))) return rc;
-  if (!e.aux && (rc = dev_alloc(e, &e.aux, (size_t)D * m.B * m.K * 20))) return rc;
-  if (!e.streamB && (rc = dev_alloc(e, &e.streamB, (size_t)D * m.K * m.I * 80))) return rc;
-  if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)D * (m.K + m.S)))) return rc;
-  if (!e.gscal && (rc = dev_alloc(e, &e.gscal, (size_t)D * m.B * m.K))) return rc;
-  const size_t hneed = std::max((size_t)D * m.B * m.K * m.S * m.S,
-                                (size_t)D * (m.Npad / 32) * m.K * 16);
-  if (hneed > e.hpartCap) {
-    if (e.hpart) {
-      e.deviceBytes -= (int64_t)(e.hpartCap * sizeof(double));
-      dev_free(e.hpart);
-    }
-    if ((rc = dev_alloc(e, &e.hpart, hneed))) return rc;
-    e.hpartCap = hneed;
-  }
-  const size_t need = fused_gspart_doubles(e, draws);
-  if (need > e.gpartCap) {
-    if (e.gpart) {
-      e.deviceBytes -= (int64_t)(e.gpartCap * sizeof(double));
-      dev_free(e.gpart);
-    }
-    if ((rc = dev_alloc(e, &e.gpart, need))) return rc;
-    e.gpartCap = need;
-  }
-  return TTB2_OK;
-}
-
-int run_forward_levels(Engine& e, int draws) {
-  int rc;
-  const int64_t before = e.launches;
-  if (e.spec4) {
-    if ((rc = s4_forward(e, draws))) return rc;
-    e.fwdLevelLaunches = (int)(e.launches - before);
-    mark(e, 2);
-    if ((rc = s4_root(e, draws))) return rc;
-  } else {
-    if ((rc = gen_forward(e, draws))) return rc;
-    e.fwdLevelLaunches = (int)(e.launches - before);
-    mark(e, 2);
-    if ((rc = gen_root(e, draws))) return rc;
-  }
-  e.lastFused = false;
-  return TTB2_OK;
-}
+int refresh_topology_tables(Engine& e) { return s4_build_cherries(e); }
 
 int run_forward(Engine& e, int draws, double* lnl, int where) {
   int rc;
   mark(e, 1);
-  if (e.fusedOK && e.mode == MODE_EIGEN) {
-    if ((rc = fused_forward(e, draws))) return rc;
-    e.fwdLevelLaunches = 1;
-    mark(e, 2);
-    if ((rc = fused_root(e, draws))) return rc;
-    e.lastFused = true;
-    mark(e, 3);
-    e.draws = draws;
-    e.preValid = false;
-    if ((rc = copy_out(e, lnl, e.lnl, (size_t)draws * sizeof(double), where))) return rc;
-    return finish(e, where);
-  }
   const int64_t before = e.launches;
-  e.lastFused = false;
   if (e.spec4) {
     if ((rc = s4_forward(e, draws))) return rc;
     e.fwdLevelLaunches = (int)(e.launches - before);
@@ -296,9 +228,9 @@ void drop_graphs(Engine& e) {
   e.gBwd = Engine::GraphSlot();
 }
 
-// (bench.py --patterns 12500 / 25000, profiles/r01_small_shard.log: replay would still gain 3 % /
-// 1.6 % there, i.e. on the 8- / 4-GPU shards of the headline problem; TTB2_GRAPH_MAX_UNITS=1.2e8
-// enables it -- not the default until replay has been run next to the NCCL all-reduce on 4-8 GPUs)
+// (bench.py --patterns 12500 / 25000, profiles/r01_small_shard.log: replay gains 3 % / 1.6 % there,
+// i.e. on the 8- / 4-GPU shards of the headline problem, so the limit covers those shards:
+// 1.2e8 unit-equivalents; TTB2_GRAPH_MAX_UNITS overrides it)
 // Graph replay pays when an evaluation is launch-bound (fluA: 79 launches of a few
 // microseconds each, 0.53 -> 0.37 ms).  When the level kernels run for milliseconds the
 // host is far ahead of the device anyway and replay only adds its own launch and
@@ -308,7 +240,7 @@ bool graphs_enabled(const Engine& e, int draws) {
   if ((e.cfg.flags & TTB2_FLAG_NO_GRAPH) || e.timing || e.ownStream == nullptr) return false;
   const double units = (double)e.dm.Npad * e.dm.I * e.dm.K * draws * (e.dm.S / 4.0);
   static const double maxUnits =
-      getenv("TTB2_GRAPH_MAX_UNITS") ? atof(getenv("TTB2_GRAPH_MAX_UNITS")) : 4.0e7;
+      getenv("TTB2_GRAPH_MAX_UNITS") ? atof(getenv("TTB2_GRAPH_MAX_UNITS")) : 1.2e8;
   return units <= maxUnits;
 }
 
@@ -372,32 +304,9 @@ int stage_grad_lnl(Engine& e, const double* grad_lnl, int where) {
   return TTB2_OK;
 }
 
-// pre-order sweep of the fused path (eigen mode only)
-int run_backward_fused(Engine& e, const double* grad_lnl, bool needQ, int where) {
-  int rc;
-  const int draws = e.draws;
-  if ((rc = ensure_fused_grad_buffers(e, draws))) return rc;
-  if ((rc = stage_grad_lnl(e, grad_lnl, where))) return rc;
-  mark(e, 4);
-  if (!e.preValid || (needQ && !e.lastNeedQ)) {
-    if ((rc = fused_backward(e, draws, needQ))) return rc;
-    e.bwdLevelLaunches = 1;
-    e.preValid = true;
-    e.lastNeedQ = needQ;
-  }
-  mark(e, 5);
-  return TTB2_OK;
-}
-
 int run_backward(Engine& e, const double* grad_lnl, int where) {
   int rc;
   const int draws = e.draws;
-  if (e.lastFused) {
-    // d lnL / d P was requested after a fused forward: the per-level pre-order
-    // pass needs the per-pattern exponents of the per-level post-order pass
-    if ((rc = run_forward_levels(e, draws))) return rc;
-    e.preValid = false;
-  }
   if ((rc = ensure_grad_buffers(e, draws))) return rc;
   if (grad_lnl) {
     if ((rc = copy_in(e, e.gradLnl, grad_lnl, (size_t)draws * sizeof(double), where))) return rc;
@@ -546,11 +455,9 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
     std::vector<double> ones(D, 1.0);
     TRY_CUDA(cudaMemcpy(e.ones, ones.data(), D * sizeof(double), cudaMemcpyHostToDevice));
   }
-  TRY(dev_alloc(e, &e.outBl, (size_t)D * m.B));
-  TRY(dev_alloc(e, &e.outRates, (size_t)D * m.K));
-  TRY(dev_alloc(e, &e.outProps, (size_t)D * m.K));
-  TRY(dev_alloc(e, &e.outFreqs, (size_t)D * m.S));
-  TRY(dev_alloc(e, &e.outQ, (size_t)D * m.S * m.S));
+  TRY(dev_alloc(e, &e.outPacked, (size_t)D * (1 + m.B + 2 * m.K + m.S * m.S + m.S)));
+  e.rateDraws = e.propDraws = e.eigDraws = e.freqDraws = 1;
+  layout_outputs(e, 1);
 
   // tips, padded with the all-ones code S; weights padded with 0
   {
@@ -583,17 +490,13 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
         sms > 0)
       e.smCount = sms;
   }
-  TRY(upload_fused_programs(e));
+  TRY(refresh_topology_tables(e));
   TRY_CUDA(cudaStreamCreateWithFlags(&e.ownStream, cudaStreamNonBlocking));
   TRY_CUDA(cudaEventCreateWithFlags(&e.evIn, cudaEventDisableTiming));
   TRY_CUDA(cudaEventCreateWithFlags(&e.evOut, cudaEventDisableTiming));
   if (c.flags & TTB2_FLAG_PREALLOC_GRAD) {
-    if (e.fusedOK) {
-      TRY(ensure_fused_grad_buffers(e, D));
-    } else {
-      TRY(ensure_grad_buffers(e, D));
-      TRY(ensure_eigen_grad_buffers(e));
-    }
+    TRY(ensure_grad_buffers(e, D));
+    TRY(ensure_eigen_grad_buffers(e));
   }
 #undef TRY
 #undef TRY_CUDA
@@ -621,10 +524,10 @@ int ttb2_set_postorder(ttb2_engine* engine, const int32_t* postorder) {
                              cudaMemcpyHostToDevice));
   e.mode = MODE_NONE;
   e.preValid = false;
-  e.lastFused = false;
   e.chunkPlanDraws = 0;
+  ++e.evalSerial;   // a deferred gradient must not be served from the old topology's buffers
   drop_graphs(e);
-  return upload_fused_programs(e);
+  return refresh_topology_tables(e);
 }
 
 void ttb2_destroy(ttb2_engine* engine) {
@@ -639,12 +542,8 @@ void ttb2_destroy(ttb2_engine* engine) {
   dev_free(e.lnl); dev_free(e.rootGrad); dev_free(e.hpart); dev_free(e.gscal);
   dev_free(e.freqs); dev_free(e.props); dev_free(e.bl); dev_free(e.rates);
   dev_free(e.evec); dev_free(e.ivec); dev_free(e.eval); dev_free(e.qnorm); dev_free(e.gradLnl); dev_free(e.ones);
-  dev_free(e.outBl); dev_free(e.outRates); dev_free(e.outProps); dev_free(e.outFreqs);
-  dev_free(e.outQ);
-  dev_free(e.fwdProg); dev_free(e.bwdProg); dev_free(e.expoK); dev_free(e.esum);
-  dev_free(e.qroot); dev_free(e.aux); dev_free(e.fusedCounter);
-  dev_free(e.tipsF4); dev_free(e.tipsB4); dev_free(e.tipOrder);
-  dev_free(e.streamF); dev_free(e.streamB);
+  dev_free(e.outPacked);
+  dev_free(e.expoK);
   dev_free(e.chunkBase); dev_free(e.chunkCount);
   dev_free(e.cherryIdx); dev_free(e.cherryInfo); dev_free(e.cherryVec); dev_free(e.cherryExp);
   dev_free(e.cherryCode);
@@ -663,9 +562,13 @@ int ttb2_set_stream(ttb2_engine* engine, void* cuda_stream) {
     return TTB2_E_INVALID;
   }
   Engine& e = *reinterpret_cast<Engine*>(engine);
+  cudaStream_t next = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (next == e.stream) return TTB2_OK;
   TTB2_CUDA_CHECK(cudaSetDevice(e.device));
-  TTB2_CUDA_CHECK(cudaStreamSynchronize(e.stream));
-  e.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  // order the new stream behind the work already queued on the old one (no host sync)
+  TTB2_CUDA_CHECK(cudaEventRecord(e.evIn, e.stream));
+  TTB2_CUDA_CHECK(cudaStreamWaitEvent(next, e.evIn, 0));
+  e.stream = next;
   return TTB2_OK;
 }
 
@@ -706,6 +609,8 @@ int ttb2_loglik_mats(ttb2_engine* engine, int32_t draws, const double* mats,
   e.rateDraws = e.eigDraws = 1;
   e.mode = MODE_MATS;
   ++e.evalSerial;
+  layout_outputs(e, draws);
+  NvtxRange range("ttb2:loglik_mats");
   return run_forward(e, draws, lnl, where);
 }
 
@@ -717,7 +622,9 @@ static int run_eigen_mode(Engine& e, int draws, int qDraws, double* lnl, int whe
   ++e.evalSerial;
   e.draws = draws;
   e.qDraws = qDraws;
-  if (e.fusedOK || !e.spec4 && !gmma_supported(e)) {
+  layout_outputs(e, draws);
+  NvtxRange range("ttb2:loglik_eigen");
+  if (!e.spec4 && !gmma_supported(e)) {
     if (qDraws && (rc = small_sym_eigh(e, qDraws, e.eigDraws))) return rc;
     if ((rc = small_pmatrix(e, draws))) return rc;
     return run_forward(e, draws, lnl, where);
@@ -866,6 +773,30 @@ int ttb2_grad_mats(ttb2_engine* engine, const double* grad_lnl, double* d_mats,
   return finish(e, where);
 }
 
+// pre-order sweep + contraction of the latest eigen-mode evaluation: fills the packed outputs
+static int grad_eigen_compute(Engine& e, const double* grad_lnl, int where) {
+  int rc;
+  const int draws = e.draws;
+  NvtxRange range("ttb2:grad_eigen");
+  if (e.preValid || !graphs_enabled(e, draws) || !(e.spec4 || gmma_supported(e))) {
+    if ((rc = ensure_eigen_grad_buffers(e))) return rc;
+    if ((rc = run_backward(e, grad_lnl, where))) return rc;
+    if ((rc = small_eigen_contract(e, draws))) return rc;
+  } else {
+    if ((rc = ensure_eigen_grad_buffers(e))) return rc;
+    if ((rc = ensure_grad_buffers(e, draws))) return rc;  // allocations + chunk plan: not capturable
+    if ((rc = stage_grad_lnl(e, grad_lnl, where))) return rc;
+    rc = run_graphed(e, e.gBwd, draws, [&]() -> int {
+      int r = e.spec4 ? s4_backward(e, draws) : gmma_backward2(e, draws);
+      if (r) return r;
+      return small_eigen_contract(e, draws);
+    });
+    if (rc) return rc;
+    e.preValid = true;
+  }
+  return TTB2_OK;
+}
+
 int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branch_lengths,
                     double* d_site_rates, double* d_props, double* d_q, double* d_freqs,
                     int32_t where) {
@@ -882,26 +813,7 @@ int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branc
   TTB2_CUDA_CHECK(cudaSetDevice(e.device));
   int rc;
   const int draws = e.draws;
-  if (e.lastFused) {
-    const bool needQ = d_q != nullptr;
-    if ((rc = run_backward_fused(e, grad_lnl, needQ, where))) return rc;
-    if ((rc = small_fused_outputs(e, draws, needQ))) return rc;
-  } else if (e.preValid || !graphs_enabled(e, draws) || !(e.spec4 || gmma_supported(e))) {
-    if ((rc = ensure_eigen_grad_buffers(e))) return rc;
-    if ((rc = run_backward(e, grad_lnl, where))) return rc;
-    if ((rc = small_eigen_contract(e, draws))) return rc;
-  } else {
-    if ((rc = ensure_eigen_grad_buffers(e))) return rc;
-    if ((rc = ensure_grad_buffers(e, draws))) return rc;  // allocations + chunk plan: not capturable
-    if ((rc = stage_grad_lnl(e, grad_lnl, where))) return rc;
-    rc = run_graphed(e, e.gBwd, draws, [&]() -> int {
-      int r = e.spec4 ? s4_backward(e, draws) : gmma_backward2(e, draws);
-      if (r) return r;
-      return small_eigen_contract(e, draws);
-    });
-    if (rc) return rc;
-    e.preValid = true;
-  }
+  if ((rc = grad_eigen_compute(e, grad_lnl, where))) return rc;
   if ((rc = copy_out(e, d_branch_lengths, e.outBl, (size_t)draws * m.B * sizeof(double), where)))
     return rc;
   if ((rc = copy_out(e, d_site_rates, e.outRates, (size_t)e.rateDraws * m.K * sizeof(double), where)))
@@ -911,6 +823,37 @@ int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branc
   if ((rc = copy_out(e, d_q, e.outQ, (size_t)e.eigDraws * m.S * m.S * sizeof(double), where)))
     return rc;
   if ((rc = copy_out(e, d_freqs, e.outFreqs, (size_t)e.freqDraws * m.S * sizeof(double), where)))
+    return rc;
+  mark(e, 6);
+  return finish(e, where);
+}
+
+int64_t ttb2_packed_count(const ttb2_engine* engine) {
+  return engine ? reinterpret_cast<const Engine*>(engine)->packedCount : 0;
+}
+
+int ttb2_grad_eigen_packed(ttb2_engine* engine, const double* grad_lnl, double* packed,
+                           int64_t capacity, int32_t where) {
+  if (!engine || !packed) {
+    set_error("ttb2_grad_eigen_packed: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  if (e.mode != MODE_EIGEN) {
+    set_error("ttb2_grad_eigen_packed: the latest evaluation was not ttb2_loglik_eigen / ttb2_loglik_q");
+    return TTB2_E_STATE;
+  }
+  if (capacity < e.packedCount) {
+    set_error("ttb2_grad_eigen_packed: output buffer holds " + std::to_string(capacity) +
+              " doubles, " + std::to_string(e.packedCount) + " needed (ttb2_packed_count)");
+    return TTB2_E_INVALID;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  if ((rc = grad_eigen_compute(e, grad_lnl, where))) return rc;
+  TTB2_CUDA_CHECK(cudaMemcpyAsync(e.outPacked, e.lnl, (size_t)e.draws * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, e.stream));
+  if ((rc = copy_out(e, packed, e.outPacked, (size_t)e.packedCount * sizeof(double), where)))
     return rc;
   mark(e, 6);
   return finish(e, where);

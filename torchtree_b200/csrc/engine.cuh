@@ -30,15 +30,6 @@ struct Dims {
 
 enum Mode { MODE_NONE = 0, MODE_MATS = 1, MODE_EIGEN = 2 };
 
-// One step of a fused traversal program (kernels_fused.cu), 16 bytes.
-//   post-order: aux = storage position of the node's vector;
-//               slots = (slot of left child, slot of right child, output slot)
-//   pre-order : aux = node id; slots = (slot of q^_node, slot for q^_left, q^_right)
-// slot bytes are signed, -1 = not applicable (tip child / root output).
-struct __align__(16) FusedRec {
-  int32_t left, right, aux, slots;
-};
-
 struct Engine {
   ttb2_config cfg{};
   Dims dm{};
@@ -90,12 +81,14 @@ struct Engine {
   double* qnorm = nullptr;      // [Dmax][S][S] generator staged for the device eigen-decomposition
   double* gradLnl = nullptr;    // [Dmax]
   double* ones = nullptr;       // [Dmax] default grad_lnl
-  // staged outputs (small)
-  double* outBl = nullptr;      // [Dmax][B]
-  double* outRates = nullptr;   // [Dmax][K]
-  double* outProps = nullptr;   // [Dmax][K]
-  double* outFreqs = nullptr;   // [Dmax][S]
-  double* outQ = nullptr;       // [Dmax][S][S]
+  // staged outputs (small): slices of one buffer, laid out per call (api.cu layout_outputs)
+  double* outPacked = nullptr;  // [lnL | d_bl | d_rates | d_props | d_q | d_freqs]
+  int64_t packedCount = 0;      // doubles in use for the latest call's draw counts
+  double* outBl = nullptr;      // [draws][B]
+  double* outRates = nullptr;   // [rateDraws][K]
+  double* outProps = nullptr;   // [propDraws][K]
+  double* outFreqs = nullptr;   // [freqDraws][S]
+  double* outQ = nullptr;       // [eigDraws][S][S]
 
   // cherry fusion (kernels_s4.cu): level-1 nodes tabulated by tip-code pair
   bool cherryOn = false;
@@ -107,26 +100,8 @@ struct Engine {
   bool smemAttrTma = false, smemAttrTips = false;  // opt-in shared-memory sizes set on this device
   uint8_t* cherryCode = nullptr;  // [nCherry][Npad] pair code = code(left tip) * C + code(right tip)
 
-  // fused-traversal path (S = 4, eigen mode)
   int smCount = 148;
-  int fusedSlots = 0;
-  bool fusedOK = false;      // programs built and the stack fits in shared memory
-  bool lastFused = false;    // the latest forward used the fused path
-  bool lastNeedQ = false;
-  std::vector<FusedRec> hostFwdProg, hostBwdProg;
-  std::vector<int> hostTipOrderF, hostTipOrderB;
-  FusedRec* fwdProg = nullptr;
-  FusedRec* bwdProg = nullptr;
-  uint32_t* tipsF4 = nullptr;   // [groups][Npad] tip codes, 4 per word, post-order use order
-  uint32_t* tipsB4 = nullptr;   // same, pre-order use order
-  int* tipOrder = nullptr;      // [T] scratch
-  double* streamF = nullptr;    // [D][K][I][32] P_l, P_r in post-order program order
-  double* streamB = nullptr;    // [D][K][I][80] P_l, P_r, aux_l, aux_r in pre-order order
-  int16_t* expoK = nullptr;     // [D][I][K][Npad] per-(pattern, category) exponents
-  int* esum = nullptr;          // [D][K][Npad] exponent sums of the chains
-  double* qroot = nullptr;      // [D][K][Npad][4] q^ of the root
-  double* aux = nullptr;        // [D][B][K][20] Phi / lambda e^{lambda tau} (or Q P)
-  int* fusedCounter = nullptr;  // dynamic work distribution
+  int16_t* expoK = nullptr;     // [D][I][K][Npad] per-(pattern, category) exponents (DMMA paths)
   size_t hpartCap = 0;
 
   int draws = 0, freqDraws = 0, propDraws = 0, rateDraws = 0, eigDraws = 0;
@@ -219,17 +194,6 @@ int small_root_outputs(Engine& e, int draws);
 int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm);
 size_t planned_gpart_doubles(const Engine& e, int draws);
 
-// fused-traversal path (kernels_fused.cu)
-int fused_build_programs(Engine& e);
-int fused_pack_tips(Engine& e);
-int fused_tip_groups(const Engine& e);
-bool fused_supported(const Engine& e);
-int fused_forward(Engine& e, int draws);
-int fused_root(Engine& e, int draws);
-int fused_backward(Engine& e, int draws, bool needQ);
-size_t fused_gspart_doubles(const Engine& e, int draws);
-int small_fused_outputs(Engine& e, int draws, bool needQ);
-
 // Programmatic dependent launch: a level kernel launched with the
 // programmaticStreamSerialization attribute may start (and run its prologue: tables,
 // matrix fragments, barrier setup -- nothing the previous level wrote) while the
@@ -279,7 +243,7 @@ inline ChainRuns chain_runs(const Engine& e) {
   // a chain trades node-level parallelism for fewer launches: only when the pattern axis alone
   // fills the GPU (measured: a gain from ~40k patterns per GPU, a small loss at 12.5k)
   const bool wide = (long)e.dm.Npad * e.cfg.max_draws >= minPatterns;
-  if (mx <= 0 || !e.spec4 || !kOk || !wide || (e.cfg.flags & TTB2_FLAG_NO_MMA)) return r;
+  if (mx <= 0 || !e.spec4 || !kOk || !wide) return r;
   int l = 1;
   while (l < nLevels) {
     int j = l;

@@ -439,136 +439,6 @@ __device__ __forceinline__ double warp_transpose_sum(double (&v)[32]) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(BWD_THREADS)
-bwd4_kernel(const NodeOp* __restrict__ ops, int opBegin,
-            const double* __restrict__ mats, const uint8_t* __restrict__ tips,
-            const double* __restrict__ codeP, const double* __restrict__ partials,
-            const int16_t* __restrict__ expo, const double* __restrict__ weights,
-            double* __restrict__ pre, double* __restrict__ gpart,
-            const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
-            int C, int B, int K, int chunkPatterns, int nChunk) {
-  extern __shared__ double sm[];
-  // sm: Pl[16] Pr[16] | cp[C][4] | ul_tab[C][4] ur_tab[C][4] | red[8][32]
-  double* Pl = sm;
-  double* Pr = sm + 16;
-  double* cp = sm + 32;
-  double* tabL = cp + C * 4;
-  double* tabR = tabL + C * 4;
-  double* red = tabR + C * 4;
-
-  const int nodeSlot = blockIdx.y / K;
-  const int k = blockIdx.y - nodeSlot * K;
-  const NodeOp op = ops[opBegin + nodeSlot];
-  const int d = blockIdx.z;
-  const int I = T - 1;
-  const bool tipL = op.left < T, tipR = op.right < T;
-  const double* matsD = mats + (size_t)d * B * K * 16;
-  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
-  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
-  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
-  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
-  for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
-  __syncthreads();
-  if (tipL || tipR) {
-    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
-      const int s = j & 3, code = j >> 2;
-      const double* c = cp + code * 4;
-      const double* rl = Pl + s * 4;
-      const double* rr = Pr + s * 4;
-      tabL[j] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
-      tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
-    }
-    __syncthreads();
-  }
-
-  const size_t nodeStride = (size_t)K * Npad * 4;
-  const size_t drawBase = (size_t)d * I * nodeStride;
-  const size_t kOff = (size_t)k * Npad * 4;
-  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
-  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
-  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
-  double* ql = tipL ? nullptr : pre + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
-  double* qr = tipR ? nullptr : pre + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
-  const int16_t* el = tipL ? nullptr : expo + ((size_t)d * I + (op.left - T)) * Npad;
-  const int16_t* er = tipR ? nullptr : expo + ((size_t)d * I + (op.right - T)) * Npad;
-  const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
-  const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
-
-  double g[32];  // g[0..15] = G_l (row-major, row = parent state), g[16..31] = G_r
-#pragma unroll
-  for (int j = 0; j < 32; ++j) g[j] = 0.0;
-
-  const int begin = blockIdx.x * chunkPatterns;
-  int end = begin + chunkPatterns;
-  end = end < Npad ? end : Npad;
-  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    const V4 q = ldg4(qn + (size_t)i * 4);
-    const double w = weights[i];
-    V4 vl, vr, ul, ur;
-    if (tipL) {
-      const int code = tl[i];
-      vl = lds4(cp + code * 4);
-      ul = lds4(tabL + code * 4);
-    } else {
-      vl = ldg4(pl + (size_t)i * 4);
-      ul = matvec(Pl, vl);
-    }
-    if (tipR) {
-      const int code = tr[i];
-      vr = lds4(cp + code * 4);
-      ur = lds4(tabR + code * 4);
-    } else {
-      vr = ldg4(prr + (size_t)i * 4);
-      ur = matvec(Pr, vr);
-    }
-    const V4 ml = mul4(q, ur);
-    const V4 mr = mul4(q, ul);
-    if (!tipL) {
-      const int e = el[i];
-      stg4(ql + (size_t)i * 4, scale4(matvec_t(Pl, ml), __hiloint2double((1023 - e) << 20, 0)));
-    }
-    if (!tipR) {
-      const int e = er[i];
-      stg4(qr + (size_t)i * 4, scale4(matvec_t(Pr, mr), __hiloint2double((1023 - e) << 20, 0)));
-    }
-    if (w != 0.0) {
-      const V4 a = scale4(ml, w);
-      const V4 b = scale4(mr, w);
-      g[0] = fma(a.x, vl.x, g[0]);   g[1] = fma(a.x, vl.y, g[1]);
-      g[2] = fma(a.x, vl.z, g[2]);   g[3] = fma(a.x, vl.w, g[3]);
-      g[4] = fma(a.y, vl.x, g[4]);   g[5] = fma(a.y, vl.y, g[5]);
-      g[6] = fma(a.y, vl.z, g[6]);   g[7] = fma(a.y, vl.w, g[7]);
-      g[8] = fma(a.z, vl.x, g[8]);   g[9] = fma(a.z, vl.y, g[9]);
-      g[10] = fma(a.z, vl.z, g[10]); g[11] = fma(a.z, vl.w, g[11]);
-      g[12] = fma(a.w, vl.x, g[12]); g[13] = fma(a.w, vl.y, g[13]);
-      g[14] = fma(a.w, vl.z, g[14]); g[15] = fma(a.w, vl.w, g[15]);
-      g[16] = fma(b.x, vr.x, g[16]); g[17] = fma(b.x, vr.y, g[17]);
-      g[18] = fma(b.x, vr.z, g[18]); g[19] = fma(b.x, vr.w, g[19]);
-      g[20] = fma(b.y, vr.x, g[20]); g[21] = fma(b.y, vr.y, g[21]);
-      g[22] = fma(b.y, vr.z, g[22]); g[23] = fma(b.y, vr.w, g[23]);
-      g[24] = fma(b.z, vr.x, g[24]); g[25] = fma(b.z, vr.y, g[25]);
-      g[26] = fma(b.z, vr.z, g[26]); g[27] = fma(b.z, vr.w, g[27]);
-      g[28] = fma(b.w, vr.x, g[28]); g[29] = fma(b.w, vr.y, g[29]);
-      g[30] = fma(b.w, vr.z, g[30]); g[31] = fma(b.w, vr.w, g[31]);
-    }
-  }
-
-  const double mine = warp_transpose_sum(g);  // lane j: warp total of g[j]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  red[warp * 32 + lane] = mine;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double t = 0.0;
-    const int nw = blockDim.x >> 5;
-    for (int w2 = 0; w2 < nw; ++w2) t += red[w2 * 32 + threadIdx.x];
-    const int branch = threadIdx.x < 16 ? op.left : op.right;
-    const int entry = threadIdx.x & 15;
-    // gpart [d][chunkBase[branch] + k * nChunk + chunk][16]
-    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
-          entry] = t;
-  }
-}
-
 // ---------------------------------------------------------------------------
 // Level 1 (both children are tips; a third of all nodes of a random tree).
 // The generic kernels spend their time in shared-memory lookups and MMA staging
@@ -640,118 +510,6 @@ fwd4_tips_kernel(const NodeOp* __restrict__ ops, int opBegin,
       stg4(q + ((size_t)k * Npad + i) * 4, V4{lo.x, lo.y, hi.x, hi.y});
     }
     eo[i] = (int16_t)pexp[pc];
-  }
-}
-
-// pre-order: no child vectors to read and no q^ to write; with 0/1 tip vectors
-// G_c[s][s'] = sum_i [s' in code_i] w_i m_c,i[s], accumulated with predicated
-// adds in registers (bit s' of codeMask[code] = codeP[code][s'] != 0).
-__global__ void __launch_bounds__(BWD_THREADS, 2)
-bwd4_tips_kernel(const NodeOp* __restrict__ ops, int opBegin,
-                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
-                 const double* __restrict__ codeP, const int* __restrict__ codeMask,
-                 const double* __restrict__ weights, const double* __restrict__ pre,
-                 double* __restrict__ gpart, const int* __restrict__ chunkBase,
-                 size_t chunkTotal, int T, int Npad, int C, int B, int K, int chunkPatterns,
-                 int nChunk) {
-  extern __shared__ double sm[];
-  // sm: Pl[16] Pr[16] | tabL[C][4] tabR[C][4] | red[8][32] | masks[C] (int)
-  double* Pl = sm;
-  double* Pr = sm + 16;
-  double* tabL = sm + 32;
-  double* tabR = tabL + C * 4;
-  double* red = tabR + C * 4;
-  int* masks = reinterpret_cast<int*>(red + (BWD_THREADS / 32) * 32);
-
-  const int nodeSlot = blockIdx.y / K;
-  const int k = blockIdx.y - nodeSlot * K;
-  const NodeOp op = ops[opBegin + nodeSlot];
-  const int d = blockIdx.z;
-  const int I = T - 1;
-  const double* matsD = mats + (size_t)d * B * K * 16;
-  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
-  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
-  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
-  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
-  for (int j = threadIdx.x; j < C; j += blockDim.x) masks[j] = codeMask[j];
-  __syncthreads();
-  for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
-    const int s = j & 3, code = j >> 2;
-    const double* c = codeP + code * 4;
-    const double* rl = Pl + s * 4;
-    const double* rr = Pr + s * 4;
-    tabL[j] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
-    tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
-  }
-  __syncthreads();
-
-  const size_t nodeStride = (size_t)K * Npad * 4;
-  const double* qn = pre + ((size_t)d * I + (op.node - T)) * nodeStride + (size_t)k * Npad * 4;
-  const uint8_t* tl = tips + (size_t)op.left * Npad;
-  const uint8_t* tr = tips + (size_t)op.right * Npad;
-
-  double g[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) g[j] = 0.0;
-  const int begin = blockIdx.x * chunkPatterns;
-  int end = begin + chunkPatterns;
-  end = end < Npad ? end : Npad;
-  // software pipeline: the loads of the next pattern are in flight while the
-  // current one is accumulated
-  struct Inputs {
-    V4 q;
-    double w;
-    int cl, cr;
-  };
-  auto fetch = [&](int i, Inputs& in) {
-    if (i < end) {
-      in.q = ldg4(qn + (size_t)i * 4);
-      in.w = weights[i];
-      in.cl = tl[i];
-      in.cr = tr[i];
-    } else {
-      in.q = V4{0.0, 0.0, 0.0, 0.0};
-      in.w = 0.0;
-      in.cl = 0;
-      in.cr = 0;
-    }
-  };
-  Inputs cur;
-  fetch(begin + threadIdx.x, cur);
-  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    Inputs nxt;
-    fetch(i + blockDim.x, nxt);
-    const V4 ul = lds4(tabL + cur.cl * 4);
-    const V4 ur = lds4(tabR + cur.cr * 4);
-    const int ml_mask = masks[cur.cl], mr_mask = masks[cur.cr];
-    const V4 a = scale4(mul4(cur.q, ur), cur.w);  // w m_l
-    const V4 b = scale4(mul4(cur.q, ul), cur.w);  // w m_r
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const double sl = (ml_mask >> c) & 1 ? 1.0 : 0.0;
-      const double sr = (mr_mask >> c) & 1 ? 1.0 : 0.0;
-      g[0 + c] = fma(a.x, sl, g[0 + c]);
-      g[4 + c] = fma(a.y, sl, g[4 + c]);
-      g[8 + c] = fma(a.z, sl, g[8 + c]);
-      g[12 + c] = fma(a.w, sl, g[12 + c]);
-      g[16 + c] = fma(b.x, sr, g[16 + c]);
-      g[20 + c] = fma(b.y, sr, g[20 + c]);
-      g[24 + c] = fma(b.z, sr, g[24 + c]);
-      g[28 + c] = fma(b.w, sr, g[28 + c]);
-    }
-    cur = nxt;
-  }
-  const double mine = warp_transpose_sum(g);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  red[warp * 32 + lane] = mine;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double t = 0.0;
-    const int nw = blockDim.x >> 5;
-    for (int w2 = 0; w2 < nw; ++w2) t += red[w2 * 32 + threadIdx.x];
-    const int branch = threadIdx.x < 16 ? op.left : op.right;
-    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
-          (threadIdx.x & 15)] = t;
   }
 }
 
@@ -976,181 +734,11 @@ fwd4c_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restri
   }
 }
 
-// fp64 tensor-core variant of the pre-order kernel.  The per-branch sums
-//   G_l = sum_i (w_i m_l,i) (x) p~_l,i ,  G_r = sum_i (w_i m_r,i) (x) p~_r,i
-// are rank-1 updates over patterns, i.e. one 8x8 += [8 x 4 patterns][4 patterns x 8]
-// product per group of four patterns with rows (w m_l | w m_r) and columns
-// (p~_l | p~_r): the diagonal 4x4 blocks of the DMMA accumulator are G_l and G_r.
-// The accumulator costs 2 registers per lane instead of 32 fp64 accumulators per
-// thread, and the block reduction shrinks to one 8x8 tile per warp.
+// fp64 tensor-core instruction: C[8x8] += A[8x4] . B[4x8]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
-}
-
-constexpr int BWDM_THREADS = 128;
-constexpr int MMA_LD = 36;               // row stride (doubles) of the staging tiles
-constexpr int MMA_STAGE = 2 * 8 * MMA_LD;  // doubles per warp: X and Y tiles
-
-__global__ void __launch_bounds__(BWDM_THREADS, 4)
-bwd4_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
-                const double* __restrict__ mats, const uint8_t* __restrict__ tips,
-                const double* __restrict__ codeP, const double* __restrict__ partials,
-                const int16_t* __restrict__ expo, const double* __restrict__ weights,
-                double* __restrict__ pre, double* __restrict__ gpart,
-                const int* __restrict__ chunkBase, size_t chunkTotal, int T, int Npad,
-                int C, int B, int K, int chunkPatterns, int nChunk) {
-  extern __shared__ __align__(16) double sm[];
-  // sm: Pl[16] Pr[16] | cp[C][4] | tabL[C][4] tabR[C][4] | stage[warps][2][8][36] | red[warps][64]
-  constexpr int NW = BWDM_THREADS / 32;
-  double* Pl = sm;
-  double* Pr = sm + 16;
-  double* cp = sm + 32;
-  double* tabL = cp + C * 4;
-  double* tabR = tabL + C * 4;
-  double* stage = tabR + C * 4;
-  double* red = stage + NW * MMA_STAGE;
-
-  const int nodeSlot = blockIdx.y / K;
-  const int k = blockIdx.y - nodeSlot * K;
-  const NodeOp op = ops[opBegin + nodeSlot];
-  const int d = blockIdx.z;
-  const int I = T - 1;
-  const bool tipL = op.left < T, tipR = op.right < T;
-  const double* matsD = mats + (size_t)d * B * K * 16;
-  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
-  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
-  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
-  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
-  for (int j = threadIdx.x; j < C * 4; j += blockDim.x) cp[j] = codeP[j];
-  __syncthreads();
-  if (tipL || tipR) {
-    for (int j = threadIdx.x; j < C * 4; j += blockDim.x) {
-      const int s = j & 3, code = j >> 2;
-      const double* c = cp + code * 4;
-      const double* rl = Pl + s * 4;
-      const double* rr = Pr + s * 4;
-      tabL[j] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
-      tabR[j] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
-    }
-    __syncthreads();
-  }
-
-  const size_t nodeStride = (size_t)K * Npad * 4;
-  const size_t drawBase = (size_t)d * I * nodeStride;
-  const size_t kOff = (size_t)k * Npad * 4;
-  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
-  const double* pl = tipL ? nullptr : partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
-  const double* prr = tipR ? nullptr : partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
-  double* ql = tipL ? nullptr : pre + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
-  double* qr = tipR ? nullptr : pre + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
-  const int16_t* el = tipL ? nullptr : expo + ((size_t)d * I + (op.left - T)) * Npad;
-  const int16_t* er = tipR ? nullptr : expo + ((size_t)d * I + (op.right - T)) * Npad;
-  const uint8_t* tl = tipL ? tips + (size_t)op.left * Npad : nullptr;
-  const uint8_t* tr = tipR ? tips + (size_t)op.right * Npad : nullptr;
-
-  const double* mPl = Pl;
-  const double* mPr = Pr;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // staging tiles [8 rows][32 patterns], row stride 36 doubles: the per-pattern
-  // stores (lane = pattern) and the MMA fragment loads (lane -> row lane>>2,
-  // pattern 4t + (lane&3)) are both bank-conflict free
-  double* sX = stage + warp * MMA_STAGE;   // rows: w m_l[0..3] | w m_r[0..3]
-  double* sY = sX + MMA_STAGE / 2;         // rows: p~_l[0..3]  | p~_r[0..3]
-  const int fragOff = (lane >> 2) * MMA_LD + (lane & 3);
-  double c0 = 0.0, c1 = 0.0;
-
-  const int begin = blockIdx.x * chunkPatterns;
-  int end = begin + chunkPatterns;
-  end = end < Npad ? end : Npad;
-
-  // software pipeline: the global loads of iteration j+1 are in flight while
-  // iteration j is computed
-  struct Inputs {
-    V4 q, vl, vr;
-    double w;
-    int el, er;  // scale exponent (internal child) or tip code (tip child)
-  };
-  auto fetch = [&](int i, Inputs& in) {
-    if (i < end) {
-      in.q = ldg4(qn + (size_t)i * 4);
-      in.w = weights[i];
-      if (tipL) in.el = tl[i];
-      else { in.vl = ldg4(pl + (size_t)i * 4); in.el = el[i]; }
-      if (tipR) in.er = tr[i];
-      else { in.vr = ldg4(prr + (size_t)i * 4); in.er = er[i]; }
-    }
-  };
-  Inputs cur;
-  fetch(begin + warp * 32 + lane, cur);
-  // warp-uniform trip count: every lane executes the MMAs
-  for (int base = begin + warp * 32; base < end; base += BWDM_THREADS) {
-    const int i = base + lane;
-    Inputs nxt;
-    fetch(i + BWDM_THREADS, nxt);
-    V4 xl{0.0, 0.0, 0.0, 0.0}, xr = xl, vl = xl, vr = xl;
-    if (i < end) {
-      V4 ul, ur;
-      if (tipL) {
-        vl = lds4(cp + cur.el * 4);
-        ul = lds4(tabL + cur.el * 4);
-      } else {
-        vl = cur.vl;
-        ul = matvec(mPl, vl);
-      }
-      if (tipR) {
-        vr = lds4(cp + cur.er * 4);
-        ur = lds4(tabR + cur.er * 4);
-      } else {
-        vr = cur.vr;
-        ur = matvec(mPr, vr);
-      }
-      const V4 ml = mul4(cur.q, ur);
-      const V4 mr = mul4(cur.q, ul);
-      if (!tipL)
-        stg4(ql + (size_t)i * 4,
-             scale4(matvec_t(mPl, ml), __hiloint2double((1023 - cur.el) << 20, 0)));
-      if (!tipR)
-        stg4(qr + (size_t)i * 4,
-             scale4(matvec_t(mPr, mr), __hiloint2double((1023 - cur.er) << 20, 0)));
-      if (cur.w != 0.0) {
-        xl = scale4(ml, cur.w);
-        xr = scale4(mr, cur.w);
-      } else {
-        vl = V4{0.0, 0.0, 0.0, 0.0};
-        vr = vl;
-      }
-    }
-    __syncwarp();
-    sX[0 * MMA_LD + lane] = xl.x; sX[1 * MMA_LD + lane] = xl.y;
-    sX[2 * MMA_LD + lane] = xl.z; sX[3 * MMA_LD + lane] = xl.w;
-    sX[4 * MMA_LD + lane] = xr.x; sX[5 * MMA_LD + lane] = xr.y;
-    sX[6 * MMA_LD + lane] = xr.z; sX[7 * MMA_LD + lane] = xr.w;
-    sY[0 * MMA_LD + lane] = vl.x; sY[1 * MMA_LD + lane] = vl.y;
-    sY[2 * MMA_LD + lane] = vl.z; sY[3 * MMA_LD + lane] = vl.w;
-    sY[4 * MMA_LD + lane] = vr.x; sY[5 * MMA_LD + lane] = vr.y;
-    sY[6 * MMA_LD + lane] = vr.z; sY[7 * MMA_LD + lane] = vr.w;
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < 8; ++t) dmma884(c0, c1, sX[t * 4 + fragOff], sY[t * 4 + fragOff]);
-    cur = nxt;
-  }
-  // accumulator fragment: row = lane>>2, cols = (lane&3)*2 + {0,1}
-  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = c0;
-  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = c1;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int child = threadIdx.x >> 4;
-    const int s = (threadIdx.x >> 2) & 3, sp = threadIdx.x & 3;
-    const int idx = (child * 4 + s) * 8 + child * 4 + sp;
-    double t = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 64 + idx];
-    const int branch = child ? op.right : op.left;
-    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
-          (threadIdx.x & 15)] = t;
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1614,192 +1202,6 @@ int fwd_patterns_per_thread(const Engine& e, int draws, int levelCount) {
   return (int)ppt;
 }
 
-// pre-order level kernel, cherry-aware: a cherry child is handled like a tip with
-// C*C symbol codes (vectors from cherryVec), except that it still receives q^.
-__global__ void __launch_bounds__(BWDM_THREADS, 4)
-bwd4c_mma_kernel(const NodeOp* __restrict__ ops, int opBegin,
-                 const double* __restrict__ mats, const uint8_t* __restrict__ tips,
-                 const double* __restrict__ codeP, const double* __restrict__ partials,
-                 const int16_t* __restrict__ expo, const double* __restrict__ weights,
-                 double* __restrict__ pre, double* __restrict__ gpart,
-                 const int* __restrict__ chunkBase, size_t chunkTotal, CherryArgs ch, int T,
-                 int Npad, int C, int B, int K, int chunkPatterns, int nChunk) {
-  extern __shared__ __align__(16) double sm[];
-  // sm: Pl[16] Pr[16] | vecL[NC][4] vecR[NC][4] tabL[NC][4] tabR[NC][4] | stage | red
-  constexpr int NW = BWDM_THREADS / 32;
-  const int NC = ch.CC > C ? ch.CC : C;
-  double* Pl = sm;
-  double* Pr = sm + 16;
-  double* vecL = sm + 32;
-  double* vecR = vecL + NC * 4;
-  double* tabL = vecR + NC * 4;
-  double* tabR = tabL + NC * 4;
-  double* stage = tabR + NC * 4;
-  double* red = stage + NW * MMA_STAGE;
-
-  const int nodeSlot = blockIdx.y / K;
-  const int k = blockIdx.y - nodeSlot * K;
-  const NodeOp op = ops[opBegin + nodeSlot];
-  const int d = blockIdx.z;
-  const int I = T - 1;
-  int cidxL, cidxR;
-  const int kindL = child_kind(op.left, T, ch, cidxL);
-  const int kindR = child_kind(op.right, T, ch, cidxR);
-  const double* matsD = mats + (size_t)d * B * K * 16;
-  const double* gPl = matsD + ((size_t)op.left * K + k) * 16;
-  const double* gPr = matsD + ((size_t)op.right * K + k) * 16;
-  if (threadIdx.x < 16) Pl[threadIdx.x] = gPl[threadIdx.x];
-  else if (threadIdx.x < 32) Pr[threadIdx.x - 16] = gPr[threadIdx.x - 16];
-  {
-    const int nL = kindL == KIND_TIP ? C : (kindL == KIND_CHERRY ? ch.CC : 0);
-    const int nR = kindR == KIND_TIP ? C : (kindR == KIND_CHERRY ? ch.CC : 0);
-    const double* srcL = kindL == KIND_TIP ? codeP
-                         : ch.vec + (((size_t)d * ch.n + (cidxL < 0 ? 0 : cidxL)) * K + k) * ch.CC * 4;
-    const double* srcR = kindR == KIND_TIP ? codeP
-                         : ch.vec + (((size_t)d * ch.n + (cidxR < 0 ? 0 : cidxR)) * K + k) * ch.CC * 4;
-    __syncthreads();  // Pl, Pr visible
-    // plane layout [half][code] (double2): conflict-free for lanes with distinct codes
-    for (int j = threadIdx.x; j < nL * 4; j += blockDim.x) {
-      const int s = j & 3, code = j >> 2;
-      const double* c = srcL + code * 4;
-      const double* rl = Pl + s * 4;
-      const int dst = (((s >> 1) * NC + code) << 1) + (s & 1);
-      vecL[dst] = c[s];
-      tabL[dst] = fma(rl[3], c[3], fma(rl[2], c[2], fma(rl[1], c[1], rl[0] * c[0])));
-    }
-    for (int j = threadIdx.x; j < nR * 4; j += blockDim.x) {
-      const int s = j & 3, code = j >> 2;
-      const double* c = srcR + code * 4;
-      const double* rr = Pr + s * 4;
-      const int dst = (((s >> 1) * NC + code) << 1) + (s & 1);
-      vecR[dst] = c[s];
-      tabR[dst] = fma(rr[3], c[3], fma(rr[2], c[2], fma(rr[1], c[1], rr[0] * c[0])));
-    }
-    __syncthreads();
-  }
-
-  const size_t nodeStride = (size_t)K * Npad * 4;
-  const size_t drawBase = (size_t)d * I * nodeStride;
-  const size_t kOff = (size_t)k * Npad * 4;
-  const double* qn = pre + drawBase + (size_t)(op.node - T) * nodeStride + kOff;
-  const bool storedL = kindL == KIND_STORED, storedR = kindR == KIND_STORED;
-  const bool tipL = kindL == KIND_TIP, tipR = kindR == KIND_TIP;
-  const double* pl = storedL ? partials + drawBase + (size_t)(op.left - T) * nodeStride + kOff : nullptr;
-  const double* prr = storedR ? partials + drawBase + (size_t)(op.right - T) * nodeStride + kOff : nullptr;
-  double* ql = tipL ? nullptr : pre + drawBase + (size_t)(op.left - T) * nodeStride + kOff;
-  double* qr = tipR ? nullptr : pre + drawBase + (size_t)(op.right - T) * nodeStride + kOff;
-  const int16_t* el = tipL ? nullptr : expo + ((size_t)d * I + (op.left - T)) * Npad;
-  const int16_t* er = tipR ? nullptr : expo + ((size_t)d * I + (op.right - T)) * Npad;
-  const uint8_t* l0 = nullptr; const uint8_t* l1 = nullptr;
-  const uint8_t* r0 = nullptr; const uint8_t* r1 = nullptr;
-  if (tipL) l0 = tips + (size_t)op.left * Npad;
-  if (kindL == KIND_CHERRY) {
-    l0 = tips + (size_t)ch.info[cidxL * 3] * Npad;
-    l1 = tips + (size_t)ch.info[cidxL * 3 + 1] * Npad;
-  }
-  if (tipR) r0 = tips + (size_t)op.right * Npad;
-  if (kindR == KIND_CHERRY) {
-    r0 = tips + (size_t)ch.info[cidxR * 3] * Npad;
-    r1 = tips + (size_t)ch.info[cidxR * 3 + 1] * Npad;
-  }
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* sX = stage + warp * MMA_STAGE;
-  double* sY = sX + MMA_STAGE / 2;
-  const int fragOff = (lane >> 2) * MMA_LD + (lane & 3);
-  double c0 = 0.0, c1 = 0.0;
-
-  const int begin = blockIdx.x * chunkPatterns;
-  int end = begin + chunkPatterns;
-  end = end < Npad ? end : Npad;
-
-  struct Inputs {
-    V4 q, vl, vr;
-    double w;
-    int el, er;      // scale exponents (stored / cherry children)
-    int cl, cr;      // symbol codes (tip / cherry children)
-  };
-  auto fetch = [&](int i, Inputs& in) {
-    if (i < end) {
-      in.q = ldg4(qn + (size_t)i * 4);
-      in.w = weights[i];
-      if (storedL) in.vl = ldg4(pl + (size_t)i * 4);
-      else { in.cl = l0[i]; if (l1) in.cl = in.cl * C + l1[i]; }
-      if (!tipL) in.el = el[i];
-      if (storedR) in.vr = ldg4(prr + (size_t)i * 4);
-      else { in.cr = r0[i]; if (r1) in.cr = in.cr * C + r1[i]; }
-      if (!tipR) in.er = er[i];
-    }
-  };
-  Inputs cur;
-  fetch(begin + warp * 32 + lane, cur);
-  for (int base = begin + warp * 32; base < end; base += BWDM_THREADS) {
-    const int i = base + lane;
-    Inputs nxt;
-    fetch(i + BWDM_THREADS, nxt);
-    V4 xl{0.0, 0.0, 0.0, 0.0}, xr = xl, vl = xl, vr = xl;
-    if (i < end) {
-      V4 ul, ur;
-      if (storedL) {
-        vl = cur.vl;
-        ul = matvec(Pl, vl);
-      } else {
-        vl = lds4_planes(vecL, 0, NC, cur.cl);
-        ul = lds4_planes(tabL, 0, NC, cur.cl);
-      }
-      if (storedR) {
-        vr = cur.vr;
-        ur = matvec(Pr, vr);
-      } else {
-        vr = lds4_planes(vecR, 0, NC, cur.cr);
-        ur = lds4_planes(tabR, 0, NC, cur.cr);
-      }
-      const V4 ml = mul4(cur.q, ur);
-      const V4 mr = mul4(cur.q, ul);
-      if (!tipL)
-        stg4(ql + (size_t)i * 4,
-             scale4(matvec_t(Pl, ml), __hiloint2double((1023 - cur.el) << 20, 0)));
-      if (!tipR)
-        stg4(qr + (size_t)i * 4,
-             scale4(matvec_t(Pr, mr), __hiloint2double((1023 - cur.er) << 20, 0)));
-      if (cur.w != 0.0) {
-        xl = scale4(ml, cur.w);
-        xr = scale4(mr, cur.w);
-      } else {
-        vl = V4{0.0, 0.0, 0.0, 0.0};
-        vr = vl;
-      }
-    }
-    __syncwarp();
-    sX[0 * MMA_LD + lane] = xl.x; sX[1 * MMA_LD + lane] = xl.y;
-    sX[2 * MMA_LD + lane] = xl.z; sX[3 * MMA_LD + lane] = xl.w;
-    sX[4 * MMA_LD + lane] = xr.x; sX[5 * MMA_LD + lane] = xr.y;
-    sX[6 * MMA_LD + lane] = xr.z; sX[7 * MMA_LD + lane] = xr.w;
-    sY[0 * MMA_LD + lane] = vl.x; sY[1 * MMA_LD + lane] = vl.y;
-    sY[2 * MMA_LD + lane] = vl.z; sY[3 * MMA_LD + lane] = vl.w;
-    sY[4 * MMA_LD + lane] = vr.x; sY[5 * MMA_LD + lane] = vr.y;
-    sY[6 * MMA_LD + lane] = vr.z; sY[7 * MMA_LD + lane] = vr.w;
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < 8; ++t) dmma884(c0, c1, sX[t * 4 + fragOff], sY[t * 4 + fragOff]);
-    cur = nxt;
-  }
-  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = c0;
-  red[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = c1;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int child = threadIdx.x >> 4;
-    const int s = (threadIdx.x >> 2) & 3, sp = threadIdx.x & 3;
-    const int idx = (child * 4 + s) * 8 + child * 4 + sp;
-    double t = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) t += red[w2 * 64 + idx];
-    const int branch = child ? op.right : op.left;
-    gpart[((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk + blockIdx.x) * 16 +
-          (threadIdx.x & 15)] = t;
-  }
-}
-
 CherryArgs cherry_args(const Engine& e) {
   CherryArgs ch;
   ch.idx = e.cherryIdx;
@@ -1855,8 +1257,7 @@ int s4_build_cherries(Engine& e) {
   const Dims& m = e.dm;
   e.cherryOn = false;
   e.nCherry = 0;
-  const bool allowed = e.spec4 && !(e.cfg.flags & TTB2_FLAG_NO_CHERRY) &&
-                       !(e.cfg.flags & TTB2_FLAG_NO_MMA) && m.C * m.C <= 64 &&
+  const bool allowed = e.spec4 && !(e.cfg.flags & TTB2_FLAG_NO_CHERRY) && m.C * m.C <= 64 &&
                        m.T > 2 && (m.K <= 6 || m.K == 8);
   if (!allowed) return TTB2_OK;
   std::vector<int> idx(m.I, -1), info;
@@ -1941,7 +1342,7 @@ int s4_forward(Engine& e, int draws) {
       if (chain) l = runs.endOfStart[l];
       continue;
     }
-    const bool tipLevel = (l == 0) && !(e.cfg.flags & TTB2_FLAG_NO_MMA);  // level 1: tip-tip nodes
+    const bool tipLevel = (l == 0);  // level 1: tip-tip nodes
     const bool pdl = l > 0 && pdl_enabled();   // the first level follows pmatrix: ordinary launch
     // grid.y is limited to 65535
     for (int done = 0; done < count; done += 65535) {
@@ -2005,12 +1406,6 @@ int s4_backward(Engine& e, int draws) {
     int rc = small_root_grad_reduce(e, draws, nblocks);
     if (rc) return rc;
   }
-  const bool useMma = !(e.cfg.flags & TTB2_FLAG_NO_MMA);
-  // TTB2_BWD_LEGACY=1: the previous kernel generation (bwd4_mma_kernel / bwd4_tips_kernel), for A/B runs
-  static const bool legacy = getenv("TTB2_BWD_LEGACY") != nullptr;
-  const size_t smem = useMma
-      ? (32 + 3 * (size_t)m.C * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) * sizeof(double)
-      : (32 + 3 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double);
   const int nLevels = (int)e.levelOff.size() - 1;
   const int maxNodes = 65535 / m.K;
   const ChainRuns runs = chain_runs(e);
@@ -2023,15 +1418,14 @@ int s4_backward(Engine& e, int draws) {
     const bool pdl = l < nLevels - 1 && pdl_enabled();   // the top level follows root4_bwd
     // a run of sparse levels ending here (we walk downwards) goes out as one chain launch
     int chainBegin = 0, chainCount = 0;
-    if (useMma && !legacy && runs.startOfEnd[l] >= 0) {
+    if (runs.startOfEnd[l] >= 0) {
       chainBegin = e.levelOff[runs.startOfEnd[l]];
       chainCount = e.levelOff[l + 1] - chainBegin;
     }
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);
-      const bool tipTip = l == 0;   // level 1: both children are tips
-      if (useMma && tipTip && e.codes01 && !legacy) {
+      if (l == 0 && e.codes01) {   // level 1: both children are tips with 0/1 code vectors
         constexpr int ST = 4;
         auto smemTips = [&](int codes) {
           return (size_t)(BWD_THREADS / 32) * ST * BTT_SLOT +
@@ -2048,22 +1442,7 @@ int s4_backward(Engine& e, int draws) {
                      e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre,
                      e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K,
                      chunkPatterns, nChunk);
-      } else if (useMma && l == 0 && e.codes01) {
-        const size_t smemT = (32 + 2 * (size_t)m.C * 4 + (BWD_THREADS / 32) * 32) * sizeof(double) +
-                             (size_t)m.C * sizeof(int);
-        bwd4_tips_kernel<<<grid, BWD_THREADS, smemT, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.codeMask, e.weights, e.pre, e.gpart,
-            e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      } else if (useMma && e.cherryOn && legacy) {
-        const CherryArgs ch = cherry_args(e);
-        const int NC = ch.CC > m.C ? ch.CC : m.C;
-        const size_t smemC = (32 + 4 * (size_t)NC * 4 + (BWDM_THREADS / 32) * (MMA_STAGE + 64)) *
-                             sizeof(double);
-        bwd4c_mma_kernel<<<grid, BWDM_THREADS, smemC, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
-            e.gpart, e.chunkBase, e.chunkTotal, ch, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns,
-            nChunk);
-      } else if (useMma && !legacy) {
+      } else {
         constexpr int ST = 3, MB = 5, NWF = BWDF_THREADS / 32;
         const CherryArgs ch = cherry_args(e);
         auto smemOf = [&](int codes, int pairCodes) {
@@ -2092,14 +1471,6 @@ int s4_backward(Engine& e, int draws) {
                        e.expo, e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, ch, m.T,
                        m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk, 0);
         }
-      } else if (useMma) {
-        bwd4_mma_kernel<<<grid, BWDM_THREADS, smem, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
-            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
-      } else {
-        bwd4_kernel<<<grid, BWD_THREADS, smem, e.stream>>>(
-            e.ops, opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expo, e.weights, e.pre,
-            e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.C, m.B, m.K, chunkPatterns, nChunk);
       }
       ++e.launches;
       if (chainCount > 0) break;

@@ -476,39 +476,4 @@ int small_eigen_contract(Engine& e, int draws) {
   return small_root_outputs(e, draws);
 }
 
-// Outputs of the fused pre-order sweep: gscal [D][B][K] and (needQ) hpart
-// [D][nBlocks*K][16] are already on the device; assemble the same outputs as
-// small_eigen_contract.
-int small_fused_outputs(Engine& e, int draws, bool needQ) {
-  const Dims& m = e.dm;
-  const int SS = m.S * m.S;
-  {
-    const int n = m.B * draws;
-    branch_grad_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
-        e.gscal, e.rates, e.rateDraws, e.gradLnl, e.outBl, m.B, m.K, draws);
-    ++e.launches;
-  }
-  {
-    const int od = e.rateDraws > 1 ? draws : 1;
-    dim3 grid(m.K, od);
-    rate_grad_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
-                                                        m.B, m.K, draws, od);
-    ++e.launches;
-  }
-  const int od = e.eigDraws > 1 ? draws : 1;
-  if (needQ) {
-    dim3 grid(SS, od);
-    h_reduce_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.hpart, e.gradLnl, e.outQ,
-                                                       (m.Npad / 32) * m.K, SS, draws, od);
-    ++e.launches;
-    q_grad_kernel<<<od, 32, 4 * (size_t)SS * sizeof(double), e.stream>>>(e.outQ, e.evec, e.ivec,
-                                                                         e.outQ, m.S);
-    ++e.launches;
-  } else {
-    TTB2_CUDA_CHECK(cudaMemsetAsync(e.outQ, 0, (size_t)od * SS * sizeof(double), e.stream));
-  }
-  TTB2_CUDA_CHECK(cudaGetLastError());
-  return small_root_outputs(e, draws);
-}
-
 }  // namespace ttb2

@@ -14,10 +14,12 @@
 // Built by torchtree_b200/build.py into torchtree_b200/_ttb200_torch.so, linked against
 // lib/libttb200.so (rpath $ORIGIN/lib).  There is no fallback: without a CUDA device the
 // C ABI calls fail and the error is raised.
+#include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
 #include <algorithm>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -41,14 +43,48 @@ void check(int status, const char* what) {
   }
 }
 
-ttb2_engine* as_engine(int64_t handle) {
-  TORCH_CHECK(handle != 0, "ttb200: null engine handle");
-  return reinterpret_cast<ttb2_engine*>(static_cast<intptr_t>(handle));
+// Owner of one ttb2_engine.  The Python `Engine` holds one reference; every autograd node
+// made from a forward on that engine holds another (through a keep-alive tensor in
+// ctx->saved_data), so a `backward` that runs after the Python object went away -- the model was
+// garbage-collected, or TreeLikelihoodModel replaced its engine by a larger one for more draws
+// -- still finds the buffers of ITS forward.  An explicit close() destroys the engine at once;
+// a later backward then raises instead of touching freed memory.
+struct EngineRef {
+  ttb2_engine* h = nullptr;
+  // host eigen-system of the latest generator (large single generators, see device_eigh)
+  Tensor cacheQ, cacheF, evec, ivec, evals;
+  explicit EngineRef(int64_t handle)
+      : h(reinterpret_cast<ttb2_engine*>(static_cast<intptr_t>(handle))) {}
+  EngineRef(const EngineRef&) = delete;
+  EngineRef& operator=(const EngineRef&) = delete;
+  ~EngineRef() { close(); }
+  void close() {
+    if (h) ttb2_destroy(h);
+    h = nullptr;
+  }
+  ttb2_engine* get() const {
+    if (!h)
+      throw std::runtime_error(
+          "ttb200: the engine of this evaluation has been closed (Engine.close()) before its "
+          "backward pass ran");
+    return h;
+  }
+};
+using EnginePtr = std::shared_ptr<EngineRef>;
+
+// a 1-element tensor whose storage deleter owns a reference to the engine
+Tensor keepalive(const EnginePtr& p) {
+  auto* box = new EnginePtr(p);
+  return at::from_blob(
+      box, {1}, [](void* b) { delete static_cast<EnginePtr*>(b); },
+      at::TensorOptions().dtype(at::kByte));
 }
 
-ttb2_config config_of(int64_t handle) {
+const EnginePtr& engine_of(const Tensor& keep) { return *static_cast<const EnginePtr*>(keep.data_ptr()); }
+
+ttb2_config config_of(ttb2_engine* eng) {
   ttb2_config cfg;
-  check(ttb2_get_config(as_engine(handle), &cfg), "ttb2_get_config");
+  check(ttb2_get_config(eng, &cfg), "ttb2_get_config");
   return cfg;
 }
 
@@ -64,9 +100,11 @@ Tensor prep(const Tensor& x, at::IntArrayRef tail, const char* name) {
   return t.contiguous();
 }
 
-// TTB2_HOST / TTB2_DEVICE for one call; device tensors must live on the engine's device
-// and are made visible to the engine's stream by synchronising the producer stream.
-int where_of(std::initializer_list<Tensor> tensors, int device) {
+// TTB2_HOST / TTB2_DEVICE for one call; device tensors must live on the engine's device.
+// With device tensors the engine is bound to torch's CURRENT stream of that device
+// (ttb2_set_stream: event-ordered, no host synchronisation), so its reads follow the producers
+// of the inputs and its outputs are ordered for whoever consumes them on that stream.
+int where_of(std::initializer_list<Tensor> tensors, int device, ttb2_engine* eng = nullptr) {
   int cuda = 0, total = 0;
   for (const Tensor& t : tensors) {
     if (!t.defined()) continue;
@@ -79,14 +117,24 @@ int where_of(std::initializer_list<Tensor> tensors, int device) {
   }
   TORCH_CHECK(cuda == 0 || cuda == total, "ttb200: inputs must be all host or all device tensors");
   if (cuda) {
-    const c10::impl::VirtualGuardImpl impl(c10::DeviceType::CUDA);
-    impl.getStream(c10::Device(c10::DeviceType::CUDA, (c10::DeviceIndex)device)).synchronize();
+    auto stream = c10::cuda::getCurrentCUDAStream((c10::DeviceIndex)device);
+    if (eng)
+      check(ttb2_set_stream(eng, stream.stream()), "ttb2_set_stream");
+    else
+      stream.synchronize();   // stateless entry points run on their own stream
     return TTB2_DEVICE;
   }
   return TTB2_HOST;
 }
 
 double* dptr(const Tensor& t) { return t.defined() ? t.data_ptr<double>() : nullptr; }
+
+// dtype policy (SURVEY 8(b) variant 5, `--dtype float32` runs): the engine computes in fp64
+// whatever the inputs are; inputs of another floating type are converted on the way in, and
+// lnL and every gradient are handed back in the dtype of the tensor they belong to.
+Tensor like_input(const Tensor& value, at::ScalarType dtype) {
+  return value.defined() && value.scalar_type() != dtype ? value.to(dtype) : value;
+}
 
 // ---------------------------------------------------------------------------------------
 // reversible models: P = V exp(L r t) V^-1 on the device (ttb2_loglik_eigen / ttb2_grad_eigen)
@@ -101,37 +149,49 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     return S <= 64 && (S <= 8 || eig_draws >= 6);
   }
 
-  static void run_forward(int64_t handle, const ttb2_config& cfg, const Tensor& bls,
+  static void run_forward(EngineRef& ref, const ttb2_config& cfg, const Tensor& bls,
                           const Tensor& rates, const Tensor& props, const Tensor& q,
                           const Tensor& freqs, Tensor& lnl) {
-    const int where = where_of({bls, rates, props, q, freqs}, cfg.device);
+    ttb2_engine* eng = ref.get();
+    const int where = where_of({bls, rates, props, q, freqs}, cfg.device, eng);
     if (device_eigh(cfg.state_count, std::max(q.size(0), freqs.size(0)))) {
-      check(ttb2_loglik_q(as_engine(handle), (int32_t)bls.size(0), dptr(bls), dptr(rates),
+      check(ttb2_loglik_q(eng, (int32_t)bls.size(0), dptr(bls), dptr(rates),
                           (int32_t)rates.size(0), dptr(props), (int32_t)props.size(0), dptr(q),
                           (int32_t)q.size(0), dptr(freqs), (int32_t)freqs.size(0), dptr(lnl),
                           where),
             "ttb2_loglik_q");
       return;
     }
-    // eigen-system through the sqrt(pi) symmetrisation (abstract.py:57-66), no graph
-    Tensor root = freqs.sqrt();
-    Tensor sym = root.unsqueeze(-1) * q / root.unsqueeze(-2);
-    auto eig = at::linalg_eigh(sym, "L");
-    Tensor evals = std::get<0>(eig).contiguous();
-    Tensor u = std::get<1>(eig);
-    Tensor evec = (u / root.unsqueeze(-1)).contiguous();
-    Tensor ivec = (u.transpose(-1, -2) * root.unsqueeze(-2)).contiguous();
-    check(ttb2_loglik_eigen(as_engine(handle), (int32_t)bls.size(0), dptr(bls), dptr(rates),
+    // eigen-system through the sqrt(pi) symmetrisation (abstract.py:57-66), no graph.  It is
+    // kept with the engine and reused while the generator does not change -- the reference
+    // decomposes empirical models (LG, WAG) once, general.py:300-306.
+    if (!(ref.cacheQ.defined() && ref.cacheQ.sizes() == q.sizes() &&
+          ref.cacheF.sizes() == freqs.sizes() && ref.cacheQ.device() == q.device() &&
+          at::equal(ref.cacheQ, q) && at::equal(ref.cacheF, freqs))) {
+      Tensor root = freqs.sqrt();
+      Tensor sym = root.unsqueeze(-1) * q / root.unsqueeze(-2);
+      auto eig = at::linalg_eigh(sym, "L");
+      Tensor u = std::get<1>(eig);
+      ref.evals = std::get<0>(eig).contiguous();
+      ref.evec = (u / root.unsqueeze(-1)).contiguous();
+      ref.ivec = (u.transpose(-1, -2) * root.unsqueeze(-2)).contiguous();
+      ref.cacheQ = q.clone();
+      ref.cacheF = freqs.clone();
+    }
+    check(ttb2_loglik_eigen(eng, (int32_t)bls.size(0), dptr(bls), dptr(rates),
                             (int32_t)rates.size(0), dptr(props), (int32_t)props.size(0),
-                            dptr(evec), dptr(ivec), dptr(evals), (int32_t)evec.size(0),
-                            dptr(freqs), (int32_t)freqs.size(0), dptr(lnl), where),
+                            dptr(ref.evec), dptr(ref.ivec), dptr(ref.evals),
+                            (int32_t)ref.evec.size(0), dptr(freqs), (int32_t)freqs.size(0),
+                            dptr(lnl), where),
           "ttb2_loglik_eigen");
   }
 
-  static Tensor forward(AutogradContext* ctx, int64_t handle, const Tensor& branch_lengths,
-                        const Tensor& site_rates, const Tensor& site_props,
-                        const Tensor& q_norm, const Tensor& frequencies) {
-    const ttb2_config cfg = config_of(handle);
+  static Tensor forward(AutogradContext* ctx, const Tensor& engine_keepalive,
+                        const Tensor& branch_lengths, const Tensor& site_rates,
+                        const Tensor& site_props, const Tensor& q_norm,
+                        const Tensor& frequencies) {
+    const EnginePtr ref = engine_of(engine_keepalive);
+    const ttb2_config cfg = config_of(ref->get());
     const int64_t S = cfg.state_count, K = cfg.category_count, B = 2 * (int64_t)cfg.tip_count - 2;
     Tensor bls = prep(branch_lengths, {B}, "branch_lengths");
     Tensor rates = prep(site_rates, {K}, "site_rates");
@@ -139,44 +199,71 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     Tensor q = prep(q_norm, {S, S}, "q_norm");
     Tensor freqs = prep(frequencies, {S}, "freqs");
     Tensor lnl = at::empty({bls.size(0)}, bls.options());
-    run_forward(handle, cfg, bls, rates, props, q, freqs, lnl);
-    ctx->saved_data["handle"] = handle;
-    ctx->saved_data["serial"] = ttb2_eval_serial(as_engine(handle));
+    {
+      pybind11::gil_scoped_release nogil;
+      run_forward(*ref, cfg, bls, rates, props, q, freqs, lnl);
+    }
+    ctx->saved_data["engine"] = engine_keepalive;
+    ctx->saved_data["serial"] = ttb2_eval_serial(ref->get());
+    ctx->saved_data["dtypes"] = std::vector<int64_t>{
+        (int64_t)branch_lengths.scalar_type(), (int64_t)site_rates.scalar_type(),
+        (int64_t)site_props.scalar_type(), (int64_t)q_norm.scalar_type(),
+        (int64_t)frequencies.scalar_type()};
     ctx->save_for_backward({bls, rates, props, q, freqs});
-    return lnl;
+    return like_input(lnl, branch_lengths.scalar_type());
   }
 
   static variable_list backward(AutogradContext* ctx, variable_list grad_out) {
-    const int64_t handle = ctx->saved_data["handle"].toInt();
-    const ttb2_config cfg = config_of(handle);
+    const EnginePtr ref = engine_of(ctx->saved_data["engine"].toTensor());
+    ttb2_engine* eng = ref->get();
+    const ttb2_config cfg = config_of(eng);
     auto saved = ctx->get_saved_variables();
     const Tensor &bls = saved[0], &rates = saved[1], &props = saved[2], &q = saved[3],
                  &freqs = saved[4];
-    if (ttb2_eval_serial(as_engine(handle)) != ctx->saved_data["serial"].toInt()) {
+    if (ttb2_eval_serial(eng) != ctx->saved_data["serial"].toInt()) {
       // another forward ran on this engine since ours and overwrote its buffers:
       // recompute (SURVEY 8(b) autograd contract)
       Tensor lnl = at::empty({bls.size(0)}, bls.options());
-      run_forward(handle, cfg, bls, rates, props, q, freqs, lnl);
-      ctx->saved_data["serial"] = ttb2_eval_serial(as_engine(handle));
+      run_forward(*ref, cfg, bls, rates, props, q, freqs, lnl);
+      ctx->saved_data["serial"] = ttb2_eval_serial(eng);
     }
-    const int64_t S = cfg.state_count;
+    const int64_t S = cfg.state_count, K = cfg.category_count, D = bls.size(0), B = bls.size(1);
     Tensor g = grad_out[0].defined()
                    ? grad_out[0].detach().to(bls.device(), at::kDouble).reshape({-1}).contiguous()
                    : Tensor();
-    TORCH_CHECK(!g.defined() || g.numel() == bls.size(0), "ttb200: grad_lnl must have one entry per draw");
-    Tensor d_bl = at::empty_like(bls), d_rates = at::empty_like(rates),
-           d_props = at::empty_like(props), d_freqs = at::empty_like(freqs);
+    TORCH_CHECK(!g.defined() || g.numel() == D, "ttb200: grad_lnl must have one entry per draw");
     // one eigen-system per generator draw or frequency draw, whichever varies; d_q has that
     // leading extent and is summed back onto a shared generator below
-    // (needs_input_grad indexes the tensor arguments only: bls 0, rates 1, props 2, q 3, freqs 4)
     const int64_t eig_draws = std::max(q.size(0), freqs.size(0));
-    Tensor d_q = ctx->needs_input_grad(3) ? at::empty({eig_draws, S, S}, bls.options()) : Tensor();
-    const int where = where_of({bls, g}, cfg.device);
-    check(ttb2_grad_eigen(as_engine(handle), dptr(g), dptr(d_bl), dptr(d_rates), dptr(d_props),
-                          dptr(d_q), dptr(d_freqs), where),
-          "ttb2_grad_eigen");
-    if (d_q.defined() && d_q.size(0) != q.size(0)) d_q = d_q.sum(0, /*keepdim=*/true);
-    return {Tensor(), d_bl, d_rates, d_props, d_q, d_freqs};
+    // the engine writes all small outputs as one vector
+    // [lnL | d_bl | d_rates | d_props | d_q | d_freqs]: one copy, then views
+    const int64_t count = ttb2_packed_count(eng);
+    TORCH_CHECK(count == D + D * B + (rates.size(0) + props.size(0)) * K + eig_draws * S * S +
+                             freqs.size(0) * S,
+                "ttb200: packed gradient layout does not match the saved inputs");
+    Tensor packed = at::empty({count}, bls.options());
+    const int where = where_of({bls, g}, cfg.device, eng);
+    check(ttb2_grad_eigen_packed(eng, dptr(g), dptr(packed), count, where),
+          "ttb2_grad_eigen_packed");
+    int64_t off = D;
+    auto take = [&](int64_t n, at::IntArrayRef shape) {
+      Tensor v = packed.narrow(0, off, n).view(shape);
+      off += n;
+      return v;
+    };
+    Tensor d_bl = take(D * B, {D, B});
+    Tensor d_rates = take(rates.size(0) * K, {rates.size(0), K});
+    Tensor d_props = take(props.size(0) * K, {props.size(0), K});
+    Tensor d_q = take(eig_draws * S * S, {eig_draws, S, S});
+    Tensor d_freqs = take(freqs.size(0) * S, {freqs.size(0), S});
+    if (d_q.size(0) != q.size(0)) d_q = d_q.sum(0, /*keepdim=*/true);
+    const auto dt = ctx->saved_data["dtypes"].toIntVector();
+    return {Tensor(),
+            like_input(d_bl, (at::ScalarType)dt[0]),
+            like_input(d_rates, (at::ScalarType)dt[1]),
+            like_input(d_props, (at::ScalarType)dt[2]),
+            ctx->needs_input_grad(4) ? like_input(d_q, (at::ScalarType)dt[3]) : Tensor(),
+            like_input(d_freqs, (at::ScalarType)dt[4])};
   }
 };
 
@@ -184,51 +271,62 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
 // caller-supplied transition matrices (ttb2_loglik_mats / ttb2_grad_mats): any
 // SubstitutionModel.p_t, e.g. NonSymmetricSubstitutionModel (abstract.py:89-94)
 struct MatsLikelihood : public torch::autograd::Function<MatsLikelihood> {
-  static void run_forward(int64_t handle, const ttb2_config& cfg, const Tensor& mats,
+  static void run_forward(EngineRef& ref, const ttb2_config& cfg, const Tensor& mats,
                           const Tensor& freqs, const Tensor& props, Tensor& lnl) {
-    const int where = where_of({mats, freqs, props}, cfg.device);
-    check(ttb2_loglik_mats(as_engine(handle), (int32_t)mats.size(0), dptr(mats), dptr(freqs),
+    ttb2_engine* eng = ref.get();
+    const int where = where_of({mats, freqs, props}, cfg.device, eng);
+    check(ttb2_loglik_mats(eng, (int32_t)mats.size(0), dptr(mats), dptr(freqs),
                            (int32_t)freqs.size(0), dptr(props), (int32_t)props.size(0), dptr(lnl),
                            where),
           "ttb2_loglik_mats");
   }
 
-  static Tensor forward(AutogradContext* ctx, int64_t handle, const Tensor& matrices,
-                        const Tensor& frequencies, const Tensor& site_props) {
-    const ttb2_config cfg = config_of(handle);
+  static Tensor forward(AutogradContext* ctx, const Tensor& engine_keepalive,
+                        const Tensor& matrices, const Tensor& frequencies,
+                        const Tensor& site_props) {
+    const EnginePtr ref = engine_of(engine_keepalive);
+    const ttb2_config cfg = config_of(ref->get());
     const int64_t S = cfg.state_count, K = cfg.category_count, B = 2 * (int64_t)cfg.tip_count - 2;
     Tensor mats = prep(matrices, {B, K, S, S}, "mats");
     Tensor freqs = prep(frequencies, {S}, "freqs");
     Tensor props = prep(site_props, {K}, "site_props");
     Tensor lnl = at::empty({mats.size(0)}, mats.options());
-    run_forward(handle, cfg, mats, freqs, props, lnl);
-    ctx->saved_data["handle"] = handle;
-    ctx->saved_data["serial"] = ttb2_eval_serial(as_engine(handle));
+    {
+      pybind11::gil_scoped_release nogil;
+      run_forward(*ref, cfg, mats, freqs, props, lnl);
+    }
+    ctx->saved_data["engine"] = engine_keepalive;
+    ctx->saved_data["serial"] = ttb2_eval_serial(ref->get());
+    ctx->saved_data["dtypes"] = std::vector<int64_t>{(int64_t)matrices.scalar_type(),
+                                                      (int64_t)frequencies.scalar_type(),
+                                                      (int64_t)site_props.scalar_type()};
     ctx->save_for_backward({mats, freqs, props});
-    return lnl;
+    return like_input(lnl, matrices.scalar_type());
   }
 
   static variable_list backward(AutogradContext* ctx, variable_list grad_out) {
-    const int64_t handle = ctx->saved_data["handle"].toInt();
-    const ttb2_config cfg = config_of(handle);
+    const EnginePtr ref = engine_of(ctx->saved_data["engine"].toTensor());
+    ttb2_engine* eng = ref->get();
+    const ttb2_config cfg = config_of(eng);
     auto saved = ctx->get_saved_variables();
     const Tensor &mats = saved[0], &freqs = saved[1], &props = saved[2];
-    if (ttb2_eval_serial(as_engine(handle)) != ctx->saved_data["serial"].toInt()) {
+    if (ttb2_eval_serial(eng) != ctx->saved_data["serial"].toInt()) {
       Tensor lnl = at::empty({mats.size(0)}, mats.options());
-      run_forward(handle, cfg, mats, freqs, props, lnl);
-      ctx->saved_data["serial"] = ttb2_eval_serial(as_engine(handle));
+      run_forward(*ref, cfg, mats, freqs, props, lnl);
+      ctx->saved_data["serial"] = ttb2_eval_serial(eng);
     }
     Tensor g = grad_out[0].defined()
                    ? grad_out[0].detach().to(mats.device(), at::kDouble).reshape({-1}).contiguous()
                    : Tensor();
     TORCH_CHECK(!g.defined() || g.numel() == mats.size(0), "ttb200: grad_lnl must have one entry per draw");
-    Tensor d_mats = ctx->needs_input_grad(0) ? at::empty_like(mats) : Tensor();
+    Tensor d_mats = ctx->needs_input_grad(1) ? at::empty_like(mats) : Tensor();
     Tensor d_freqs = at::empty_like(freqs), d_props = at::empty_like(props);
-    const int where = where_of({mats, g}, cfg.device);
-    check(ttb2_grad_mats(as_engine(handle), dptr(g), dptr(d_mats), dptr(d_freqs), dptr(d_props),
-                         where),
+    const int where = where_of({mats, g}, cfg.device, eng);
+    check(ttb2_grad_mats(eng, dptr(g), dptr(d_mats), dptr(d_freqs), dptr(d_props), where),
           "ttb2_grad_mats");
-    return {Tensor(), d_mats, d_freqs, d_props};
+    const auto dt = ctx->saved_data["dtypes"].toIntVector();
+    return {Tensor(), like_input(d_mats, (at::ScalarType)dt[0]),
+            like_input(d_freqs, (at::ScalarType)dt[1]), like_input(d_props, (at::ScalarType)dt[2])};
   }
 };
 
@@ -314,14 +412,18 @@ Tensor constant_coalescent(int64_t device, const Tensor& node_heights, const Ten
   return ConstantCoalescent::apply(device, node_heights, theta);
 }
 
-Tensor log_likelihood_eigen(int64_t handle, const Tensor& branch_lengths, const Tensor& site_rates,
-                            const Tensor& site_props, const Tensor& q_norm, const Tensor& freqs) {
-  return EigenLikelihood::apply(handle, branch_lengths, site_rates, site_props, q_norm, freqs);
+Tensor log_likelihood_eigen(const EnginePtr& engine, const Tensor& branch_lengths,
+                            const Tensor& site_rates, const Tensor& site_props,
+                            const Tensor& q_norm, const Tensor& freqs) {
+  TORCH_CHECK(engine, "ttb200: null engine");
+  return EigenLikelihood::apply(keepalive(engine), branch_lengths, site_rates, site_props, q_norm,
+                                freqs);
 }
 
-Tensor log_likelihood_mats(int64_t handle, const Tensor& mats, const Tensor& freqs,
+Tensor log_likelihood_mats(const EnginePtr& engine, const Tensor& mats, const Tensor& freqs,
                            const Tensor& site_props) {
-  return MatsLikelihood::apply(handle, mats, freqs, site_props);
+  TORCH_CHECK(engine, "ttb200: null engine");
+  return MatsLikelihood::apply(keepalive(engine), mats, freqs, site_props);
 }
 
 Tensor node_heights(int64_t plan, int64_t device, const Tensor& x) {
@@ -332,12 +434,21 @@ Tensor node_heights(int64_t plan, int64_t device, const Tensor& x) {
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "torchtree_b200: torch autograd Functions over the ttb200 C ABI (include/ttb200.h)";
+  py::class_<EngineRef, EnginePtr>(m, "EngineRef",
+                                   "Owner of one ttb2_engine handle (shared with the autograd "
+                                   "nodes of its evaluations)")
+      .def(py::init<int64_t>(), py::arg("handle"))
+      .def("close", &EngineRef::close, "destroy the engine now")
+      .def_property_readonly("closed", [](const EngineRef& r) { return r.h == nullptr; })
+      .def_property_readonly("handle", [](const EngineRef& r) {
+        return (int64_t) reinterpret_cast<intptr_t>(r.h);
+      });
   m.def("log_likelihood_eigen", &log_likelihood_eigen,
         "lnL [D] of a reversible model; backward = analytic pre-order gradient",
-        py::arg("engine_handle"), py::arg("branch_lengths"), py::arg("site_rates"),
+        py::arg("engine"), py::arg("branch_lengths"), py::arg("site_rates"),
         py::arg("site_props"), py::arg("q_norm"), py::arg("freqs"));
   m.def("log_likelihood_mats", &log_likelihood_mats,
-        "lnL [D] from caller-supplied transition matrices [D,B,K,S,S]", py::arg("engine_handle"),
+        "lnL [D] from caller-supplied transition matrices [D,B,K,S,S]", py::arg("engine"),
         py::arg("mats"), py::arg("freqs"), py::arg("site_props"));
   m.def("node_heights", &node_heights, "ratios / root height -> internal node heights",
         py::arg("plan_handle"), py::arg("device"), py::arg("x"));

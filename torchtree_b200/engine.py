@@ -102,18 +102,42 @@ class Engine:
             "ttb2_create",
         )
         self._h = handle
+        self._ref = None
         self._draws = 0
         self._shapes = None
 
     # -- life-cycle ---------------------------------------------------------
+    def share(self, ext):
+        """Hand the ownership of the native engine to the torch extension's `EngineRef`
+        (shared with the autograd nodes of its evaluations, csrc/torch_ext.cpp); from then on
+        dropping this object only drops one reference."""
+        if self._ref is None:
+            self._ref = ext.EngineRef(int(self._h.value))
+        return self._ref
+
     def close(self):
+        """Destroy the native engine now.  A backward pass of an earlier evaluation that runs
+        after this raises an error."""
         if self._h is not None:
-            self._lib.ttb2_destroy(self._h)
+            if self._ref is not None:
+                self._ref.close()
+                self._ref = None
+            else:
+                self._lib.ttb2_destroy(self._h)
             self._h = None
+
+    def release(self):
+        """Drop this object's reference without destroying an engine that pending autograd
+        nodes still hold (TreeLikelihoodModel replaces its engine this way)."""
+        if self._h is not None and self._ref is not None:
+            self._ref = None
+            self._h = None
+        else:
+            self.close()
 
     def __del__(self):
         try:
-            self.close()
+            self.release()
         except Exception:
             pass
 

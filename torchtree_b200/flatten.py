@@ -54,7 +54,7 @@ def normalised_generator(subst_model):
     freqs = subst_model.frequencies
     if "GeneralJC69" in names:
         S = subst_model.state_count
-        q = torch.full((S, S), 1.0 / (S - 1), dtype=freqs.dtype)
+        q = torch.full((S, S), 1.0 / (S - 1), dtype=freqs.dtype, device=freqs.device)
         q = q - torch.diag_embed(q.sum(-1))
         return q, freqs
     q = subst_model.q()
@@ -79,28 +79,46 @@ def scaled_branch_lengths(tree_model, clock_model, sample_shape):
     return clock_model.rates * branch_lengths
 
 
-def evaluate_models(engine, tree_model, site_model, subst_model, clock_model, sample_shape):
+def _flat(x, sample_shape, tail):
+    """`x` = [batch..., *tail] -> [1 or D, *tail].  A tensor without batch dimensions (or with
+    extents of 1 only) stays shared by all draws; any other batch shape -- also a partial one
+    such as [m, K] or [n, 1, K] under sample_shape [n, m] -- is broadcast to `sample_shape`
+    first, as the reference's tensor arithmetic would (tree_likelihood.py:313-356)."""
+    tail = tuple(tail)
+    batch = tuple(x.shape[:x.dim() - len(tail)])
+    if all(int(b) == 1 for b in batch):
+        return x.reshape((1,) + tail)
+    return x.expand(tuple(sample_shape) + tail).reshape((-1,) + tail)
+
+
+def evaluate_models(engine, tree_model, site_model, subst_model, clock_model, sample_shape,
+                    shard=None):
     """lnL with the reference's output contract: shape sample_shape + (1,)
-    (SURVEY F9), differentiable w.r.t. every parameter the sub-models carry."""
+    (SURVEY F9), differentiable w.r.t. every parameter the sub-models carry.
+
+    `shard` = None, or ("patterns" | "draws", process group): this process holds one shard of
+    a multi-GPU evaluation (torchtree_b200.sharded); `engine` is then the engine of this rank's
+    patterns (or of all patterns, for draw sharding), or None when the rank owns nothing."""
     sample_shape = torch.Size(sample_shape)
     D = 1
     for n in sample_shape:
         D *= int(n)
     bls = scaled_branch_lengths(tree_model, clock_model, sample_shape)
     B = bls.shape[-1]
-    bls = bls.reshape(-1, B)
+    bls = _flat(bls, sample_shape, (B,))
     if bls.shape[0] != D:
         bls = bls.expand(D, B)
     rates = site_model.rates()
     K = rates.shape[-1]
-    rates = rates.reshape(-1, K)
-    props = site_model.probabilities().reshape(-1, K)
+    rates = _flat(rates, sample_shape, (K,))
+    props = _flat(site_model.probabilities(), sample_shape, (K,))
     route = substitution_route(subst_model)
     if route == "eigen":
         q, freqs = normalised_generator(subst_model)
         S = freqs.shape[-1]
-        lnl = log_likelihood_eigen(engine, bls, rates, props, q.reshape(-1, S, S),
-                                   freqs.reshape(-1, S))
+        tensors = (bls, rates, props, _flat(q, sample_shape, (S, S)),
+                   _flat(freqs, sample_shape, (S,)))
+        local = lambda *a: log_likelihood_eigen(engine, *a)  # noqa: E731
     else:
         freqs = subst_model.frequencies
         S = freqs.shape[-1]
@@ -108,5 +126,16 @@ def evaluate_models(engine, tree_model, site_model, subst_model, clock_model, sa
         # the model may carry its own sample shape: hand p_t the reference's layout
         mats = subst_model.p_t(t.reshape(sample_shape + (B, K)))
         mats = mats.expand(sample_shape + (B, K, S, S)).reshape(D, B, K, S, S)
-        lnl = log_likelihood_mats(engine, mats, freqs.reshape(-1, S), props)
+        tensors = (mats, _flat(freqs, sample_shape, (S,)), props)
+        local = lambda *a: log_likelihood_mats(engine, *a)  # noqa: E731
+    if shard is None:
+        lnl = local(*tensors)
+    else:
+        from .sharded import draw_sharded_log_likelihood, sharded_log_likelihood
+
+        kind, group = shard
+        if kind == "draws":
+            lnl = draw_sharded_log_likelihood(local, tensors, D, group)
+        else:
+            lnl = sharded_log_likelihood(local if engine is not None else None, tensors, group)
     return lnl.reshape(sample_shape + (1,))

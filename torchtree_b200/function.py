@@ -44,11 +44,14 @@ def _ext():
     return _ttb200_torch
 
 
-def _handle(engine: Engine) -> int:
+def _handle(engine: Engine):
+    """The extension's owner object of the engine (`EngineRef`, csrc/torch_ext.cpp): every
+    autograd node made from a forward keeps a reference to it, so the engine outlives the
+    Python `Engine` for as long as a backward may still need its buffers."""
     h = getattr(engine, "_h", None)
     if h is None or not h.value:
         raise EngineError("engine is closed")
-    return int(h.value)
+    return engine.share(_ext())
 
 
 def _lead(x: torch.Tensor, tail: int) -> torch.Tensor:

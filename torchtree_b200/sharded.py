@@ -13,6 +13,27 @@ import torch
 import torch.distributed as dist
 
 
+def _world(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum all-reduce of `t` over the ranks of `group`.  torchtree keeps its Parameters
+    (and therefore lnL and the gradients) on the host while NCCL only moves device memory: a host
+    tensor goes through one device staging buffer -- host -> device, ncclAllReduce over
+    NVLink, device -> host (the payload is the scalar lnL or the ~16 KB packed gradient)."""
+    if _world(group) <= 1:
+        return t
+    backend = dist.get_backend(group)
+    if t.is_cuda or "nccl" not in backend:
+        dist.all_reduce(t, group=group)
+        return t
+    staged = t.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+    dist.all_reduce(staged, group=group)
+    t.copy_(staged)
+    return t
+
+
 def shard_range(pattern_count: int, rank: int, world_size: int):
     """Contiguous, balanced slice [lo, hi) of the patterns owned by `rank`."""
     per = (pattern_count + world_size - 1) // world_size
@@ -33,9 +54,9 @@ class _CopyToShards(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         live = [g for g in grads if g is not None]
-        if live and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+        if live and _world(ctx.group) > 1:
             flat = torch.cat([g.reshape(-1) for g in live])
-            dist.all_reduce(flat, group=ctx.group)
+            all_reduce_sum(flat, ctx.group)
             out, off = [], 0
             for g in grads:
                 if g is None:
@@ -53,10 +74,7 @@ class _SumOverShards(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, group, lnl):
-        out = lnl.clone()
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(out, group=group)
-        return out
+        return all_reduce_sum(lnl.clone(), group)
 
     @staticmethod
     def backward(ctx, grad):
@@ -68,11 +86,18 @@ def sharded_log_likelihood(local_fn, tensors, group=None):
 
     `local_fn(*tensors) -> lnL[D]` evaluates this rank's pattern shard (e.g.
     `lambda *a: log_likelihood_eigen(engine, *a)` with an engine built on
-    `shard_range(...)`).  Returns the full lnL on every rank; after `.backward()`
-    every rank holds the full gradient of every tensor in `tensors`.
+    `shard_range(...)`; None if the rank owns no patterns).  Returns the full lnL on every
+    rank; after `.backward()` every rank holds the full gradient of every tensor in `tensors`.
     """
     copies = _CopyToShards.apply(group, *tensors)
-    return _SumOverShards.apply(group, local_fn(*copies))
+    if local_fn is None:
+        # this rank owns no patterns (more ranks than patterns): contributes 0, joins the collectives
+        draws = max(int(t.shape[0]) for t in copies)
+        local = sum((t.sum() * 0.0 for t in copies)) + torch.zeros(
+            draws, dtype=copies[0].dtype, device=copies[0].device)
+    else:
+        local = local_fn(*copies)
+    return _SumOverShards.apply(group, local)
 
 
 # ---- draw sharding (BASELINE config 3: a batch of ADVI / HMC draws per step) -------------------
@@ -106,9 +131,9 @@ class _ScatterDraws(torch.autograd.Function):
             else:
                 full.append(g.contiguous())
         live = [g for g in full if g is not None]
-        if live and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+        if live and _world(ctx.group) > 1:
             flat = torch.cat([g.reshape(-1) for g in live])
-            dist.all_reduce(flat, group=ctx.group)
+            all_reduce_sum(flat, ctx.group)
             off = 0
             for i, g in enumerate(full):
                 if g is not None:
@@ -125,9 +150,7 @@ class _GatherDraws(torch.autograd.Function):
         ctx.lo, ctx.hi = lo, hi
         out = lnl.new_zeros((draws,) + tuple(lnl.shape[1:]))
         out[lo:hi] = lnl
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(out, group=group)
-        return out
+        return all_reduce_sum(out, group)
 
     @staticmethod
     def backward(ctx, grad):
@@ -142,8 +165,8 @@ def draw_sharded_log_likelihood(local_fn, tensors, draws, group=None):
     holds the whole alignment (`max_draws >= ceil(D / world_size)`).  Every rank receives lnL of
     all draws and, after `.backward()`, the full gradient of every tensor.
     """
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = _world(group)
+    rank = dist.get_rank(group) if world > 1 else 0
     lo, hi = shard_range(draws, rank, world)
     local = _ScatterDraws.apply(group, lo, hi, draws, *tensors)
     if hi > lo:

@@ -7,13 +7,26 @@ Same constructor arguments, JSON keys and output contract as the reference class
      "tree_model": ..., "site_model": ..., "substitution_model": ...,
      "site_pattern": ..., ["branch_model": ...],
      ["use_ambiguities": false], ["use_tip_states": false],
-     ["device": 0]}
+     ["device": 0], ["devices": [0, 1, ...]], ["shard": "patterns" | "draws"]}
+
+Multi-GPU: one process per GPU (`torchrun --nproc-per-node G torchtree-b200 cfg.json`,
+or any launcher that sets RANK / LOCAL_RANK / WORLD_SIZE).  With `"shard": "patterns"` every
+rank builds its engine on its slice of the site patterns; with `"shard": "draws"` every rank
+holds the whole alignment and evaluates its slice of the batch of draws.  `"devices"` maps the
+local rank to a CUDA ordinal (default: the local rank itself).  The exchange per evaluation is
+one all-reduce of lnL and one of the packed gradient (torchtree_b200/sharded.py).
+
+dtype policy: the engine computes in fp64 whatever `--dtype` says; float32 parameters are
+converted on the way in and lnL / gradients come back as float32 (csrc/torch_ext.cpp).
 
 This module needs torchtree importable; the engine underneath does not.
 """
 from __future__ import annotations
 
+import os
+
 import torch
+import torch.distributed as dist
 from torchtree.core.model import CallableModel
 from torchtree.core.utils import process_object, register_class
 from torchtree.evolution.branch_model import BranchModel
@@ -26,6 +39,25 @@ from .engine import Engine, codes_from_tip_partials
 from .flatten import evaluate_models
 
 
+MAX_STATES = 64   # ttb2_create's limit (include/ttb200.h)
+
+
+def _join_process_group():
+    """(rank, world size) of this process; initialises torch.distributed from the launcher's
+    environment (RANK / WORLD_SIZE / MASTER_*) when a launcher is present and nobody did yet."""
+    if not dist.is_available():
+        return 0, 1
+    if not dist.is_initialized():
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1:
+            return 0, 1
+        backend = os.environ.get("TTB200_DIST_BACKEND", "nccl")
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
 class TreeLikelihoodModel(CallableModel):
     """B200-native replacement of torchtree's TreeLikelihoodModel.
 
@@ -36,8 +68,26 @@ class TreeLikelihoodModel(CallableModel):
 
     def __init__(self, id_, site_pattern, tree_model, subst_model, site_model,
                  clock_model=None, use_ambiguities=False, use_tip_states=False,
-                 device: int = 0):
+                 device: int = 0, devices=None, shard=None):
         super().__init__(id_)
+        state_count = subst_model.frequencies.shape[-1]
+        if state_count > MAX_STATES:
+            # no CPU fallback and no silent substitute (SURVEY 8(b) policy): say so at construction
+            raise NotImplementedError(
+                "torchtree_b200.TreeLikelihoodModel supports at most %d states (got %d); keep the "
+                "reference TreeLikelihoodModel for this likelihood" % (MAX_STATES, state_count))
+        if shard not in (None, "patterns", "draws"):
+            raise ValueError('"shard" must be "patterns" or "draws", got %r' % (shard,))
+        self.shard = shard
+        self._group = None
+        self._rank, self._world = 0, 1
+        if shard is not None:
+            self._rank, self._world = _join_process_group()
+        local_rank = int(os.environ.get("LOCAL_RANK", self._rank))
+        if devices:
+            device = list(devices)[local_rank % len(devices)]
+        elif shard is not None and self._world > 1:
+            device = local_rank
         self.site_pattern = site_pattern
         self.tree_model = tree_model
         self.subst_model = subst_model
@@ -46,7 +96,6 @@ class TreeLikelihoodModel(CallableModel):
         self.use_tip_states = use_tip_states
         self.use_ambiguities = use_ambiguities
         self.device_index = int(device)
-        state_count = subst_model.frequencies.shape[-1]
         if type(site_pattern) is SitePattern:
             # stock SitePattern: compress natively (patterns.py, ttb2_compress_patterns)
             # instead of the per-character Python loops of site_pattern.py:69-151
@@ -67,19 +116,31 @@ class TreeLikelihoodModel(CallableModel):
             self._tip_codes, self._code_partials = codes_from_tip_partials(
                 [p.numpy() for p in partials], state_count)
         self._state_count = int(state_count)
+        self.pattern_range = (0, int(self.weights.shape[0]))
+        if shard == "patterns" and self._world > 1:
+            from .sharded import shard_range
+
+            lo, hi = shard_range(int(self.weights.shape[0]), self._rank, self._world)
+            self.pattern_range = (lo, hi)
         self._engine = None
         self._engine_postorder = None
 
     # -- engine management ---------------------------------------------------
-    def _get_engine(self, draws: int) -> Engine:
+    def _get_engine(self, draws: int):
         postorder = self.tree_model.postorder
         K = self.site_model.rates().shape[-1]
+        lo, hi = self.pattern_range
+        if hi <= lo:
+            return None   # more ranks than patterns: this rank only joins the collectives
+        if self.shard == "draws" and self._world > 1:
+            draws = (draws + self._world - 1) // self._world
         if (self._engine is None or self._engine.max_draws < draws or self._engine.K != K):
             if self._engine is not None:
-                self._engine.close()
+                # not close(): a pending backward of an earlier evaluation may still need it
+                self._engine.release()
             self._engine = Engine(
-                self._tip_codes, self.weights.to(torch.float64).numpy(), postorder,
-                self._state_count, K, code_partials=self._code_partials,
+                self._tip_codes[:, lo:hi], self.weights.to(torch.float64).numpy()[lo:hi],
+                postorder, self._state_count, K, code_partials=self._code_partials,
                 max_draws=draws, device=self.device_index)
             self._engine_postorder = list(postorder)
         elif self._engine_postorder != list(postorder):
@@ -94,8 +155,9 @@ class TreeLikelihoodModel(CallableModel):
         for n in sample_shape:
             draws *= int(n)
         engine = self._get_engine(draws)
+        shard = (self.shard, self._group) if self.shard is not None and self._world > 1 else None
         return evaluate_models(engine, self.tree_model, self.site_model, self.subst_model,
-                               self.clock_model, sample_shape)
+                               self.clock_model, sample_shape, shard=shard)
 
     def handle_parameter_changed(self, variable, index, event):
         pass
@@ -116,7 +178,8 @@ class TreeLikelihoodModel(CallableModel):
         if BranchModel.tag in data:
             clock_model = process_object(data[BranchModel.tag], dic)
         return cls(id_, site_pattern, tree_model, subst_model, site_model, clock_model,
-                   use_ambiguities, use_tip_states, device=data.get("device", 0))
+                   use_ambiguities, use_tip_states, device=data.get("device", 0),
+                   devices=data.get("devices"), shard=data.get("shard"))
 
 
 def install(override_reference: bool = True, height_transform: bool = False,
