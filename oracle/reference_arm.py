@@ -75,7 +75,7 @@ class ReferenceProblem:
             n_ex = S * (S - 1) // 2
             self.subst = GeneralSymmetricSubstitutionModel(
                 "sym", GeneralDataType("dt", [str(i) for i in range(S)]),
-                torch.arange(n_ex), self.rates6, self.freqs)
+                Parameter(None, torch.arange(n_ex)), self.rates6, self.freqs)
         if K > 1:
             self.shape = Parameter("shape", torch.tensor(
                 [float(prob.model_params["weibull_shape"][0])]))

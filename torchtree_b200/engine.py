@@ -316,6 +316,39 @@ class Engine:
             "ttb2_grad_eigen")
         return out
 
+    def grad_eigen_packed(self, grad_lnl=None, out=None) -> torch.Tensor:
+        """The gradient of the latest eigen-mode call as one vector
+        [lnL | d_bl | d_rates | d_props | d_q | d_freqs] (ttb2_grad_eigen_packed): the payload
+        of the all-reduce of a pattern-sharded run.  `unpack` gives the views."""
+        sh = self._shapes
+        if sh is None or "ed" not in sh:
+            raise EngineError("grad_eigen_packed before loglik_eigen")
+        dev = sh["dev"]
+        g = None
+        if grad_lnl is not None:
+            g = self._prep(grad_lnl.reshape(-1), (), "grad_lnl").reshape(-1).to(dev)
+        count = int(self._lib.ttb2_packed_count(self._h))
+        if out is None:
+            out = torch.empty(count, dtype=torch.float64, device=dev)
+        _lib.check(self._lib.ttb2_grad_eigen_packed(self._h, _ptr(g), _ptr(out), out.numel(),
+                                                    sh["where"]), "ttb2_grad_eigen_packed")
+        return out
+
+    def unpack(self, packed: torch.Tensor) -> dict:
+        """Views of a packed gradient vector, keyed like `grad_eigen`'s result (+ "lnL")."""
+        sh, S, K, B = self._shapes, self.S, self.K, self.B
+        D = sh["D"]
+        out, off = {}, 0
+        for key, shape in (("lnL", (D,)), ("branch_lengths", (D, B)), ("site_rates", (sh["rd"], K)),
+                           ("props", (sh["pd"], K)), ("q", (sh["ed"], S, S)),
+                           ("freqs", (sh["fd"], S))):
+            n = 1
+            for x in shape:
+                n *= x
+            out[key] = packed[off:off + n].view(shape)
+            off += n
+        return out
+
     # -- inspection -----------------------------------------------------------
     def site_loglik(self) -> torch.Tensor:
         sh = self._shapes

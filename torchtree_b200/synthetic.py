@@ -271,3 +271,29 @@ def _evolve_tips(post, T, N, S, bl, q, freqs, rng):
             u = rng.random(N)
             states[child] = (u[:, None] > cdf[states[node]]).sum(axis=1).clip(0, S - 1)
     return states[:T]
+
+
+def make_time_tree(postorder: np.ndarray, tip_count: int, draws: int, seed: int = 3,
+                   dated_fraction: float = 0.6):
+    """Heterochronous time-tree inputs on a given topology (BASELINE config 3 shape;
+    torchtree/evolution/tree_model.py:380-424, tree_height_transform.py:36-56):
+
+    times   [T]      sampling times of the tips (a fraction is 0 = contemporaneous)
+    bounds  [T-1]    lower bound of every internal node = the oldest tip below it
+    x       [D,T-1]  ratios in (0.1, 0.9) and, at the root's slot, the root height
+    child / parent [2T-2]  node and parent-node index of every branch (branch b = node b)
+    """
+    rng = np.random.default_rng(seed)
+    T = tip_count
+    times = rng.uniform(0.0, 3.0, T) * (rng.random(T) < dated_fraction)
+    node_bound = np.concatenate([times, np.zeros(T - 1)])
+    parent = np.full(2 * T - 1, -1, dtype=np.int64)
+    for node, left, right in postorder:
+        node_bound[node] = max(node_bound[left], node_bound[right])
+        parent[left] = parent[right] = node
+    root = int(postorder[-1][0])
+    x = rng.random((draws, T - 1)) * 0.8 + 0.1
+    x[:, root - T] = node_bound[root] + 5.0 + 4.0 * rng.random(draws)
+    child = np.array([n for n in range(2 * T - 1) if n != root], dtype=np.int64)
+    return dict(times=times, bounds=node_bound[T:].copy(), x=x, child=child,
+                parent=parent[child], root=root)
