@@ -643,3 +643,125 @@ def test_time_tree_with_per_branch_clock_rates(patched):
     for a, b in zip(g_new, g_ref):
         assert a.shape == b.shape
         assert torch.allclose(a, b, rtol=1e-8, atol=1e-8 * b.abs().max())
+
+
+def test_codon_mg94_on_fluA(patched):
+    """61-state codon model (MG94, substitution_model/codon.py) on fluA read as codons (the
+    shape of BASELINE config 5 on real data): value and gradients w.r.t. branch lengths, Weibull
+    shape, kappa / alpha / beta and the 61 codon frequencies equal the reference class's."""
+    from torchtree import Parameter
+    from torchtree.evolution.alignment import Alignment, Sequence
+    from torchtree.evolution.datatype import CodonDataType
+    from torchtree.evolution.site_model import WeibullSiteModel
+    from torchtree.evolution.site_pattern import SitePattern
+    from torchtree.evolution.substitution_model import MG94
+    from torchtree.evolution.taxa import Taxa, Taxon
+    from torchtree.evolution.tree_likelihood import TreeLikelihoodModel as Reference
+    from torchtree.evolution.tree_model import UnRootedTreeModel
+
+    # SURVEY F11: MG94.handle_parameter_changed calls a method that does not exist; patched in
+    # the harness (as tests/golden/make_golden.py does), never in the reference
+    MG94.handle_parameter_changed = lambda self, v, i, e: self.fire_model_changed()
+    names, seqs = [], []
+    with open(DATA + "/fluA.fa") as fp:
+        for line in fp:
+            line = line.strip()
+            if line.startswith(">"):
+                names.append(line[1:])
+                seqs.append("")
+            elif line:
+                seqs[-1] += line
+    with open(DATA + "/fluA.tree") as fp:
+        newick = fp.read().strip()
+    rng = np.random.default_rng(17)
+    bl0 = rng.uniform(0.005, 0.05, 2 * len(names) - 3)
+    f0 = rng.dirichlet(np.full(61, 20.0))
+    results = []
+    for cls in (Reference, patched.TreeLikelihoodModel):
+        datatype = CodonDataType("codon", "Universal")
+        taxa = Taxa("taxa", [Taxon(n, None) for n in names])
+        aln = Alignment("aln", [Sequence(n, s) for n, s in zip(names, seqs)], taxa, datatype)
+        sp = SitePattern("sp", aln)
+        dic = {"taxa": taxa, "blens": Parameter("blens", torch.tensor(bl0))}
+        tree = UnRootedTreeModel.from_json(
+            {"id": "tree", "type": "UnRootedTreeModel", "newick": newick,
+             "branch_lengths": "blens", "taxa": "taxa"}, dic)
+        leaves = {"blens": dic["blens"], "shape": Parameter("shape", torch.tensor([0.6])),
+                  "kappa": Parameter("kappa", torch.tensor([2.7])),
+                  "alpha": Parameter("alpha", torch.tensor([1.3])),
+                  "beta": Parameter("beta", torch.tensor([0.4])),
+                  "freqs": Parameter("freqs", torch.tensor(f0))}
+        subst = MG94("mg94", datatype, leaves["alpha"], leaves["beta"], leaves["kappa"],
+                     leaves["freqs"])
+        like = cls("like", sp, tree, subst, WeibullSiteModel("sm", leaves["shape"], 4))
+        for p in leaves.values():
+            p.requires_grad = True
+        value = like()
+        value.sum().backward()
+        results.append((value.detach().clone(), {k: p.grad.clone() for k, p in leaves.items()},
+                        int(like.weights.sum())))
+    (v_ref, g_ref, n_ref), (v_new, g_new, n_new) = results
+    assert n_ref == n_new == 329      # 987 nucleotides = 329 codon sites
+    assert torch.allclose(v_new, v_ref, rtol=1e-10, atol=0), (v_new, v_ref)
+    for n in g_ref:
+        tol = 1e-8 if n in ("blens", "shape") else 1e-7   # eigh backward of the reference (F12)
+        assert torch.allclose(g_new[n], g_ref[n], rtol=tol, atol=tol * g_ref[n].abs().max()), \
+            (n, (g_new[n] - g_ref[n]).abs().max().item(), g_ref[n].abs().max().item())
+
+
+def test_cli_time_tree_advi_with_device_heights_and_coalescent(patched, tmp_path, capsys):
+    """BASELINE config 3's model on real data, end to end: `torchtree-cli advi -m JC69 --clock strict
+    --coalescent constant --heights ratio` writes the JSON; the stock runner optimises it once as
+    generated and once with the likelihood (`--b200`), the constant coalescent (`--b200_coalescent`)
+    and the ratio -> node-height transform (`--b200-heights`, console-script flag) on the device:
+    same seed, same draws -> the same ELBO trace."""
+    import re
+
+    from torchtree.core.utils import REGISTERED_CLASSES
+
+    import torchtree.evolution.tree_height_transform as ref_transform
+    import torchtree.evolution.tree_likelihood as refmod
+    import torchtree.evolution.tree_model as ref_tree_model
+
+    sys.path.insert(0, REPO)
+    base = ["advi", "-i", DATA + "/fluA.fa", "-t", DATA + "/fluA.tree", "-m", "JC69",
+            "--clock", "strict", "--coalescent", "constant", "--heights", "ratio",
+            "--iter", "6", "--elbo_samples", "3", "--grad_samples", "2", "--convergence_every", "2",
+            "--stem", str(tmp_path / "run")]
+    traces = {}
+    saved_reg = dict(REGISTERED_CLASSES)
+    saved = (refmod.TreeLikelihoodModel, ref_transform.GeneralNodeHeightTransform,
+             ref_tree_model.GeneralNodeHeightTransform)
+    try:
+        for tag, extra in (("reference", []), ("b200", ["--b200", "--b200_coalescent"])):
+            cfg = _run_cli(base + extra, capsys)
+            assert ("torchtree_b200.TreeLikelihoodModel" in cfg) == bool(extra)
+            assert ("torchtree_b200.coalescent.ConstantCoalescentModel" in cfg) == bool(extra)
+            path = tmp_path / (tag + ".json")
+            path.write_text(cfg)
+            if extra and patched.BACKEND == "cuda":
+                # the device height transform as well (what `torchtree-b200 --b200-heights` installs)
+                patched.install(override_reference=False, height_transform=True)
+            if extra and patched.BACKEND == "oracle":
+                import torchtree_b200.coalescent as cmod
+                from oracle.coalescent import constant_log_prob
+
+                cmod.constant_coalescent_log_prob = lambda h, th, device=0: constant_log_prob(h, th)
+            out = _run_torchtree(str(path), capsys)
+            elbos = [float(m.group(1)) for m in
+                     re.finditer(r"^\s*\d+\s+(-?\d+\.\d+)\s+\d+\.\d+\s+\d+\.\d+", out, flags=re.M)]
+            assert len(elbos) >= 3, out[-2000:]
+            traces[tag] = elbos
+    finally:
+        REGISTERED_CLASSES.clear()
+        REGISTERED_CLASSES.update(saved_reg)
+        refmod.TreeLikelihoodModel = saved[0]
+        ref_transform.GeneralNodeHeightTransform = saved[1]
+        ref_tree_model.GeneralNodeHeightTransform = saved[2]
+        if patched.BACKEND == "oracle":
+            import importlib
+
+            import torchtree_b200.coalescent as cmod
+
+            importlib.reload(cmod)
+    np.testing.assert_allclose(np.array(traces["b200"]), np.array(traces["reference"]), rtol=1e-7)

@@ -1,0 +1,70 @@
+"""Whose error is the 1e-7?  The engine's gradients against a 50-digit mpmath ground truth
+(tests/golden/truth_mpmath.npz, made by tests/golden/make_truth_mpmath.py): lnL, branch lengths,
+Weibull shape, GTR exchangeabilities and frequencies at a generic point and at a point whose
+symmetrised generator has two eigenvalues 1e-7 apart.  The parity tests compare
+substitution-parameter gradients with the *reference's autograd* at 1e-7 (its `eigh`
+backward divides by eigenvalue gaps); here the engine meets north_star's 1e-8 -- in fact 1e-10 --
+against the truth at both points, while the fixture records the reference at 1.6e-8 on the
+near-degenerate one.  So the slack in those comparisons is the reference's, not the engine's."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import treelik as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load():
+    return np.load(os.path.join(HERE, "golden", "truth_mpmath.npz"))
+
+
+def _rel(got, want):
+    floor = 1e-8 * np.abs(want).max()
+    return float((np.abs(got - want) / np.maximum(np.abs(want), floor)).max())
+
+
+def test_fixture_records_the_reference_error():
+    z = _load()
+    nb = 2 * int(z["T"]) - 3
+    for case in ("generic", "near_degenerate"):
+        assert abs(z[case + "_ref_lnL"] - z[case + "_lnL"]) <= 1e-13 * abs(z[case + "_lnL"])
+        assert _rel(z[case + "_ref_grad"][:nb + 1], z[case + "_grad"][:nb + 1]) <= 1e-11
+    # the reference's GTR-rate gradient degrades with the eigenvalue gap (generic: ~1e-12)
+    assert _rel(z["generic_ref_grad"][nb + 1:nb + 7], z["generic_grad"][nb + 1:nb + 7]) <= 1e-10
+    assert _rel(z["near_degenerate_ref_grad"][nb + 1:nb + 7],
+                z["near_degenerate_grad"][nb + 1:nb + 7]) >= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["generic", "near_degenerate"])
+def test_engine_gradients_match_the_mpmath_truth(case):
+    from torchtree_b200 import Engine, log_likelihood_eigen
+
+    z = _load()
+    T, K = int(z["T"]), int(z["K"])
+    nb = 2 * T - 3
+    theta = z[case + "_theta"]
+    bl = torch.tensor(theta[:nb], requires_grad=True)
+    shape = torch.tensor(theta[nb:nb + 1], requires_grad=True)
+    rates6 = torch.tensor(theta[nb + 1:nb + 7], requires_grad=True)
+    freqs = torch.tensor(theta[nb + 7:nb + 11], requires_grad=True)
+    eng = Engine(z["tips"], z["weights"], z["postorder"], 4, K, max_draws=1)
+    site_rates, props = orc.weibull_site_model(shape, K)
+    q = orc.normalise_q(orc.gtr_q_unnorm(rates6, freqs), freqs)
+    bls = torch.cat((bl, torch.zeros(1, dtype=torch.float64)))
+    lnl = log_likelihood_eigen(eng, bls[None], site_rates[None], props[None], q[None], freqs[None])
+    lnl.sum().backward()
+    eng.close()
+    want = z[case + "_grad"]
+    assert abs(lnl.item() - float(z[case + "_lnL"])) <= 1e-13 * abs(float(z[case + "_lnL"]))
+    got = torch.cat([bl.grad, shape.grad, rates6.grad, freqs.grad]).numpy()
+    errs = {"bl": _rel(got[:nb], want[:nb]), "shape": _rel(got[nb:nb + 1], want[nb:nb + 1]),
+            "rates": _rel(got[nb + 1:nb + 7], want[nb + 1:nb + 7]),
+            "freqs": _rel(got[nb + 7:], want[nb + 7:])}
+    assert max(errs.values()) <= 1e-10, errs
+    if case == "near_degenerate":
+        ref_err = _rel(z[case + "_ref_grad"][nb + 1:nb + 7], want[nb + 1:nb + 7])
+        assert errs["rates"] < 1e-2 * ref_err, (errs, ref_err)
