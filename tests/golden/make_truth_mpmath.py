@@ -11,7 +11,7 @@ side the slack belongs to: two points, one generic and one where two eigenvalues
 symmetrised generator are 1e-7 apart, each with the truth and with what the real reference
 (imported here from /root/reference or baseline/_ref) returns.
 
-    python tests/golden/make_truth_mpmath.py      # writes tests/golden/truth_mpmath.npz
+    python tests/golden/make_truth_mpmath.py      # writes tests/golden/truth/truth_mpmath.npz
 """
 import os
 import sys
@@ -150,7 +150,7 @@ def main():
         print(name, "lnL", v, "reference rel err of lnL %.2e" % (abs(vr - v) / abs(v)),
               "max rel err of the reference gradient: bl %.2e shape %.2e rates %.2e freqs %.2e"
               % (err[:nb].max(), err[nb], err[nb + 1:nb + 7].max(), err[nb + 7:].max()))
-    np.savez(os.path.join(HERE, "truth_mpmath.npz"), T=T, N=N, K=K, postorder=np.array(POST),
+    np.savez(os.path.join(HERE, "truth", "truth_mpmath.npz"), T=T, N=N, K=K, postorder=np.array(POST),
              tips=TIPS, weights=WEIGHTS, **cases)
 
 

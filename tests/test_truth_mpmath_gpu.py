@@ -1,5 +1,5 @@
 """Whose error is the 1e-7?  The engine's gradients against a 50-digit mpmath ground truth
-(tests/golden/truth_mpmath.npz, made by tests/golden/make_truth_mpmath.py): lnL, branch lengths,
+(tests/golden/truth/truth_mpmath.npz, made by tests/golden/make_truth_mpmath.py): lnL, branch lengths,
 Weibull shape, GTR exchangeabilities and frequencies at a generic point and at a point whose
 symmetrised generator has two eigenvalues 1e-7 apart.  The parity tests compare
 substitution-parameter gradients with the *reference's autograd* at 1e-7 (its `eigh`
@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _load():
-    return np.load(os.path.join(HERE, "golden", "truth_mpmath.npz"))
+    return np.load(os.path.join(HERE, "golden", "truth", "truth_mpmath.npz"))
 
 
 def _rel(got, want):

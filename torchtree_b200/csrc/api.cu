@@ -127,6 +127,45 @@ int finish(Engine& e, int where) {
 
 bool bad_draws(int d, int draws) { return !(d == 1 || d == draws); }
 
+// The small inputs of an evaluation are staged back to back in one device buffer,
+//   [ bl[D][B] | rates[rd][K] | props[pd][K] | freqs[fd][S] | q_norm[qd][S][S] ],
+// so that host inputs cost ONE host-to-device copy (through a pinned mirror; a pageable
+// cudaMemcpyAsync per array is a driver-staged, synchronous copy each) and device inputs ONE
+// gather kernel instead of five copy launches -- at the 8-GPU shard of the headline problem the
+// per-call fixed costs are what limits scaling.
+struct InSeg {
+  const double* src;
+  double** slot;
+  size_t n;
+};
+
+int stage_inputs(Engine& e, const InSeg* segs, int nseg, int where) {
+  size_t off[8], total = 0;
+  for (int j = 0; j < nseg; ++j) {
+    off[j] = total;
+    *segs[j].slot = e.inPacked + total;
+    total += segs[j].n;
+  }
+  if (total > e.inCap) {
+    set_error("internal: staged inputs exceed the staging buffer");
+    return TTB2_E_INVALID;
+  }
+  if (where == TTB2_HOST) {
+    for (int j = 0; j < nseg; ++j)
+      std::memcpy(e.hostIn + off[j], segs[j].src, segs[j].n * sizeof(double));
+    TTB2_CUDA_CHECK(cudaMemcpyAsync(e.inPacked, e.hostIn, total * sizeof(double),
+                                    cudaMemcpyHostToDevice, e.stream));
+    return TTB2_OK;
+  }
+  const double* src[8];
+  size_t n[8];
+  for (int j = 0; j < nseg; ++j) {
+    src[j] = segs[j].src;
+    n[j] = segs[j].n;
+  }
+  return small_gather_inputs(e, src, off, n, nseg);
+}
+
 // The small outputs of a gradient call live back to back in one buffer,
 //   [ lnL[D] | d_bl[D][B] | d_rates[rd][K] | d_props[pd][K] | d_q[ed][S][S] | d_freqs[fd][S] ],
 // so that a caller that reduces them across shards (NCCL all-reduce over NVLink) or copies them
@@ -187,6 +226,7 @@ int ensure_eigen_grad_buffers(Engine& e) {
     e.hpartCap = matN;
   }
   if (!e.gscal && (rc = dev_alloc(e, &e.gscal, (size_t)e.cfg.max_draws * m.B * m.K))) return rc;
+  if (!e.hred && (rc = dev_alloc(e, &e.hred, (size_t)e.cfg.max_draws * 8 * m.S * m.S))) return rc;
   return TTB2_OK;
 }
 
@@ -441,14 +481,12 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
   e.redPartCap = (size_t)D * nblocks * (m.K + m.S);
   TRY(dev_alloc(e, &e.redPart, e.redPartCap));
   TRY(dev_alloc(e, &e.lnl, (size_t)D));
-  TRY(dev_alloc(e, &e.freqs, (size_t)D * m.S));
-  TRY(dev_alloc(e, &e.props, (size_t)D * m.K));
-  TRY(dev_alloc(e, &e.bl, (size_t)D * m.B));
-  TRY(dev_alloc(e, &e.rates, (size_t)D * m.K));
+  e.inCap = (size_t)D * (m.B + 2 * m.K + m.S + m.S * m.S);
+  TRY(dev_alloc(e, &e.inPacked, e.inCap));
+  TRY_CUDA(cudaHostAlloc((void**)&e.hostIn, e.inCap * sizeof(double), cudaHostAllocDefault));
   TRY(dev_alloc(e, &e.evec, (size_t)D * m.S * m.S));
   TRY(dev_alloc(e, &e.ivec, (size_t)D * m.S * m.S));
   TRY(dev_alloc(e, &e.eval, (size_t)D * m.S));
-  TRY(dev_alloc(e, &e.qnorm, (size_t)D * m.S * m.S));
   TRY(dev_alloc(e, &e.gradLnl, (size_t)D));
   TRY(dev_alloc(e, &e.ones, (size_t)D));
   {
@@ -539,9 +577,11 @@ void ttb2_destroy(ttb2_engine* engine) {
   dev_free(e.tips); dev_free(e.weights); dev_free(e.codeP); dev_free(e.codeMask); dev_free(e.ops);
   dev_free(e.partials); dev_free(e.expo); dev_free(e.pre); dev_free(e.mats);
   dev_free(e.dmat); dev_free(e.gpart); dev_free(e.siteLnl); dev_free(e.redPart);
-  dev_free(e.lnl); dev_free(e.rootGrad); dev_free(e.hpart); dev_free(e.gscal);
-  dev_free(e.freqs); dev_free(e.props); dev_free(e.bl); dev_free(e.rates);
-  dev_free(e.evec); dev_free(e.ivec); dev_free(e.eval); dev_free(e.qnorm); dev_free(e.gradLnl); dev_free(e.ones);
+  dev_free(e.lnl); dev_free(e.rootGrad); dev_free(e.hpart); dev_free(e.gscal); dev_free(e.hred);
+  dev_free(e.inPacked);
+  if (e.hostIn) cudaFreeHost(e.hostIn);
+  e.hostIn = nullptr;
+  dev_free(e.evec); dev_free(e.ivec); dev_free(e.eval); dev_free(e.gradLnl); dev_free(e.ones);
   dev_free(e.outPacked);
   dev_free(e.expoK);
   dev_free(e.chunkBase); dev_free(e.chunkCount);
@@ -602,8 +642,11 @@ int ttb2_loglik_mats(ttb2_engine* engine, int32_t draws, const double* mats,
   mark(e, 0);
   if ((rc = copy_in(e, e.mats, mats, (size_t)draws * m.B * m.K * m.S * m.S * sizeof(double), where)))
     return rc;
-  if ((rc = copy_in(e, e.freqs, freqs, (size_t)freq_draws * m.S * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.props, props, (size_t)prop_draws * m.K * sizeof(double), where))) return rc;
+  {
+    const InSeg segs[] = {{props, &e.props, (size_t)prop_draws * m.K},
+                          {freqs, &e.freqs, (size_t)freq_draws * m.S}};
+    if ((rc = stage_inputs(e, segs, 2, where))) return rc;
+  }
   e.freqDraws = freq_draws;
   e.propDraws = prop_draws;
   e.rateDraws = e.eigDraws = 1;
@@ -664,13 +707,16 @@ int ttb2_loglik_eigen(ttb2_engine* engine, int32_t draws, const double* branch_l
   int rc;
   mark(e, 0);
   const size_t SS = (size_t)m.S * m.S;
-  if ((rc = copy_in(e, e.bl, branch_lengths, (size_t)draws * m.B * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.rates, site_rates, (size_t)rate_draws * m.K * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.props, props, (size_t)prop_draws * m.K * sizeof(double), where))) return rc;
+  {
+    const InSeg segs[] = {{branch_lengths, &e.bl, (size_t)draws * m.B},
+                          {site_rates, &e.rates, (size_t)rate_draws * m.K},
+                          {props, &e.props, (size_t)prop_draws * m.K},
+                          {freqs, &e.freqs, (size_t)freq_draws * m.S}};
+    if ((rc = stage_inputs(e, segs, 4, where))) return rc;
+  }
   if ((rc = copy_in(e, e.evec, evec, eig_draws * SS * sizeof(double), where))) return rc;
   if ((rc = copy_in(e, e.ivec, ivec, eig_draws * SS * sizeof(double), where))) return rc;
   if ((rc = copy_in(e, e.eval, eval, (size_t)eig_draws * m.S * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.freqs, freqs, (size_t)freq_draws * m.S * sizeof(double), where))) return rc;
   e.freqDraws = freq_draws;
   e.propDraws = prop_draws;
   e.rateDraws = rate_draws;
@@ -702,11 +748,14 @@ int ttb2_loglik_q(ttb2_engine* engine, int32_t draws, const double* branch_lengt
   int rc;
   mark(e, 0);
   const size_t SS = (size_t)m.S * m.S;
-  if ((rc = copy_in(e, e.bl, branch_lengths, (size_t)draws * m.B * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.rates, site_rates, (size_t)rate_draws * m.K * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.props, props, (size_t)prop_draws * m.K * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.qnorm, q_norm, q_draws * SS * sizeof(double), where))) return rc;
-  if ((rc = copy_in(e, e.freqs, freqs, (size_t)freq_draws * m.S * sizeof(double), where))) return rc;
+  {
+    const InSeg segs[] = {{branch_lengths, &e.bl, (size_t)draws * m.B},
+                          {site_rates, &e.rates, (size_t)rate_draws * m.K},
+                          {props, &e.props, (size_t)prop_draws * m.K},
+                          {freqs, &e.freqs, (size_t)freq_draws * m.S},
+                          {q_norm, &e.qnorm, (size_t)q_draws * SS}};
+    if ((rc = stage_inputs(e, segs, 5, where))) return rc;
+  }
   e.freqDraws = freq_draws;
   e.propDraws = prop_draws;
   e.rateDraws = rate_draws;
@@ -778,6 +827,12 @@ static int grad_eigen_compute(Engine& e, const double* grad_lnl, int where) {
   int rc;
   const int draws = e.draws;
   NvtxRange range("ttb2:grad_eigen");
+  // the contraction kernel reduces the per-chunk sums of G itself (one launch less)
+  struct Defer {
+    Engine& e;
+    explicit Defer(Engine& e_) : e(e_) { e.deferGpart = true; }
+    ~Defer() { e.deferGpart = false; }
+  } defer(e);
   if (e.preValid || !graphs_enabled(e, draws) || !(e.spec4 || gmma_supported(e))) {
     if ((rc = ensure_eigen_grad_buffers(e))) return rc;
     if ((rc = run_backward(e, grad_lnl, where))) return rc;

@@ -70,15 +70,21 @@ struct Engine {
   double* rootGrad = nullptr;   // [D][K+S] (d_props | d_freqs) per draw
   double* hpart = nullptr;      // [D][B*K][S][S] (M o Phi) per branch x category
   double* gscal = nullptr;      // [D][B*K] d lnL / d (r t)
-  // staged inputs
-  double* freqs = nullptr;      // [Dmax][S]
-  double* props = nullptr;      // [Dmax][K]
-  double* bl = nullptr;         // [Dmax][B]
-  double* rates = nullptr;      // [Dmax][K]
-  double* evec = nullptr;       // [Dmax][S][S]
+  double* hred = nullptr;       // [D][8][S][S] slice sums of hpart (h_reduce_kernel -> q_grad_kernel)
+  bool deferGpart = false;      // the caller's eigen contraction reduces the G chunks itself
+  bool gpartPending = false;    // ... and this sweep left them unreduced
+  // staged inputs: slices of one staging buffer, laid out per call (api.cu stage_inputs)
+  double* inPacked = nullptr;   // [bl | rates | props | freqs | q_norm]
+  double* hostIn = nullptr;     // pinned host mirror (one H2D copy for host inputs)
+  size_t inCap = 0;             // doubles
+  double* freqs = nullptr;      // [freqDraws][S]
+  double* props = nullptr;      // [propDraws][K]
+  double* bl = nullptr;         // [draws][B]
+  double* rates = nullptr;      // [rateDraws][K]
+  double* qnorm = nullptr;      // [qDraws][S][S] generator for the device eigen-decomposition
+  double* evec = nullptr;       // [Dmax][S][S] (supplied, or computed by sym_eigh_kernel)
   double* ivec = nullptr;
   double* eval = nullptr;       // [Dmax][S]
-  double* qnorm = nullptr;      // [Dmax][S][S] generator staged for the device eigen-decomposition
   double* gradLnl = nullptr;    // [Dmax]
   double* ones = nullptr;       // [Dmax] default grad_lnl
   // staged outputs (small): slices of one buffer, laid out per call (api.cu layout_outputs)
@@ -178,6 +184,9 @@ int gwarp_backward_levels(Engine& e, int draws);
 
 // small kernels (kernels_small.cu)
 int small_pmatrix(Engine& e, int draws);
+// copies up to 8 device arrays into e.inPacked at the given offsets (one launch)
+int small_gather_inputs(Engine& e, const double* const* src, const size_t* off, const size_t* n,
+                        int nseg);
 // batched Jacobi eigen-decomposition of the staged generators (eigen.cu)
 int small_sym_eigh(Engine& e, int qDraws, int eigDraws);
 int small_reduce_lnl(Engine& e, int draws, int nblocks);

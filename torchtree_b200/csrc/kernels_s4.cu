@@ -309,7 +309,7 @@ root4_kernel(const double* __restrict__ partials, const int16_t* __restrict__ ex
 // The same for small shards.  Block = 32 patterns x ROOT_SLICES node slices: the sum of
 // the I scale exponents of a pattern (I dependent-free loads per pattern, the long part)
 // is split over the slices so that a few thousand patterns still put enough loads in flight.
-constexpr int ROOT_SLICES = 8;
+constexpr int ROOT_SLICES = 32;
 
 __global__ void __launch_bounds__(32 * ROOT_SLICES)
 root4_small_kernel(const double* __restrict__ partials, const int16_t* __restrict__ expo,

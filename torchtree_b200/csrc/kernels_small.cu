@@ -115,10 +115,13 @@ __global__ void scale_rows_kernel(const double* __restrict__ in, const double* _
   out[idx] = in[idx] * g[idx / width];
 }
 
-// out[od][j] = sum_d g[d] in[d][j*stride + off]  (od == 1)  or  g[d] in[d][...] (od == D)
-__global__ void combine_draws_kernel(const double* __restrict__ in, const double* __restrict__ g,
-                                     double* __restrict__ out, int width, int inWidth, int off,
-                                     int draws, int outDraws) {
+// d_props (blockIdx.y == 0) and the root term of d_freqs (blockIdx.y == 1) from rootGrad [D][K+S]
+__global__ void root_outputs_kernel(const double* __restrict__ in, const double* __restrict__ g,
+                                    double* __restrict__ outProps, double* __restrict__ outFreqs,
+                                    int K, int S, int inWidth, int draws, int propOut, int freqOut) {
+  const bool second = blockIdx.y == 1;
+  const int width = second ? S : K, off = second ? K : 0, outDraws = second ? freqOut : propOut;
+  double* out = second ? outFreqs : outProps;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (outDraws > 1) {
     if (idx >= width * draws) return;
@@ -137,7 +140,14 @@ __global__ void combine_draws_kernel(const double* __restrict__ in, const double
 //   hpart = M o Phi(tau), Phi_ij = (e^{l_i tau} - e^{l_j tau}) / (l_i - l_j),
 //           Phi_ii = tau e^{l_i tau}   (divided differences, expm1 form: finite
 //           and accurate at repeated eigenvalues -- SURVEY F12, Appendix B)
-__global__ void eigen_contract_kernel(const double* __restrict__ dmat,
+// With `gpart` != nullptr the per-chunk partial sums of G are reduced here (fixed order:
+// groups of threads stride over the chunks, then a serial sum over the groups) and the result
+// is also stored to `dmat` -- one launch and one pass over G less than gpart_reduce_kernel +
+// this kernel (the small-kernel tail is 10 % of an 8-GPU shard's step).
+__global__ void eigen_contract_kernel(double* __restrict__ dmat,
+                                      const double* __restrict__ gpart,
+                                      const int* __restrict__ chunkBase,
+                                      const int* __restrict__ chunkCount, size_t chunkTotal,
                                       const double* __restrict__ bl,
                                       const double* __restrict__ rates, int rateDraws,
                                       const double* __restrict__ evec,
@@ -159,9 +169,33 @@ __global__ void eigen_contract_kernel(const double* __restrict__ dmat,
   const int de = eigDraws > 1 ? d : 0;
   const double tau = bl[(size_t)d * B + b] * rates[(size_t)(rateDraws > 1 ? d : 0) * K + k];
   const size_t item = ((size_t)d * B + b) * K + k;
-  const double* G = dmat + item * S * S;
+  double* G = dmat + item * S * S;
+  if (gpart != nullptr) {
+    const int SS = S * S;
+    const int n = chunkCount[b];
+    const double* p = gpart + ((size_t)d * chunkTotal + chunkBase[b] + (size_t)k * n) * SS;
+    double* part = sEx + S;   // scratch [groups][per] = blockDim.x doubles behind the tables
+    const int per = SS < (int)blockDim.x ? SS : (int)blockDim.x;
+    const int groups = SS < (int)blockDim.x ? (int)blockDim.x / SS : 1;
+    for (int e0 = 0; e0 < SS; e0 += per) {
+      const int e = e0 + (int)(threadIdx.x % per);
+      const int r = (int)(threadIdx.x / per);
+      double acc = 0.0;
+      if (r < groups && e < SS)
+        for (int c = r; c < n; c += groups) acc += p[(size_t)c * SS + e];
+      if (r < groups && e < SS) part[r * per + (e - e0)] = acc;
+      __syncthreads();
+      if (r == 0 && e < SS) {
+        double t = 0.0;
+        for (int g = 0; g < groups; ++g) t += part[g * per + (e - e0)];
+        sG[e] = t;
+        G[e] = t;
+      }
+      __syncthreads();
+    }
+  }
   for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
-    sG[idx] = G[idx];
+    if (gpart == nullptr) sG[idx] = G[idx];
     sV[idx] = evec[(size_t)de * S * S + idx];
     sVi[idx] = ivec[(size_t)de * S * S + idx];
   }
@@ -237,30 +271,36 @@ rate_grad_kernel(const double* __restrict__ gscal, const double* __restrict__ bl
   if (threadIdx.x == 0) out[(size_t)od * K + k] = t;
 }
 
-// H[od][e] = sum_d g[d] sum_item hpart[d][item][e]  (one block per (e, od))
+// Hs[od][slice][e] = sum_d g[d] sum_{item in slice} hpart[d][item][e]  (one block per
+// (e, od, slice); q_grad_kernel adds the H_SLICES slices in fixed order)
+constexpr int H_SLICES = 8;
+
 __global__ void __launch_bounds__(RED_THREADS)
 h_reduce_kernel(const double* __restrict__ hpart, const double* __restrict__ g,
-                double* __restrict__ H, int items, int SS, int draws, int outDraws) {
+                double* __restrict__ Hs, int items, int SS, int draws, int outDraws) {
   __shared__ double red[RED_THREADS / 32];
   const int e = blockIdx.x;
   const int od = blockIdx.y;
+  const int slice = blockIdx.z;
+  const int per = (items + H_SLICES - 1) / H_SLICES;
+  const int lo = slice * per, hi = min(items, lo + per);
   const int d0 = outDraws > 1 ? od : 0;
   const int d1 = outDraws > 1 ? od + 1 : draws;
   double acc = 0.0;
   for (int d = d0; d < d1; ++d) {
     double a = 0.0;
-    for (int it = threadIdx.x; it < items; it += blockDim.x)
+    for (int it = lo + threadIdx.x; it < hi; it += blockDim.x)
       a += hpart[((size_t)d * items + it) * SS + e];
     acc = fma(g[d], a, acc);
   }
   const double t = block_sum256(acc, red);
-  if (threadIdx.x == 0) H[(size_t)od * SS + e] = t;
+  if (threadIdx.x == 0) Hs[((size_t)od * H_SLICES + slice) * SS + e] = t;
 }
 
 // dQ = V^-T H V^T  (one block per eigen-system)
 // (H and dQ may alias: H is fully staged in shared memory before dQ is written)
-__global__ void q_grad_kernel(const double* H, const double* __restrict__ evec,
-                              const double* __restrict__ ivec, double* dQ, int S) {
+__global__ void q_grad_kernel(const double* __restrict__ Hs, const double* __restrict__ evec,
+                              const double* __restrict__ ivec, double* __restrict__ dQ, int S) {
   extern __shared__ double sm[];
   double* sH = sm;
   double* sT = sH + S * S;
@@ -268,7 +308,11 @@ __global__ void q_grad_kernel(const double* H, const double* __restrict__ evec,
   double* sVi = sV + S * S;
   const size_t off = (size_t)blockIdx.x * S * S;
   for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
-    sH[idx] = H[off + idx];
+    double h = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < H_SLICES; ++sl)
+      h += Hs[((size_t)blockIdx.x * H_SLICES + sl) * S * S + idx];
+    sH[idx] = h;
     sV[idx] = evec[off + idx];
     sVi[idx] = ivec[off + idx];
   }
@@ -288,6 +332,21 @@ __global__ void q_grad_kernel(const double* H, const double* __restrict__ evec,
     for (int j = 0; j < S; ++j) acc = fma(sT[a * S + j], sV[b * S + j], acc);
     dQ[off + idx] = acc;
   }
+}
+
+struct GatherArgs {
+  const double* src[8];
+  unsigned long long off[8], n[8];
+};
+
+// block y = segment: dst[off + i] = src[i]
+__global__ void gather_inputs_kernel(GatherArgs a, double* __restrict__ dst) {
+  const int seg = blockIdx.y;
+  const double* __restrict__ src = a.src[seg];
+  double* out = dst + a.off[seg];
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+       i < a.n[seg]; i += (unsigned long long)gridDim.x * blockDim.x)
+    out[i] = src[i];
 }
 
 int round_threads(int n, int cap) {
@@ -365,6 +424,23 @@ int small_pmatrix(Engine& e, int draws) {
   return TTB2_OK;
 }
 
+int small_gather_inputs(Engine& e, const double* const* src, const size_t* off, const size_t* n,
+                        int nseg) {
+  GatherArgs a{};
+  size_t longest = 1;
+  for (int j = 0; j < nseg; ++j) {
+    a.src[j] = src[j];
+    a.off[j] = off[j];
+    a.n[j] = n[j];
+    if (n[j] > longest) longest = n[j];
+  }
+  const unsigned bx = (unsigned)std::min<size_t>((longest + 255) / 256, 64);
+  gather_inputs_kernel<<<dim3(bx, nseg), 256, 0, e.stream>>>(a, e.inPacked);
+  ++e.launches;
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
 int small_reduce_lnl(Engine& e, int draws, int nblocks) {
   dim3 grid(1, draws);
   reduce_rows_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.redPart, e.lnl, nblocks, 1, 0);
@@ -385,6 +461,10 @@ int small_root_grad_reduce(Engine& e, int draws, int nblocks) {
 
 int small_gpart_reduce(Engine& e, int draws) {
   const Dims& m = e.dm;
+  if (e.deferGpart) {   // the eigen contraction that follows reduces the chunks itself
+    e.gpartPending = true;
+    return TTB2_OK;
+  }
   const size_t items = (size_t)draws * m.B * m.K;
   const int SS = m.S * m.S;
   gpart_reduce_kernel<<<(unsigned)items, GR_THREADS, GR_THREADS * sizeof(double), e.stream>>>(
@@ -406,22 +486,16 @@ int small_scale_dmat(Engine& e, int draws, double* out) {
   return TTB2_OK;
 }
 
-// rootGrad [D][K+S] -> outProps [propDraws][K], outFreqs [freqDraws][S]
+// rootGrad [D][K+S] -> outProps [propDraws][K], outFreqs [freqDraws][S] (one launch: block y = 0 / 1)
 int small_root_outputs(Engine& e, int draws) {
   const Dims& m = e.dm;
   const int w = m.K + m.S;
-  {
-    const int n = m.K * (e.propDraws > 1 ? draws : 1);
-    combine_draws_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
-        e.rootGrad, e.gradLnl, e.outProps, m.K, w, 0, draws, e.propDraws > 1 ? draws : 1);
-    ++e.launches;
-  }
-  {
-    const int n = m.S * (e.freqDraws > 1 ? draws : 1);
-    combine_draws_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
-        e.rootGrad, e.gradLnl, e.outFreqs, m.S, w, m.K, draws, e.freqDraws > 1 ? draws : 1);
-    ++e.launches;
-  }
+  const int nP = m.K * (e.propDraws > 1 ? draws : 1), nF = m.S * (e.freqDraws > 1 ? draws : 1);
+  dim3 grid(((nP > nF ? nP : nF) + 127) / 128, 2);
+  root_outputs_kernel<<<grid, 128, 0, e.stream>>>(e.rootGrad, e.gradLnl, e.outProps, e.outFreqs,
+                                                  m.K, m.S, w, draws, e.propDraws > 1 ? draws : 1,
+                                                  e.freqDraws > 1 ? draws : 1);
+  ++e.launches;
   TTB2_CUDA_CHECK(cudaGetLastError());
   return TTB2_OK;
 }
@@ -431,14 +505,16 @@ int small_eigen_contract(Engine& e, int draws) {
   const int SS = m.S * m.S;
   {
     dim3 grid(m.B * m.K, draws);
-    const int threads = round_threads(SS, 256);
-    const size_t smem = (4 * (size_t)SS + 2 * m.S) * sizeof(double);
+    const bool fused = e.gpartPending;
+    e.gpartPending = false;
+    const int threads = fused ? 256 : round_threads(SS, 256);
+    const size_t smem = (4 * (size_t)SS + 2 * m.S + (fused ? threads : 0)) * sizeof(double);
     if (smem > 48 * 1024)
       TTB2_CUDA_CHECK(cudaFuncSetAttribute(eigen_contract_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
     eigen_contract_kernel<<<grid, threads, smem, e.stream>>>(
-        e.dmat, e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.hpart,
+        e.dmat, fused ? e.gpart : nullptr, e.chunkBase, e.chunkCount, e.chunkTotal, e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.hpart,
         e.gscal, m.B, m.K, m.S);
     ++e.launches;
   }
@@ -457,10 +533,8 @@ int small_eigen_contract(Engine& e, int draws) {
   }
   {
     const int od = e.eigDraws > 1 ? draws : 1;
-    dim3 grid(SS, od);
-    // reuse outQ as H then transform in place via a second buffer: H lives in hpart's
-    // tail?  keep it simple: H is written to e.outQ, dQ overwrites it after staging in smem
-    h_reduce_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.hpart, e.gradLnl, e.outQ,
+    dim3 grid(SS, od, H_SLICES);
+    h_reduce_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.hpart, e.gradLnl, e.hred,
                                                        m.B * m.K, SS, draws, od);
     ++e.launches;
     const int threads = round_threads(SS, 256);
@@ -469,7 +543,7 @@ int small_eigen_contract(Engine& e, int draws) {
       TTB2_CUDA_CHECK(cudaFuncSetAttribute(q_grad_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
-    q_grad_kernel<<<od, threads, smem, e.stream>>>(e.outQ, e.evec, e.ivec, e.outQ, m.S);
+    q_grad_kernel<<<od, threads, smem, e.stream>>>(e.hred, e.evec, e.ivec, e.outQ, m.S);
     ++e.launches;
   }
   TTB2_CUDA_CHECK(cudaGetLastError());
