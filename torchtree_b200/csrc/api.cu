@@ -199,7 +199,9 @@ int ensure_grad_buffers(Engine& e, int draws) {
   // CTAs per SM aimed at per pre-order launch: many short CTAs shorten the last wave of the
   // big levels, but a CTA needs a few hundred patterns to amortise its prologue -- measured
   // optimum on the 1000-taxon problem: 8 at 12.5k patterns, 16 at 25k, 32 from 50k up
-  int perSm = e.dm.S <= 32 ? 32 : 16;
+  // (large alphabets run one CTA per SM and pay ~4 us per CTA for staging two S x S matrices:
+  // 8 per SM measured best on the 61-state config, 18.3 ms vs 18.6 at 16 and 19.2 at 32)
+  int perSm = e.dm.S <= 32 ? 32 : 8;
   if (gwarp_supported(e, true)) perSm = 16;   // warp-autonomous 20-state kernels: 9.8 ms vs 10.0 at 32
   if (e.spec4) perSm = e.dm.Npad < 20000 ? 8 : (e.dm.Npad < 40000 ? 16 : 32);
   if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, perSm))) return rc;

@@ -425,10 +425,16 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   else gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
   pdl_wait_then_trigger();
 
-  // persistent G accumulators: items (child, mt, mt2) dealt round-robin to the warps
-  double acc[GM_MAXACC][2];
+  // persistent G accumulators: (child, row tile) combos dealt round-robin to the warps, NCJ per
+  // warp (16 combos at most: 2 children x 8 row tiles), 8 column tiles each
+  constexpr int NCJ = (16 + NW - 1) / NW;
+  double acc[NCJ * 8][2];
 #pragma unroll
-  for (int j = 0; j < GM_MAXACC; ++j) acc[j][0] = acc[j][1] = 0.0;
+  for (int j = 0; j < NCJ * 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+  // Tip children whose codes are unit vectors or the all-ones gap (no ambiguity rows in the code
+  // table): the B operand of the G product, v_c[t][p] = [code_p == t or gap], is made in
+  // registers from the tile's 32 codes -- no tile of code vectors is staged or read for them.
+  const bool hotL = tabL && codeCount == S + 1, hotR = tabR && codeCount == S + 1;
 
   const int begin = blockIdx.x * chunkPatterns;
   int end = begin + chunkPatterns;
@@ -442,8 +448,8 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   const int16_t* erp = tipR ? nullptr : expoK + (((size_t)d * I + (op.right - T)) * K + k) * Npad;
   auto stage = [&](int b, int i0) {
     gm_stage_tile_async<NW>(tqB + b * tileN, false, nullptr, codeP, qsrc, i0, Npad, g);
-    gm_stage_tile_async<NW>(vlB + b * tileN, tipL, tl, codeP, lsrc, i0, Npad, g);
-    gm_stage_tile_async<NW>(vrB + b * tileN, tipR, tr, codeP, rsrc, i0, Npad, g);
+    if (!hotL) gm_stage_tile_async<NW>(vlB + b * tileN, tipL, tl, codeP, lsrc, i0, Npad, g);
+    if (!hotR) gm_stage_tile_async<NW>(vrB + b * tileN, tipR, tr, codeP, rsrc, i0, Npad, g);
     // weights, child exponents and tip codes: asynchronous copies too -- a plain load + shared
     // store would park warp 0 on the load while the other warps wait for it at the barrier
     if (warp == 0) {
@@ -523,28 +529,47 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     // (child, row tile) combos and all their column tiles: one A fragment (w o m)
     // feeds MT independent accumulator chains.
 #pragma unroll
-    for (int cj = 0; cj < 2; ++cj) {
+    for (int cj = 0; cj < NCJ; ++cj) {
       const int combo = warp + cj * NW;
       if (combo < 2 * MT) {
         const int side = combo / MT;
         const int mt = combo - side * MT;
         const double* mm = (side ? mr : ml) + (mt * 8 + (lane >> 2)) * GM_LDT + (lane & 3);
-        const double* vv = (side ? vr : vl) + (lane >> 2) * GM_LDT + (lane & 3);
         const double* wp = ws + (lane & 3);
+        if (side ? hotR : hotL) {
+          // (skipping the column tiles that hold none of a k-step's 4 codes was tried: fewer
+          // DMMAs, but the warp-uniform branches cost more than they save -- 12.8 vs 12.4 ms)
+          const uint8_t* cds = codesS + buf * 64 + side * 32 + (lane & 3);
+          const int colBase = lane >> 2;
 #pragma unroll
-        for (int kt = 0; kt < GM_TP / 4; ++kt) {
-          const double av = mm[kt * 4] * wp[kt * 4];
+          for (int kt = 0; kt < GM_TP / 4; ++kt) {
+            const double av = mm[kt * 4] * wp[kt * 4];
+            const int code = cds[kt * 4];
 #pragma unroll
-          for (int mt2 = 0; mt2 < 8; ++mt2)
-            if (mt2 < MT)
-              dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av,
-                      vv[mt2 * 8 * GM_LDT + kt * 4]);
+            for (int mt2 = 0; mt2 < 8; ++mt2)
+              if (mt2 < MT) {
+                const int col = mt2 * 8 + colBase;
+                const double bv = (col < S && (code == col || code == S)) ? 1.0 : 0.0;
+                dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av, bv);
+              }
+          }
+        } else {
+          const double* vv = (side ? vr : vl) + (lane >> 2) * GM_LDT + (lane & 3);
+#pragma unroll
+          for (int kt = 0; kt < GM_TP / 4; ++kt) {
+            const double av = mm[kt * 4] * wp[kt * 4];
+#pragma unroll
+            for (int mt2 = 0; mt2 < 8; ++mt2)
+              if (mt2 < MT)
+                dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av,
+                        vv[mt2 * 8 * GM_LDT + kt * 4]);
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int cj = 0; cj < 2; ++cj) {
+  for (int cj = 0; cj < NCJ; ++cj) {
     const int combo = warp + cj * NW;
     if (combo < 2 * MT) {
       const int side = combo / MT;
@@ -615,7 +640,11 @@ int gmma_forward2(Engine& e, int draws) {
   // (<1,4>: 26.6 ms, <1,8>: 22.5, <2,4>: 26.8, <2,8>: 21.6 per evaluation)
   if (m.S == 20) nw = 8;
   // 61 states: <2,8>, <4,16>, <2,16> all measured within 2 % of <4,8> on config 5
-  auto kern = m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
+  const char* v61 = getenv("TTB2_GM61F");
+  const bool wide61 = m.S == 61 && v61 && atoi(v61) == 16;
+  if (wide61) nw = 16;
+  auto kern = wide61 ? gm_fwd2_kernel<2, 16, 61>
+              : m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
               : m.S == 20 ? gm_fwd2_kernel<2, 8, 20>
               : ntg == 4  ? gm_fwd2_kernel<4, 8, 0>
               : nw == 8   ? gm_fwd2_kernel<2, 8, 0>
@@ -683,7 +712,15 @@ int gmma_backward2(Engine& e, int draws) {
   // (<1,4>: 26.6 ms, <1,8>: 22.5, <2,4>: 26.8, <2,8>: 21.6 per evaluation)
   if (m.S == 20) nw = 8;
   // 61 states: <2,8>, <4,16>, <2,16> all measured within 2 % of <4,8> on config 5
-  auto kern = m.S == 61 ? gm_bwd2_kernel<4, 8, 61>
+  // TTB2_GM61=16: the 16-warp instance (one (child, row tile) combo per warp), for A/B runs
+  // 61 states: 16 warps (one (child, row tile) combo of the G product per warp) keep the fp64
+  // tensor pipe busier than 8 (DMMA pipe 66 % vs 58 %, profiles/r02_codon_ncu.md); TTB2_GM61=8
+  // selects the 8-warp instance for A/B runs
+  const char* v61 = getenv("TTB2_GM61");
+  const bool wide61 = m.S == 61 && !(v61 && atoi(v61) == 8);
+  if (wide61) nw = 16;
+  auto kern = wide61 ? gm_bwd2_kernel<2, 16, 61>
+              : m.S == 61 ? gm_bwd2_kernel<4, 8, 61>
               : m.S == 20 ? gm_bwd2_kernel<2, 8, 20>
               : ntg == 4  ? gm_bwd2_kernel<4, 8, 0>
               : nw == 8   ? gm_bwd2_kernel<2, 8, 0>

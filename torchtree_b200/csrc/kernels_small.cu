@@ -72,8 +72,11 @@ reduce_rows_kernel(const double* __restrict__ part, double* __restrict__ out, in
 }
 
 // dmat[d][b][k][e] = sum_chunk gpart[d][chunkBase[b] + k * chunkCount[b] + chunk][e]
-// One block per (d, b, k): GR_ROWS row groups stride over the chunks (the few branches
-// near the root have hundreds of chunks), then a fixed-order sum over the groups.
+// Grid (items = d x b x k, element blocks of GR_THREADS): the few branches near the root have
+// hundreds of chunks, so the elements of one item are spread over blocks (a 61-state item has
+// 3721) and every thread keeps four loads in flight.  SS <= GR_THREADS: GR_THREADS / SS row
+// groups stride over the chunks, then a fixed-order sum over the groups.  The order of the
+// additions is fixed by (SS, chunk count) alone: results are reproducible bit for bit.
 constexpr int GR_THREADS = 256;
 
 __global__ void __launch_bounds__(GR_THREADS)
@@ -87,23 +90,33 @@ gpart_reduce_kernel(const double* __restrict__ gpart, const int* __restrict__ ch
   const size_t d = item / ((size_t)K * B);
   const int n = chunkCount[b];
   const double* p = gpart + (d * chunkTotal + chunkBase[b] + (size_t)k * n) * SS;
-  // thread -> (element e, row group r); SS <= GR_THREADS uses GR_THREADS / SS groups
-  const int per = SS < GR_THREADS ? SS : GR_THREADS;
-  const int groups = SS < GR_THREADS ? GR_THREADS / SS : 1;
-  for (int e0 = 0; e0 < SS; e0 += per) {
-    const int e = e0 + (int)(threadIdx.x % per);
-    const int r = (int)(threadIdx.x / per);
-    double acc = 0.0;
-    if (r < groups && e < SS)
-      for (int c = r; c < n; c += groups) acc += p[(size_t)c * SS + e];
-    if (r < groups && e < SS) part[r * per + (e - e0)] = acc;
-    __syncthreads();
-    if (r == 0 && e < SS) {
-      double t = 0.0;
-      for (int g = 0; g < groups; ++g) t += part[g * per + (e - e0)];
-      dmat[item * SS + e] = t;
+  if (SS >= GR_THREADS) {
+    const int e = blockIdx.y * GR_THREADS + threadIdx.x;
+    if (e >= SS) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = 0;
+    for (; c + 4 <= n; c += 4) {
+      a0 += p[(size_t)c * SS + e];
+      a1 += p[(size_t)(c + 1) * SS + e];
+      a2 += p[(size_t)(c + 2) * SS + e];
+      a3 += p[(size_t)(c + 3) * SS + e];
     }
-    __syncthreads();
+    for (; c < n; ++c) a0 += p[(size_t)c * SS + e];
+    dmat[item * SS + e] = (a0 + a1) + (a2 + a3);
+    return;
+  }
+  const int groups = GR_THREADS / SS;
+  const int e = (int)(threadIdx.x % SS);
+  const int r = (int)(threadIdx.x / SS);
+  double acc = 0.0;
+  if (r < groups)
+    for (int c = r; c < n; c += groups) acc += p[(size_t)c * SS + e];
+  if (r < groups) part[r * SS + e] = acc;
+  __syncthreads();
+  if (r == 0) {
+    double t = 0.0;
+    for (int g = 0; g < groups; ++g) t += part[g * SS + e];
+    dmat[item * SS + e] = t;
   }
 }
 
@@ -461,13 +474,14 @@ int small_root_grad_reduce(Engine& e, int draws, int nblocks) {
 
 int small_gpart_reduce(Engine& e, int draws) {
   const Dims& m = e.dm;
-  if (e.deferGpart) {   // the eigen contraction that follows reduces the chunks itself
+  if (e.deferGpart && m.S * m.S < GR_THREADS) {   // small alphabets: the eigen contraction that follows reduces the chunks itself
     e.gpartPending = true;
     return TTB2_OK;
   }
   const size_t items = (size_t)draws * m.B * m.K;
   const int SS = m.S * m.S;
-  gpart_reduce_kernel<<<(unsigned)items, GR_THREADS, GR_THREADS * sizeof(double), e.stream>>>(
+  const dim3 grid((unsigned)items, SS >= GR_THREADS ? (SS + GR_THREADS - 1) / GR_THREADS : 1);
+  gpart_reduce_kernel<<<grid, GR_THREADS, GR_THREADS * sizeof(double), e.stream>>>(
       e.gpart, e.chunkBase, e.chunkCount, e.dmat, e.chunkTotal, m.B, m.K, SS);
   ++e.launches;
   TTB2_CUDA_CHECK(cudaGetLastError());
