@@ -181,13 +181,30 @@ int ttb2_loglik_q(ttb2_engine* engine, int32_t draws, const double* branch_lengt
                   int32_t prop_draws, const double* q_norm, int32_t q_draws,
                   const double* freqs, int32_t freq_draws, double* lnl, int32_t where);
 
+/*
+ * The same evaluation for a GENERAL generator (not necessarily reversible: complex spectrum, no
+ * real eigen route): P = exp(Q r t) by scaling and squaring on the device, one CTA per branch x
+ * category x draw (csrc/expm.cu) -- replaces NonSymmetricSubstitutionModel.p_t =
+ * torch.matrix_exp(Q t), substitution_model/abstract.py:89-94, the route of
+ * GeneralNonSymmetricSubstitutionModel and the discrete-trait likelihoods of
+ * cli/evolution.py:540-611.
+ *   q [q_draws][S][S]  generator as the model normalises it (abstract.py:90-91)
+ * ttb2_grad_eigen / ttb2_grad_eigen_packed follow it exactly as they follow ttb2_loglik_q; d_q
+ * ([q_draws][S][S], all S*S entries independent) comes from the exact adjoint of the matrix
+ * exponential (Frechet derivative in dual arithmetic, no stored intermediates).
+ */
+int ttb2_loglik_expm(ttb2_engine* engine, int32_t draws, const double* branch_lengths,
+                     const double* site_rates, int32_t rate_draws, const double* props,
+                     int32_t prop_draws, const double* q, int32_t q_draws, const double* freqs,
+                     int32_t freq_draws, double* lnl, int32_t where);
+
 /* The eigen-system used by the latest eigen-mode call: evec / ivec [eig_draws][S][S],
  * eval [eig_draws][S] (ascending); any pointer may be NULL. */
 int ttb2_get_eigen(ttb2_engine* engine, double* evec, double* ivec, double* eval,
                    int32_t where);
 
 /*
- * Gradient for the latest ttb2_loglik_eigen / ttb2_loglik_q call.
+ * Gradient for the latest ttb2_loglik_eigen / ttb2_loglik_q / ttb2_loglik_expm call.
  *   d_branch_lengths [D][B]; d_site_rates [rate_draws][K];
  *   d_props [prop_draws][K]; d_freqs [freq_draws][S] (root term only);
  *   d_q [eig_draws][S][S] = d lnL / d Q for the generator Q = V L V^-1 with all

@@ -101,6 +101,7 @@ def patched(request, torchtree_env, monkeypatch):
     monkeypatch.setattr(tlmod, "BACKEND", request.param, raising=False)
     if request.param == "oracle":
         monkeypatch.setattr(flatten, "log_likelihood_eigen", fake_eigen)
+        monkeypatch.setattr(flatten, "log_likelihood_expm", fake_eigen)
         monkeypatch.setattr(flatten, "log_likelihood_mats", fake_mats)
         monkeypatch.setattr(tlmod, "Engine", FakeEngine)
     else:
@@ -765,3 +766,46 @@ def test_cli_time_tree_advi_with_device_heights_and_coalescent(patched, tmp_path
 
             importlib.reload(cmod)
     np.testing.assert_allclose(np.array(traces["b200"]), np.array(traces["reference"]), rtol=1e-7)
+
+
+def test_discrete_trait_likelihood_general_nonsymmetric(patched):
+    """The phylogeography likelihood the CLI builds for a discrete trait (cli/evolution.py:540-611):
+    `AttributePattern` (one pattern, weight 1.0) + `GeneralNonSymmetricSubstitutionModel` over a
+    `GeneralDataType` + `ConstantSiteModel` on the fluA tree.  The reference computes P with
+    torch.matrix_exp (abstract.py:89-94); the drop-in runs the matrix exponential and its adjoint on
+    the device (csrc/expm.cu, `expm` route of flatten.substitution_route)."""
+    from torchtree_b200.flatten import substitution_route
+
+    objs, like = _flu_json()
+    places = ["HK", "NY", "TX", "SF", "UK"]
+    rng = np.random.default_rng(23)
+    for taxon in objs[0]["taxa"]:
+        taxon["attributes"]["location"] = places[int(rng.integers(0, 5))]
+    objs[0]["taxa"][3]["attributes"]["location"] = "?"        # unknown location: all-ones partial
+    n = len(places)
+    trait = {
+        "id": "like", "type": "TreeLikelihoodModel",
+        "tree_model": like["tree_model"],
+        "site_model": {"id": "sm", "type": "ConstantSiteModel"},
+        "substitution_model": {
+            "id": "subst", "type": "GeneralNonSymmetricSubstitutionModel",
+            "data_type": {"id": "loc", "type": "GeneralDataType", "codes": places},
+            "mapping": list(range(n * (n - 1))),
+            "rates": _P("rates", rng.gamma(2.0, 0.5, n * (n - 1)).tolist()),
+            "frequencies": _P("freqs", rng.dirichlet(np.full(n, 8.0)).tolist())},
+        "site_pattern": {"id": "sp", "type": "torchtree.evolution.attribute_pattern.AttributePattern",
+                         "taxa": "taxa",
+                         "data_type": "loc", "attribute": "location"},
+    }
+    ref = _build(objs[:1], trait, "torchtree.evolution.tree_likelihood.TreeLikelihoodModel")
+    new = _build(objs[:1], trait, "torchtree_b200.TreeLikelihoodModel")
+    assert substitution_route(new["like"].subst_model) == "expm"
+    assert new["like"]._state_count == n and int(new["like"].weights.numel()) == 1
+    names = ["blens", "rates", "freqs"]
+    v_ref, g_ref = _grads(ref, names)
+    v_new, g_new = _grads(new, names)
+    assert v_new.shape == v_ref.shape
+    assert torch.allclose(v_new, v_ref, rtol=1e-10, atol=0), (v_new, v_ref)
+    for name in names:   # matrix_exp on both sides: no eigen-gap slack, 1e-8 throughout
+        assert torch.allclose(g_new[name], g_ref[name], rtol=1e-8,
+                              atol=1e-8 * g_ref[name].abs().max()), name

@@ -11,6 +11,7 @@ __plugin__ = "cli.B200Plugin"
 from .engine import Engine, codes_from_tip_partials, default_code_partials  # noqa: F401
 from .function import (  # noqa: F401
     log_likelihood_eigen,
+    log_likelihood_expm,
     log_likelihood_mats,
     reversible_eigensystem,
 )

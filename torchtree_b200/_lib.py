@@ -55,6 +55,7 @@ EXPORTED_SYMBOLS = (
     "ttb2_grad_eigen_packed",
     "ttb2_packed_count",
     "ttb2_loglik_q",
+    "ttb2_loglik_expm",
     "ttb2_get_eigen",
     "ttb2_site_loglik",
     "ttb2_get_mats",
@@ -113,6 +114,9 @@ def load():
     lib.ttb2_loglik_q.argtypes = [
         vp, c_int32, vp, vp, c_int32, vp, c_int32, vp, c_int32, vp, c_int32, vp, c_int32]
     lib.ttb2_loglik_q.restype = c_int32
+    lib.ttb2_loglik_expm.argtypes = [
+        vp, c_int32, vp, vp, c_int32, vp, c_int32, vp, c_int32, vp, c_int32, vp, c_int32]
+    lib.ttb2_loglik_expm.restype = c_int32
     lib.ttb2_get_eigen.argtypes = [vp, vp, vp, vp, c_int32]
     lib.ttb2_get_eigen.restype = c_int32
     lib.ttb2_grad_eigen.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int32]

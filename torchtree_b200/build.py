@@ -22,7 +22,8 @@ LIBDIR = os.path.join(PKG, "lib")
 BUILD = os.path.join(PKG, "_obj")
 LIB = os.path.join(LIBDIR, "libttb200.so")
 SOURCES = ["api.cu", "kernels_s4.cu", "kernels_small.cu", "kernels_gen.cu",
-           "kernels_gmma.cu", "patterns.cu", "heights.cu", "eigen.cu", "kernels_gwarp.cu", "coalescent.cu"]
+           "kernels_gmma.cu", "patterns.cu", "heights.cu", "eigen.cu", "kernels_gwarp.cu", "coalescent.cu",
+           "expm.cu"]
 HEADERS = [os.path.join(CSRC, "engine.cuh"), os.path.join(PKG, "..", "include", "ttb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -766,6 +766,47 @@ int ttb2_loglik_q(ttb2_engine* engine, int32_t draws, const double* branch_lengt
   return run_eigen_mode(e, draws, q_draws, lnl, where);
 }
 
+int ttb2_loglik_expm(ttb2_engine* engine, int32_t draws, const double* branch_lengths,
+                     const double* site_rates, int32_t rate_draws, const double* props,
+                     int32_t prop_draws, const double* q, int32_t q_draws, const double* freqs,
+                     int32_t freq_draws, double* lnl, int32_t where) {
+  if (!engine || !branch_lengths || !site_rates || !props || !q || !freqs) {
+    set_error("ttb2_loglik_expm: null argument");
+    return TTB2_E_INVALID;
+  }
+  Engine& e = *reinterpret_cast<Engine*>(engine);
+  const Dims& m = e.dm;
+  if (draws < 1 || draws > e.cfg.max_draws || bad_draws(freq_draws, draws) ||
+      bad_draws(prop_draws, draws) || bad_draws(rate_draws, draws) || bad_draws(q_draws, draws)) {
+    set_error("ttb2_loglik_expm: draws out of range (or a *_draws that is neither 1 nor draws)");
+    return TTB2_E_INVALID;
+  }
+  TTB2_CUDA_CHECK(cudaSetDevice(e.device));
+  int rc;
+  mark(e, 0);
+  const size_t SS = (size_t)m.S * m.S;
+  {
+    const InSeg segs[] = {{branch_lengths, &e.bl, (size_t)draws * m.B},
+                          {site_rates, &e.rates, (size_t)rate_draws * m.K},
+                          {props, &e.props, (size_t)prop_draws * m.K},
+                          {freqs, &e.freqs, (size_t)freq_draws * m.S},
+                          {q, &e.qnorm, (size_t)q_draws * SS}};
+    if ((rc = stage_inputs(e, segs, 5, where))) return rc;
+  }
+  e.freqDraws = freq_draws;
+  e.propDraws = prop_draws;
+  e.rateDraws = rate_draws;
+  e.eigDraws = q_draws;   // leading extent of d_q
+  e.qDraws = q_draws;
+  e.mode = MODE_EXPM;
+  ++e.evalSerial;
+  e.draws = draws;
+  layout_outputs(e, draws);
+  NvtxRange range("ttb2:loglik_expm");
+  if ((rc = small_expm_forward(e, draws))) return rc;
+  return run_forward(e, draws, lnl, where);
+}
+
 int ttb2_get_eigen(ttb2_engine* engine, double* evec, double* ivec, double* eval, int32_t where) {
   if (!engine) {
     set_error("ttb2_get_eigen: null engine");
@@ -773,7 +814,7 @@ int ttb2_get_eigen(ttb2_engine* engine, double* evec, double* ivec, double* eval
   }
   Engine& e = *reinterpret_cast<Engine*>(engine);
   if (e.mode != MODE_EIGEN) {
-    set_error("ttb2_get_eigen: no eigen-mode evaluation yet");
+    set_error("ttb2_get_eigen: the latest evaluation was not an eigen-mode one");
     return TTB2_E_STATE;
   }
   const Dims& m = e.dm;
@@ -829,6 +870,12 @@ static int grad_eigen_compute(Engine& e, const double* grad_lnl, int where) {
   int rc;
   const int draws = e.draws;
   NvtxRange range("ttb2:grad_eigen");
+  if (e.mode == MODE_EXPM) {
+    // general generator: pre-order sweep -> d lnL / d P, then the Frechet adjoint of exp
+    if ((rc = ensure_eigen_grad_buffers(e))) return rc;
+    if ((rc = run_backward(e, grad_lnl, where))) return rc;
+    return small_expm_contract(e, draws);
+  }
   // the contraction kernel reduces the per-chunk sums of G itself (one launch less)
   struct Defer {
     Engine& e;
@@ -863,8 +910,8 @@ int ttb2_grad_eigen(ttb2_engine* engine, const double* grad_lnl, double* d_branc
   }
   Engine& e = *reinterpret_cast<Engine*>(engine);
   const Dims& m = e.dm;
-  if (e.mode != MODE_EIGEN) {
-    set_error("ttb2_grad_eigen: the latest evaluation was not ttb2_loglik_eigen");
+  if (e.mode != MODE_EIGEN && e.mode != MODE_EXPM) {
+    set_error("ttb2_grad_eigen: the latest evaluation was not ttb2_loglik_eigen / _q / _expm");
     return TTB2_E_STATE;
   }
   TTB2_CUDA_CHECK(cudaSetDevice(e.device));
@@ -896,8 +943,8 @@ int ttb2_grad_eigen_packed(ttb2_engine* engine, const double* grad_lnl, double* 
     return TTB2_E_INVALID;
   }
   Engine& e = *reinterpret_cast<Engine*>(engine);
-  if (e.mode != MODE_EIGEN) {
-    set_error("ttb2_grad_eigen_packed: the latest evaluation was not ttb2_loglik_eigen / ttb2_loglik_q");
+  if (e.mode != MODE_EIGEN && e.mode != MODE_EXPM) {
+    set_error("ttb2_grad_eigen_packed: the latest evaluation was not ttb2_loglik_eigen / _q / _expm");
     return TTB2_E_STATE;
   }
   if (capacity < e.packedCount) {

@@ -28,7 +28,7 @@ struct Dims {
   int C;     // tip symbol codes
 };
 
-enum Mode { MODE_NONE = 0, MODE_MATS = 1, MODE_EIGEN = 2 };
+enum Mode { MODE_NONE = 0, MODE_MATS = 1, MODE_EIGEN = 2, MODE_EXPM = 3 };
 
 struct Engine {
   ttb2_config cfg{};
@@ -195,6 +195,10 @@ int small_gpart_reduce(Engine& e, int draws);
 int small_scale_dmat(Engine& e, int draws, double* out);
 int small_eigen_contract(Engine& e, int draws);
 int small_root_outputs(Engine& e, int draws);
+// matrix-exponential route for general generators (expm.cu)
+int small_expm_forward(Engine& e, int draws);
+int small_expm_backward(Engine& e, int draws);
+int small_expm_contract(Engine& e, int draws);
 
 // Plans how many pattern chunks every level's pre-order launch uses (enough CTAs
 // to fill the GPU on small levels, long-lived CTAs on large ones) and uploads the

@@ -362,6 +362,17 @@ __global__ void gather_inputs_kernel(GatherArgs a, double* __restrict__ dst) {
     out[i] = src[i];
 }
 
+// out[od][e] = sum_slice Hs[od][slice][e]  (the expm route needs no change of basis)
+__global__ void sum_slices_kernel(const double* __restrict__ Hs, double* __restrict__ out, int SS) {
+  const int od = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= SS) return;
+  double h = 0.0;
+#pragma unroll
+  for (int sl = 0; sl < H_SLICES; ++sl) h += Hs[((size_t)od * H_SLICES + sl) * SS + e];
+  out[(size_t)od * SS + e] = h;
+}
+
 int round_threads(int n, int cap) {
   int t = (n + 31) / 32 * 32;
   if (t < 32) t = 32;
@@ -558,6 +569,40 @@ int small_eigen_contract(Engine& e, int draws) {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
     q_grad_kernel<<<od, threads, smem, e.stream>>>(e.hred, e.evec, e.ivec, e.outQ, m.S);
+    ++e.launches;
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return small_root_outputs(e, draws);
+}
+
+// Gradient outputs of the matrix-exponential route (expm.cu): the Frechet adjoint per branch x
+// category, then the same reductions as the eigen route -- d_bl, d_rates, d lnL / d Q (no change
+// of basis), d_props, d_freqs.
+int small_expm_contract(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const int SS = m.S * m.S;
+  int rc = small_expm_backward(e, draws);
+  if (rc) return rc;
+  {
+    const int n = m.B * draws;
+    branch_grad_kernel<<<(n + 127) / 128, 128, 0, e.stream>>>(
+        e.gscal, e.rates, e.rateDraws, e.gradLnl, e.outBl, m.B, m.K, draws);
+    ++e.launches;
+  }
+  {
+    const int od = e.rateDraws > 1 ? draws : 1;
+    dim3 grid(m.K, od);
+    rate_grad_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
+                                                        m.B, m.K, draws, od);
+    ++e.launches;
+  }
+  {
+    const int od = e.eigDraws > 1 ? draws : 1;
+    dim3 grid(SS, od, H_SLICES);
+    h_reduce_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.hpart, e.gradLnl, e.hred,
+                                                       m.B * m.K, SS, draws, od);
+    ++e.launches;
+    sum_slices_kernel<<<dim3((SS + 127) / 128, od), 128, 0, e.stream>>>(e.hred, e.outQ, SS);
     ++e.launches;
   }
   TTB2_CUDA_CHECK(cudaGetLastError());

@@ -149,11 +149,21 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     return S <= 64 && (S <= 8 || eig_draws >= 6);
   }
 
+  // `general`: the generator is not reversible -- P = exp(Q r t) by scaling and squaring on
+  // the device (ttb2_loglik_expm, csrc/expm.cu) instead of the eigen route
   static void run_forward(EngineRef& ref, const ttb2_config& cfg, const Tensor& bls,
                           const Tensor& rates, const Tensor& props, const Tensor& q,
-                          const Tensor& freqs, Tensor& lnl) {
+                          const Tensor& freqs, Tensor& lnl, bool general) {
     ttb2_engine* eng = ref.get();
     const int where = where_of({bls, rates, props, q, freqs}, cfg.device, eng);
+    if (general) {
+      check(ttb2_loglik_expm(eng, (int32_t)bls.size(0), dptr(bls), dptr(rates),
+                             (int32_t)rates.size(0), dptr(props), (int32_t)props.size(0), dptr(q),
+                             (int32_t)q.size(0), dptr(freqs), (int32_t)freqs.size(0), dptr(lnl),
+                             where),
+            "ttb2_loglik_expm");
+      return;
+    }
     if (device_eigh(cfg.state_count, std::max(q.size(0), freqs.size(0)))) {
       check(ttb2_loglik_q(eng, (int32_t)bls.size(0), dptr(bls), dptr(rates),
                           (int32_t)rates.size(0), dptr(props), (int32_t)props.size(0), dptr(q),
@@ -189,7 +199,7 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
   static Tensor forward(AutogradContext* ctx, const Tensor& engine_keepalive,
                         const Tensor& branch_lengths, const Tensor& site_rates,
                         const Tensor& site_props, const Tensor& q_norm,
-                        const Tensor& frequencies) {
+                        const Tensor& frequencies, bool general) {
     const EnginePtr ref = engine_of(engine_keepalive);
     const ttb2_config cfg = config_of(ref->get());
     const int64_t S = cfg.state_count, K = cfg.category_count, B = 2 * (int64_t)cfg.tip_count - 2;
@@ -201,9 +211,10 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     Tensor lnl = at::empty({bls.size(0)}, bls.options());
     {
       pybind11::gil_scoped_release nogil;
-      run_forward(*ref, cfg, bls, rates, props, q, freqs, lnl);
+      run_forward(*ref, cfg, bls, rates, props, q, freqs, lnl, general);
     }
     ctx->saved_data["engine"] = engine_keepalive;
+    ctx->saved_data["general"] = general;
     ctx->saved_data["serial"] = ttb2_eval_serial(ref->get());
     ctx->saved_data["dtypes"] = std::vector<int64_t>{
         (int64_t)branch_lengths.scalar_type(), (int64_t)site_rates.scalar_type(),
@@ -220,11 +231,12 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     auto saved = ctx->get_saved_variables();
     const Tensor &bls = saved[0], &rates = saved[1], &props = saved[2], &q = saved[3],
                  &freqs = saved[4];
+    const bool general = ctx->saved_data["general"].toBool();
     if (ttb2_eval_serial(eng) != ctx->saved_data["serial"].toInt()) {
       // another forward ran on this engine since ours and overwrote its buffers:
       // recompute (SURVEY 8(b) autograd contract)
       Tensor lnl = at::empty({bls.size(0)}, bls.options());
-      run_forward(*ref, cfg, bls, rates, props, q, freqs, lnl);
+      run_forward(*ref, cfg, bls, rates, props, q, freqs, lnl, general);
       ctx->saved_data["serial"] = ttb2_eval_serial(eng);
     }
     const int64_t S = cfg.state_count, K = cfg.category_count, D = bls.size(0), B = bls.size(1);
@@ -234,7 +246,7 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
     TORCH_CHECK(!g.defined() || g.numel() == D, "ttb200: grad_lnl must have one entry per draw");
     // one eigen-system per generator draw or frequency draw, whichever varies; d_q has that
     // leading extent and is summed back onto a shared generator below
-    const int64_t eig_draws = std::max(q.size(0), freqs.size(0));
+    const int64_t eig_draws = general ? q.size(0) : std::max(q.size(0), freqs.size(0));
     // the engine writes all small outputs as one vector
     // [lnL | d_bl | d_rates | d_props | d_q | d_freqs]: one copy, then views
     const int64_t count = ttb2_packed_count(eng);
@@ -263,7 +275,7 @@ struct EigenLikelihood : public torch::autograd::Function<EigenLikelihood> {
             like_input(d_rates, (at::ScalarType)dt[1]),
             like_input(d_props, (at::ScalarType)dt[2]),
             ctx->needs_input_grad(4) ? like_input(d_q, (at::ScalarType)dt[3]) : Tensor(),
-            like_input(d_freqs, (at::ScalarType)dt[4])};
+            like_input(d_freqs, (at::ScalarType)dt[4]), Tensor()};
   }
 };
 
@@ -417,7 +429,15 @@ Tensor log_likelihood_eigen(const EnginePtr& engine, const Tensor& branch_length
                             const Tensor& q_norm, const Tensor& freqs) {
   TORCH_CHECK(engine, "ttb200: null engine");
   return EigenLikelihood::apply(keepalive(engine), branch_lengths, site_rates, site_props, q_norm,
-                                freqs);
+                                freqs, false);
+}
+
+Tensor log_likelihood_expm(const EnginePtr& engine, const Tensor& branch_lengths,
+                           const Tensor& site_rates, const Tensor& site_props, const Tensor& q,
+                           const Tensor& freqs) {
+  TORCH_CHECK(engine, "ttb200: null engine");
+  return EigenLikelihood::apply(keepalive(engine), branch_lengths, site_rates, site_props, q,
+                                freqs, true);
 }
 
 Tensor log_likelihood_mats(const EnginePtr& engine, const Tensor& mats, const Tensor& freqs,
@@ -447,6 +467,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         "lnL [D] of a reversible model; backward = analytic pre-order gradient",
         py::arg("engine"), py::arg("branch_lengths"), py::arg("site_rates"),
         py::arg("site_props"), py::arg("q_norm"), py::arg("freqs"));
+  m.def("log_likelihood_expm", &log_likelihood_expm,
+        "lnL [D] of a general (non-reversible) generator: P = exp(Q r t) on the device; backward = "
+        "pre-order gradient + Frechet adjoint of the matrix exponential",
+        py::arg("engine"), py::arg("branch_lengths"), py::arg("site_rates"), py::arg("site_props"),
+        py::arg("q"), py::arg("freqs"));
   m.def("log_likelihood_mats", &log_likelihood_mats,
         "lnL [D] from caller-supplied transition matrices [D,B,K,S,S]", py::arg("engine"),
         py::arg("mats"), py::arg("freqs"), py::arg("site_props"));

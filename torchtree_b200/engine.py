@@ -281,6 +281,27 @@ class Engine:
                             rd=rates.shape[0], ed=max(q.shape[0], freqs.shape[0]))
         return lnl
 
+    def loglik_expm(self, branch_lengths, site_rates, props, q, freqs, out=None) -> torch.Tensor:
+        """lnL [D] for a general (non-reversible) generator: P = exp(Q r t) on the device
+        (ttb2_loglik_expm, csrc/expm.cu).  `grad_eigen` follows as usual."""
+        S, K, B = self.S, self.K, self.B
+        bl = self._prep(branch_lengths, (B,), "branch_lengths")
+        rates = self._prep(site_rates, (K,), "site_rates")
+        props = self._prep(props, (K,), "props")
+        q = self._prep(q, (S, S), "q")
+        freqs = self._prep(freqs, (S,), "freqs")
+        D = bl.shape[0]
+        where, dev = self._where([bl, rates, props, q, freqs])
+        lnl = out if out is not None else torch.empty(D, dtype=torch.float64, device=dev)
+        _lib.check(self._lib.ttb2_loglik_expm(
+            self._h, D, _ptr(bl), _ptr(rates), rates.shape[0], _ptr(props), props.shape[0],
+            _ptr(q), q.shape[0], _ptr(freqs), freqs.shape[0], _ptr(lnl), where),
+            "ttb2_loglik_expm")
+        self._draws = D
+        self._shapes = dict(where=where, dev=dev, D=D, fd=freqs.shape[0], pd=props.shape[0],
+                            rd=rates.shape[0], ed=q.shape[0])
+        return lnl
+
     def get_eigen(self):
         """(evec, ivec, evals) of the latest eigen-mode call, as the engine holds them."""
         sh = self._shapes

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import torch
 
-from .function import log_likelihood_eigen, log_likelihood_mats
+from .function import log_likelihood_eigen, log_likelihood_expm, log_likelihood_mats
 
 
 def _mro_names(obj):
@@ -32,14 +32,16 @@ def substitution_route(subst_model) -> str:
              abstract.py:57-76: HKY, GTR, MG94, GeneralSymmetric...), the
              closed-form JC69 family (nucleotide.py:102-113, general.py:51-69)
              and the empirical amino-acid models (general.py:295-331);
-    "mats":  anything else (e.g. NonSymmetricSubstitutionModel -> matrix_exp,
-             abstract.py:89-94, or a user-defined model): the model's own
-             p_t() supplies the matrices and autograd carries the gradient
-             from d lnL / d P back into its parameters.
+    "expm":  NonSymmetricSubstitutionModel (p_t = matrix_exp(Q t), abstract.py:89-94;
+             GeneralNonSymmetricSubstitutionModel, the discrete-trait models): the
+             matrix exponential and its adjoint run on the device (csrc/expm.cu);
+    "mats":  anything else (a user-defined model): the model's own p_t()
+             supplies the matrices and autograd carries the gradient from
+             d lnL / d P back into its parameters.
     """
     names = _mro_names(subst_model)
     if "NonSymmetricSubstitutionModel" in names:
-        return "mats"
+        return "expm"
     if names & {"SymmetricSubstitutionModel", "JC69", "GeneralJC69",
                 "EmpiricalSubstitutionModel"}:
         return "eigen"
@@ -113,12 +115,13 @@ def evaluate_models(engine, tree_model, site_model, subst_model, clock_model, sa
     rates = _flat(rates, sample_shape, (K,))
     props = _flat(site_model.probabilities(), sample_shape, (K,))
     route = substitution_route(subst_model)
-    if route == "eigen":
+    if route in ("eigen", "expm"):
         q, freqs = normalised_generator(subst_model)
         S = freqs.shape[-1]
         tensors = (bls, rates, props, _flat(q, sample_shape, (S, S)),
                    _flat(freqs, sample_shape, (S,)))
-        local = lambda *a: log_likelihood_eigen(engine, *a)  # noqa: E731
+        op = log_likelihood_eigen if route == "eigen" else log_likelihood_expm
+        local = lambda *a: op(engine, *a)  # noqa: E731
     else:
         freqs = subst_model.frequencies
         S = freqs.shape[-1]

@@ -81,6 +81,19 @@ def log_likelihood_eigen(engine: Engine, branch_lengths, site_rates, site_props,
         q_norm, freqs)
 
 
+def log_likelihood_expm(engine: Engine, branch_lengths, site_rates, site_props, q, freqs):
+    """lnL [D] of a GENERAL generator (not necessarily reversible), differentiable w.r.t. every
+    tensor argument: P = exp(Q r t) for every branch x category x draw by scaling and squaring on
+    the device, gradient through the exact Frechet adjoint (csrc/expm.cu) -- the device version of
+    NonSymmetricSubstitutionModel.p_t = torch.matrix_exp(Q t) (abstract.py:89-94) and its tape.
+
+    Shapes as `log_likelihood_eigen`; `q` [1 or D,S,S] is the generator as the model normalises it;
+    d/d freqs is the root term only."""
+    return _ext().log_likelihood_expm(
+        _handle(engine), _lead(branch_lengths, 1), _lead(site_rates, 1), _lead(site_props, 1),
+        _lead(q, 2), _lead(freqs, 1))
+
+
 def log_likelihood_mats(engine: Engine, mats, freqs, site_props):
     """lnL [D] from transition matrices [D,B,K,S,S] computed by the caller
     (any SubstitutionModel.p_t); differentiable w.r.t. mats, freqs, site_props."""
