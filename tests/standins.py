@@ -66,6 +66,25 @@ class ConstantSiteModel:  # site_model.py:36-50
     sample_shape = torch.Size([])
 
 
+class UserDefinedSubstitutionModel:
+    """A model the engine knows nothing about (no reference base class in its MRO): its own p_t
+    supplies the matrices and autograd carries d lnL / d P back (the "mats" route)."""
+
+    def __init__(self, rates, freqs):
+        self._rates, self._freqs = rates, freqs
+
+    @property
+    def frequencies(self):
+        return self._freqs
+
+    def p_t(self, t):
+        q = orc.gtr_q_unnorm(self._rates, self._freqs)
+        norm = -(torch.diagonal(q, dim1=-2, dim2=-1) * self._freqs).sum(-1)
+        return orc.p_t_expm(q / norm[..., None, None], t)
+
+    sample_shape = torch.Size([])
+
+
 class SymmetricSubstitutionModel:  # substitution_model/abstract.py:53-85
     def norm(self, Q):
         return -torch.sum(torch.diagonal(Q, dim1=-2, dim2=-1) * self.frequencies, -1)

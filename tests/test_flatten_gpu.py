@@ -20,7 +20,7 @@ def _engine(prob, draws=1):
 
 @pytest.mark.parametrize("name", ["fluA_gtr_w4_generic", "fluA_gtr_w4_ambig", "syn40_gtr_w4",
                                   "fluA_gtr_w4_batch3", "syn17_gtr_w3"])
-@pytest.mark.parametrize("route", ["eigen", "mats"])
+@pytest.mark.parametrize("route", ["eigen", "expm", "mats"])
 def test_unrooted_gtr_weibull_matches_reference_model(name, route):
     from torchtree_b200.flatten import evaluate_models, substitution_route
 
@@ -32,7 +32,8 @@ def test_unrooted_gtr_weibull_matches_reference_model(name, route):
     shape = torch.tensor(rec["param_shape"], requires_grad=True)
     tree = sm.UnRootedTreeModel(blens, prob.postorder)
     site = sm.WeibullSiteModel(shape, prob.category_count)
-    subst = (sm.GTR if route == "eigen" else sm.NonSymmetricSubstitutionModel)(rates6, freqs)
+    subst = {"eigen": sm.GTR, "expm": sm.NonSymmetricSubstitutionModel,
+             "mats": sm.UserDefinedSubstitutionModel}[route](rates6, freqs)
     assert substitution_route(subst) == route
     sample_shape = torch.Size([D]) if D > 1 else torch.Size([])
     eng = _engine(prob, D)
