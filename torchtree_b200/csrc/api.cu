@@ -204,7 +204,12 @@ int ensure_grad_buffers(Engine& e, int draws) {
   int perSm = e.dm.S <= 32 ? 32 : 8;
   if (gwarp_supported(e, true)) perSm = 16;   // warp-autonomous 20-state kernels: 9.8 ms vs 10.0 at 32
   if (e.spec4) perSm = e.dm.Npad < 20000 ? 8 : (e.dm.Npad < 40000 ? 16 : 32);
-  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, perSm))) return rc;
+  // CTAs co-resident per SM of the pre-order kernel, for whole-wave launches of the compute-bound
+  // DMMA kernels (0: memory-bound 4-state path and SIMT fallback, where a partial last wave simply
+  // gets more bandwidth per CTA)
+  int resident = 0;
+  if (!e.spec4 && gmma_supported(e)) resident = gwarp_supported(e, true) ? 3 : 1;
+  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, perSm, resident))) return rc;
   if (planBefore != e.chunkPlanDraws) drop_graphs(e);
   const size_t need = planned_gpart_doubles(e, draws);
   if (need > e.gpartCap) {

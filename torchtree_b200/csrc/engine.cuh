@@ -204,7 +204,32 @@ int small_expm_contract(Engine& e, int draws);
 // to fill the GPU on small levels, long-lived CTAs on large ones) and uploads the
 // per-branch offsets into the partial-sum buffer.  `granule` = patterns a chunk
 // must be a multiple of.
-int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm);
+int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPerSm = 0);
+
+// Chunk count near `want` whose launch of items * chunks CTAs fills whole waves of `slots`
+// co-resident CTAs: with one or a few CTAs resident per SM (the DMMA kernels) a launch of
+// 8.03 waves costs nine -- e.g. 132 (node, category) items x 9 chunks = 1188 CTAs on 148
+// single-CTA SMs; x 10 chunks = 1320 = 8.92 waves fills the ninth.
+inline long wave_aware_chunks(long items, long want, long maxChunks, long slots) {
+  if (slots <= 0 || items <= 0) return want;
+  long lo = want * 2 / 3, hi = want * 3 / 2 + 1;
+  if (lo < 1) lo = 1;
+  if (hi > maxChunks) hi = maxChunks;
+  long best = want < 1 ? 1 : (want > maxChunks ? maxChunks : want);
+  double bestScore = -1.0;
+  for (long c = lo; c <= hi; ++c) {
+    const long n = items * c;
+    const long waves = (n + slots - 1) / slots;
+    const double eff = (double)n / (double)(waves * slots);
+    const double dist = want > 0 ? (double)(c > want ? c - want : want - c) / (double)want : 0.0;
+    const double score = eff - 0.02 * dist;
+    if (score > bestScore) {
+      bestScore = score;
+      best = c;
+    }
+  }
+  return best;
+}
 size_t planned_gpart_doubles(const Engine& e, int draws);
 
 // Programmatic dependent launch: a level kernel launched with the

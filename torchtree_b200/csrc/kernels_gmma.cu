@@ -70,19 +70,28 @@ __host__ __device__ inline bool gm_utab_fits(const GmShape g, int codeCount) {
   return (long)codeCount * (g.Sp + 1) <= (long)g.Sp * g.PLD;
 }
 
+// (CTA-uniform call: contains a __syncthreads.)  P is read row by row, coalesced, and stored
+// transposed -- the unit-vector codes' rows are the columns of P; gap / ambiguity rows are then
+// summed from the transposed copy in shared memory.  (Reading P[s][code] per table entry was a
+// strided 8-byte gather: tens of microseconds per CTA at 61 states.)
 __device__ __forceinline__ void gm_stage_utab(double* dst, const double* P, const double* codeP,
                                               int codeCount, const GmShape g) {
   const int uld = g.Sp + 1;
-  for (int j = threadIdx.x; j < codeCount * g.Sp; j += blockDim.x) {
-    const int code = j / g.Sp, s2 = j - code * g.Sp;
+  for (int j = threadIdx.x; j < g.S * g.S; j += blockDim.x) {
+    const int s2 = j / g.S, code = j - s2 * g.S;
+    dst[code * uld + s2] = P[j];
+  }
+  for (int j = threadIdx.x; j < g.S * (g.Sp - g.S); j += blockDim.x) {   // padding rows s2 >= S
+    const int code = j / (g.Sp - g.S), s2 = g.S + j - code * (g.Sp - g.S);
+    dst[code * uld + s2] = 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < (codeCount - g.S) * g.Sp; j += blockDim.x) {
+    const int code = g.S + j / g.Sp, s2 = j - (code - g.S) * g.Sp;
     double v = 0.0;
     if (s2 < g.S) {
-      if (code < g.S) {
-        v = P[s2 * g.S + code];
-      } else {
-        const double* cp = codeP + (size_t)code * g.S;
-        for (int t = 0; t < g.S; ++t) v = fma(P[s2 * g.S + t], cp[t], v);
-      }
+      const double* cp = codeP + (size_t)code * g.S;
+      for (int t = 0; t < g.S; ++t) v = fma(dst[t * uld + s2], cp[t], v);
     }
     dst[code * uld + s2] = v;
   }
@@ -271,6 +280,246 @@ gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     for (int s2 = warp; s2 < S; s2 += NW)
       qn[(size_t)s2 * Npad + i0 + lane] = out[s2 * GM_LDT + lane] * f;
     if (warp == 0) en[i0 + lane] = (int16_t)e;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// post-order v3 (61-state codon path): warp-specialised.  gm_fwd2_kernel runs each 32-pattern
+// tile as MMA phase -> barrier -> column maximum -> barrier -> rescale + store, all 8 warps in
+// lock step, and the fp64 tensor pipe idles through every epilogue and every tile load (35 %
+// busy, profiles/r02_codon_ncu.md).  Here two groups of 8 warps take alternate tiles and only
+// stage + multiply (while one group waits for its cp.async tile the other is in the tensor
+// cores), and 8 more warps take the per-pattern maximum, rescale and store the finished tiles;
+// the roles meet through named barriers (producer bar.arrive / consumer bar.sync on FULL[group]
+// and EMPTY[group]) instead of CTA-wide __syncthreads.
+// shared: Pl Pr [Sp*PLD] | cl[2] cr[2] [R*LDT] | out[2] [Sp*LDT] | wmax [2][8*32] | codes
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int CS>
+__global__ void __launch_bounds__(768)
+gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
+               const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
+               double* __restrict__ partials, int16_t* __restrict__ expoK, int T, int Npad, int B,
+               int K, int Srt, int chunkPatterns, int codeCount) {
+  extern __shared__ double sm[];
+  // 24 warps: two DMMA groups of 8 (group g takes the tiles t = g, g + 2, ...: while one group
+  // waits for its tile to land the other one is in the tensor cores) and 8 epilogue warps
+  constexpr int NTG = 4, NWG = 8;
+  constexpr int BAR_GROUP = 1, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 6;
+  const int S = CS ? CS : Srt;
+  const GmShape g = gm_shape(S);
+  const int SS = S * S;
+  const int tileN = g.R * GM_LDT;
+  double* Pl = sm;
+  double* Pr = Pl + g.Sp * g.PLD;
+  double* cl = Pr + g.Sp * g.PLD;   // one buffer per group
+  double* cr = cl + 2 * tileN;      // one buffer per group
+  double* outB = cr + 2 * tileN;    // one buffer per group
+  double* wmaxB = outB + 2 * tileN; // [2][8][32]
+  uint8_t* codesS = reinterpret_cast<uint8_t*>(wmaxB + 2 * NWG * 32);  // [2 groups][2 sides][32]
+  const bool utab = gm_utab_fits(g, codeCount);
+  const int uld = g.Sp + 1;
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const size_t plane = (size_t)S * Npad;
+  const size_t nodeStride = (size_t)K * plane;
+  double* base = partials + (size_t)d * I * nodeStride + k * plane;
+  const double* matsD = mats + (size_t)d * B * K * SS;
+  const int MT = g.Sp / 8, KT = g.Kp / 4;
+  const uint8_t* tl = tips + (size_t)(tipL ? op.left : 0) * Npad;
+  const uint8_t* tr = tips + (size_t)(tipR ? op.right : 0) * Npad;
+  const double* pl = base + (size_t)(tipL ? 0 : op.left - T) * nodeStride;
+  const double* pr = base + (size_t)(tipR ? 0 : op.right - T) * nodeStride;
+  double* qn = base + (size_t)(op.node - T) * nodeStride;
+  int16_t* en = expoK + (((size_t)d * I + (op.node - T)) * K + k) * Npad;
+
+  const bool tabL = tipL && utab, tabR = tipR && utab;
+  if (tabL) gm_stage_utab(Pl, matsD + ((size_t)op.left * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
+  if (tabR) gm_stage_utab(Pr, matsD + ((size_t)op.right * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+  pdl_wait_then_trigger();
+  __syncthreads();   // the matrices are staged by all warps
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+
+  if (warp < 2 * NWG) {
+    // ---- DMMA groups: stage own tile, multiply, write u_l o u_r into the group's buffer ----
+    const int grp = warp / NWG, gw = warp - grp * NWG;
+    double* tcl = cl + grp * tileN;
+    double* tcr = cr + grp * tileN;
+    uint8_t* cds = codesS + grp * 64;
+    double* out = outB + grp * tileN;
+    int round = 0;
+    for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP, ++round) {
+      // (the group's previous tile was fully read before the barrier at the end of the last trip)
+      const int i = i0 + lane;
+      if (tabL) { if (gw == 0 && lane < 8) cp_async4(cds + 4 * lane, tl + i0 + 4 * lane); }
+      else if (tipL) {
+        const double* cp = codeP + (size_t)tl[i] * g.S;
+        for (int s2 = gw; s2 < g.R; s2 += NWG) tcl[s2 * GM_LDT + lane] = s2 < g.S ? cp[s2] : 0.0;
+      } else {
+        for (int s2 = gw; s2 < g.R; s2 += NWG) {
+          if (s2 < g.S) cp_async8(tcl + s2 * GM_LDT + lane, pl + (size_t)s2 * Npad + i);
+          else tcl[s2 * GM_LDT + lane] = 0.0;
+        }
+      }
+      if (tabR) { if (gw == 1 && lane < 8) cp_async4(cds + 32 + 4 * lane, tr + i0 + 4 * lane); }
+      else if (tipR) {
+        const double* cp = codeP + (size_t)tr[i] * g.S;
+        for (int s2 = gw; s2 < g.R; s2 += NWG) tcr[s2 * GM_LDT + lane] = s2 < g.S ? cp[s2] : 0.0;
+      } else {
+        for (int s2 = gw; s2 < g.R; s2 += NWG) {
+          if (s2 < g.S) cp_async8(tcr + s2 * GM_LDT + lane, pr + (size_t)s2 * Npad + i);
+          else tcr[s2 * GM_LDT + lane] = 0.0;
+        }
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      named_sync(BAR_GROUP + grp, NWG * 32);   // the tile is visible to the whole group
+      if (round >= 1) named_sync(BAR_EMPTY + grp, 512);   // the epilogue released out[grp]
+      for (int mt = gw; mt < MT; mt += NWG) {
+        double accL[NTG][2], accR[NTG][2];
+#pragma unroll
+        for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
+        if (tabL) gm_u_tip<NTG>(accL, Pl, uld, cds, mt, 0, lane);
+        else gm_mma_ab_g<NTG>(accL, Pl, g.PLD, tcl, mt, 0, KT, lane);
+        if (tabR) gm_u_tip<NTG>(accR, Pr, uld, cds + 32, mt, 0, lane);
+        else gm_mma_ab_g<NTG>(accR, Pr, g.PLD, tcr, mt, 0, KT, lane);
+        double* o = out + (mt * 8 + (lane >> 2)) * GM_LDT + (lane & 3) * 2;
+#pragma unroll
+        for (int n = 0; n < NTG; ++n) {
+          o[n * 8] = accL[n][0] * accR[n][0];
+          o[n * 8 + 1] = accL[n][1] * accR[n][1];
+        }
+      }
+      __threadfence_block();
+      named_arrive(BAR_FULL + grp, 512);
+      named_sync(BAR_GROUP + grp, NWG * 32);   // every warp is done reading the tile
+    }
+  } else {
+    // ---- epilogue warps: per-pattern maximum, power-of-two rescaling, stores ----
+    const int ew = warp - 2 * NWG;
+    int t = 0;
+    for (int i0 = begin; i0 < end; i0 += GM_TP, ++t) {
+      const int buf = t & 1;
+      named_sync(BAR_FULL + buf, 512);
+      const double* out = outB + buf * tileN;
+      double* wmax = wmaxB + buf * NWG * 32;
+      double m = 0.0;
+      for (int s2 = ew; s2 < S; s2 += NWG) m = fmax(m, out[s2 * GM_LDT + lane]);
+      wmax[ew * 32 + lane] = m;
+      named_sync(BAR_EPI, NWG * 32);
+      double mm = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWG; ++w) mm = fmax(mm, wmax[w * 32 + lane]);
+      const int eb = (__double2hiint(mm) >> 20) & 0x7ff;
+      const int e = (mm > 0.0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
+      const double f = __hiloint2double((1023 - e) << 20, 0);
+      for (int s2 = ew; s2 < S; s2 += NWG)
+        qn[(size_t)s2 * Npad + i0 + lane] = out[s2 * GM_LDT + lane] * f;
+      if (ew == 0) en[i0 + lane] = (int16_t)e;
+      __threadfence_block();
+      named_arrive(BAR_EMPTY + buf, 512);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// post-order, level 1 (both children are tips; a third of the nodes of a random tree): no GEMM
+// at all -- u_c = P_c . codeP[code] is a table row, so the node's vector is the product of two
+// table rows.  The tile kernels spend 1.7 us per 32-pattern tile on this (barriers, 1 CTA per
+// SM: 1.4 TB/s of stores, profiles/r02_codon_ncu.md); this kernel is a plain streaming kernel:
+// thread = pattern, the two C x S tables in shared memory, coalesced stores.
+// grid (pattern blocks, nodes x K, draws), 128 threads
+// ---------------------------------------------------------------------------
+constexpr int GMC_THREADS = 256;
+
+template <int CS>
+__global__ void __launch_bounds__(GMC_THREADS)
+gm_cherry_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
+                     const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
+                     double* __restrict__ partials, int16_t* __restrict__ expoK, int T, int Npad,
+                     int B, int K, int Srt, int patternsPerBlock, int codeCount) {
+  extern __shared__ double sm[];
+  const int S = CS ? CS : Srt;
+  const int LD = S | 1;   // odd leading dimension: rows of different codes in different banks
+  double* utL = sm;
+  double* utR = sm + (size_t)codeCount * LD;
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int SS = S * S;
+  const double* matsD = mats + (size_t)d * B * K * SS;
+  for (int j = threadIdx.x; j < 2 * SS; j += blockDim.x) {   // transposed, coalesced reads of P
+    const int side = j >= SS, jj = j - side * SS;
+    const int s2 = jj / S, code = jj - s2 * S;
+    const double* P = matsD + ((size_t)(side ? op.right : op.left) * K + k) * SS;
+    (side ? utR : utL)[code * LD + s2] = P[jj];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * (codeCount - S) * S; j += blockDim.x) {   // gap / ambiguity rows
+    const int side = j >= (codeCount - S) * S, jj = j - side * (codeCount - S) * S;
+    const int code = S + jj / S, s2 = jj - (code - S) * S;
+    double* ut = side ? utR : utL;
+    const double* cp = codeP + (size_t)code * S;
+    double v = 0.0;
+    for (int t = 0; t < S; ++t) v = fma(ut[t * LD + s2], cp[t], v);
+    ut[code * LD + s2] = v;
+  }
+  pdl_wait_then_trigger();
+  __syncthreads();
+  const size_t plane = (size_t)S * Npad;
+  double* qn = partials + ((size_t)d * I + (op.node - T)) * K * plane + k * plane;
+  int16_t* en = expoK + (((size_t)d * I + (op.node - T)) * K + k) * Npad;
+  const uint8_t* tl = tips + (size_t)op.left * Npad;
+  const uint8_t* tr = tips + (size_t)op.right * Npad;
+  const int begin = blockIdx.x * patternsPerBlock;
+  int end = begin + patternsPerBlock;
+  end = end < Npad ? end : Npad;
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const double* a = utL + (int)tl[i] * LD;
+    const double* b = utR + (int)tr[i] * LD;
+    double m = 0.0;
+    if (CS > 0) {   // compile-time state count: the products stay in registers
+      double v[CS > 0 ? CS : 1];
+#pragma unroll
+      for (int s2 = 0; s2 < CS; ++s2) {
+        v[s2] = a[s2] * b[s2];
+        m = fmax(m, v[s2]);
+      }
+      const int eb = (__double2hiint(m) >> 20) & 0x7ff;
+      const int e = (m > 0.0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
+      const double f = __hiloint2double((1023 - e) << 20, 0);
+#pragma unroll
+      for (int s2 = 0; s2 < CS; ++s2) qn[(size_t)s2 * Npad + i] = v[s2] * f;
+      en[i] = (int16_t)e;
+    } else {
+#pragma unroll 4
+      for (int s2 = 0; s2 < S; ++s2) m = fmax(m, a[s2] * b[s2]);
+      const int eb = (__double2hiint(m) >> 20) & 0x7ff;
+      const int e = (m > 0.0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
+      const double f = __hiloint2double((1023 - e) << 20, 0);
+#pragma unroll 4
+      for (int s2 = 0; s2 < S; ++s2) qn[(size_t)s2 * Npad + i] = a[s2] * b[s2] * f;
+      en[i] = (int16_t)e;
+    }
   }
 }
 
@@ -595,6 +844,11 @@ size_t gm_fwd2_smem(const Dims& m) {
   return (2 * (size_t)g.Sp * g.PLD + 5 * (size_t)g.R * GM_LDT + 16 * 32) * sizeof(double) + 128;
 }
 
+size_t gm_fwd3_smem(const Dims& m) {
+  const GmShape g = gm_shape(m.S);
+  return (2 * (size_t)g.Sp * g.PLD + 6 * (size_t)g.R * GM_LDT + 2 * 8 * 32) * sizeof(double) + 128;
+}
+
 size_t gm_bwd2_smem(const Dims& m) {
   const GmShape g = gm_shape(m.S);
   return (2 * (size_t)g.Sp * g.PLD + 8 * (size_t)g.R * GM_LDT + 64) * sizeof(double) +
@@ -623,6 +877,9 @@ static int gm_fwd_chunk(const Engine& e, int draws, int count) {
   const long target = (long)e.smCount * (m.S <= 32 ? 32 : 8);
   long chunks = (target + (long)count * m.K * draws - 1) / ((long)count * m.K * draws);
   const long maxChunks = m.Npad / GM_TP;
+  // large alphabets run one CTA per SM: launch whole waves (engine.cuh wave_aware_chunks)
+  if (m.S > 32)
+    chunks = wave_aware_chunks((long)count * m.K * draws, chunks, maxChunks, e.smCount);
   if (chunks > maxChunks) chunks = maxChunks;
   if (chunks < 1) chunks = 1;
   int chunkPatterns = (int)((m.Npad + chunks - 1) / chunks);
@@ -640,11 +897,65 @@ int gmma_forward2(Engine& e, int draws) {
   // (<1,4>: 26.6 ms, <1,8>: 22.5, <2,4>: 26.8, <2,8>: 21.6 per evaluation)
   if (m.S == 20) nw = 8;
   // 61 states: <2,8>, <4,16>, <2,16> all measured within 2 % of <4,8> on config 5
+  // 61 states: the warp-specialised kernel (8 DMMA warps + 8 epilogue warps); TTB2_GM61F=2 keeps
+  // the lock-step tile kernel for A/B runs
   const char* v61 = getenv("TTB2_GM61F");
-  const bool wide61 = m.S == 61 && v61 && atoi(v61) == 16;
-  if (wide61) nw = 16;
-  auto kern = wide61 ? gm_fwd2_kernel<2, 16, 61>
-              : m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
+  const bool spec61 = m.S == 61 && !(v61 && atoi(v61) == 2) && gm_fwd3_smem(m) <= 227 * 1024;
+  // level 1 (tip-tip nodes) as a streaming kernel when its two code tables fit in shared memory
+  const size_t cherrySmem = 2 * (size_t)e.cfg.code_count * (m.S | 1) * sizeof(double);
+  const bool cherryLevel = cherrySmem <= 200 * 1024 && !getenv("TTB2_GM_NO_CHERRY");
+  auto launch_cherry_level = [&]() -> int {
+    auto ck = m.S == 61 ? gm_cherry_fwd_kernel<61> : gm_cherry_fwd_kernel<0>;
+    if (cherrySmem > 48 * 1024)
+      TTB2_CUDA_CHECK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)cherrySmem));
+    const int opBegin = e.levelOff[0];
+    const int count = e.levelOff[1] - opBegin;
+    // ~4 blocks per SM and (node, category): long enough to amortise the table build
+    long blocks = ((long)e.smCount * 8 + (long)count * m.K * draws - 1) / ((long)count * m.K * draws);
+    if (blocks < 1) blocks = 1;
+    int per = (int)((m.Npad + blocks - 1) / blocks);
+    per = (per + GMC_THREADS - 1) / GMC_THREADS * GMC_THREADS;
+    const int nBlock = (m.Npad + per - 1) / per;
+    const int maxNodes = 65535 / m.K;
+    for (int done = 0; done < count; done += maxNodes) {
+      const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+      dim3 grid(nBlock, c * m.K, draws);
+      launch_level(ck, grid, GMC_THREADS, cherrySmem, e.stream, false, e.ops, opBegin + done,
+                   e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad, m.B, m.K, m.S, per,
+                   e.cfg.code_count);
+      ++e.launches;
+    }
+    return TTB2_OK;
+  };
+  if (spec61) {
+    const size_t smem3 = gm_fwd3_smem(m);
+    TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_fwd3_kernel<61>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    const int nLevels = (int)e.levelOff.size() - 1;
+    const int maxNodes = 65535 / m.K;
+    if (cherryLevel) {
+      const int rc = launch_cherry_level();
+      if (rc) return rc;
+    }
+    for (int l = cherryLevel ? 1 : 0; l < nLevels; ++l) {
+      const int opBegin = e.levelOff[l];
+      const int count = e.levelOff[l + 1] - opBegin;
+      const int chunkPatterns = gm_fwd_chunk(e, draws, count);
+      const int nChunk = (m.Npad + chunkPatterns - 1) / chunkPatterns;
+      for (int done = 0; done < count; done += maxNodes) {
+        const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+        dim3 grid(nChunk, c * m.K, draws);
+        launch_level(gm_fwd3_kernel<61>, grid, 768, smem3, e.stream, l > 0 && pdl_enabled(), e.ops,
+                     opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad,
+                     m.B, m.K, m.S, chunkPatterns, e.cfg.code_count);
+        ++e.launches;
+      }
+    }
+    TTB2_CUDA_CHECK(cudaGetLastError());
+    return TTB2_OK;
+  }
+  auto kern = m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
               : m.S == 20 ? gm_fwd2_kernel<2, 8, 20>
               : ntg == 4  ? gm_fwd2_kernel<4, 8, 0>
               : nw == 8   ? gm_fwd2_kernel<2, 8, 0>
@@ -655,7 +966,11 @@ int gmma_forward2(Engine& e, int draws) {
                                          (int)smem));
   const int nLevels = (int)e.levelOff.size() - 1;
   const int maxNodes = 65535 / m.K;
-  for (int l = 0; l < nLevels; ++l) {
+  if (cherryLevel) {
+    const int rc = launch_cherry_level();
+    if (rc) return rc;
+  }
+  for (int l = cherryLevel ? 1 : 0; l < nLevels; ++l) {
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
     const int chunkPatterns = gm_fwd_chunk(e, draws, count);

@@ -381,7 +381,7 @@ int round_threads(int n, int cap) {
 
 }  // namespace
 
-int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm) {
+int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPerSm) {
   const Dims& m = e.dm;
   if (e.chunkPlanDraws == draws && e.chunkBase) return TTB2_OK;
   const int nLevels = (int)e.levelOff.size() - 1;
@@ -405,6 +405,8 @@ int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm) {
     const long count = e.levelOff[l + 1] - e.levelOff[l];
     long want = (target + count * m.K * draws - 1) / (count * m.K * draws);
     if (inRun[l]) want = ((long)e.smCount * 5 + (long)m.K * draws - 1) / ((long)m.K * draws);
+    else if (residentPerSm > 0)
+      want = wave_aware_chunks(count * m.K * draws, want, maxChunks, (long)e.smCount * residentPerSm);
     if (want > maxChunks) want = maxChunks;
     if (want < 1) want = 1;
     e.levelChunks[l] = (int)want;
