@@ -31,6 +31,52 @@ __global__ void __launch_bounds__(256) peak_kernel(double* out, int iters, doubl
   if (s == 12345.678) out[0] = s;
 }
 
+// DMMA with operands fetched from shared memory like the tile kernels do: `LPM4` quarter-LDS.64
+// per DMMA (5 = one B load per DMMA + one A load per four: the 1.25 LDS / DMMA of gm_*_kernel)
+template <int LPM4>
+__global__ void __launch_bounds__(256) peak_lds_kernel(double* out, int iters) {
+  __shared__ double tile[64 * 36];
+  for (int i = threadIdx.x; i < 64 * 36; i += 256) tile[i] = 1.0 + 1e-9 * i;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const double* a = tile + (lane >> 2) * 36 + (lane & 3);
+  const double* b = tile + (lane & 3) * 36 + (lane >> 2);
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
+  for (int it = 0; it < iters; ++it) {
+    const int kt = it & 7;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double av = a[(kt * 4 + h * 32) % 28];
+      if (LPM4 <= 4) av = 1.0000001;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        double bv = LPM4 >= 4 ? b[kt * 4 * 36 % 1000 + n * 8 + h] : 0.9999999;
+        dmma(c[h * 4 + n][0], c[h * 4 + n][1], av, bv);
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+template <int LPM4>
+double run_lds(int ctas, int iters) {
+  double* d; cudaMalloc(&d, 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  peak_lds_kernel<LPM4><<<ctas, 256>>>(d, iters);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  peak_lds_kernel<LPM4><<<ctas, 256>>>(d, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  cudaFree(d);
+  return ms;
+}
+
 template <int MODE>
 double run(int ctas, int iters) {
   double* d; cudaMalloc(&d, 8);
@@ -54,6 +100,10 @@ int main() {
     const double warps = (double)ctas * 8, threads = (double)ctas * 256;
     const double t0 = run<0>(ctas, iters), t1 = run<1>(ctas, iters), t2 = run<2>(ctas, iters);
     const double fl_dmma = warps * iters * 8.0 * 512.0, fl_dfma = threads * iters * 8.0 * 2.0;
+    const double l0 = run_lds<0>(ctas, iters), l4 = run_lds<4>(ctas, iters), l5 = run_lds<5>(ctas, iters);
+    printf("{\"ctas_per_sm\": %d, \"dmma_regs_only_tflops\": %.2f, \"dmma_lds_b_tflops\": %.2f, "
+           "\"dmma_lds_a_and_b_tflops\": %.2f}\n", per, fl_dmma / l0 * 1e-9, fl_dmma / l4 * 1e-9,
+           fl_dmma / l5 * 1e-9);
     printf("{\"ctas_per_sm\": %d, \"warps_per_sm\": %d, \"dmma_tflops\": %.2f, \"dfma_tflops\": %.2f, "
            "\"both_tflops\": %.2f, \"both_ms\": %.3f, \"dmma_ms\": %.3f, \"dfma_ms\": %.3f}\n",
            per, per * 8, fl_dmma / t0 * 1e-9, fl_dfma / t1 * 1e-9, (fl_dmma + fl_dfma) / t2 * 1e-9, t2, t0, t1);

@@ -209,7 +209,9 @@ int ensure_grad_buffers(Engine& e, int draws) {
   // gets more bandwidth per CTA)
   int resident = 0;
   if (!e.spec4 && gmma_supported(e)) resident = gwarp_supported(e, true) ? 3 : 1;
-  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, perSm, resident))) return rc;
+  // (the codon path's tip-tip level has its own kernel, two CTAs per SM: kernels_gmma.cu)
+  const int residentLevel1 = (resident == 1 && e.dm.S == 61 && e.cfg.code_count == e.dm.S + 1) ? 2 : 0;
+  if ((rc = plan_chunks(e, draws, e.spec4 ? 128 : 32, perSm, resident, residentLevel1))) return rc;
   if (planBefore != e.chunkPlanDraws) drop_graphs(e);
   const size_t need = planned_gpart_doubles(e, draws);
   if (need > e.gpartCap) {

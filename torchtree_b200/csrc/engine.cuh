@@ -204,7 +204,8 @@ int small_expm_contract(Engine& e, int draws);
 // to fill the GPU on small levels, long-lived CTAs on large ones) and uploads the
 // per-branch offsets into the partial-sum buffer.  `granule` = patterns a chunk
 // must be a multiple of.
-int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPerSm = 0);
+int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPerSm = 0,
+                int residentLevel1 = 0);
 
 // Chunk count near `want` whose launch of items * chunks CTAs fills whole waves of `slots`
 // co-resident CTAs: with one or a few CTAs resident per SM (the DMMA kernels) a launch of

@@ -12,6 +12,7 @@
 //
 // Layout in HBM is the generic one ([draw][inode][k][s][pattern], kernels_gen.cu)
 // and the root / reduction kernels are shared with it.
+#include <algorithm>
 #include <climits>
 #include <cstdlib>
 
@@ -27,6 +28,9 @@ constexpr int GM_LDT = 36;   // leading dimension of [rows][32 patterns] tiles
 constexpr int GM_MAXACC = 16;  // G accumulator tiles per warp: 2 * (64/8)^2 / 8
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  // volatile: the DMMAs issue in program order -- the call sites interleave their independent
+  // accumulator chains explicitly (left to itself the compiler hoists loads across whole phases
+  // and spills at the 128-register cap of the 16-warp kernels)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
@@ -123,6 +127,25 @@ __device__ __forceinline__ void gm_mma_ab_g(double (&c)[NTG][2], const double* A
     const double av = a[kt * 4];
 #pragma unroll
     for (int n = 0; n < NTG; ++n) dmma884(c[n][0], c[n][1], av, b[kt * 4 * GM_LDT + n * 8]);
+  }
+}
+
+// both children in one k loop: 2 * NTG independent accumulator chains in flight
+template <int NTG>
+__device__ __forceinline__ void gm_mma_ab_g2(double (&cl)[NTG][2], double (&cr)[NTG][2],
+                                             const double* Al, const double* Ar, int lda,
+                                             const double* Bl, const double* Br, int mt, int nt0,
+                                             int ksteps, int lane) {
+  const int ao = (mt * 8 + (lane >> 2)) * lda + (lane & 3);
+  const int bo = (lane & 3) * GM_LDT + nt0 * 8 + (lane >> 2);
+#pragma unroll 4
+  for (int kt = 0; kt < ksteps; ++kt) {
+    const double al = Al[ao + kt * 4], ar = Ar[ao + kt * 4];
+#pragma unroll
+    for (int n = 0; n < NTG; ++n) {
+      dmma884(cl[n][0], cl[n][1], al, Bl[bo + kt * 4 * GM_LDT + n * 8]);
+      dmma884(cr[n][0], cr[n][1], ar, Br[bo + kt * 4 * GM_LDT + n * 8]);
+    }
   }
 }
 
@@ -396,10 +419,14 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
         double accL[NTG][2], accR[NTG][2];
 #pragma unroll
         for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
-        if (tabL) gm_u_tip<NTG>(accL, Pl, uld, cds, mt, 0, lane);
-        else gm_mma_ab_g<NTG>(accL, Pl, g.PLD, tcl, mt, 0, KT, lane);
-        if (tabR) gm_u_tip<NTG>(accR, Pr, uld, cds + 32, mt, 0, lane);
-        else gm_mma_ab_g<NTG>(accR, Pr, g.PLD, tcr, mt, 0, KT, lane);
+        if (!tabL && !tabR) {
+          gm_mma_ab_g2<NTG>(accL, accR, Pl, Pr, g.PLD, tcl, tcr, mt, 0, KT, lane);
+        } else {
+          if (tabL) gm_u_tip<NTG>(accL, Pl, uld, cds, mt, 0, lane);
+          else gm_mma_ab_g<NTG>(accL, Pl, g.PLD, tcl, mt, 0, KT, lane);
+          if (tabR) gm_u_tip<NTG>(accR, Pr, uld, cds + 32, mt, 0, lane);
+          else gm_mma_ab_g<NTG>(accR, Pr, g.PLD, tcr, mt, 0, KT, lane);
+        }
         double* o = out + (mt * 8 + (lane >> 2)) * GM_LDT + (lane & 3) * 2;
 #pragma unroll
         for (int n = 0; n < NTG; ++n) {
@@ -839,6 +866,384 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   }
 }
 
+// ---------------------------------------------------------------------------
+// pre-order v3 (61-state codon path): two groups of 8 warps take alternate 32-pattern tiles.
+// gm_bwd2_kernel has all its warps in lock step (tile wait -> U phase -> barrier -> Q + G phase),
+// so the fp64 tensor pipe idles while a tile lands and around every barrier (66 % busy on the
+// large levels, profiles/r02_codon_ncu.md).  Here each group owns single-buffered tiles and
+// synchronises only with itself (named barriers): while one group waits for its cp.async tile
+// or sits at its barrier the other is in the tensor cores.  m_l overwrites the q^ tile in place
+// (every element is read and written by the same thread), so a group needs four tiles
+// (q^ -> m_l, v_l, v_r, m_r) and both groups fit beside the two staged matrices.  Each group
+// accumulates its own partial G in registers; they are added in fixed order (group 0 + group 1)
+// through shared memory at the end.
+// shared: Pl Pr [Sp*PLD] | per group: tq vl vr mr [R*LDT] , ws [32], se [64 int16], codes [64]
+// ---------------------------------------------------------------------------
+template <int CS>
+__global__ void __launch_bounds__(512)
+gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
+               const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
+               const double* __restrict__ partials, const int16_t* __restrict__ expoK,
+               const double* __restrict__ weights, double* __restrict__ pre,
+               double* __restrict__ gpart, const int* __restrict__ chunkBase, size_t chunkTotal,
+               int T, int Npad, int B, int K, int chunkPatterns, int nChunk, int codeCount) {
+  extern __shared__ double sm[];
+  constexpr int S = CS, NTG = 4, NWG = 8, BAR_GROUP = 1;
+  const GmShape g = gm_shape(S);
+  constexpr int SS = S * S;
+  const bool utab = gm_utab_fits(g, codeCount);
+  const int uld = g.Sp + 1;
+  double* Pl = sm;
+  double* Pr = Pl + g.Sp * g.PLD;
+  const int tileN = g.R * GM_LDT;
+  const int groupN = 4 * tileN + 32 + 16 + 8;   // tiles | weights | exponents | codes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = warp / NWG, gw = warp - grp * NWG;
+  double* mine = Pr + g.Sp * g.PLD + grp * groupN;
+  double* tq = mine;                 // becomes m_l after the U phase
+  double* vl = tq + tileN;
+  double* vr = vl + tileN;
+  double* mr = vr + tileN;
+  double* ws = mr + tileN;
+  int16_t* se = reinterpret_cast<int16_t*>(ws + 32);            // [el[32], er[32]]
+  uint8_t* codesS = reinterpret_cast<uint8_t*>(ws + 32 + 16);   // [2 sides][32]
+
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const bool tipL = op.left < T, tipR = op.right < T;
+  const size_t plane = (size_t)S * Npad;
+  const size_t nodeStride = (size_t)K * plane;
+  const size_t drawBase = (size_t)d * I * nodeStride;
+  const double* matsD = mats + (size_t)d * B * K * SS;
+  const int MT = g.Sp / 8, KT = g.Kp / 4, KTr = g.Sp / 4;
+  const bool tabL = tipL && utab, tabR = tipR && utab;
+  if (tabL) gm_stage_utab(Pl, matsD + ((size_t)op.left * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pl, matsD + ((size_t)op.left * K + k) * SS, g);
+  if (tabR) gm_stage_utab(Pr, matsD + ((size_t)op.right * K + k) * SS, codeP, codeCount, g);
+  else gm_stage_matrix(Pr, matsD + ((size_t)op.right * K + k) * SS, g);
+  pdl_wait_then_trigger();
+  __syncthreads();
+
+  constexpr int NCJ = 2;   // 16 (child, row tile) combos over the 8 warps of a group
+  double acc[NCJ * 8][2];
+#pragma unroll
+  for (int j = 0; j < NCJ * 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+  const bool hotL = tabL && codeCount == S + 1, hotR = tabR && codeCount == S + 1;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  const double* qsrc = pre + drawBase + (size_t)(op.node - T) * nodeStride + k * plane;
+  const double* lsrc = partials + drawBase + (size_t)(tipL ? 0 : op.left - T) * nodeStride + k * plane;
+  const double* rsrc = partials + drawBase + (size_t)(tipR ? 0 : op.right - T) * nodeStride + k * plane;
+  const uint8_t* tl = tips + (size_t)(tipL ? op.left : 0) * Npad;
+  const uint8_t* tr = tips + (size_t)(tipR ? op.right : 0) * Npad;
+  const int16_t* elp = tipL ? nullptr : expoK + (((size_t)d * I + (op.left - T)) * K + k) * Npad;
+  const int16_t* erp = tipR ? nullptr : expoK + (((size_t)d * I + (op.right - T)) * K + k) * Npad;
+  // one [R][LDT] tile of this group <- rows of `plane`, or the code vectors of a tip
+  auto stage_tile = [&](double* tile, bool tip, const uint8_t* tipRow, const double* src, int i0) {
+    const int i = i0 + lane;
+    if (tip) {
+      const double* cp = codeP + (size_t)tipRow[i] * S;
+      for (int s2 = gw; s2 < g.R; s2 += NWG) tile[s2 * GM_LDT + lane] = s2 < S ? cp[s2] : 0.0;
+    } else {
+      for (int s2 = gw; s2 < g.R; s2 += NWG) {
+        if (s2 < S) cp_async8(tile + s2 * GM_LDT + lane, src + (size_t)s2 * Npad + i);
+        else tile[s2 * GM_LDT + lane] = 0.0;
+      }
+    }
+  };
+  for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP) {
+    // (the group finished reading its buffers before the barrier at the end of the last trip)
+    stage_tile(tq, false, nullptr, qsrc, i0);
+    if (!hotL) stage_tile(vl, tipL, tl, lsrc, i0);
+    if (!hotR) stage_tile(vr, tipR, tr, rsrc, i0);
+    if (gw == 0) {
+      cp_async8(ws + lane, weights + i0 + lane);
+      if (lane < 16) {
+        if (!tipL) cp_async4(se + 2 * lane, elp + i0 + 2 * lane);
+        if (!tipR) cp_async4(se + 32 + 2 * lane, erp + i0 + 2 * lane);
+      } else if (lane < 24) {
+        if (tabL) cp_async4(codesS + 4 * (lane - 16), tl + i0 + 4 * (lane - 16));
+      } else {
+        if (tabR) cp_async4(codesS + 32 + 4 * (lane - 24), tr + i0 + 4 * (lane - 24));
+      }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    named_sync(BAR_GROUP + grp, NWG * 32);   // the group's tiles are visible
+    // U phase: u_l = P_l v_l, u_r = P_r v_r;  m_l = q^ o u_r (in place of q^), m_r = q^ o u_l
+    for (int mt = gw; mt < MT; mt += NWG) {
+      double accL[NTG][2], accR[NTG][2];
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
+      if (!tabL && !tabR) {
+        gm_mma_ab_g2<NTG>(accL, accR, Pl, Pr, g.PLD, vl, vr, mt, 0, KT, lane);
+      } else {
+        if (tabL) gm_u_tip<NTG>(accL, Pl, uld, codesS, mt, 0, lane);
+        else gm_mma_ab_g<NTG>(accL, Pl, g.PLD, vl, mt, 0, KT, lane);
+        if (tabR) gm_u_tip<NTG>(accR, Pr, uld, codesS + 32, mt, 0, lane);
+        else gm_mma_ab_g<NTG>(accR, Pr, g.PLD, vr, mt, 0, KT, lane);
+      }
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) {
+        const int off = (mt * 8 + (lane >> 2)) * GM_LDT + n * 8 + (lane & 3) * 2;
+        const double q0 = tq[off], q1 = tq[off + 1];
+        tq[off] = q0 * accR[n][0];
+        tq[off + 1] = q1 * accR[n][1];
+        mr[off] = q0 * accL[n][0];
+        mr[off + 1] = q1 * accL[n][1];
+      }
+    }
+    named_sync(BAR_GROUP + grp, NWG * 32);
+    const double* ml = tq;
+    // Q phase: q^_c = P_c^T m_c * 2^{-e_c}  (internal children)
+    for (int side = 0; side < 2; ++side) {
+      if (side ? tipR : tipL) continue;
+      const double* P = side ? Pr : Pl;
+      const double* mm = side ? mr : ml;
+      const int child = side ? op.right : op.left;
+      double* qout = pre + drawBase + (size_t)(child - T) * nodeStride + k * plane + i0;
+      for (int mt = gw; mt < MT; mt += NWG) {
+        double c[NTG][2];
+#pragma unroll
+        for (int n = 0; n < NTG; ++n) c[n][0] = c[n][1] = 0.0;
+        gm_mma_atb_g<NTG>(c, P, g.PLD, mm, mt, 0, KTr, lane);
+        const int row = mt * 8 + (lane >> 2);
+        if (row < S) {
+#pragma unroll
+          for (int n = 0; n < NTG; ++n) {
+            const int col = n * 8 + (lane & 3) * 2;
+            const double f0 = __hiloint2double((1023 - (int)se[side * 32 + col]) << 20, 0);
+            const double f1 = __hiloint2double((1023 - (int)se[side * 32 + col + 1]) << 20, 0);
+            *reinterpret_cast<double2*>(qout + (size_t)row * Npad + col) =
+                make_double2(c[n][0] * f0, c[n][1] * f1);
+          }
+        }
+      }
+    }
+    // G phase: G_c[s][t] += sum_p (w_p m_c[s][p]) v_c[t][p]
+#pragma unroll
+    for (int cj = 0; cj < NCJ; ++cj) {
+      const int combo = gw + cj * NWG;
+      if (combo < 2 * MT) {
+        const int side = combo / MT;
+        const int mt = combo - side * MT;
+        const double* mm = (side ? mr : ml) + (mt * 8 + (lane >> 2)) * GM_LDT + (lane & 3);
+        const double* wp = ws + (lane & 3);
+        if (side ? hotR : hotL) {
+          const uint8_t* cds = codesS + side * 32 + (lane & 3);
+          const int colBase = lane >> 2;
+#pragma unroll
+          for (int kt = 0; kt < GM_TP / 4; ++kt) {
+            const double av = mm[kt * 4] * wp[kt * 4];
+            const int code = cds[kt * 4];
+#pragma unroll
+            for (int mt2 = 0; mt2 < 8; ++mt2)
+              if (mt2 < MT) {
+                const int col = mt2 * 8 + colBase;
+                const double bv = (col < S && (code == col || code == S)) ? 1.0 : 0.0;
+                dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av, bv);
+              }
+          }
+        } else {
+          const double* vv = (side ? vr : vl) + (lane >> 2) * GM_LDT + (lane & 3);
+#pragma unroll
+          for (int kt = 0; kt < GM_TP / 4; ++kt) {
+            const double av = mm[kt * 4] * wp[kt * 4];
+#pragma unroll
+            for (int mt2 = 0; mt2 < 8; ++mt2)
+              if (mt2 < MT)
+                dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av,
+                        vv[mt2 * 8 * GM_LDT + kt * 4]);
+          }
+        }
+      }
+    }
+    named_sync(BAR_GROUP + grp, NWG * 32);   // every warp of the group is done with the tiles
+  }
+  // partial G of group 1 -> shared memory (its own tile area: 4 tiles hold 2 * 64 * 64 doubles
+  // only if LDT >= 32: 4 * 64 * 36 = 9216 >= 8192), then group 0 adds and stores
+  __syncthreads();
+  double* stash = Pr + g.Sp * g.PLD + groupN;   // group 1's area
+  if (grp == 1) {
+#pragma unroll
+    for (int j = 0; j < NCJ * 8; ++j) {
+      stash[((gw * NCJ * 8 + j) * 32 + lane) * 2] = acc[j][0];
+      stash[((gw * NCJ * 8 + j) * 32 + lane) * 2 + 1] = acc[j][1];
+    }
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int cj = 0; cj < NCJ; ++cj) {
+      const int combo = gw + cj * NWG;
+      if (combo < 2 * MT) {
+        const int side = combo / MT;
+        const int mt = combo - side * MT;
+        const int branch = side ? op.right : op.left;
+        double* o = gpart + ((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk +
+                             blockIdx.x) * SS;
+        const int row = mt * 8 + (lane >> 2);
+#pragma unroll
+        for (int mt2 = 0; mt2 < 8; ++mt2) {
+          if (mt2 < MT && row < S) {
+            const int j = cj * 8 + mt2;
+            const double g0 = acc[j][0] + stash[((gw * NCJ * 8 + j) * 32 + lane) * 2];
+            const double g1 = acc[j][1] + stash[((gw * NCJ * 8 + j) * 32 + lane) * 2 + 1];
+            const int col = mt2 * 8 + (lane & 3) * 2;
+            if (col < S) o[row * S + col] = g0;
+            if (col + 1 < S) o[row * S + col + 1] = g1;
+          }
+        }
+      }
+    }
+  }
+}
+
+size_t gm_bwd3_smem(int S) {
+  const GmShape g = gm_shape(S);
+  return (2 * (size_t)g.Sp * g.PLD + 2 * (4 * (size_t)g.R * GM_LDT + 56)) * sizeof(double);
+}
+
+// ---------------------------------------------------------------------------
+// pre-order, level 1 (both children are tips): the children receive no q^ and their u vectors
+// are table rows, so the only GEMM left is G_c += (w o m_c) . onehot(code_c)^T.  The general
+// kernel still stages two S x S matrices and runs its U phase, barrier, ml / mr round trip
+// through shared memory (one CTA per SM, DMMA pipe 54 % busy on this level,
+// profiles/r02_codon_ncu.md).  Here the A operand w_p q^[s][p] u_sib[code_sib(p)][s] is formed
+// in registers straight from the q^ tile and the sibling's table, the one-hot B operand from the
+// child's own code: one phase per tile, no ml / mr tiles, 102 KB of shared memory -> two CTAs
+// per SM whose barriers and tile waits overlap.
+// Needs unit-vector / gap codes only (codeCount == S + 1).
+// shared: utL utR [S+1][Sp+1] | ring[2]: tq [Sp][LDT], w [32], codes [2][32]
+// ---------------------------------------------------------------------------
+template <int CS>
+__global__ void __launch_bounds__(256, 2)
+gm_cherry_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
+                     const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
+                     const double* __restrict__ weights, const double* __restrict__ pre,
+                     double* __restrict__ gpart, const int* __restrict__ chunkBase,
+                     size_t chunkTotal, int T, int Npad, int B, int K, int chunkPatterns,
+                     int nChunk) {
+  extern __shared__ double sm[];
+  constexpr int S = CS, NW = 8;
+  const GmShape g = gm_shape(S);
+  constexpr int SS = S * S;
+  const int uld = g.Sp + 1;
+  const int tileN = g.Sp * GM_LDT;
+  const int slotN = tileN + 32 + 8;          // tile | weights | 64 code bytes
+  double* utL = sm;
+  double* utR = utL + (S + 1) * uld;
+  double* ring = utR + (S + 1) * uld;
+  const int nodeSlot = blockIdx.y / K;
+  const int k = blockIdx.y - nodeSlot * K;
+  const NodeOp op = ops[opBegin + nodeSlot];
+  const int d = blockIdx.z;
+  const int I = T - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t plane = (size_t)S * Npad;
+  const size_t nodeStride = (size_t)K * plane;
+  const double* matsD = mats + (size_t)d * B * K * SS;
+  gm_stage_utab(utL, matsD + ((size_t)op.left * K + k) * SS, codeP, S + 1, g);
+  gm_stage_utab(utR, matsD + ((size_t)op.right * K + k) * SS, codeP, S + 1, g);
+  // rows S .. Sp-1 of the q^ tiles are never copied: keep them zero
+  for (int j = threadIdx.x; j < 2 * (g.Sp - S) * GM_LDT; j += blockDim.x) {
+    const int b = j / ((g.Sp - S) * GM_LDT), r = j - b * (g.Sp - S) * GM_LDT;
+    ring[b * slotN + S * GM_LDT + r] = 0.0;
+  }
+  pdl_wait_then_trigger();
+
+  constexpr int MT = (S + 7) / 8;
+  constexpr int NCJ = (2 * MT + NW - 1) / NW;
+  double acc[NCJ * 8][2];
+#pragma unroll
+  for (int j = 0; j < NCJ * 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+
+  const int begin = blockIdx.x * chunkPatterns;
+  int end = begin + chunkPatterns;
+  end = end < Npad ? end : Npad;
+  const double* qsrc = pre + (size_t)d * I * nodeStride + (size_t)(op.node - T) * nodeStride + k * plane;
+  const uint8_t* tl = tips + (size_t)op.left * Npad;
+  const uint8_t* tr = tips + (size_t)op.right * Npad;
+  auto stage = [&](int b, int i0) {
+    double* slot = ring + b * slotN;
+    for (int s2 = warp; s2 < S; s2 += NW)
+      cp_async8(slot + s2 * GM_LDT + lane, qsrc + (size_t)s2 * Npad + i0 + lane);
+    if (warp == 0) cp_async8(slot + tileN + lane, weights + i0 + lane);
+    if (warp == 1 && lane < 16) {
+      uint8_t* cd = reinterpret_cast<uint8_t*>(slot + tileN + 32);
+      if (lane < 8) cp_async4(cd + 4 * lane, tl + i0 + 4 * lane);
+      else cp_async4(cd + 32 + 4 * (lane - 8), tr + i0 + 4 * (lane - 8));
+    }
+  };
+  if (begin < end) stage(0, begin);
+  cp_async_commit();
+  int buf = 0;
+  for (int i0 = begin; i0 < end; i0 += GM_TP, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();   // slot `buf` (and the tables on the first trip) visible; slot `buf^1` free
+    if (i0 + GM_TP < end) stage(buf ^ 1, i0 + GM_TP);
+    cp_async_commit();
+    const double* slot = ring + buf * slotN;
+    const double* ws = slot + tileN + (lane & 3);
+    const uint8_t* cd = reinterpret_cast<const uint8_t*>(slot + tileN + 32) + (lane & 3);
+#pragma unroll
+    for (int cj = 0; cj < NCJ; ++cj) {
+      const int combo = warp + cj * NW;
+      if (combo < 2 * MT) {
+        const int side = combo / MT;
+        const int mt = combo - side * MT;
+        const int row = mt * 8 + (lane >> 2);
+        const double* tq = slot + row * GM_LDT + (lane & 3);
+        const double* utSib = (side ? utL : utR) + row;   // m_side = q^ o u_sibling
+        const uint8_t* own = cd + side * 32;
+        const uint8_t* sib = cd + (1 - side) * 32;
+        const int colBase = lane >> 2;
+#pragma unroll
+        for (int kt = 0; kt < GM_TP / 4; ++kt) {
+          const double av = ws[kt * 4] * tq[kt * 4] * utSib[(int)sib[kt * 4] * uld];
+          const int code = own[kt * 4];
+#pragma unroll
+          for (int mt2 = 0; mt2 < MT; ++mt2) {
+            const int col = mt2 * 8 + colBase;
+            const double bv = (col < S && (code == col || code == S)) ? 1.0 : 0.0;
+            dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av, bv);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int cj = 0; cj < NCJ; ++cj) {
+    const int combo = warp + cj * NW;
+    if (combo < 2 * MT) {
+      const int side = combo / MT;
+      const int mt = combo - side * MT;
+      const int branch = side ? op.right : op.left;
+      double* o = gpart + ((size_t)d * chunkTotal + chunkBase[branch] + (size_t)k * nChunk +
+                           blockIdx.x) * SS;
+      const int row = mt * 8 + (lane >> 2);
+#pragma unroll
+      for (int mt2 = 0; mt2 < MT; ++mt2) {
+        if (row < S) {
+          const int col = mt2 * 8 + (lane & 3) * 2;
+          if (col < S) o[row * S + col] = acc[cj * 8 + mt2][0];
+          if (col + 1 < S) o[row * S + col + 1] = acc[cj * 8 + mt2][1];
+        }
+      }
+    }
+  }
+}
+
+size_t gm_cherry_bwd_smem(int S) {
+  const GmShape g = gm_shape(S);
+  return (2 * (size_t)(S + 1) * (g.Sp + 1) + 2 * ((size_t)g.Sp * GM_LDT + 40)) * sizeof(double);
+}
+
 size_t gm_fwd2_smem(const Dims& m) {
   const GmShape g = gm_shape(m.S);
   return (2 * (size_t)g.Sp * g.PLD + 5 * (size_t)g.R * GM_LDT + 16 * 32) * sizeof(double) + 128;
@@ -876,7 +1281,8 @@ static int gm_fwd_chunk(const Engine& e, int draws, int count) {
   // alphabets (config 4, S=20: 32/SM best), few long ones for large (config 5, S=61: 8/SM)
   const long target = (long)e.smCount * (m.S <= 32 ? 32 : 8);
   long chunks = (target + (long)count * m.K * draws - 1) / ((long)count * m.K * draws);
-  const long maxChunks = m.Npad / GM_TP;
+  // large alphabets: at least 8 tiles per CTA (staging the two matrices costs about one tile)
+  const long maxChunks = m.S > 32 ? std::max(1, m.Npad / (8 * GM_TP)) : m.Npad / GM_TP;
   // large alphabets run one CTA per SM: launch whole waves (engine.cuh wave_aware_chunks)
   if (m.S > 32)
     chunks = wave_aware_chunks((long)count * m.K * draws, chunks, maxChunks, e.smCount);
@@ -1052,6 +1458,39 @@ int gmma_backward2(Engine& e, int draws) {
     const int nChunk = e.levelChunks[l];
     int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
     chunkPatterns = (chunkPatterns + GM_TP - 1) / GM_TP * GM_TP;
+    // level 1 of the codon path: tip-tip nodes through the dedicated kernel (unit / gap codes)
+    const bool cherry = l == 0 && m.S == 61 && e.cfg.code_count == m.S + 1 &&
+                        !getenv("TTB2_GM_NO_CHERRY");
+    if (cherry) {
+      const size_t csm = gm_cherry_bwd_smem(m.S);
+      TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_cherry_bwd_kernel<61>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+      for (int done = 0; done < count; done += maxNodes) {
+        const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+        dim3 grid(nChunk, c * m.K, draws);
+        launch_level(gm_cherry_bwd_kernel<61>, grid, 256, csm, e.stream,
+                     l < nLevels - 1 && pdl_enabled(), e.ops, opBegin + done, e.mats, e.tips,
+                     e.codeP, e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad,
+                     m.B, m.K, chunkPatterns, nChunk);
+        ++e.launches;
+      }
+      continue;
+    }
+    if (m.S == 61 && !v61) {   // two-group kernel (TTB2_GM61=8 / 16 select the lock-step instances)
+      const size_t sm3 = gm_bwd3_smem(m.S);
+      TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_bwd3_kernel<61>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+      for (int done = 0; done < count; done += maxNodes) {
+        const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+        dim3 grid(nChunk, c * m.K, draws);
+        launch_level(gm_bwd3_kernel<61>, grid, 512, sm3, e.stream,
+                     l < nLevels - 1 && pdl_enabled(), e.ops, opBegin + done, e.mats, e.tips,
+                     e.codeP, e.partials, e.expoK, e.weights, e.pre, e.gpart, e.chunkBase,
+                     e.chunkTotal, m.T, m.Npad, m.B, m.K, chunkPatterns, nChunk, e.cfg.code_count);
+        ++e.launches;
+      }
+      continue;
+    }
     for (int done = 0; done < count; done += maxNodes) {
       const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
       dim3 grid(nChunk, c * m.K, draws);

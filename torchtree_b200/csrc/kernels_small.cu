@@ -381,7 +381,8 @@ int round_threads(int n, int cap) {
 
 }  // namespace
 
-int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPerSm) {
+int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPerSm,
+                int residentLevel1) {
   const Dims& m = e.dm;
   if (e.chunkPlanDraws == draws && e.chunkBase) return TTB2_OK;
   const int nLevels = (int)e.levelOff.size() - 1;
@@ -390,7 +391,9 @@ int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPe
   static const int envPerSm = getenv("TTB2_CHUNK_TARGET") ? atoi(getenv("TTB2_CHUNK_TARGET")) : 0;
   const int perSm = envPerSm > 0 ? envPerSm : ctasPerSm;
   const long target = (long)e.smCount * perSm;
-  const int maxChunks = std::max(1, m.Npad / (2 * granule));
+  // never less than 2 granules per chunk; 8 for large alphabets, whose CTAs stage two S x S
+  // matrices (about the cost of one 32-pattern tile) before their first pattern
+  const int maxChunks = std::max(1, m.Npad / ((m.S > 32 ? 8 : 2) * granule));
   e.levelChunks.assign(nLevels, 1);
   e.hostChunkBase.assign(m.B + 1, 0);
   e.hostChunkCount.assign(m.B + 1, 0);
@@ -406,7 +409,9 @@ int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPe
     long want = (target + count * m.K * draws - 1) / (count * m.K * draws);
     if (inRun[l]) want = ((long)e.smCount * 5 + (long)m.K * draws - 1) / ((long)m.K * draws);
     else if (residentPerSm > 0)
-      want = wave_aware_chunks(count * m.K * draws, want, maxChunks, (long)e.smCount * residentPerSm);
+      want = wave_aware_chunks(count * m.K * draws, want, maxChunks,
+                               (long)e.smCount * (l == 0 && residentLevel1 > 0 ? residentLevel1
+                                                                                : residentPerSm));
     if (want > maxChunks) want = maxChunks;
     if (want < 1) want = 1;
     e.levelChunks[l] = (int)want;
