@@ -174,6 +174,12 @@ bool gmma_supported(const Engine& e);
 // per-(pattern, category) rescaling, pipelined staging (own root kernels, expoK layout)
 size_t gmma_expo_elems(const Engine& e);
 int gmma_forward2(Engine& e, int draws);
+// post-order level 1 (both children tips) as a streaming kernel, any 8 <= S <= 64
+bool gmma_cherry_level_supported(const Engine& e);
+int gmma_cherry_forward_level(Engine& e, int draws);
+// pre-order level 1 (tip-tip nodes, unit / gap codes): G-only kernel for S = 20 / 61
+bool gmma_cherry_backward_supported(const Engine& e);
+int gmma_cherry_backward_level(Engine& e, int draws, bool pdl);
 int gmma_root2(Engine& e, int draws);
 int gmma_backward2(Engine& e, int draws);
 // warp-autonomous DMMA level kernels for 20 states (kernels_gwarp.cu); TTB2_GM_LEGACY=1 keeps

@@ -1121,8 +1121,8 @@ size_t gm_bwd3_smem(int S) {
 // Needs unit-vector / gap codes only (codeCount == S + 1).
 // shared: utL utR [S+1][Sp+1] | ring[2]: tq [Sp][LDT], w [32], codes [2][32]
 // ---------------------------------------------------------------------------
-template <int CS>
-__global__ void __launch_bounds__(256, 2)
+template <int CS, int NW>
+__global__ void __launch_bounds__(NW * 32, 2)
 gm_cherry_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
                      const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
                      const double* __restrict__ weights, const double* __restrict__ pre,
@@ -1130,7 +1130,7 @@ gm_cherry_bwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* 
                      size_t chunkTotal, int T, int Npad, int B, int K, int chunkPatterns,
                      int nChunk) {
   extern __shared__ double sm[];
-  constexpr int S = CS, NW = 8;
+  constexpr int S = CS;
   const GmShape g = gm_shape(S);
   constexpr int SS = S * S;
   const int uld = g.Sp + 1;
@@ -1274,6 +1274,73 @@ size_t gmma_expo_elems(const Engine& e) {
   return (size_t)e.cfg.max_draws * m.I * m.K * m.Npad;
 }
 
+bool gmma_cherry_level_supported(const Engine& e) {
+  const size_t smem = 2 * (size_t)e.cfg.code_count * (e.dm.S | 1) * sizeof(double);
+  return smem <= 200 * 1024 && !getenv("TTB2_GM_NO_CHERRY");
+}
+
+// post-order level 1 (nodes whose two children are tips) for any 8 <= S <= 64
+int gmma_cherry_forward_level(Engine& e, int draws) {
+  const Dims& m = e.dm;
+  const size_t cherrySmem = 2 * (size_t)e.cfg.code_count * (m.S | 1) * sizeof(double);
+  auto ck = m.S == 61 ? gm_cherry_fwd_kernel<61>
+            : m.S == 20 ? gm_cherry_fwd_kernel<20> : gm_cherry_fwd_kernel<0>;
+  if (cherrySmem > 48 * 1024)
+    TTB2_CUDA_CHECK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)cherrySmem));
+  const int opBegin = e.levelOff[0];
+  const int count = e.levelOff[1] - opBegin;
+  // ~8 blocks per SM: long enough to amortise the table build
+  long blocks = ((long)e.smCount * 8 + (long)count * m.K * draws - 1) / ((long)count * m.K * draws);
+  if (blocks < 1) blocks = 1;
+  int per = (int)((m.Npad + blocks - 1) / blocks);
+  per = (per + GMC_THREADS - 1) / GMC_THREADS * GMC_THREADS;
+  const int nBlock = (m.Npad + per - 1) / per;
+  const int maxNodes = 65535 / m.K;
+  for (int done = 0; done < count; done += maxNodes) {
+    const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+    dim3 grid(nBlock, c * m.K, draws);
+    launch_level(ck, grid, GMC_THREADS, cherrySmem, e.stream, false, e.ops, opBegin + done,
+                 e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad, m.B, m.K, m.S, per,
+                 e.cfg.code_count);
+    ++e.launches;
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
+// pre-order level 1 (both children tips, unit / gap codes) for the compiled alphabets
+bool gmma_cherry_backward_supported(const Engine& e) {
+  return (e.dm.S == 61 || e.dm.S == 20) && e.cfg.code_count == e.dm.S + 1 &&
+         !getenv("TTB2_GM_NO_CHERRY");
+}
+
+int gmma_cherry_backward_level(Engine& e, int draws, bool pdl) {
+  const Dims& m = e.dm;
+  const int opBegin = e.levelOff[0];
+  const int count = e.levelOff[1] - opBegin;
+  const int nChunk = e.levelChunks[0];
+  int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
+  chunkPatterns = (chunkPatterns + GM_TP - 1) / GM_TP * GM_TP;
+  const int maxNodes = 65535 / m.K;
+  const size_t csm = gm_cherry_bwd_smem(m.S);
+  auto kern = m.S == 61 ? gm_cherry_bwd_kernel<61, 8> : gm_cherry_bwd_kernel<20, 6>;
+  const int threads = m.S == 61 ? 256 : 192;
+  if (csm > 48 * 1024)
+    TTB2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)csm));
+  for (int done = 0; done < count; done += maxNodes) {
+    const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
+    dim3 grid(nChunk, c * m.K, draws);
+    launch_level(kern, grid, threads, csm, e.stream, pdl, e.ops, opBegin + done, e.mats, e.tips,
+                 e.codeP, e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad, m.B,
+                 m.K, chunkPatterns, nChunk);
+    ++e.launches;
+  }
+  TTB2_CUDA_CHECK(cudaGetLastError());
+  return TTB2_OK;
+}
+
 // chunk of patterns per post-order CTA (enough CTAs to fill the GPU, long-lived otherwise)
 static int gm_fwd_chunk(const Engine& e, int draws, int count) {
   const Dims& m = e.dm;
@@ -1308,32 +1375,8 @@ int gmma_forward2(Engine& e, int draws) {
   const char* v61 = getenv("TTB2_GM61F");
   const bool spec61 = m.S == 61 && !(v61 && atoi(v61) == 2) && gm_fwd3_smem(m) <= 227 * 1024;
   // level 1 (tip-tip nodes) as a streaming kernel when its two code tables fit in shared memory
-  const size_t cherrySmem = 2 * (size_t)e.cfg.code_count * (m.S | 1) * sizeof(double);
-  const bool cherryLevel = cherrySmem <= 200 * 1024 && !getenv("TTB2_GM_NO_CHERRY");
-  auto launch_cherry_level = [&]() -> int {
-    auto ck = m.S == 61 ? gm_cherry_fwd_kernel<61> : gm_cherry_fwd_kernel<0>;
-    if (cherrySmem > 48 * 1024)
-      TTB2_CUDA_CHECK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)cherrySmem));
-    const int opBegin = e.levelOff[0];
-    const int count = e.levelOff[1] - opBegin;
-    // ~4 blocks per SM and (node, category): long enough to amortise the table build
-    long blocks = ((long)e.smCount * 8 + (long)count * m.K * draws - 1) / ((long)count * m.K * draws);
-    if (blocks < 1) blocks = 1;
-    int per = (int)((m.Npad + blocks - 1) / blocks);
-    per = (per + GMC_THREADS - 1) / GMC_THREADS * GMC_THREADS;
-    const int nBlock = (m.Npad + per - 1) / per;
-    const int maxNodes = 65535 / m.K;
-    for (int done = 0; done < count; done += maxNodes) {
-      const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
-      dim3 grid(nBlock, c * m.K, draws);
-      launch_level(ck, grid, GMC_THREADS, cherrySmem, e.stream, false, e.ops, opBegin + done,
-                   e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad, m.B, m.K, m.S, per,
-                   e.cfg.code_count);
-      ++e.launches;
-    }
-    return TTB2_OK;
-  };
+  const bool cherryLevel = gmma_cherry_level_supported(e);
+  auto launch_cherry_level = [&]() -> int { return gmma_cherry_forward_level(e, draws); };
   if (spec61) {
     const size_t smem3 = gm_fwd3_smem(m);
     TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_fwd3_kernel<61>,
@@ -1459,21 +1502,9 @@ int gmma_backward2(Engine& e, int draws) {
     int chunkPatterns = (m.Npad + nChunk - 1) / nChunk;
     chunkPatterns = (chunkPatterns + GM_TP - 1) / GM_TP * GM_TP;
     // level 1 of the codon path: tip-tip nodes through the dedicated kernel (unit / gap codes)
-    const bool cherry = l == 0 && m.S == 61 && e.cfg.code_count == m.S + 1 &&
-                        !getenv("TTB2_GM_NO_CHERRY");
-    if (cherry) {
-      const size_t csm = gm_cherry_bwd_smem(m.S);
-      TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_cherry_bwd_kernel<61>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-      for (int done = 0; done < count; done += maxNodes) {
-        const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
-        dim3 grid(nChunk, c * m.K, draws);
-        launch_level(gm_cherry_bwd_kernel<61>, grid, 256, csm, e.stream,
-                     l < nLevels - 1 && pdl_enabled(), e.ops, opBegin + done, e.mats, e.tips,
-                     e.codeP, e.weights, e.pre, e.gpart, e.chunkBase, e.chunkTotal, m.T, m.Npad,
-                     m.B, m.K, chunkPatterns, nChunk);
-        ++e.launches;
-      }
+    if (l == 0 && gmma_cherry_backward_supported(e)) {
+      const int rc = gmma_cherry_backward_level(e, draws, l < nLevels - 1 && pdl_enabled());
+      if (rc) return rc;
       continue;
     }
     if (m.S == 61 && !v61) {   // two-group kernel (TTB2_GM61=8 / 16 select the lock-step instances)

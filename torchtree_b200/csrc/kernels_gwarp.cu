@@ -602,7 +602,13 @@ int gw_launch_fwd(Engine& e, int draws, int ctas) {
                                          (int)smem));
   const int nLevels = (int)e.levelOff.size() - 1;
   const int maxNodes = 65535 / m.K;
-  for (int l = 0; l < nLevels; ++l) {
+  // level 1 (tip-tip nodes) needs no tensor cores: the streaming kernel of kernels_gmma.cu
+  const bool cherryLevel = gmma_cherry_level_supported(e);
+  if (cherryLevel) {
+    const int rc = gmma_cherry_forward_level(e, draws);
+    if (rc) return rc;
+  }
+  for (int l = cherryLevel ? 1 : 0; l < nLevels; ++l) {
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
     // patterns per CTA: `ctas` CTAs per SM per launch
@@ -638,6 +644,11 @@ int gw_launch_bwd(Engine& e, int draws) {
   const int nLevels = (int)e.levelOff.size() - 1;
   const int maxNodes = 65535 / m.K;
   for (int l = nLevels - 1; l >= 0; --l) {
+    if (l == 0 && gmma_cherry_backward_supported(e)) {   // tip-tip level: G-only kernel
+      const int rc = gmma_cherry_backward_level(e, draws, l < nLevels - 1 && pdl_enabled());
+      if (rc) return rc;
+      continue;
+    }
     const int opBegin = e.levelOff[l];
     const int count = e.levelOff[l + 1] - opBegin;
     const int nChunk = e.levelChunks[l];
