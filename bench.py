@@ -536,9 +536,13 @@ def run_engine(cfg, args, rank, local_rank, world, dist, with_clocks=True):
         tensor_bound = S > 32
         names = {4: ("bwd4_tma_kernel<3,5> (pre-order sweep, one launch per tree level; level 1 is "
                      "bwd4_tips_tma_kernel<4>)", "fwd4c_kernel<K> (post-order sweep; cherries tabulated)"),
-                 20: ("gw_bwd_kernel<20,4,2> (warp-autonomous DMMA pre-order sweep)",
-                      "gw_fwd_kernel<20,...> (post-order sweep)"),
-                 61: ("gm_bwd2_kernel<...,61> (DMMA pre-order sweep)", "gm_fwd2_kernel<...,61>")}
+                 20: ("gw_bwd_kernel<20,4,2> (warp-autonomous DMMA pre-order sweep; level 1 is "
+                      "gm_cherry_bwd_kernel<20,6>)",
+                      "gw_fwd_kernel<20,8,3> (post-order sweep; level 1 is gm_cherry_fwd_kernel<20>)"),
+                 61: ("gm_bwd3_kernel<61> (two-group DMMA pre-order sweep; level 1 is "
+                      "gm_cherry_bwd_kernel<61,8>)",
+                      "gm_fwd3_kernel<61> (warp-specialised DMMA post-order sweep; level 1 is "
+                      "gm_cherry_fwd_kernel<61>)")}
         kpre, kpost = names.get(S, ("pre-order sweep", "post-order sweep"))
         ncu = ncu_traffic_for_build() if (cfg["index"] == 2 and world == 1 and N == 100_000
                                           and cfg.get("topology") == "random") else None

@@ -290,7 +290,8 @@ int ttb2_heights_backward(ttb2_heights* plan, int32_t draws, const double* x,
  * Constant-population coalescent log-density of a batch of time trees on the device -- replaces
  * ConstantCoalescent.log_prob, torchtree/evolution/coalescent.py:112-134 (argsort of the 2T-1 node
  * heights, lineage counts by cumulative sum, sum of C(k,2) x interval / theta) and its autograd
- * backward (closed form once the order is known).  One CTA per draw; 2 <= T <= 4096.
+ * backward (closed form once the order is known).  One CTA per draw; T >= 2 (up to
+ * 4096 tips the sort runs in shared memory, beyond that on a global-memory scratch area).
  *   node_heights [draws][2T-1]  tips first (sampling times), then the T-1 internal nodes
  *   theta        [theta_draws]  population size, theta_draws = 1 (shared) or draws
  *   log_prob     [draws]

@@ -67,7 +67,8 @@ def test_native_matches_reference_golden(path, where):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("T,D,shared", [(500, 128, True), (2, 3, False), (3, 1, True),
-                                        (1000, 16, False), (4096, 2, True)])
+                                        (1000, 16, False), (4096, 2, True),
+                                        (4097, 2, False), (10000, 3, True)])
 def test_native_matches_oracle(T, D, shared):
     from oracle.coalescent import constant_log_prob
     from torchtree_b200.coalescent import constant_coalescent_log_prob
@@ -109,9 +110,11 @@ def test_unbatched_heights_with_batched_theta_and_limits():
     constant_log_prob(h2, t2).sum().backward()
     np.testing.assert_allclose(h.grad.numpy(), h2.grad.numpy(), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(theta.grad.numpy(), t2.grad.numpy(), rtol=1e-10)
-    with pytest.raises(RuntimeError, match="4096 tips"):
-        constant_coalescent_log_prob(torch.zeros(1, 2 * 4097 - 1, dtype=torch.float64),
-                                     torch.ones(1, 1, dtype=torch.float64))
+    # beyond 4096 tips the sort runs on a global-memory scratch area: device tensors too
+    big = torch.rand(2, 2 * 5000 - 1, dtype=torch.float64)
+    on_host = constant_coalescent_log_prob(big, torch.ones(1, 1, dtype=torch.float64))
+    on_dev = constant_coalescent_log_prob(big.cuda(), torch.ones(1, 1, dtype=torch.float64).cuda())
+    assert torch.equal(on_host, on_dev.cpu())
     nan = torch.tensor(rec["heights"][:1]).clone()
     nan[0, -1] = float("nan")
     nan.requires_grad_(True)

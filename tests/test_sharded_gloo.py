@@ -173,3 +173,65 @@ def test_draw_sharding_with_more_ranks_than_draws(tmp_path):
         np.testing.assert_allclose(got["gx"], [[2 * 1.5 * 3.0, 2 * 2.0 * 3.0]])
         np.testing.assert_allclose(got["gs"], [[1.5 ** 2 + 2.0 ** 2]])
         assert got["calls"].tolist() == ([1] if rank == 0 else [])
+
+
+# ---- the drop-in class with its "shard" JSON key -------------------------
+def _model_worker(rank, world, port, out_dir, shard):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank), TTB200_DIST_BACKEND="gloo")
+    import refenv
+
+    refenv.activate()
+    torch.set_default_dtype(torch.float64)
+    import test_plugin_reference as tp
+    import torchtree_b200.flatten as flatten
+    import torchtree_b200.tree_likelihood as tlmod
+
+    flatten.log_likelihood_eigen = tp.fake_eigen      # no GPU here: the pinned oracle evaluates
+    tlmod.Engine = tp.FakeEngine                      # this rank's shard
+    objs, like = tp._flu_json(batch=3 if shard == "draws" else None)
+    like = dict(like, shard=shard)
+    dic = tp._build(objs, like, "torchtree_b200.TreeLikelihoodModel")
+    model = dic["like"]
+    assert model._world == world and model.shard == shard
+    if shard == "patterns":
+        lo, hi = model.pattern_range
+        assert (hi - lo) in (119, 119) and model._get_engine(1).tip_codes.shape[1] == hi - lo
+    val, grads = tp._grads(dic, ["blens", "shape", "rates", "freqs"])
+    np.savez(os.path.join(out_dir, "model_rank%d.npz" % rank), lnL=val.numpy(),
+             **{k: v.numpy() for k, v in grads.items()})
+    dist.destroy_process_group()
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("shard", ["patterns", "draws"])
+def test_model_shard_key_two_ranks(tmp_path, shard):
+    """`"shard": "patterns" | "draws"` on the drop-in class: two gloo ranks, each with its slice of
+    the 238 fluA patterns (or of a batch of 3 draws), end up with the reference's value and the full
+    gradient of every torchtree Parameter."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import refenv
+
+    refenv.activate()
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        import test_plugin_reference as tp
+        import torchtree_b200.tree_likelihood  # noqa: F401  (imports and registers torchtree's classes)
+
+        port = 31500 + (os.getpid() % 2000) + (7 if shard == "draws" else 0)
+        mp.spawn(_model_worker, args=(2, port, str(tmp_path), shard), nprocs=2, join=True)
+        objs, like = tp._flu_json(batch=3 if shard == "draws" else None)
+        ref = tp._build(objs, like, "torchtree.evolution.tree_likelihood.TreeLikelihoodModel")
+        v_ref, g_ref = tp._grads(ref, ["blens", "shape", "rates", "freqs"])
+    finally:
+        torch.set_default_dtype(old)
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), "model_rank%d.npz" % rank))
+        np.testing.assert_allclose(got["lnL"], v_ref.numpy(), rtol=1e-10)
+        for k, v in g_ref.items():
+            tol = 1e-7 if k in ("rates", "freqs") else 1e-8
+            np.testing.assert_allclose(got[k], v.numpy(), rtol=tol, atol=tol * float(v.abs().max()),
+                                       err_msg=k)

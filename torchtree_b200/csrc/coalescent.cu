@@ -9,7 +9,8 @@
 // One CTA per draw: bitonic sort of (height, node index) pairs in shared memory (ties broken
 // by index, i.e. like a stable sort: intervals between tied events have zero length and do
 // not contribute), an integer scan for the lineage counts, and a fixed-order block reduction
-// (bit-wise reproducible).  2T-1 <= 8192 (16 bytes of shared memory per node).
+// (bit-wise reproducible).  Up to 4096 tips the 16 bytes per node live in shared memory; larger
+// trees run the same kernel on a global-memory scratch area (any T that fits in memory).
 #include <climits>
 #include <math_constants.h>
 #include <string>
@@ -26,10 +27,11 @@ __global__ void __launch_bounds__(CO_THREADS)
 coalescent_constant_kernel(const double* __restrict__ heights, const double* __restrict__ theta,
                            int thetaDraws, double* __restrict__ logp,
                            double* __restrict__ dHeights, double* __restrict__ dTheta, int T,
-                           int np2) {
+                           int np2, double* __restrict__ scratch) {
   extern __shared__ double sm[];
   const int n = 2 * T - 1;
-  double* key = sm;                                       // [np2]
+  // working arrays: shared memory, or this draw's slice of the global scratch (large trees)
+  double* key = scratch ? scratch + (size_t)blockIdx.x * np2 * 2 : sm;   // [np2]
   int* idx = reinterpret_cast<int*>(key + np2);           // [np2]
   int* cnt = idx + np2;                                   // [np2] lineage counts k_i
   __shared__ int chunkSum[CO_THREADS];
@@ -153,10 +155,7 @@ extern "C" int ttb2_coalescent_constant(int32_t device, int32_t draws, int32_t t
   const int n = 2 * tip_count - 1;
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
-  if (np2 > 8192) {
-    set_error("ttb2_coalescent_constant: at most 4096 tips");
-    return TTB2_E_INVALID;
-  }
+  const bool big = np2 > 8192;   // beyond 4096 tips the working arrays do not fit in shared memory
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("ttb2_coalescent_constant: no CUDA device available (sm_100a required; there is no CPU fallback)");
@@ -172,8 +171,8 @@ extern "C" int ttb2_coalescent_constant(int32_t device, int32_t draws, int32_t t
   const double* dT = theta;
   double *dL = log_prob, *dGH = d_heights, *dGT = d_theta;
   if (where == TTB2_HOST) {
-    // layout: heights | theta | logp | d_heights | d_theta
-    const size_t need = nh + theta_draws + draws + nh + draws;
+    // layout: heights | theta | logp | d_heights | d_theta | [sort scratch of large trees]
+    const size_t need = nh + theta_draws + draws + nh + draws + (big ? (size_t)draws * np2 * 2 : 0);
     CoScratch& sc = co_scratch;
     if (sc.device != device || sc.cap < need) {
       if (sc.buf) {
@@ -196,13 +195,32 @@ extern "C" int ttb2_coalescent_constant(int32_t device, int32_t draws, int32_t t
     dGH = d_heights ? dL + draws : nullptr;
     dGT = d_theta ? dL + draws + nh : nullptr;
   }
-  const size_t smem = (size_t)np2 * (sizeof(double) + 2 * sizeof(int));
+  double* sortScratch = nullptr;
+  if (big) {
+    if (where == TTB2_HOST) {
+      sortScratch = co_scratch.buf + (nh + theta_draws + draws + nh + draws);
+    } else {
+      TTB2_CUDA_CHECK(cudaMalloc((void**)&sortScratch, (size_t)draws * np2 * 2 * sizeof(double)));
+    }
+  }
+  const size_t smem = big ? 0 : (size_t)np2 * (sizeof(double) + 2 * sizeof(int));
   if (smem > 48 * 1024)
     TTB2_CUDA_CHECK(cudaFuncSetAttribute(coalescent_constant_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   coalescent_constant_kernel<<<draws, CO_THREADS, smem, 0>>>(dH, dT, theta_draws, dL, dGH, dGT,
-                                                            tip_count, np2);
-  TTB2_CUDA_CHECK(cudaGetLastError());
+                                                            tip_count, np2, sortScratch);
+  {
+    const cudaError_t lerr = cudaGetLastError();
+    if (lerr != cudaSuccess) {
+      if (big && where != TTB2_HOST) cudaFree(sortScratch);
+      set_error(std::string("coalescent_constant_kernel: ") + cudaGetErrorString(lerr));
+      return TTB2_E_CUDA;
+    }
+  }
+  if (big && where != TTB2_HOST) {
+    TTB2_CUDA_CHECK(cudaStreamSynchronize(0));
+    cudaFree(sortScratch);
+  }
   if (where == TTB2_HOST) {
     TTB2_CUDA_CHECK(cudaMemcpyAsync(log_prob, dL, draws * sizeof(double), cudaMemcpyDeviceToHost, 0));
     if (d_heights)
