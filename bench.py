@@ -78,7 +78,7 @@ def parse_args():
                     help="tree shape (the headline workload is the random-join tree)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
-    ap.add_argument("--ref-budget-s", type=float, default=420.0,
+    ap.add_argument("--ref-budget-s", type=float, default=600.0,
                     help="--impl reference: wall-clock budget for warm-up + timed steps")
     ap.add_argument("--engine-flags", type=int, default=0,
                     help="extra TTB2_FLAG_* bits for experiments (32 = no CUDA graphs)")

@@ -18,5 +18,9 @@ def constant_log_prob(node_heights: torch.Tensor, theta: torch.Tensor) -> torch.
     heights = torch.gather(node_heights, -1, order)                          # :125
     lineages = torch.gather(mask, -1, order).cumsum(-1)[..., :-1]            # :126-127
     durations = heights[..., 1:] - heights[..., :-1]                         # :129
-    lchoose2 = lineages * (lineages - 1) / 2.0                               # :130
+    # :130 -- the reference divides the integer product by 2.0, which yields the DEFAULT float
+    # dtype (float64 under the runner's fp64 default, torchtree.py:43-66); stated explicitly here
+    # so that the oracle does not depend on the process-wide default (float32 would round
+    # C(k, 2) beyond 2^24, i.e. from ~5800 lineages on)
+    lchoose2 = (lineages * (lineages - 1)).to(node_heights.dtype) / 2.0
     return torch.sum(-lchoose2 * durations / theta, -1, keepdim=True) - (taxa - 1) * torch.log(theta)
