@@ -300,3 +300,79 @@ def test_torch_extension_frequency_draws_broadcast_the_generator():
     assert torch.equal(lnl2.detach(), lnl.detach())
     assert_grad_close(q.grad.numpy(), q2.grad.sum(0, keepdim=True).numpy(), rtol=1e-12, what="d_q")
     eng.close()
+
+
+def test_backward_outlives_the_python_engine_and_close_raises():
+    """the autograd node keeps the native engine alive.  A backward that runs after
+    the Python `Engine` is gone (model garbage-collected, or TreeLikelihoodModel swapped its
+    engine for a larger one) still finds the buffers of its forward; after an explicit close()
+    it raises instead of touching freed memory."""
+    import gc
+
+    from torchtree_b200 import log_likelihood_eigen
+
+    prob, rec = load_golden("fluA_gtr_w4_generic")
+
+    def leaves():
+        return [torch.tensor(x, requires_grad=True) for x in
+                (prob.branch_lengths, prob.site_rates, prob.site_props, prob.q_matrix, prob.freqs)]
+
+    eng = _engine(prob)
+    a = leaves()
+    lnl = log_likelihood_eigen(eng, *a)
+    eng.release()          # what TreeLikelihoodModel._get_engine does when it needs a bigger engine
+    del eng
+    gc.collect()
+    other = _engine(prob)  # a new engine may even reuse the freed address
+    log_likelihood_eigen(other, *leaves())
+    lnl.sum().backward()
+    assert_grad_close(a[0].grad.numpy(), rec["d_branch_lengths"], what="d_bl after release")
+    other.close()
+
+    eng = _engine(prob)
+    b = leaves()
+    lnl = log_likelihood_eigen(eng, *b)
+    eng.close()
+    with pytest.raises(RuntimeError, match="has been closed"):
+        lnl.sum().backward()
+
+
+def test_float32_inputs_come_back_as_float32():
+    """dtype policy: fp64 inside, the caller's dtype outside (`--dtype float32` runs)."""
+    from torchtree_b200 import log_likelihood_eigen
+
+    prob, rec = load_golden("fluA_gtr_w4_generic")
+    eng = _engine(prob)
+    leaves = [torch.tensor(x, dtype=torch.float32, requires_grad=True) for x in
+              (prob.branch_lengths, prob.site_rates, prob.site_props, prob.q_matrix, prob.freqs)]
+    lnl = log_likelihood_eigen(eng, *leaves)
+    assert lnl.dtype == torch.float32
+    lnl.sum().backward()
+    assert all(t.grad.dtype == torch.float32 for t in leaves)
+    assert abs(lnl.item() - rec["lnL"][0]) <= 1e-5 * abs(rec["lnL"][0])
+    eng.close()
+
+
+def test_inputs_on_a_side_stream_are_ordered():
+    """with device tensors the engine runs on torch's current stream, so a producer and
+    a consumer on a non-default stream need no host synchronisation."""
+    from torchtree_b200 import log_likelihood_eigen
+
+    prob, rec = load_golden("syn40_gtr_w4")
+    eng = _engine(prob)
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(device=dev)
+    host = [torch.tensor(x) for x in (prob.branch_lengths, prob.site_rates, prob.site_props,
+                                      prob.q_matrix, prob.freqs)]
+    with torch.cuda.stream(side):
+        big = torch.randn(4096, 4096, device=dev)
+        for _ in range(10):                         # keep the side stream busy ahead of the inputs
+            big = big @ big * 1e-3
+        leaves = [t.to(dev, non_blocking=True).requires_grad_(True) for t in host]
+        lnl = log_likelihood_eigen(eng, *leaves)
+        total = lnl.sum() * 2.0                     # consumer on the same stream
+        total.backward()
+    side.synchronize()
+    assert_lnl_close((total / 2.0).detach().cpu().numpy(), rec["lnL"])
+    assert_grad_close(leaves[0].grad.cpu().numpy() / 2.0, rec["d_branch_lengths"], what="d_bl")
+    eng.close()

@@ -9,6 +9,7 @@ bench.py checks before quoting `roofline.traffic`).
 import collections
 import csv
 import json
+import re
 import sys
 
 
@@ -43,7 +44,9 @@ def main():
     last = launches[half:]           # second evaluation
     agg = collections.OrderedDict()
     for l in last:
-        name = l["name"].split("(")[0].replace("void ", "").replace("ttb2::<unnamed>::", "")
+        m = re.search(r"([A-Za-z_][A-Za-z0-9_]*(?:<[^>()]*>)?)\(", l["name"].replace("(int)", "")
+                      .replace("(bool)", ""))
+        name = m.group(1) if m else l["name"][:60]
         a = agg.setdefault(name, dict(n=0, us=0.0, rd=0.0, wr=0.0, dmma=0.0))
         a["n"] += 1
         us = to_us(l.get("gpu__time_duration.sum", 0.0), l.get("unit:gpu__time_duration.sum", "ns"))
