@@ -397,7 +397,7 @@ def run_engine(cfg, args, rank, local_rank, world, dist, with_clocks=True):
     """Times one configuration on this process group; returns the JSON fields (rank 0) or None."""
     from torchtree_b200 import Engine, log_likelihood_eigen
     from torchtree_b200.sharded import (draw_sharded_log_likelihood, shard_range,
-                                        sharded_log_likelihood)
+                                        sharded_engine_log_likelihood)
 
     dev = torch.device("cuda", local_rank)
     T, N, S, K, D = cfg["taxa"], cfg["patterns"], cfg["states"], cfg["categories"], cfg["draws"]
@@ -467,8 +467,8 @@ def run_engine(cfg, args, rank, local_rank, world, dist, with_clocks=True):
             lnl = fn(*user_in)
         elif by_draws:
             lnl = draw_sharded_log_likelihood(fn, user_in, D, group)
-        else:
-            lnl = sharded_log_likelihood(fn, user_in, group)
+        else:   # what TreeLikelihoodModel(shard="patterns") calls (flatten.evaluate_models)
+            lnl = sharded_engine_log_likelihood(eng, user_in, group)
         lnl.sum().backward()
         return lnl.detach()
 
@@ -607,7 +607,7 @@ def run_engine(cfg, args, rank, local_rank, world, dist, with_clocks=True):
                                "" if world == 1 else
                                ", inside torchtree_b200.sharded.%s (NCCL all-reduce of lnL and of the "
                                "packed gradient)" % ("draw_sharded_log_likelihood" if by_draws
-                                                     else "sharded_log_likelihood"))},
+                                                     else "sharded_engine_log_likelihood"))},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "phases_ms": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in ph.items()},
             "device_bytes": eng.device_bytes,

@@ -19,7 +19,7 @@ sys.path.insert(0, REPO)
 
 from torchtree_b200 import Engine, log_likelihood_eigen  # noqa: E402
 from torchtree_b200.sharded import (draw_sharded_log_likelihood, shard_range,  # noqa: E402
-                                    sharded_log_likelihood)
+                                    sharded_engine_log_likelihood, sharded_log_likelihood)
 from torchtree_b200.synthetic import make_problem  # noqa: E402
 
 
@@ -53,6 +53,14 @@ def main():
     v_one.sum().backward()
     out["patterns_lnL"] = rel(v_sh, v_one)
     out["patterns_grads"] = max(rel(x.grad, y.grad) for x, y in zip(a, b))
+
+    # ---- the engine-aware fast path (collectives on the device): what the model's
+    # "shard": "patterns" key uses over NCCL ----
+    c = leaves(prob)
+    v_fast = sharded_engine_log_likelihood(shard, c)
+    v_fast.sum().backward()
+    out["fast_lnL"] = rel(v_fast, v_one)
+    out["fast_grads"] = max(rel(x.grad, y.grad) for x, y in zip(c, b))
 
     # ---- the packed gradient, reduced in place on the device ----
     dev = torch.device("cuda", local)

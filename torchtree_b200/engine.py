@@ -168,6 +168,12 @@ class Engine:
         return out
 
     @property
+    def eval_serial(self) -> int:
+        """Number of loglik calls served so far (ttb2_eval_serial): a deferred gradient compares
+        it with the value it saw after its own forward."""
+        return int(self._lib.ttb2_eval_serial(self._h))
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.ttb2_launch_count(self._h))
 

@@ -93,6 +93,12 @@ def _flat(x, sample_shape, tail):
     return x.expand(tuple(sample_shape) + tail).reshape((-1,) + tail)
 
 
+def _nccl(group) -> bool:
+    import torch.distributed as dist
+
+    return dist.is_available() and dist.is_initialized() and "nccl" in dist.get_backend(group)
+
+
 def evaluate_models(engine, tree_model, site_model, subst_model, clock_model, sample_shape,
                     shard=None):
     """lnL with the reference's output contract: shape sample_shape + (1,)
@@ -134,11 +140,15 @@ def evaluate_models(engine, tree_model, site_model, subst_model, clock_model, sa
     if shard is None:
         lnl = local(*tensors)
     else:
-        from .sharded import draw_sharded_log_likelihood, sharded_log_likelihood
+        from .sharded import (draw_sharded_log_likelihood, sharded_engine_log_likelihood,
+                              sharded_log_likelihood)
 
         kind, group = shard
         if kind == "draws":
             lnl = draw_sharded_log_likelihood(local, tensors, D, group)
+        elif engine is not None and route in ("eigen", "expm") and _nccl(group):
+            # collectives on the device, next to the engine's packed outputs
+            lnl = sharded_engine_log_likelihood(engine, tensors, group, general=route == "expm")
         else:
             lnl = sharded_log_likelihood(local if engine is not None else None, tensors, group)
     return lnl.reshape(sample_shape + (1,))

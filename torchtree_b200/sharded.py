@@ -100,6 +100,83 @@ def sharded_log_likelihood(local_fn, tensors, group=None):
     return _SumOverShards.apply(group, local)
 
 
+# ---- pattern sharding, engine-aware fast path --------------------------------------------------
+class _ShardedEngineLikelihood(torch.autograd.Function):
+    """`sharded_log_likelihood(lambda *a: log_likelihood_eigen(engine, *a), tensors)` with the
+    collectives moved onto the device: the shard's lnL and its packed gradient vector
+    (`ttb2_grad_eigen_packed`: written in one piece by the engine's output kernels) are
+    all-reduced over NCCL where they are produced and cross to the host once, already summed --
+    instead of device -> host -> device -> NCCL -> host per collective.  Host or device tensors;
+    every rank ends with the full value and the full gradients."""
+
+    @staticmethod
+    def forward(ctx, engine, group, general, bls, rates, props, q, freqs):
+        from .function import reversible_eigensystem
+
+        dev = torch.device("cuda", engine.device)
+        src = (bls, rates, props, q, freqs)
+        if all(not t.is_cuda for t in src):
+            # host tensors (the stock torchtree set-up): one packed host -> device copy, then views
+            flat = torch.cat([t.detach().reshape(-1).to(torch.float64) for t in src]).to(dev)
+            ins, off = [], 0
+            for t in src:
+                ins.append(flat[off:off + t.numel()].view(t.shape))
+                off += t.numel()
+        else:
+            ins = [t.detach().to(dev, torch.float64).contiguous() for t in src]
+
+        def run():
+            S = engine.S
+            if general:
+                return engine.loglik_expm(*ins)
+            if S > 8 and max(ins[3].shape[0], ins[4].shape[0]) < 6:
+                # one large generator: LAPACK on the host, as the torch extension does
+                evec, ivec, evals = reversible_eigensystem(q.detach().double().cpu(),
+                                                           freqs.detach().double().cpu())
+                return engine.loglik_eigen(ins[0], ins[1], ins[2], evec.to(dev), ivec.to(dev),
+                                           evals.to(dev), ins[4])
+            return engine.loglik_q(*ins)
+
+        lnl = run()
+        if _world(group) > 1:
+            dist.all_reduce(lnl, group=group)
+        ctx.engine, ctx.group, ctx.run = engine, group, run
+        ctx.serial = engine.eval_serial
+        ctx.meta = [(t.shape, t.dtype, t.device) for t in src]
+        ctx.q_draws = q.shape[0]
+        return lnl.to(bls.device, bls.dtype)
+
+    @staticmethod
+    def backward(ctx, grad):
+        engine = ctx.engine
+        if engine.eval_serial != ctx.serial:   # another forward ran on this engine: recompute
+            ctx.run()
+            ctx.serial = engine.eval_serial
+        dev = torch.device("cuda", engine.device)
+        packed = engine.grad_eigen_packed(grad.detach().to(dev, torch.float64).reshape(-1))
+        if _world(ctx.group) > 1:
+            dist.all_reduce(packed, group=ctx.group)
+        if all(device.type == "cpu" for _, _, device in ctx.meta):
+            packed = packed.cpu()   # one device -> host copy of the summed vector
+        views = engine.unpack(packed)
+        out = []
+        for key, (shape, dtype, device) in zip(("branch_lengths", "site_rates", "props", "q",
+                                                "freqs"), ctx.meta):
+            g = views[key]
+            if key == "q" and g.shape[0] != ctx.q_draws:
+                g = g.sum(0, keepdim=True)
+            out.append(g.to(device, dtype).reshape(shape))
+        return (None, None, None) + tuple(out)
+
+
+def sharded_engine_log_likelihood(engine, tensors, group=None, general=False):
+    """Pattern-sharded lnL [D] of `engine`'s shard for `tensors` = (branch_lengths [D,B],
+    site_rates, site_props, q [.,S,S], freqs) -- the arguments of `log_likelihood_eigen`
+    (`general=True`: of `log_likelihood_expm`) -- summed over the ranks of `group`; after
+    `.backward()` every rank holds the full gradient of every tensor."""
+    return _ShardedEngineLikelihood.apply(engine, group, bool(general), *tensors)
+
+
 # ---- draw sharding (BASELINE config 3: a batch of ADVI / HMC draws per step) -------------------
 # Draws are independent evaluations of the same data with different parameters: rank g owns the
 # draws [g*D/G, (g+1)*D/G) of every per-draw tensor (leading extent D) and the whole of every
