@@ -304,6 +304,26 @@ int ttb2_coalescent_constant(int32_t device, int32_t draws, int32_t tip_count,
                              int32_t theta_draws, double* log_prob, double* d_heights,
                              double* d_theta, int32_t where);
 
+/*
+ * Piecewise-constant coalescents of a batch of time trees on the device: the skyride (one
+ * population size per inter-coalescent interval; grid_count = 0, theta_count = T - 1) and the
+ * skygrid (one per segment of a fixed time grid; theta_count = grid_count + 1) -- replace
+ * PiecewiseConstantCoalescent.log_prob, torchtree/evolution/coalescent.py:311-396, and
+ * PiecewiseConstantCoalescentGrid.log_prob, :459-549, with their autograd backward.  Same
+ * structure as ttb2_coalescent_constant (sort of the events -- node heights and grid points --,
+ * scans for the lineage count and the population-size index of every interval, closed-form
+ * derivatives).
+ *   node_heights [draws][2T-1]; theta [theta_draws][theta_count], theta_draws = 1 or draws;
+ *   grid [grid_count] ascending (NULL for the skyride)
+ *   log_prob [draws]; d_heights [draws][2T-1]; d_theta [draws][theta_count] (per draw; sum them
+ *   for a shared theta); either gradient pointer may be NULL.
+ */
+int ttb2_coalescent_piecewise(int32_t device, int32_t draws, int32_t tip_count,
+                              const double* node_heights, const double* theta,
+                              int32_t theta_draws, int32_t theta_count, const double* grid,
+                              int32_t grid_count, double* log_prob, double* d_heights,
+                              double* d_theta, int32_t where);
+
 /* Kernels launched by this engine since creation (bench `gpu_launches`). */
 int64_t ttb2_launch_count(const ttb2_engine* engine);
 /* Device bytes currently held by this engine. */

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle", "dendropy_shim"))
 sys.path.insert(0, "/root/reference")
 
-from torchtree.evolution.coalescent import ConstantCoalescent  # noqa: E402
+from torchtree.evolution.coalescent import (ConstantCoalescent, PiecewiseConstantCoalescent,  # noqa: E402
+                                            PiecewiseConstantCoalescentGrid)
 
 torch.set_default_dtype(torch.float64)
 
@@ -49,7 +50,40 @@ def case(name, T, D, heterochronous, shared_theta, seed):
     print(name, lp.detach().numpy().reshape(-1)[:3])
 
 
+def piecewise_case(name, T, D, heterochronous, shared_theta, seed, grid_points=0):
+    """Skyride (grid_points = 0: T-1 population sizes, coalescent.py:311-396) or skygrid
+    (coalescent.py:459-549) from the real reference distribution."""
+    rng = np.random.default_rng(seed)
+    hv = heights(rng, T, D, heterochronous)
+    h = torch.tensor(hv, requires_grad=True)
+    M = grid_points + 1 if grid_points else T - 1
+    theta = torch.tensor(rng.uniform(1.0, 9.0, (1 if shared_theta else D, M)), requires_grad=True)
+    if shared_theta:
+        theta_in = theta.reshape(M) if D == 1 else theta.expand(D, M)
+    else:
+        theta_in = theta
+    if grid_points:
+        grid = torch.tensor(np.linspace(0.0, 0.8 * hv.max(), grid_points + 1)[1:])
+        lp = PiecewiseConstantCoalescentGrid(theta_in, grid).log_prob(h)
+    else:
+        grid = torch.zeros(0)
+        lp = PiecewiseConstantCoalescent(theta_in).log_prob(h)
+    w = torch.tensor(rng.uniform(-1.0, 2.0, (D, 1)))
+    (lp * w).sum().backward()
+    np.savez(os.path.join(HERE, "coalescent_piecewise", name + ".npz"), heights=hv,
+             theta=theta.detach().numpy(), grid=grid.numpy(), log_prob=lp.detach().numpy(),
+             grad_out=w.numpy(), d_heights=h.grad.numpy(), d_theta=theta.grad.numpy())
+    print(name, lp.detach().numpy().reshape(-1)[:3])
+
+
 if __name__ == "__main__":
+    os.makedirs(os.path.join(HERE, "coalescent_piecewise"), exist_ok=True)
+    piecewise_case("skyride_T12_D3", 12, 3, True, False, 11)
+    piecewise_case("skyride_T60_D4_shared", 60, 4, True, True, 12)
+    piecewise_case("skyride_iso_T33_D2", 33, 2, False, False, 13)
+    piecewise_case("skygrid_T12_D3_G5", 12, 3, True, False, 21, grid_points=5)
+    piecewise_case("skygrid_T60_D4_G20_shared", 60, 4, True, True, 22, grid_points=20)
+    piecewise_case("skygrid_T200_D2_G50", 200, 2, True, False, 23, grid_points=50)
     case("hetero_T12_D3", 12, 3, True, False, 1)
     case("hetero_T60_D5_shared", 60, 5, True, True, 2)
     case("iso_T33_D4", 33, 4, False, False, 3)      # all tips at time 0: ties among the tips

@@ -229,7 +229,6 @@ def test_install_overrides_bare_and_dotted_type_names(patched):
         assert isinstance(dic["like"], patched.TreeLikelihoodModel)
         assert dic["like"]().shape == (1,)
     finally:
-        REGISTERED_CLASSES.clear()
         REGISTERED_CLASSES.update(saved_reg)
         refmod.TreeLikelihoodModel = saved_cls
 
@@ -332,7 +331,6 @@ def test_install_height_transform_rebinds_and_fails_loudly_without_gpu(patched):
             with pytest.raises(EngineError, match="no CUDA device"):
                 build().branch_lengths()
     finally:
-        REGISTERED_CLASSES.clear()
         REGISTERED_CLASSES.update(saved_reg)
         refmod.TreeLikelihoodModel = saved[0]
         ref_transform.GeneralNodeHeightTransform = saved[1]
@@ -587,9 +585,11 @@ def test_device_coalescent_class_is_a_dropin(patched, monkeypatch):
         assert get_class("torchtree.evolution.coalescent.ConstantCoalescentModel") \
             is cmod.ConstantCoalescentModel
     finally:
-        REGISTERED_CLASSES.clear()
         REGISTERED_CLASSES.update(saved_reg)
         refmod.ConstantCoalescentModel = saved_cls
+        for other in ("PiecewiseConstantCoalescentModel", "PiecewiseConstantCoalescentGridModel"):
+            if hasattr(refmod, "Reference" + other):
+                setattr(refmod, other, getattr(refmod, "Reference" + other))
 
 
 def test_time_tree_with_per_branch_clock_rates(patched):
@@ -710,7 +710,9 @@ def test_codon_mg94_on_fluA(patched):
             (n, (g_new[n] - g_ref[n]).abs().max().item(), g_ref[n].abs().max().item())
 
 
-def test_cli_time_tree_advi_with_device_heights_and_coalescent(patched, tmp_path, capsys):
+@pytest.mark.parametrize("coalescent", ["constant", "skyride", "skygrid"])
+def test_cli_time_tree_advi_with_device_heights_and_coalescent(patched, tmp_path, capsys, monkeypatch,
+                                                               coalescent):
     """BASELINE config 3's model on real data, end to end: `torchtree-cli advi -m JC69 --clock strict
     --coalescent constant --heights ratio` writes the JSON; the stock runner optimises it once as
     generated and once with the likelihood (`--b200`), the constant coalescent (`--b200_coalescent`)
@@ -726,9 +728,14 @@ def test_cli_time_tree_advi_with_device_heights_and_coalescent(patched, tmp_path
 
     sys.path.insert(0, REPO)
     base = ["advi", "-i", DATA + "/fluA.fa", "-t", DATA + "/fluA.tree", "-m", "JC69",
-            "--clock", "strict", "--coalescent", "constant", "--heights", "ratio",
-            "--iter", "6", "--elbo_samples", "3", "--grad_samples", "2", "--convergence_every", "2",
+            "--clock", "strict", "--coalescent", coalescent, "--heights", "ratio",
+            "--iter", "4", "--elbo_samples", "3", "--grad_samples", "2", "--convergence_every", "2",
             "--stem", str(tmp_path / "run")]
+    if coalescent == "skygrid":
+        base += ["--grid", "6", "--cutoff", "30"]
+    model_name = {"constant": "ConstantCoalescentModel",
+                  "skyride": "PiecewiseConstantCoalescentModel",
+                  "skygrid": "PiecewiseConstantCoalescentGridModel"}[coalescent]
     traces = {}
     saved_reg = dict(REGISTERED_CLASSES)
     saved = (refmod.TreeLikelihoodModel, ref_transform.GeneralNodeHeightTransform,
@@ -737,7 +744,7 @@ def test_cli_time_tree_advi_with_device_heights_and_coalescent(patched, tmp_path
         for tag, extra in (("reference", []), ("b200", ["--b200", "--b200_coalescent"])):
             cfg = _run_cli(base + extra, capsys)
             assert ("torchtree_b200.TreeLikelihoodModel" in cfg) == bool(extra)
-            assert ("torchtree_b200.coalescent.ConstantCoalescentModel" in cfg) == bool(extra)
+            assert (("torchtree_b200.coalescent." + model_name) in cfg) == bool(extra)
             path = tmp_path / (tag + ".json")
             path.write_text(cfg)
             if extra and patched.BACKEND == "cuda":
@@ -745,27 +752,28 @@ def test_cli_time_tree_advi_with_device_heights_and_coalescent(patched, tmp_path
                 patched.install(override_reference=False, height_transform=True)
             if extra and patched.BACKEND == "oracle":
                 import torchtree_b200.coalescent as cmod
-                from oracle.coalescent import constant_log_prob
+                from oracle.coalescent import (constant_log_prob, piecewise_grid_log_prob,
+                                               piecewise_log_prob)
 
-                cmod.constant_coalescent_log_prob = lambda h, th, device=0: constant_log_prob(h, th)
+                monkeypatch.setattr(cmod, "constant_coalescent_log_prob",
+                                    lambda h, th, device=0: constant_log_prob(h, th))
+                monkeypatch.setattr(
+                    cmod, "piecewise_coalescent_log_prob",
+                    lambda h, th, grid=None, device=0: piecewise_log_prob(h, th) if grid is None
+                    else piecewise_grid_log_prob(h, th, grid))
             out = _run_torchtree(str(path), capsys)
             elbos = [float(m.group(1)) for m in
                      re.finditer(r"^\s*\d+\s+(-?\d+\.\d+)\s+\d+\.\d+\s+\d+\.\d+", out, flags=re.M)]
-            assert len(elbos) >= 3, out[-2000:]
+            assert len(elbos) >= 2, out[-2000:]
             traces[tag] = elbos
     finally:
-        REGISTERED_CLASSES.clear()
         REGISTERED_CLASSES.update(saved_reg)
         refmod.TreeLikelihoodModel = saved[0]
         ref_transform.GeneralNodeHeightTransform = saved[1]
         ref_tree_model.GeneralNodeHeightTransform = saved[2]
-        if patched.BACKEND == "oracle":
-            import importlib
-
-            import torchtree_b200.coalescent as cmod
-
-            importlib.reload(cmod)
-    np.testing.assert_allclose(np.array(traces["b200"]), np.array(traces["reference"]), rtol=1e-7)
+    # (the runner prints three decimals: allow one unit in the last printed place)
+    np.testing.assert_allclose(np.array(traces["b200"]), np.array(traces["reference"]), rtol=1e-7,
+                               atol=1.5e-3)
 
 
 def test_discrete_trait_likelihood_general_nonsymmetric(patched):
@@ -809,3 +817,68 @@ def test_discrete_trait_likelihood_general_nonsymmetric(patched):
     for name in names:   # matrix_exp on both sides: no eigen-gap slack, 1e-8 throughout
         assert torch.allclose(g_new[name], g_ref[name], rtol=1e-8,
                               atol=1e-8 * g_ref[name].abs().max()), name
+
+
+@pytest.mark.parametrize("kind", ["skyride", "skygrid"])
+def test_device_piecewise_coalescent_classes_are_dropins(patched, monkeypatch, kind):
+    """`PiecewiseConstantCoalescentModel` (skyride) and `PiecewiseConstantCoalescentGridModel`
+    (skygrid) with the device log-density: same JSON, same value and gradients as the reference
+    classes; `install(coalescent=True)` rebinds their bare and dotted names."""
+    from torchtree.core.utils import REGISTERED_CLASSES, get_class, process_objects
+
+    import torchtree.evolution.coalescent as refmod
+
+    import torchtree_b200.coalescent as cmod
+    from oracle.coalescent import piecewise_grid_log_prob, piecewise_log_prob
+
+    rng = np.random.default_rng(31)
+    T = 9
+    tips = rng.uniform(0, 3, T)
+    inner = tips.max() + np.cumsum(rng.exponential(0.5, T - 1))
+    heights = np.concatenate([tips, inner])
+    name = "PiecewiseConstantCoalescentModel" if kind == "skyride" \
+        else "PiecewiseConstantCoalescentGridModel"
+    M = T - 1 if kind == "skyride" else 6
+
+    def build(type_name, batch):
+        dic = {}
+        th = rng.uniform(1.0, 6.0, M if batch is None else (batch, M))
+        data = {"id": "coal", "type": type_name, "theta": _P("theta", th.tolist()),
+                "times": heights.tolist(), "events": [1] * T + [0] * (T - 1)}
+        if kind == "skygrid":
+            data["cutoff"] = float(0.8 * heights.max())
+        process_objects(json.loads(json.dumps(data)), dic)
+        return dic
+
+    saved_reg, saved_cls = dict(REGISTERED_CLASSES), getattr(refmod, name)
+    backend, install = patched.BACKEND, patched.install
+    if backend == "oracle":
+        monkeypatch.setattr(
+            cmod, "piecewise_coalescent_log_prob",
+            lambda h, th, grid=None, device=0: piecewise_log_prob(h, th) if grid is None
+            else piecewise_grid_log_prob(h, th, grid))
+    try:
+        for batch in (None, 3):
+            state = rng.bit_generator.state
+            ref = build("torchtree.evolution.coalescent." + name, batch)
+            rng.bit_generator.state = state          # the same thetas for both classes
+            new = build("torchtree_b200.coalescent." + name, batch)
+            assert type(new["coal"]).__module__ == "torchtree_b200.coalescent"
+            assert isinstance(new["coal"], saved_cls)
+            for dic in (ref, new):
+                dic["theta"].requires_grad = True
+                dic["coal"]().sum().backward()
+            assert new["coal"]().shape == ref["coal"]().shape
+            assert torch.allclose(new["coal"](), ref["coal"](), rtol=1e-12, atol=0)
+            assert torch.allclose(new["theta"].grad, ref["theta"].grad, rtol=1e-9,
+                                  atol=1e-9 * ref["theta"].grad.abs().max())
+        install(override_reference=False, coalescent=True)
+        assert get_class(name) is getattr(cmod, name)
+        assert get_class("torchtree.evolution.coalescent." + name) is getattr(cmod, name)
+    finally:
+        REGISTERED_CLASSES.update(saved_reg)
+        setattr(refmod, name, saved_cls)
+        for other in ("ConstantCoalescentModel", "PiecewiseConstantCoalescentModel",
+                      "PiecewiseConstantCoalescentGridModel"):
+            if hasattr(refmod, "Reference" + other):
+                setattr(refmod, other, getattr(refmod, "Reference" + other))

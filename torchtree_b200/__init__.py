@@ -16,7 +16,7 @@ from .function import (  # noqa: F401
     reversible_eigensystem,
 )
 from ._lib import EngineError  # noqa: F401
-from .coalescent import constant_coalescent_log_prob  # noqa: F401
+from .coalescent import constant_coalescent_log_prob, piecewise_coalescent_log_prob  # noqa: F401
 
 
 def __getattr__(name):

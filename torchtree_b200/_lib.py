@@ -67,6 +67,7 @@ EXPORTED_SYMBOLS = (
     "ttb2_heights_forward",
     "ttb2_heights_backward",
     "ttb2_coalescent_constant",
+    "ttb2_coalescent_piecewise",
     "ttb2_launch_count",
     "ttb2_device_bytes",
     "ttb2_eval_serial",
@@ -146,6 +147,9 @@ def load():
     lib.ttb2_coalescent_constant.argtypes = [c_int32, c_int32, c_int32, vp, vp, c_int32, vp, vp, vp,
                                              c_int32]
     lib.ttb2_coalescent_constant.restype = c_int32
+    lib.ttb2_coalescent_piecewise.argtypes = [c_int32, c_int32, c_int32, vp, vp, c_int32, c_int32,
+                                              vp, c_int32, vp, vp, vp, c_int32]
+    lib.ttb2_coalescent_piecewise.restype = c_int32
     lib.ttb2_launch_count.argtypes = [vp]
     lib.ttb2_launch_count.restype = c_int64
     lib.ttb2_device_bytes.argtypes = [vp]

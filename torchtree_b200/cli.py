@@ -52,10 +52,12 @@ class B200Plugin(Plugin):
                          "patterns or the batch of draws across the ranks")
 
     def process_coalescent(self, arg, data):
-        # constant-population coalescent on the device (coalescent.py); other demographic models
-        # keep the reference class
-        if getattr(arg, "b200_coalescent", False) and data.get("type") == "ConstantCoalescentModel":
-            data["type"] = "torchtree_b200.coalescent.ConstantCoalescentModel"
+        # constant, skyride and skygrid coalescents on the device (coalescent.py); other
+        # demographic models keep the reference class
+        if getattr(arg, "b200_coalescent", False) and data.get("type") in (
+                "ConstantCoalescentModel", "PiecewiseConstantCoalescentModel",
+                "PiecewiseConstantCoalescentGridModel") and "temperature" not in data:
+            data["type"] = "torchtree_b200.coalescent." + data["type"]
 
     def process_tree_likelihood(self, arg, data):
         if not getattr(arg, "b200", False):

@@ -420,6 +420,48 @@ struct ConstantCoalescent : public torch::autograd::Function<ConstantCoalescent>
   }
 };
 
+// piecewise-constant coalescents: skyride (grid empty) and skygrid (ttb2_coalescent_piecewise),
+// replacing PiecewiseConstantCoalescent(.Grid).log_prob (coalescent.py:311-396, :459-549)
+struct PiecewiseCoalescent : public torch::autograd::Function<PiecewiseCoalescent> {
+  static Tensor forward(AutogradContext* ctx, int64_t device, const Tensor& node_heights,
+                        const Tensor& theta, const Tensor& grid) {
+    TORCH_CHECK(node_heights.dim() == 2, "ttb200: node_heights must be [draws, 2T-1]");
+    TORCH_CHECK(theta.dim() == 2, "ttb200: theta must be [1 or draws, M]");
+    Tensor h = node_heights.detach().to(at::kDouble).contiguous();
+    Tensor th = theta.detach().to(at::kDouble).contiguous();
+    Tensor gr = grid.detach().to(h.device(), at::kDouble).contiguous();
+    const int64_t D = h.size(0), n = h.size(1), M = th.size(1), G = gr.numel();
+    TORCH_CHECK(n % 2 == 1 && n >= 3, "ttb200: node_heights needs 2T-1 columns");
+    TORCH_CHECK(th.size(0) == 1 || th.size(0) == D, "ttb200: theta must have 1 or `draws` rows");
+    Tensor lp = at::empty({D}, h.options()), dh = at::empty_like(h),
+           dth = at::empty({D, M}, h.options());
+    const int where = where_of({h, th, gr}, (int)device);
+    check(ttb2_coalescent_piecewise((int32_t)device, (int32_t)D, (int32_t)((n + 1) / 2), dptr(h),
+                                    dptr(th), (int32_t)th.size(0), (int32_t)M,
+                                    G ? dptr(gr) : nullptr, (int32_t)G, dptr(lp), dptr(dh),
+                                    dptr(dth), where),
+          "ttb2_coalescent_piecewise");
+    ctx->saved_data["theta_draws"] = th.size(0);
+    ctx->save_for_backward({dh, dth});
+    return lp.to(node_heights.scalar_type());
+  }
+
+  static variable_list backward(AutogradContext* ctx, variable_list grad_out) {
+    auto saved = ctx->get_saved_variables();
+    const Tensor &dh = saved[0], &dth = saved[1];
+    Tensor g = grad_out[0].to(dh.device(), at::kDouble).reshape({-1, 1});
+    Tensor gh = dh * g;
+    Tensor gt = dth * g;
+    if (ctx->saved_data["theta_draws"].toInt() == 1) gt = gt.sum(0, /*keepdim=*/true);
+    return {Tensor(), gh, gt, Tensor()};
+  }
+};
+
+Tensor piecewise_coalescent(int64_t device, const Tensor& node_heights, const Tensor& theta,
+                            const Tensor& grid) {
+  return PiecewiseCoalescent::apply(device, node_heights, theta, grid);
+}
+
 Tensor constant_coalescent(int64_t device, const Tensor& node_heights, const Tensor& theta) {
   return ConstantCoalescent::apply(device, node_heights, theta);
 }
@@ -480,5 +522,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("constant_coalescent", &constant_coalescent,
         "log-density [D] of the constant-population coalescent for node heights [D, 2T-1]",
         py::arg("device"), py::arg("node_heights"), py::arg("theta"));
+  m.def("piecewise_coalescent", &piecewise_coalescent,
+        "log-density [D] of the skyride (empty grid) / skygrid coalescent for node heights [D, 2T-1]",
+        py::arg("device"), py::arg("node_heights"), py::arg("theta"), py::arg("grid"));
   m.def("abi_version", []() { return ttb2_version(); });
 }

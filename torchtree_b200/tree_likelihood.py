@@ -193,8 +193,9 @@ def install(override_reference: bool = True, height_transform: bool = False,
     * `height_transform=True` additionally rebinds `GeneralNodeHeightTransform`
       where `ReparameterizedTimeTreeModel` looks it up (tree_model.py:539, :587), so
       time trees map ratios to node heights on the GPU (height_transform.py);
-    * `coalescent=True` makes `ConstantCoalescentModel` (bare and dotted) resolve to the device
-      version (coalescent.py).
+    * `coalescent=True` makes `ConstantCoalescentModel`, `PiecewiseConstantCoalescentModel` (skyride)
+      and `PiecewiseConstantCoalescentGridModel` (skygrid), bare and dotted, resolve to the device
+      versions (coalescent.py).
     """
     import torchtree.evolution.tree_likelihood as ref_module
     from torchtree.evolution.substitution_model.amino_acid import LG, WAG
@@ -211,12 +212,14 @@ def install(override_reference: bool = True, height_transform: bool = False,
         import torchtree.evolution.coalescent as ref_coalescent
 
         from . import coalescent as b200_coalescent
-        cls = b200_coalescent.ConstantCoalescentModel
-        register_class(cls, "torchtree_b200.ConstantCoalescentModel")
-        register_class(cls, "ConstantCoalescentModel")
-        if not hasattr(ref_coalescent, "ReferenceConstantCoalescentModel"):
-            ref_coalescent.ReferenceConstantCoalescentModel = ref_coalescent.ConstantCoalescentModel
-        ref_coalescent.ConstantCoalescentModel = cls
+        for name in ("ConstantCoalescentModel", "PiecewiseConstantCoalescentModel",
+                     "PiecewiseConstantCoalescentGridModel"):
+            cls = getattr(b200_coalescent, name)
+            register_class(cls, "torchtree_b200." + name)
+            register_class(cls, name)
+            if not hasattr(ref_coalescent, "Reference" + name):
+                setattr(ref_coalescent, "Reference" + name, getattr(ref_coalescent, name))
+            setattr(ref_coalescent, name, cls)
     if height_transform:
         import torchtree.evolution.tree_height_transform as ref_transform
         import torchtree.evolution.tree_model as ref_tree_model
