@@ -334,7 +334,7 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   // 24 warps: two DMMA groups of 8 (group g takes the tiles t = g, g + 2, ...: while one group
   // waits for its tile to land the other one is in the tensor cores) and 8 epilogue warps
   constexpr int NTG = 4, NWG = 8;
-  constexpr int BAR_GROUP = 1, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 6;
+  constexpr int BAR_GROUP = 1, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 6, BAR_STAGGER = 8;
   const int S = CS ? CS : Srt;
   const GmShape g = gm_shape(S);
   const int SS = S * S;
@@ -388,6 +388,10 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     uint8_t* cds = codesS + grp * 64;
     double* out = outB + grp * tileN;
     int round = 0;
+    // stagger the two groups by half a period: group 1 starts loading when group 0's first tile
+    // has landed, so that one group's load wait falls into the other's DMMA phase (started
+    // together they stay in lock step: both wait, then both share the pipe)
+    if (grp == 1 && begin < end) named_sync(BAR_STAGGER, 512);
     for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP, ++round) {
       // (the group's previous tile was fully read before the barrier at the end of the last trip)
       const int i = i0 + lane;
@@ -414,6 +418,7 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       cp_async_commit();
       cp_async_wait_all();
       named_sync(BAR_GROUP + grp, NWG * 32);   // the tile is visible to the whole group
+      if (grp == 0 && round == 0) named_arrive(BAR_STAGGER, 512);
       if (round >= 1) named_sync(BAR_EMPTY + grp, 512);   // the epilogue released out[grp]
       for (int mt = gw; mt < MT; mt += NWG) {
         double accL[NTG][2], accR[NTG][2];
@@ -888,7 +893,7 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
                double* __restrict__ gpart, const int* __restrict__ chunkBase, size_t chunkTotal,
                int T, int Npad, int B, int K, int chunkPatterns, int nChunk, int codeCount) {
   extern __shared__ double sm[];
-  constexpr int S = CS, NTG = 4, NWG = 8, BAR_GROUP = 1;
+  constexpr int S = CS, NTG = 4, NWG = 8, BAR_GROUP = 1, BAR_STAGGER = 3;
   const GmShape g = gm_shape(S);
   constexpr int SS = S * S;
   const bool utab = gm_utab_fits(g, codeCount);
@@ -956,6 +961,9 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       }
     }
   };
+  // stagger the groups by half a period (see gm_fwd3_kernel)
+  if (grp == 1 && begin < end) named_sync(BAR_STAGGER, 512);
+  bool first = true;
   for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP) {
     // (the group finished reading its buffers before the barrier at the end of the last trip)
     stage_tile(tq, false, nullptr, qsrc, i0);
@@ -975,6 +983,8 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     cp_async_commit();
     cp_async_wait_all();
     named_sync(BAR_GROUP + grp, NWG * 32);   // the group's tiles are visible
+    if (grp == 0 && first) named_arrive(BAR_STAGGER, 512);
+    first = false;
     // U phase: u_l = P_l v_l, u_r = P_r v_r;  m_l = q^ o u_r (in place of q^), m_r = q^ o u_l
     for (int mt = gw; mt < MT; mt += NWG) {
       double accL[NTG][2], accR[NTG][2];
