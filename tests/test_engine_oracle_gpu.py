@@ -424,3 +424,63 @@ def test_chain_launches_draws_and_set_postorder(chain_mode_for_small_problems):
     want = orc.evaluate(b, want_grad=True)
     assert_lnl_close(out[1][0], want["lnL"])
     assert_grad_close(out[1][1], want["branch_lengths"], what="d_bl after set_postorder")
+
+
+@pytest.mark.parametrize("gaps,ambiguous", [(0.0, False), (0.1, False), (0.1, True)],
+                         ids=["unit", "gaps", "ambiguity-codes"])
+def test_codon_sweeps_with_kept_u_vectors(gaps, ambiguous, monkeypatch):
+    """61 states: the first evaluation of an engine repeats u_c = P_c p_c in the pre-order sweep;
+    once the gradient buffers exist the post-order sweep keeps them and the pre-order sweep reads
+    them back (kernels_gmma.cu gm_bwd3_kernel<61, true>).  Every evaluation of a sequence with
+    changing parameters must equal the oracle, and equal an engine that never keeps u bit for bit
+    (the same products in the same order, only computed once)."""
+    import dataclasses
+
+    from oracle import treelik as orc
+    from torchtree_b200 import Engine, reversible_eigensystem
+    from torchtree_b200.synthetic import make_problem
+
+    prob = make_problem(23, 150, 61, 2, seed=9, gap_fraction=gaps)
+    if ambiguous:   # a third kind of code: the tip tables no longer are unit vectors + gap only
+        table = np.concatenate([np.eye(61), np.ones((1, 61)), np.zeros((1, 61))])
+        table[-1, [3, 17, 44]] = 1.0
+        tips = prob.tip_states.copy()
+        tips[::3, ::7] = table.shape[0] - 1
+        prob = dataclasses.replace(prob, code_partials=table, tip_states=tips)
+
+    def engine():
+        return Engine(prob.tip_states, prob.weights, prob.postorder, 61, 2,
+                      code_partials=prob.code_partials, max_draws=1)
+
+    evec, ivec, evals = reversible_eigensystem(torch.tensor(prob.q_matrix), torch.tensor(prob.freqs))
+    rng = np.random.default_rng(4)
+    kept = engine()
+    monkeypatch.setenv("TTB2_GM_NO_USTORE", "1")
+    plain = engine()
+    base_bytes = None
+    for trip in range(3):
+        bl = prob.branch_lengths * rng.uniform(0.5, 1.5, prob.branch_lengths.shape)
+        bl[..., -1] = 0.0
+        outs = []
+        for eng in (kept, plain):
+            if eng is kept:
+                monkeypatch.delenv("TTB2_GM_NO_USTORE", raising=False)
+            else:
+                monkeypatch.setenv("TTB2_GM_NO_USTORE", "1")
+            lnl = eng.loglik_eigen(bl, prob.site_rates, prob.site_props, evec, ivec, evals,
+                                   prob.freqs).numpy().copy()
+            g = {k: v.numpy().copy() for k, v in eng.grad_eigen().items()}
+            outs.append((lnl, g))
+        want = orc.evaluate(dataclasses.replace(prob, branch_lengths=bl), want_grad=True,
+                            through_q=True)
+        assert_lnl_close(outs[0][0], want["lnL"])
+        assert_grad_close(outs[0][1]["branch_lengths"], want["branch_lengths"], what="d_bl")
+        assert_grad_close(outs[0][1]["site_rates"], want["site_rates"], what="d_rates")
+        assert np.array_equal(outs[0][0], outs[1][0])
+        for key in outs[0][1]:
+            assert np.array_equal(outs[0][1][key], outs[1][1][key]), (trip, key)
+        if trip == 0:
+            base_bytes = (kept.device_bytes, plain.device_bytes)
+    # the kept-u engine holds one more buffer of the size of the partials
+    assert base_bytes[0] > base_bytes[1]
+    kept.close(); plain.close()

@@ -20,6 +20,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--evals", type=int, default=2)
 ap.add_argument("--patterns", type=int, default=None)
+ap.add_argument("--trace", action="store_true",
+                help="print the phase timeline of gm_bwd3_kernel (library built with -DTTB2_GM_TRACE)")
 a = ap.parse_args()
 cfg = dict(bench.CONFIGS[a.config], index=a.config, topology="random")
 if a.patterns:
@@ -36,3 +38,25 @@ for _ in range(a.evals):
     eng.grad_eigen_packed()
 torch.cuda.synchronize()
 print("done", eng.launch_count)
+
+if a.trace:
+    import ctypes
+
+    import numpy as np
+
+    from torchtree_b200 import _lib
+
+    lib = _lib.load()
+    buf = np.zeros(2 * 64 * 6, dtype=np.int64)
+    rc = lib.ttb2_debug_gm_trace(buf.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, rc
+    t = buf.reshape(2, 64, 6)
+    t0 = t[t > 0].min()
+    print("group trip  start    load      U  token      Q      G   (SM clocks; start relative to the first stamp)")
+    for trip in range(12):
+        for grp in range(2):
+            r = t[grp, trip]
+            if r[0] == 0:
+                continue
+            print("%5d %4d %7d %6d %6d %6d %6d %6d" % (grp, trip, r[0] - t0, r[1] - r[0], r[2] - r[1],
+                                                      r[3] - r[2], r[4] - r[3], r[5] - r[4]))

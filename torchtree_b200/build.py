@@ -30,7 +30,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--fmad=true",  # fp64 fma contraction only; no fast-math, no ftz
-]
+] + os.environ.get("TTB2_NVCC_EXTRA", "").split()   # e.g. -DTTB2_GM_TRACE (tools/profile_eval.py --trace)
 
 
 def _nvcc() -> str:

@@ -191,6 +191,17 @@ int ensure_grad_buffers(Engine& e, int draws) {
     const size_t n = (size_t)e.cfg.max_draws * m.I * m.K * m.Npad * m.S;
     if ((rc = dev_alloc(e, &e.pre, n))) return rc;
   }
+  // codon path: keep the u vectors of the post-order sweep from the next evaluation on (a third
+  // buffer of the size of the partials: only when it leaves half of the free memory alone)
+  if (!e.uTried && gmma_keeps_u(e)) {
+    e.uTried = true;
+    const size_t n = (size_t)e.cfg.max_draws * m.I * m.K * m.Npad * m.S;
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && n * sizeof(double) <= freeB / 2) {
+      if ((rc = dev_alloc(e, &e.ustore, n))) return rc;
+      drop_graphs(e);
+    }
+  }
   const size_t matN = (size_t)e.cfg.max_draws * m.B * m.K * m.S * m.S;
   if (!e.dmat && (rc = dev_alloc(e, &e.dmat, matN))) return rc;
   if (!e.rootGrad && (rc = dev_alloc(e, &e.rootGrad, (size_t)e.cfg.max_draws * (m.K + m.S))))
@@ -295,7 +306,7 @@ bool graphs_enabled(const Engine& e, int draws) {
 
 bool slot_matches(const Engine::GraphSlot& g, const Engine& e, int draws) {
   return g.exec && g.draws == draws && g.fd == e.freqDraws && g.pd == e.propDraws &&
-         g.rd == e.rateDraws && g.ed == e.eigDraws && g.qd == e.qDraws;
+         g.rd == e.rateDraws && g.ed == e.eigDraws && g.qd == e.qDraws && g.us == e.uValid;
 }
 
 // Runs `body` (a sequence of kernel launches on e.stream) through a cached CUDA
@@ -335,6 +346,7 @@ int run_graphed(Engine& e, Engine::GraphSlot& slot, int draws, Body body) {
     slot.draws = draws;
     slot.fd = e.freqDraws; slot.pd = e.propDraws; slot.rd = e.rateDraws; slot.ed = e.eigDraws;
     slot.qd = e.qDraws;
+    slot.us = e.uValid;
   }
   TTB2_CUDA_CHECK(cudaEventRecord(e.evIn, user));
   TTB2_CUDA_CHECK(cudaStreamWaitEvent(e.ownStream, e.evIn, 0));
@@ -584,7 +596,7 @@ void ttb2_destroy(ttb2_engine* engine) {
   cudaSetDevice(e.device);
   cudaStreamSynchronize(e.stream);
   dev_free(e.tips); dev_free(e.weights); dev_free(e.codeP); dev_free(e.codeMask); dev_free(e.ops);
-  dev_free(e.partials); dev_free(e.expo); dev_free(e.pre); dev_free(e.mats);
+  dev_free(e.partials); dev_free(e.expo); dev_free(e.pre); dev_free(e.ustore); dev_free(e.mats);
   dev_free(e.dmat); dev_free(e.gpart); dev_free(e.siteLnl); dev_free(e.redPart);
   dev_free(e.lnl); dev_free(e.rootGrad); dev_free(e.hpart); dev_free(e.gscal); dev_free(e.hred);
   dev_free(e.inPacked);

@@ -51,6 +51,11 @@ struct Engine {
   double* partials = nullptr;   // spec4: [D][I][K][Npad][4]; generic: [D][I][K][S][Npad]
   int16_t* expo = nullptr;      // [D][I][Npad] power-of-two scale exponents
   double* pre = nullptr;        // pre-order vectors, same layout as partials
+  // codon path: u_c = P_c p_c of every internal child, written by the post-order sweep and read by
+  // the pre-order sweep (same layout as partials, indexed by the child).  Allocated with the
+  // gradient buffers when it fits; uValid: the last post-order sweep filled it.
+  double* ustore = nullptr;
+  bool uValid = false, uTried = false;
   double* mats = nullptr;       // [D][B][K][S][S]
   double* dmat = nullptr;       // d lnL / d mats, same shape
   double* gpart = nullptr;      // per-chunk partial sums of dmat
@@ -124,6 +129,7 @@ struct Engine {
     cudaGraphExec_t exec = nullptr;
     int draws = -1, fd = -1, pd = -1, rd = -1, ed = -1, qd = -1;
     int64_t kernels = 0;
+    bool us = false;   // captured with the kept u vectors (Engine::uValid)
   };
   GraphSlot gFwd, gBwd;
   cudaStream_t ownStream = nullptr;   // capture / replay stream
@@ -171,6 +177,7 @@ int gen_backward(Engine& e, int draws);
 
 // fp64 tensor-core path for 8 <= S <= 64 (kernels_gmma.cu); shares the generic layout
 bool gmma_supported(const Engine& e);
+bool gmma_keeps_u(const Engine& e);   // the post-order sweep can keep u_c = P_c p_c for the pre-order sweep
 // per-(pattern, category) rescaling, pipelined staging (own root kernels, expoK layout)
 size_t gmma_expo_elems(const Engine& e);
 int gmma_forward2(Engine& e, int draws);

@@ -175,6 +175,10 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -328,13 +332,14 @@ template <int CS>
 __global__ void __launch_bounds__(768)
 gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
                const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
-               double* __restrict__ partials, int16_t* __restrict__ expoK, int T, int Npad, int B,
-               int K, int Srt, int chunkPatterns, int codeCount) {
+               double* __restrict__ partials, int16_t* __restrict__ expoK,
+               double* __restrict__ ustore, int T, int Npad, int B, int K, int Srt,
+               int chunkPatterns, int codeCount, int tokenAt) {
   extern __shared__ double sm[];
   // 24 warps: two DMMA groups of 8 (group g takes the tiles t = g, g + 2, ...: while one group
   // waits for its tile to land the other one is in the tensor cores) and 8 epilogue warps
   constexpr int NTG = 4, NWG = 8;
-  constexpr int BAR_GROUP = 1, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 6, BAR_STAGGER = 8;
+  constexpr int BAR_GROUP = 1, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 6, BAR_GO = 8;
   const int S = CS ? CS : Srt;
   const GmShape g = gm_shape(S);
   const int SS = S * S;
@@ -367,6 +372,12 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   const double* pr = base + (size_t)(tipR ? 0 : op.right - T) * nodeStride;
   double* qn = base + (size_t)(op.node - T) * nodeStride;
   int16_t* en = expoK + (((size_t)d * I + (op.node - T)) * K + k) * Npad;
+  // u_c = P_c p_c of the internal children, kept for the pre-order sweep (gm_bwd3_kernel<., true>
+  // reads them instead of repeating these two products); null: not kept
+  double* ul = (ustore && !tipL)
+      ? ustore + (size_t)d * I * nodeStride + k * plane + (size_t)(op.left - T) * nodeStride : nullptr;
+  double* ur = (ustore && !tipR)
+      ? ustore + (size_t)d * I * nodeStride + k * plane + (size_t)(op.right - T) * nodeStride : nullptr;
 
   const bool tabL = tipL && utab, tabR = tipR && utab;
   if (tabL) gm_stage_utab(Pl, matsD + ((size_t)op.left * K + k) * SS, codeP, codeCount, g);
@@ -388,21 +399,22 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     uint8_t* cds = codesS + grp * 64;
     double* out = outB + grp * tileN;
     int round = 0;
-    // stagger the two groups by half a period: group 1 starts loading when group 0's first tile
-    // has landed, so that one group's load wait falls into the other's DMMA phase (started
-    // together they stay in lock step: both wait, then both share the pipe)
-    if (grp == 1 && begin < end) named_sync(BAR_STAGGER, 512);
+    // the two groups take turns in the tensor cores (token through BAR_GO + group, see
+    // gm_bwd3_kernel): left to themselves they fall into lock step, both waiting for tiles and
+    // then sharing the pipe
     for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP, ++round) {
       // (the group's previous tile was fully read before the barrier at the end of the last trip)
       const int i = i0 + lane;
+      // 16 bytes per lane: one instruction moves two rows of the 32-pattern tile
+      const int half = lane >> 4, l2 = (lane & 15) * 2;
       if (tabL) { if (gw == 0 && lane < 8) cp_async4(cds + 4 * lane, tl + i0 + 4 * lane); }
       else if (tipL) {
         const double* cp = codeP + (size_t)tl[i] * g.S;
         for (int s2 = gw; s2 < g.R; s2 += NWG) tcl[s2 * GM_LDT + lane] = s2 < g.S ? cp[s2] : 0.0;
       } else {
-        for (int s2 = gw; s2 < g.R; s2 += NWG) {
-          if (s2 < g.S) cp_async8(tcl + s2 * GM_LDT + lane, pl + (size_t)s2 * Npad + i);
-          else tcl[s2 * GM_LDT + lane] = 0.0;
+        for (int s2 = gw * 2 + half; s2 < g.R; s2 += 2 * NWG) {
+          if (s2 < g.S) cp_async16(tcl + s2 * GM_LDT + l2, pl + (size_t)s2 * Npad + i0 + l2);
+          else tcl[s2 * GM_LDT + l2] = tcl[s2 * GM_LDT + l2 + 1] = 0.0;
         }
       }
       if (tabR) { if (gw == 1 && lane < 8) cp_async4(cds + 32 + 4 * lane, tr + i0 + 4 * lane); }
@@ -410,16 +422,16 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
         const double* cp = codeP + (size_t)tr[i] * g.S;
         for (int s2 = gw; s2 < g.R; s2 += NWG) tcr[s2 * GM_LDT + lane] = s2 < g.S ? cp[s2] : 0.0;
       } else {
-        for (int s2 = gw; s2 < g.R; s2 += NWG) {
-          if (s2 < g.S) cp_async8(tcr + s2 * GM_LDT + lane, pr + (size_t)s2 * Npad + i);
-          else tcr[s2 * GM_LDT + lane] = 0.0;
+        for (int s2 = gw * 2 + half; s2 < g.R; s2 += 2 * NWG) {
+          if (s2 < g.S) cp_async16(tcr + s2 * GM_LDT + l2, pr + (size_t)s2 * Npad + i0 + l2);
+          else tcr[s2 * GM_LDT + l2] = tcr[s2 * GM_LDT + l2 + 1] = 0.0;
         }
       }
       cp_async_commit();
       cp_async_wait_all();
       named_sync(BAR_GROUP + grp, NWG * 32);   // the tile is visible to the whole group
-      if (grp == 0 && round == 0) named_arrive(BAR_STAGGER, 512);
       if (round >= 1) named_sync(BAR_EMPTY + grp, 512);   // the epilogue released out[grp]
+      if (tokenAt && (grp == 1 || round > 0)) named_sync(BAR_GO + grp, 512);
       for (int mt = gw; mt < MT; mt += NWG) {
         double accL[NTG][2], accR[NTG][2];
 #pragma unroll
@@ -438,7 +450,23 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
           o[n * 8] = accL[n][0] * accR[n][0];
           o[n * 8 + 1] = accL[n][1] * accR[n][1];
         }
+        // straight from the accumulator fragments: 64-byte runs per row
+        const int row = mt * 8 + (lane >> 2);
+        if (row < S) {
+          const size_t at = (size_t)row * Npad + i0 + (lane & 3) * 2;
+          if (ul) {
+#pragma unroll
+            for (int n = 0; n < NTG; ++n)
+              *reinterpret_cast<double2*>(ul + at + n * 8) = make_double2(accL[n][0], accL[n][1]);
+          }
+          if (ur) {
+#pragma unroll
+            for (int n = 0; n < NTG; ++n)
+              *reinterpret_cast<double2*>(ur + at + n * 8) = make_double2(accR[n][0], accR[n][1]);
+          }
+        }
       }
+      if (tokenAt && i0 + GM_TP < end) named_arrive(BAR_GO + (grp ^ 1), 512);
       __threadfence_block();
       named_arrive(BAR_FULL + grp, 512);
       named_sync(BAR_GROUP + grp, NWG * 32);   // every warp is done reading the tile
@@ -884,16 +912,33 @@ gm_bwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
 // through shared memory at the end.
 // shared: Pl Pr [Sp*PLD] | per group: tq vl vr mr [R*LDT] , ws [32], se [64 int16], codes [64]
 // ---------------------------------------------------------------------------
-template <int CS>
+#ifdef TTB2_GM_TRACE
+// phase timeline of one CTA (tools/profile_eval.py --trace): [group][trip][6] SM clock stamps
+__device__ long long gm_trace[2 * 64 * 6];
+#define GM_TRACE(slot)                                                                    \
+  if (blockIdx.x == 1 && blockIdx.y == 0 && gw == 0 && lane == 0 && trip < 64)            \
+    gm_trace[(grp * 64 + trip) * 6 + (slot)] = clock64();
+#else
+#define GM_TRACE(slot)
+#endif
+
+// US: the post-order sweep kept u_c = P_c p_c of every internal child (Engine::ustore), so the U
+// phase is two element-wise products instead of two of the six matrix products per tile: the
+// u_r tile lands in the m_l buffer and the u_l tile in the m_r buffer (m_l = q^ o u_r, m_r =
+// q^ o u_l are formed in place, every element by the thread that read it), and q^ is read
+// straight into the accumulator-fragment layout.
+template <int CS, bool US>
 __global__ void __launch_bounds__(512)
 gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restrict__ mats,
                const uint8_t* __restrict__ tips, const double* __restrict__ codeP,
                const double* __restrict__ partials, const int16_t* __restrict__ expoK,
+               const double* __restrict__ ustore,
                const double* __restrict__ weights, double* __restrict__ pre,
                double* __restrict__ gpart, const int* __restrict__ chunkBase, size_t chunkTotal,
-               int T, int Npad, int B, int K, int chunkPatterns, int nChunk, int codeCount) {
+               int T, int Npad, int B, int K, int chunkPatterns, int nChunk, int codeCount,
+               int tokenAt) {
   extern __shared__ double sm[];
-  constexpr int S = CS, NTG = 4, NWG = 8, BAR_GROUP = 1, BAR_STAGGER = 3;
+  constexpr int S = CS, NTG = 4, NWG = 8, BAR_GROUP = 1, BAR_GO = 3;
   const GmShape g = gm_shape(S);
   constexpr int SS = S * S;
   const bool utab = gm_utab_fits(g, codeCount);
@@ -944,6 +989,9 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   const double* qsrc = pre + drawBase + (size_t)(op.node - T) * nodeStride + k * plane;
   const double* lsrc = partials + drawBase + (size_t)(tipL ? 0 : op.left - T) * nodeStride + k * plane;
   const double* rsrc = partials + drawBase + (size_t)(tipR ? 0 : op.right - T) * nodeStride + k * plane;
+  const double* ulsrc = US ? ustore + drawBase + (size_t)(tipL ? 0 : op.left - T) * nodeStride + k * plane : nullptr;
+  const double* ursrc = US ? ustore + drawBase + (size_t)(tipR ? 0 : op.right - T) * nodeStride + k * plane : nullptr;
+  static_assert(!US || (CS + 7) / 8 == NWG, "US: one row tile per warp of a group");
   const uint8_t* tl = tips + (size_t)(tipL ? op.left : 0) * Npad;
   const uint8_t* tr = tips + (size_t)(tipR ? op.right : 0) * Npad;
   const int16_t* elp = tipL ? nullptr : expoK + (((size_t)d * I + (op.left - T)) * K + k) * Npad;
@@ -955,18 +1003,35 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       const double* cp = codeP + (size_t)tipRow[i] * S;
       for (int s2 = gw; s2 < g.R; s2 += NWG) tile[s2 * GM_LDT + lane] = s2 < S ? cp[s2] : 0.0;
     } else {
-      for (int s2 = gw; s2 < g.R; s2 += NWG) {
-        if (s2 < S) cp_async8(tile + s2 * GM_LDT + lane, src + (size_t)s2 * Npad + i);
-        else tile[s2 * GM_LDT + lane] = 0.0;
+      // 16 bytes per lane: one instruction moves two rows of the 32-pattern tile
+      const int half = lane >> 4, l2 = (lane & 15) * 2;
+      for (int s2 = gw * 2 + half; s2 < g.R; s2 += 2 * NWG) {
+        if (s2 < S) cp_async16(tile + s2 * GM_LDT + l2, src + (size_t)s2 * Npad + i0 + l2);
+        else tile[s2 * GM_LDT + l2] = tile[s2 * GM_LDT + l2 + 1] = 0.0;
       }
     }
   };
-  // stagger the groups by half a period (see gm_fwd3_kernel)
-  if (grp == 1 && begin < end) named_sync(BAR_STAGGER, 512);
-  bool first = true;
-  for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP) {
+  // The two groups take turns in the tensor cores: a group enters its Q + G phases when the other
+  // one has left its own (token through the named barriers BAR_GO + group), so that one group's
+  // tile wait and element-wise U phase always fall into the other's DMMA phases.  Left to
+  // themselves -- even started half a period apart -- the groups drift into lock step within two
+  // trips (both wait for tiles, then both share the pipe: 56 % busy, profiles/r02_codon.md).
+  int trip = 0;
+  for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP, ++trip) {
+    GM_TRACE(0)
     // (the group finished reading its buffers before the barrier at the end of the last trip)
-    stage_tile(tq, false, nullptr, qsrc, i0);
+    double2 qf[NTG];
+    if (US) {
+      const int row = gw * 8 + (lane >> 2);
+      const double* qp = qsrc + (size_t)row * Npad + i0 + (lane & 3) * 2;
+#pragma unroll
+      for (int n = 0; n < NTG; ++n)
+        qf[n] = row < S ? __ldg(reinterpret_cast<const double2*>(qp + n * 8)) : make_double2(0.0, 0.0);
+      if (!tipR) stage_tile(tq, false, nullptr, ursrc, i0);   // u_r, becomes m_l
+      if (!tipL) stage_tile(mr, false, nullptr, ulsrc, i0);   // u_l, becomes m_r
+    } else {
+      stage_tile(tq, false, nullptr, qsrc, i0);
+    }
     if (!hotL) stage_tile(vl, tipL, tl, lsrc, i0);
     if (!hotR) stage_tile(vr, tipR, tr, rsrc, i0);
     if (gw == 0) {
@@ -983,14 +1048,33 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     cp_async_commit();
     cp_async_wait_all();
     named_sync(BAR_GROUP + grp, NWG * 32);   // the group's tiles are visible
-    if (grp == 0 && first) named_arrive(BAR_STAGGER, 512);
-    first = false;
+    GM_TRACE(1)
     // U phase: u_l = P_l v_l, u_r = P_r v_r;  m_l = q^ o u_r (in place of q^), m_r = q^ o u_l
     for (int mt = gw; mt < MT; mt += NWG) {
       double accL[NTG][2], accR[NTG][2];
 #pragma unroll
       for (int n = 0; n < NTG; ++n) accL[n][0] = accL[n][1] = accR[n][0] = accR[n][1] = 0.0;
-      if (!tabL && !tabR) {
+      if (US) {
+        const int off0 = (mt * 8 + (lane >> 2)) * GM_LDT + (lane & 3) * 2;
+        if (tabL) gm_u_tip<NTG>(accL, Pl, uld, codesS, mt, 0, lane);
+        else if (tipL) gm_mma_ab_g<NTG>(accL, Pl, g.PLD, vl, mt, 0, KT, lane);
+        else {
+#pragma unroll
+          for (int n = 0; n < NTG; ++n) {
+            const double2 u = *reinterpret_cast<const double2*>(mr + off0 + n * 8);
+            accL[n][0] = u.x; accL[n][1] = u.y;
+          }
+        }
+        if (tabR) gm_u_tip<NTG>(accR, Pr, uld, codesS + 32, mt, 0, lane);
+        else if (tipR) gm_mma_ab_g<NTG>(accR, Pr, g.PLD, vr, mt, 0, KT, lane);
+        else {
+#pragma unroll
+          for (int n = 0; n < NTG; ++n) {
+            const double2 u = *reinterpret_cast<const double2*>(tq + off0 + n * 8);
+            accR[n][0] = u.x; accR[n][1] = u.y;
+          }
+        }
+      } else if (!tabL && !tabR) {
         gm_mma_ab_g2<NTG>(accL, accR, Pl, Pr, g.PLD, vl, vr, mt, 0, KT, lane);
       } else {
         if (tabL) gm_u_tip<NTG>(accL, Pl, uld, codesS, mt, 0, lane);
@@ -1001,7 +1085,7 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
 #pragma unroll
       for (int n = 0; n < NTG; ++n) {
         const int off = (mt * 8 + (lane >> 2)) * GM_LDT + n * 8 + (lane & 3) * 2;
-        const double q0 = tq[off], q1 = tq[off + 1];
+        const double q0 = US ? qf[n].x : tq[off], q1 = US ? qf[n].y : tq[off + 1];
         tq[off] = q0 * accR[n][0];
         tq[off + 1] = q1 * accR[n][1];
         mr[off] = q0 * accL[n][0];
@@ -1009,6 +1093,9 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       }
     }
     named_sync(BAR_GROUP + grp, NWG * 32);
+    GM_TRACE(2)
+    if (grp == 1 || trip > 0) named_sync(BAR_GO + grp, 512);   // the other group left the pipe
+    GM_TRACE(3)
     const double* ml = tq;
     // Q phase: q^_c = P_c^T m_c * 2^{-e_c}  (internal children)
     for (int side = 0; side < 2; ++side) {
@@ -1035,9 +1122,14 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
         }
       }
     }
+    // pass the token if the other group has a trip left that waits for it (group 1's trip
+    // `trip` after group 0's, group 0's trip `trip + 1` after group 1's: both start at i0 + 32)
+    if (tokenAt == 0 && i0 + GM_TP < end) named_arrive(BAR_GO + (grp ^ 1), 512);
+    GM_TRACE(4)
     // G phase: G_c[s][t] += sum_p (w_p m_c[s][p]) v_c[t][p]
 #pragma unroll
     for (int cj = 0; cj < NCJ; ++cj) {
+      if (cj == 1 && tokenAt == 1 && i0 + GM_TP < end) named_arrive(BAR_GO + (grp ^ 1), 512);
       const int combo = gw + cj * NWG;
       if (combo < 2 * MT) {
         const int side = combo / MT;
@@ -1073,7 +1165,9 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
         }
       }
     }
+    if (tokenAt == 2 && i0 + GM_TP < end) named_arrive(BAR_GO + (grp ^ 1), 512);
     named_sync(BAR_GROUP + grp, NWG * 32);   // every warp of the group is done with the tiles
+    GM_TRACE(5)
   }
   // partial G of group 1 -> shared memory (its own tile area: 4 tiles hold 2 * 64 * 64 doubles
   // only if LDT >= 32: 4 * 64 * 36 = 9216 >= 8192), then group 0 adds and stores
@@ -1279,6 +1373,13 @@ bool gmma_supported(const Engine& e) {
          gm_fwd2_smem(m) <= 227 * 1024 && gm_bwd2_smem(m) <= 227 * 1024;
 }
 
+// 61 states through gm_fwd3_kernel / gm_bwd3_kernel (TTB2_GM_NO_USTORE=1: always recompute)
+bool gmma_keeps_u(const Engine& e) {
+  const char* f = getenv("TTB2_GM61F");
+  return gmma_supported(e) && e.dm.S == 61 && !(f && atoi(f) == 2) && !getenv("TTB2_GM61") &&
+         !getenv("TTB2_GM_NO_USTORE");
+}
+
 size_t gmma_expo_elems(const Engine& e) {
   const Dims& m = e.dm;
   return (size_t)e.cfg.max_draws * m.I * m.K * m.Npad;
@@ -1370,6 +1471,7 @@ static int gm_fwd_chunk(const Engine& e, int draws, int count) {
 }
 
 int gmma_forward2(Engine& e, int draws) {
+  e.uValid = false;
   if (gwarp_supported(e, false)) return gwarp_forward(e, draws);
   const Dims& m = e.dm;
   const size_t smem = gm_fwd2_smem(m);
@@ -1388,6 +1490,7 @@ int gmma_forward2(Engine& e, int draws) {
   const bool cherryLevel = gmma_cherry_level_supported(e);
   auto launch_cherry_level = [&]() -> int { return gmma_cherry_forward_level(e, draws); };
   if (spec61) {
+    static const int tokenF = getenv("TTB2_GM_TOKENF") ? atoi(getenv("TTB2_GM_TOKENF")) : 1;
     const size_t smem3 = gm_fwd3_smem(m);
     TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_fwd3_kernel<61>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
@@ -1406,12 +1509,13 @@ int gmma_forward2(Engine& e, int draws) {
         const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
         dim3 grid(nChunk, c * m.K, draws);
         launch_level(gm_fwd3_kernel<61>, grid, 768, smem3, e.stream, l > 0 && pdl_enabled(), e.ops,
-                     opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, m.T, m.Npad,
-                     m.B, m.K, m.S, chunkPatterns, e.cfg.code_count);
+                     opBegin + done, e.mats, e.tips, e.codeP, e.partials, e.expoK, e.ustore, m.T,
+                     m.Npad, m.B, m.K, m.S, chunkPatterns, e.cfg.code_count, tokenF);
         ++e.launches;
       }
     }
     TTB2_CUDA_CHECK(cudaGetLastError());
+    e.uValid = e.ustore != nullptr;
     return TTB2_OK;
   }
   auto kern = m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
@@ -1519,15 +1623,19 @@ int gmma_backward2(Engine& e, int draws) {
     }
     if (m.S == 61 && !v61) {   // two-group kernel (TTB2_GM61=8 / 16 select the lock-step instances)
       const size_t sm3 = gm_bwd3_smem(m.S);
-      TTB2_CUDA_CHECK(cudaFuncSetAttribute(gm_bwd3_kernel<61>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+      // with the u vectors of this evaluation's post-order sweep when it kept them
+      auto k3 = e.uValid ? gm_bwd3_kernel<61, true> : gm_bwd3_kernel<61, false>;
+      static const int tokenAt = getenv("TTB2_GM_TOKEN") ? atoi(getenv("TTB2_GM_TOKEN")) : 1;
+      TTB2_CUDA_CHECK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sm3));
       for (int done = 0; done < count; done += maxNodes) {
         const int c = (count - done) < maxNodes ? (count - done) : maxNodes;
         dim3 grid(nChunk, c * m.K, draws);
-        launch_level(gm_bwd3_kernel<61>, grid, 512, sm3, e.stream,
+        launch_level(k3, grid, 512, sm3, e.stream,
                      l < nLevels - 1 && pdl_enabled(), e.ops, opBegin + done, e.mats, e.tips,
-                     e.codeP, e.partials, e.expoK, e.weights, e.pre, e.gpart, e.chunkBase,
-                     e.chunkTotal, m.T, m.Npad, m.B, m.K, chunkPatterns, nChunk, e.cfg.code_count);
+                     e.codeP, e.partials, e.expoK, e.ustore, e.weights, e.pre, e.gpart, e.chunkBase,
+                     e.chunkTotal, m.T, m.Npad, m.B, m.K, chunkPatterns, nChunk, e.cfg.code_count,
+                     tokenAt);
         ++e.launches;
       }
       continue;
@@ -1547,3 +1655,9 @@ int gmma_backward2(Engine& e, int draws) {
 }
 
 }  // namespace ttb2
+
+#ifdef TTB2_GM_TRACE
+extern "C" int ttb2_debug_gm_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, ttb2::gm_trace, sizeof(long long) * 2 * 64 * 6);
+}
+#endif
