@@ -77,6 +77,39 @@ double run_lds(int ctas, int iters) {
   return ms;
 }
 
+// dependent-issue latency: NACC independent accumulator chains per warp, WARPS warps per CTA
+// (one CTA per SM), register operands
+template <int NACC>
+__global__ void chain_kernel(double* out, int iters, double a, double b) {
+  double c[NACC][2];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16 / NACC; ++r)
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) dmma(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+template <int NACC>
+double run_chain(int ctas, int warps, int iters) {
+  double* d; cudaMalloc(&d, 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  chain_kernel<NACC><<<ctas, warps * 32>>>(d, iters, 1.0000001, 0.9999999);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  chain_kernel<NACC><<<ctas, warps * 32>>>(d, iters, 1.0000001, 0.9999999);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  cudaFree(d);
+  return (double)ctas * warps * iters * 16.0 * 512.0 / ms * 1e-9;
+}
+
 template <int MODE>
 double run(int ctas, int iters) {
   double* d; cudaMalloc(&d, 8);
@@ -95,6 +128,12 @@ int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   const int sms = p.multiProcessorCount;
   const int iters = 20000;
+  for (int warps = 4; warps <= 16; warps *= 2)
+    printf("{\"warps_per_sm\": %d, \"chains_1_tflops\": %.2f, \"chains_2_tflops\": %.2f, "
+           "\"chains_4_tflops\": %.2f, \"chains_8_tflops\": %.2f, \"chains_16_tflops\": %.2f}\n", warps,
+           run_chain<1>(sms, warps, iters), run_chain<2>(sms, warps, iters),
+           run_chain<4>(sms, warps, iters), run_chain<8>(sms, warps, iters),
+           run_chain<16>(sms, warps, iters));
   for (int per = 1; per <= 8; per *= 2) {
     const int ctas = sms * per;
     const double warps = (double)ctas * 8, threads = (double)ctas * 256;

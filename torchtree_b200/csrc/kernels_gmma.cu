@@ -162,6 +162,44 @@ __device__ __forceinline__ void gm_mma_atb_g(double (&c)[NTG][2], const double* 
   }
 }
 
+// gm_mma_atb_g with the operands of k-step kt + 1 loaded before the MMAs of k-step kt (compile-
+// time trip count, fully unrolled): with two warps per scheduler in the tensor cores a warp that
+// loads each B fragment right before its MMA issues one MMA per shared-memory latency and the
+// pipe starves (profiles/r02_codon.md)
+// shared-memory load the compiler may not move (ptxas otherwise sinks every operand load to
+// right before its MMA to save a register)
+__device__ __forceinline__ double lds_pinned(unsigned addr) {
+  double v;
+  asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+template <int NTG, int KSTEPS>
+__device__ __forceinline__ void gm_mma_atb_pf(double (&c)[NTG][2], const double* A, int lda,
+                                              const double* Bt, int mt, int lane) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(A + (lane & 3) * lda + mt * 8 + (lane >> 2));
+  const unsigned b = (unsigned)__cvta_generic_to_shared(Bt + (lane & 3) * GM_LDT + (lane >> 2));
+  double av = lds_pinned(a), bv[NTG];
+#pragma unroll
+  for (int n = 0; n < NTG; ++n) bv[n] = lds_pinned(b + n * 64);
+#pragma unroll
+  for (int kt = 0; kt < KSTEPS; ++kt) {
+    double an = 0.0, bn[NTG];
+    if (kt + 1 < KSTEPS) {
+      an = lds_pinned(a + (kt + 1) * 4 * lda * 8);
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) bn[n] = lds_pinned(b + ((kt + 1) * 4 * GM_LDT + n * 8) * 8);
+    }
+#pragma unroll
+    for (int n = 0; n < NTG; ++n) dmma884(c[n][0], c[n][1], av, bv[n]);
+    if (kt + 1 < KSTEPS) {
+      av = an;
+#pragma unroll
+      for (int n = 0; n < NTG; ++n) bv[n] = bn[n];
+    }
+  }
+}
+
 // ===========================================================================
 // Per-(pattern, category) rescaling + software-pipelined staging.
 // Every (node, category) is independent of the other categories (their chains
@@ -399,33 +437,44 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     uint8_t* cds = codesS + grp * 64;
     double* out = outB + grp * tileN;
     int round = 0;
+    // 16 bytes per lane: one instruction moves two rows of the 32-pattern tile; row offsets fixed
+    // up front (S <= 64: at most four row pairs per thread); the padding rows are zeroed in the
+    // first trip only (nothing overwrites them)
+    const int half = lane >> 4, l2 = (lane & 15) * 2;
+    const int row0 = gw * 2 + half;
+    const size_t srcOff = (size_t)row0 * Npad + l2, srcStep = (size_t)(2 * NWG) * Npad;
+    const int dstOff = row0 * GM_LDT + l2;
     // the two groups take turns in the tensor cores (token through BAR_GO + group, see
     // gm_bwd3_kernel): left to themselves they fall into lock step, both waiting for tiles and
     // then sharing the pipe
     for (int i0 = begin + grp * GM_TP; i0 < end; i0 += 2 * GM_TP, ++round) {
       // (the group's previous tile was fully read before the barrier at the end of the last trip)
       const int i = i0 + lane;
-      // 16 bytes per lane: one instruction moves two rows of the 32-pattern tile
-      const int half = lane >> 4, l2 = (lane & 15) * 2;
       if (tabL) { if (gw == 0 && lane < 8) cp_async4(cds + 4 * lane, tl + i0 + 4 * lane); }
       else if (tipL) {
         const double* cp = codeP + (size_t)tl[i] * g.S;
         for (int s2 = gw; s2 < g.R; s2 += NWG) tcl[s2 * GM_LDT + lane] = s2 < g.S ? cp[s2] : 0.0;
       } else {
-        for (int s2 = gw * 2 + half; s2 < g.R; s2 += 2 * NWG) {
-          if (s2 < g.S) cp_async16(tcl + s2 * GM_LDT + l2, pl + (size_t)s2 * Npad + i0 + l2);
-          else tcl[s2 * GM_LDT + l2] = tcl[s2 * GM_LDT + l2 + 1] = 0.0;
-        }
+        const double* sp = pl + srcOff + i0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (row0 + j * 2 * NWG < g.R) {
+            if (row0 + j * 2 * NWG < g.S) cp_async16(tcl + dstOff + j * 2 * NWG * GM_LDT, sp + j * srcStep);
+            else if (round == 0) tcl[dstOff + j * 2 * NWG * GM_LDT] = tcl[dstOff + j * 2 * NWG * GM_LDT + 1] = 0.0;
+          }
       }
       if (tabR) { if (gw == 1 && lane < 8) cp_async4(cds + 32 + 4 * lane, tr + i0 + 4 * lane); }
       else if (tipR) {
         const double* cp = codeP + (size_t)tr[i] * g.S;
         for (int s2 = gw; s2 < g.R; s2 += NWG) tcr[s2 * GM_LDT + lane] = s2 < g.S ? cp[s2] : 0.0;
       } else {
-        for (int s2 = gw * 2 + half; s2 < g.R; s2 += 2 * NWG) {
-          if (s2 < g.S) cp_async16(tcr + s2 * GM_LDT + l2, pr + (size_t)s2 * Npad + i0 + l2);
-          else tcr[s2 * GM_LDT + l2] = tcr[s2 * GM_LDT + l2 + 1] = 0.0;
-        }
+        const double* sp = pr + srcOff + i0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (row0 + j * 2 * NWG < g.R) {
+            if (row0 + j * 2 * NWG < g.S) cp_async16(tcr + dstOff + j * 2 * NWG * GM_LDT, sp + j * srcStep);
+            else if (round == 0) tcr[dstOff + j * 2 * NWG * GM_LDT] = tcr[dstOff + j * 2 * NWG * GM_LDT + 1] = 0.0;
+          }
       }
       cp_async_commit();
       cp_async_wait_all();
@@ -996,19 +1045,30 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
   const uint8_t* tr = tips + (size_t)(tipR ? op.right : 0) * Npad;
   const int16_t* elp = tipL ? nullptr : expoK + (((size_t)d * I + (op.left - T)) * K + k) * Npad;
   const int16_t* erp = tipR ? nullptr : expoK + (((size_t)d * I + (op.right - T)) * K + k) * Npad;
-  // one [R][LDT] tile of this group <- rows of `plane`, or the code vectors of a tip
+  // one [R][LDT] tile of this group <- rows of `plane`, or the code vectors of a tip.
+  // 16 bytes per lane: one instruction moves two rows of the 32-pattern tile, four per tile and
+  // thread with the row offsets fixed up front (the staging code used to be the largest block of
+  // executed instructions of the kernel, profiles/r02_codon.md); rows S .. R - 1 are zeroed once
+  constexpr int RR = (CS + 7) / 8 * 8;
+  static_assert(RR % (2 * NWG) == 0, "row pairs per warp");
+  const int half = lane >> 4, l2 = (lane & 15) * 2;
+  const int row0 = gw * 2 + half;
+  const size_t srcOff = (size_t)row0 * Npad + l2, srcStep = (size_t)(2 * NWG) * Npad;
+  const int dstOff = row0 * GM_LDT + l2;
+  for (int idx = gw * 32 + lane; idx < 4 * (RR - S) * GM_LDT; idx += NWG * 32) {
+    const int t4 = idx / ((RR - S) * GM_LDT), rem = idx - t4 * ((RR - S) * GM_LDT);
+    mine[t4 * tileN + S * GM_LDT + rem] = 0.0;
+  }
   auto stage_tile = [&](double* tile, bool tip, const uint8_t* tipRow, const double* src, int i0) {
-    const int i = i0 + lane;
     if (tip) {
-      const double* cp = codeP + (size_t)tipRow[i] * S;
+      const double* cp = codeP + (size_t)tipRow[i0 + lane] * S;
       for (int s2 = gw; s2 < g.R; s2 += NWG) tile[s2 * GM_LDT + lane] = s2 < S ? cp[s2] : 0.0;
     } else {
-      // 16 bytes per lane: one instruction moves two rows of the 32-pattern tile
-      const int half = lane >> 4, l2 = (lane & 15) * 2;
-      for (int s2 = gw * 2 + half; s2 < g.R; s2 += 2 * NWG) {
-        if (s2 < S) cp_async16(tile + s2 * GM_LDT + l2, src + (size_t)s2 * Npad + i0 + l2);
-        else tile[s2 * GM_LDT + l2] = tile[s2 * GM_LDT + l2 + 1] = 0.0;
-      }
+      const double* sp = src + srcOff + i0;
+#pragma unroll
+      for (int j = 0; j < RR / (2 * NWG); ++j)
+        if (row0 + j * 2 * NWG < S)
+          cp_async16(tile + dstOff + j * 2 * NWG * GM_LDT, sp + j * srcStep);
     }
   };
   // The two groups take turns in the tensor cores: a group enters its Q + G phases when the other
@@ -1108,7 +1168,7 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
         double c[NTG][2];
 #pragma unroll
         for (int n = 0; n < NTG; ++n) c[n][0] = c[n][1] = 0.0;
-        gm_mma_atb_g<NTG>(c, P, g.PLD, mm, mt, 0, KTr, lane);
+        gm_mma_atb_pf<NTG, (CS + 7) / 8 * 2>(c, P, g.PLD, mm, mt, lane);
         const int row = mt * 8 + (lane >> 2);
         if (row < S) {
 #pragma unroll
@@ -1153,14 +1213,26 @@ gm_bwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
           }
         } else {
           const double* vv = (side ? vr : vl) + (lane >> 2) * GM_LDT + (lane & 3);
+          // operands four MMAs ahead (see gm_mma_atb_pf)
+          constexpr int NJ = (GM_TP / 4) * 8, AHEAD = 4;
+          double bq[AHEAD], av = mm[0] * wp[0];
+#pragma unroll
+          for (int j = 0; j < AHEAD; ++j) bq[j] = vv[(j & 7) * 8 * GM_LDT + (j >> 3) * 4];
 #pragma unroll
           for (int kt = 0; kt < GM_TP / 4; ++kt) {
-            const double av = mm[kt * 4] * wp[kt * 4];
+            double avn = 0.0;
+            if (kt + 1 < GM_TP / 4) avn = mm[(kt + 1) * 4] * wp[(kt + 1) * 4];
 #pragma unroll
-            for (int mt2 = 0; mt2 < 8; ++mt2)
-              if (mt2 < MT)
-                dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av,
-                        vv[mt2 * 8 * GM_LDT + kt * 4]);
+            for (int mt2 = 0; mt2 < 8; ++mt2) {
+              const int j = kt * 8 + mt2;
+              const double bcur = bq[j % AHEAD];
+              if (j + AHEAD < NJ) {
+                const int j2 = j + AHEAD;
+                bq[j % AHEAD] = vv[(j2 & 7) * 8 * GM_LDT + (j2 >> 3) * 4];
+              }
+              if (mt2 < MT) dmma884(acc[cj * 8 + mt2][0], acc[cj * 8 + mt2][1], av, bcur);
+            }
+            av = avn;
           }
         }
       }
