@@ -230,7 +230,7 @@ def workload_config(cfg, world):
 # ------------------------------------------------------------------------------------------
 # what one evaluation must move / compute, counted from the topology (per pattern, category, draw)
 # ------------------------------------------------------------------------------------------
-def traffic_model(postorder, T, S, cherries: bool):
+def traffic_model(postorder, T, S, cherries: bool, kept_u: bool = False):
     """Bytes per (pattern, category) that the engine's algorithm has to move through HBM in the
     two sweeps, and the fp64 flops of its GEMM-shaped work, from the tree alone.
 
@@ -238,7 +238,9 @@ def traffic_model(postorder, T, S, cherries: bool):
     and read once by its parent; tips are 1-byte codes; with cherry tabulation (4-state path) a
     node whose two children are tips is a table entry, never stored.  Pre-order: a parent reads
     its own q^ and the stored vectors of its internal children and writes q^ of every internal
-    child (a tabulated cherry still receives q^)."""
+    child (a tabulated cherry still receives q^).  kept_u (the 61-state path from an engine's
+    second evaluation on): the post-order sweep also writes u_c = P_c p~_c of every internal child
+    and the pre-order sweep reads it back instead of repeating the product."""
     V = S * 8
     post = np.asarray(postorder)
     root = int(post[-1][0])
@@ -258,7 +260,10 @@ def traffic_model(postorder, T, S, cherries: bool):
         # q^_c = P^T m per internal child, G_c += m (x) p~ for both children
         inner = (l >= T) + (r >= T)
         flops_post += 2 * S * S * inner
-        flops_pre += 2 * S * S * inner * 2 + 2 * S * S * 2
+        flops_pre += 2 * S * S * inner * (1 if kept_u else 2) + 2 * S * S * 2
+        if kept_u:
+            post_bytes += V * inner
+            pre_bytes += V * inner
     I = len(post)
     return {"post_bytes": post_bytes / I, "pre_bytes": pre_bytes / I,
             "flops_post": flops_post / I, "flops_pre": flops_pre / I,
@@ -526,7 +531,8 @@ def run_engine(cfg, args, rank, local_rank, world, dist, with_clocks=True):
     line = None
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
-        tm = traffic_model(prob.postorder, T, S, cherries=(S == 4))
+        kept_u = S == 61 and not os.environ.get("TTB2_GM_NO_USTORE")
+        tm = traffic_model(prob.postorder, T, S, cherries=(S == 4), kept_u=kept_u)
         per = prob.pattern_count * K * local_draws * (T - 1)   # (pattern, node, cat, draw) units of this rank
         V = S * 8
         moved_pre, moved_post = per * tm["pre_bytes"], per * tm["post_bytes"]
@@ -555,9 +561,13 @@ def run_engine(cfg, args, rank, local_rank, world, dist, with_clocks=True):
                                  "tools/fp64_peak.cu); MEASURED_PEAKS.json holds no fp64 figure",
                     "traffic": None,
                     "flops_per_launch": fl_pre / launches_pre,
-                    "flops_note": "fp64 flops of the GEMM-shaped work the sweep needs, counted from "
-                                  "the tree: u = P p~ and q^ = P^T m per internal child, G += m (x) p~ "
-                                  "per child (tip children are table look-ups)"}
+                    "flops_note": "fp64 flops of the GEMM-shaped work the sweep executes, counted from "
+                                  "the tree (unpadded, 61 not 64): q^ = P^T m per internal child, G += "
+                                  "m (x) p~ per child" + (
+                                      "; u = P p~ is read back from the post-order sweep (kept u), "
+                                      "not recomputed and not counted" if kept_u else
+                                      ", u = P p~ per internal child") +
+                                  " (tip children are table look-ups)"}
         else:
             ach = moved_pre / (ph_pre * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": kpre, "achieved": ach, "peak": peak, "unit": "GB/s",

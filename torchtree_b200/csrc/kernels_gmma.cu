@@ -359,6 +359,9 @@ gm_fwd2_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
 // and EMPTY[group]) instead of CTA-wide __syncthreads.
 // shared: Pl Pr [Sp*PLD] | cl[2] cr[2] [R*LDT] | out[2] [Sp*LDT] | wmax [2][8*32] | codes
 // ---------------------------------------------------------------------------
+// bar.arrive / bar.sync order the shared-memory writes of the arriving threads before the reads
+// of the threads the barrier releases, so no fence is needed in front of an arrive (a
+// __threadfence_block there would also wait for the thread's GLOBAL stores to drain)
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -516,7 +519,6 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
         }
       }
       if (tokenAt && i0 + GM_TP < end) named_arrive(BAR_GO + (grp ^ 1), 512);
-      __threadfence_block();
       named_arrive(BAR_FULL + grp, 512);
       named_sync(BAR_GROUP + grp, NWG * 32);   // every warp is done reading the tile
     }
@@ -542,7 +544,6 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
       for (int s2 = ew; s2 < S; s2 += NWG)
         qn[(size_t)s2 * Npad + i0 + lane] = out[s2 * GM_LDT + lane] * f;
       if (ew == 0) en[i0 + lane] = (int16_t)e;
-      __threadfence_block();
       named_arrive(BAR_EMPTY + buf, 512);
     }
   }
