@@ -524,25 +524,46 @@ gm_fwd3_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __rest
     }
   } else {
     // ---- epilogue warps: per-pattern maximum, power-of-two rescaling, stores ----
+    // The fp64 pipe belongs to the DMMAs: an fmax (DSETP + selects) or DMUL issued from here
+    // queues behind them ("math pipe throttle" was the top stall of these warps,
+    // profiles/r02_codon.md).  The maximum is therefore taken on the integer pipe: for
+    // non-negative doubles the order of the high words is the order of the values and only the
+    // exponent of the maximum is needed.  mh: largest high word; lz: OR of the low words of the
+    // values whose high word is zero (max > 0 <=> mh > 0 or lz != 0, as in the floating-point
+    // test); each value is read from shared memory once and kept for the rescaled store.
     const int ew = warp - 2 * NWG;
+    constexpr int RPW = CS ? (CS + NWG - 1) / NWG : 8;   // rows per warp (S <= 64)
+    int2* wmax2 = reinterpret_cast<int2*>(wmaxB);        // [2][NWG][32]
+    double* qrow = qn + (size_t)ew * Npad + lane;
+    const size_t rowStep = (size_t)NWG * Npad;
     int t = 0;
     for (int i0 = begin; i0 < end; i0 += GM_TP, ++t) {
       const int buf = t & 1;
       named_sync(BAR_FULL + buf, 512);
-      const double* out = outB + buf * tileN;
-      double* wmax = wmaxB + buf * NWG * 32;
-      double m = 0.0;
-      for (int s2 = ew; s2 < S; s2 += NWG) m = fmax(m, out[s2 * GM_LDT + lane]);
-      wmax[ew * 32 + lane] = m;
-      named_sync(BAR_EPI, NWG * 32);
-      double mm = 0.0;
+      const double* out = outB + buf * tileN + ew * GM_LDT + lane;
+      double v[RPW];
+      int mh = 0, lz = 0;
 #pragma unroll
-      for (int w = 0; w < NWG; ++w) mm = fmax(mm, wmax[w * 32 + lane]);
-      const int eb = (__double2hiint(mm) >> 20) & 0x7ff;
-      const int e = (mm > 0.0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
+      for (int j = 0; j < RPW; ++j) {
+        v[j] = (ew + j * NWG < S) ? out[j * NWG * GM_LDT] : 0.0;
+        const int hi = __double2hiint(v[j]), lo = __double2loint(v[j]);
+        mh = max(mh, hi);
+        lz |= (hi == 0) ? lo : 0;
+      }
+      wmax2[(buf * NWG + ew) * 32 + lane] = make_int2(mh, lz);
+      named_sync(BAR_EPI, NWG * 32);
+#pragma unroll
+      for (int w = 0; w < NWG; ++w) {
+        const int2 o = wmax2[(buf * NWG + w) * 32 + lane];
+        mh = max(mh, o.x);
+        lz |= o.y;
+      }
+      const int eb = (mh >> 20) & 0x7ff;
+      const int e = (mh > 0 || lz != 0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
       const double f = __hiloint2double((1023 - e) << 20, 0);
-      for (int s2 = ew; s2 < S; s2 += NWG)
-        qn[(size_t)s2 * Npad + i0 + lane] = out[s2 * GM_LDT + lane] * f;
+#pragma unroll
+      for (int j = 0; j < RPW; ++j)
+        if (ew + j * NWG < S) qrow[j * rowStep + i0] = v[j] * f;
       if (ew == 0) en[i0 + lane] = (int16_t)e;
       named_arrive(BAR_EMPTY + buf, 512);
     }
