@@ -302,17 +302,24 @@ gw_fwd_kernel(const NodeOp* __restrict__ ops, int opBegin, const double* __restr
     }
   };
   auto finish_group = [&](double (&accL)[G::NT][2], double (&accR)[G::NT][2], int i0) {
-    double m = 0.0;
+    // maximum over the states on the integer pipe (the fp64 pipe is the DMMAs'): for non-negative
+    // doubles the high words order like the values; lz = OR of the low words of values whose
+    // high word is zero, so that (mh > 0 || lz != 0) <=> max > 0 (kernels_gmma.cu, gm_fwd3_kernel)
+    int mh = 0, lz = 0;
 #pragma unroll
     for (int nt = 0; nt < G::NT; ++nt) {
       accL[nt][0] *= accR[nt][0];
       accL[nt][1] *= accR[nt][1];
-      m = fmax(m, fmax(accL[nt][0], accL[nt][1]));
+      const int h0 = __double2hiint(accL[nt][0]), h1 = __double2hiint(accL[nt][1]);
+      mh = max(mh, max(h0, h1));
+      lz |= (h0 == 0 ? __double2loint(accL[nt][0]) : 0) | (h1 == 0 ? __double2loint(accL[nt][1]) : 0);
     }
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    const int eb = (__double2hiint(m) >> 20) & 0x7ff;
-    const int e = (m > 0.0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
+    mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, 1));
+    lz |= __shfl_xor_sync(0xffffffffu, lz, 1);
+    mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, 2));
+    lz |= __shfl_xor_sync(0xffffffffu, lz, 2);
+    const int eb = (mh >> 20) & 0x7ff;
+    const int e = (mh > 0 || lz != 0) ? (eb > 2044 ? 2044 : eb) - 1022 : 0;
     const double f = __hiloint2double((1023 - e) << 20, 0);
     double* o = qn + i0 + r;
 #pragma unroll
