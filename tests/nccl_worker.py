@@ -61,6 +61,14 @@ def main():
     v_fast.sum().backward()
     out["fast_lnL"] = rel(v_fast, v_one)
     out["fast_grads"] = max(rel(x.grad, y.grad) for x, y in zip(c, b))
+    # (one draw: the gradient travels with the forward pass and backward() scales it; without a
+    # gradient request only lnL is reduced)
+    c2 = leaves(prob)
+    (2.5 * sharded_engine_log_likelihood(shard, c2)).sum().backward()
+    out["fast_scaled_grads"] = max(rel(x.grad, 2.5 * y.grad) for x, y in zip(c2, b))
+    with torch.no_grad():
+        out["fast_nograd_lnL"] = rel(sharded_engine_log_likelihood(shard, [t.detach() for t in c2]),
+                                     v_one)
 
     # ---- the packed gradient, reduced in place on the device ----
     dev = torch.device("cuda", local)

@@ -34,6 +34,7 @@ def test_sharded_equals_single_gpu_over_nccl():
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["world"] == world
-    for key in ("patterns_lnL", "patterns_grads", "fast_lnL", "fast_grads", "packed_lnL",
+    for key in ("patterns_lnL", "patterns_grads", "fast_lnL", "fast_grads", "fast_scaled_grads",
+                "fast_nograd_lnL", "packed_lnL",
                 "packed_grads", "draws_lnL", "draws_grads"):
         assert out[key] <= 1e-12, (key, out)

@@ -138,17 +138,41 @@ class _ShardedEngineLikelihood(torch.autograd.Function):
             return engine.loglik_q(*ins)
 
         lnl = run()
-        if _world(group) > 1:
-            dist.all_reduce(lnl, group=group)
         ctx.engine, ctx.group, ctx.run = engine, group, run
-        ctx.serial = engine.eval_serial
         ctx.meta = [(t.shape, t.dtype, t.device) for t in src]
         ctx.q_draws = q.shape[0]
+        ctx.views = None
+        if lnl.numel() == 1 and any(ctx.needs_input_grad[3:]):
+            # One draw and a gradient is wanted: run the pre-order sweep right behind the post-order
+            # sweep (d lnL / d theta for grad_lnL = 1; backward() scales it -- the gradient is
+            # linear in the one incoming scalar) and all-reduce the packed vector, which starts
+            # with lnL: ONE collective and ONE device -> host copy per evaluation instead of two of
+            # each with a host round trip between the sweeps.
+            packed = engine.grad_eigen_packed(None)
+            if _world(group) > 1:
+                dist.all_reduce(packed, group=group)
+            if all(device.type == "cpu" for _, _, device in ctx.meta):
+                packed = packed.cpu()
+            ctx.views = engine.unpack(packed)
+            return ctx.views["lnL"].to(bls.device, bls.dtype).clone()
+        if _world(group) > 1:
+            dist.all_reduce(lnl, group=group)
+        ctx.serial = engine.eval_serial
         return lnl.to(bls.device, bls.dtype)
 
     @staticmethod
     def backward(ctx, grad):
         engine = ctx.engine
+        if ctx.views is not None:   # gradient for grad_lnL = 1 came with the forward pass
+            out = []
+            for key, (shape, dtype, device) in zip(("branch_lengths", "site_rates", "props", "q",
+                                                    "freqs"), ctx.meta):
+                g = ctx.views[key]
+                if key == "q" and g.shape[0] != ctx.q_draws:
+                    g = g.sum(0, keepdim=True)
+                scale = grad.detach().reshape(-1)[0].to(g.device, g.dtype)
+                out.append((g * scale).to(device, dtype).reshape(shape))
+            return (None, None, None) + tuple(out)
         if engine.eval_serial != ctx.serial:   # another forward ran on this engine: recompute
             ctx.run()
             ctx.serial = engine.eval_serial
