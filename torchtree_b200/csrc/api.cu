@@ -498,7 +498,7 @@ int ttb2_create(const ttb2_config* config, const uint8_t* tip_codes,
   TRY(dev_alloc(e, &e.expo, (size_t)D * m.I * m.Npad));
   TRY(dev_alloc(e, &e.mats, (size_t)D * m.B * m.K * m.S * m.S));
   TRY(dev_alloc(e, &e.siteLnl, (size_t)D * m.Npad));
-  const int nblocks = (m.Npad + 127) / 128;
+  const int nblocks = m.Npad / 32;   // the root kernels write one row of partial sums per 32 patterns
   e.redPartCap = (size_t)D * nblocks * (m.K + m.S);
   TRY(dev_alloc(e, &e.redPart, e.redPartCap));
   TRY(dev_alloc(e, &e.lnl, (size_t)D));

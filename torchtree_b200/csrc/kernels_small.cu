@@ -248,6 +248,145 @@ __global__ void eigen_contract_kernel(double* __restrict__ dmat,
   if (threadIdx.x == 0) gscal[item] = t;
 }
 
+// ---------------------------------------------------------------------------
+// Large alphabets (S > 32: the 61-state codon path).  The two kernels above read both operands
+// of every FMA from memory (global for pmatrix, shared for the contraction: two LDS per FMA, so
+// the shared-memory pipe bounded them: 0.16 and 0.29 ms per evaluation at config 5).  Here the
+// operands are staged once in shared memory as [S][LD] (LD = S rounded up to 4, zero padding
+// columns) and a thread owns FOUR adjacent columns of a row: per reduction step one broadcast
+// load of A and two 128-bit loads of B feed four FMAs.
+// ---------------------------------------------------------------------------
+// c[0..3] += sum_m A(i, m) B[m][j0 .. j0 + 3];  A(i, m) = TRANS_A ? A[m][i] : A[i][m]
+template <bool TRANS_A>
+__device__ __forceinline__ void mm_row4(double (&c)[4], const double* A, const double* B, int i,
+                                        int j0, int S, int LD) {
+  for (int m = 0; m < S; ++m) {
+    const double a = TRANS_A ? A[m * LD + i] : A[i * LD + m];
+    const double2 b0 = *reinterpret_cast<const double2*>(B + m * LD + j0);
+    const double2 b1 = *reinterpret_cast<const double2*>(B + m * LD + j0 + 2);
+    c[0] = fma(a, b0.x, c[0]);
+    c[1] = fma(a, b0.y, c[1]);
+    c[2] = fma(a, b1.x, c[2]);
+    c[3] = fma(a, b1.y, c[3]);
+  }
+}
+
+// shared: A = V diag(exp(lambda tau)) [S][LD] | B = V^-1 [S][LD] | ex [S]
+__global__ void __launch_bounds__(512)
+pmatrix_tiled_kernel(const double* __restrict__ bl, const double* __restrict__ rates, int rateDraws,
+                     const double* __restrict__ evec, const double* __restrict__ ivec,
+                     const double* __restrict__ eval, int eigDraws, double* __restrict__ mats,
+                     int B, int K, int S) {
+  extern __shared__ __align__(16) double sm[];
+  const int LD = (S + 3) & ~3;
+  double* sA = sm;
+  double* sB = sA + S * LD;
+  double* ex = sB + S * LD;
+  const int bk = blockIdx.x;
+  const int b = bk / K, k = bk - b * K;
+  const int d = blockIdx.y;
+  const int de = eigDraws > 1 ? d : 0;
+  const double t = bl[(size_t)d * B + b] * rates[(size_t)(rateDraws > 1 ? d : 0) * K + k];
+  const double* lam = eval + (size_t)de * S;
+  for (int m = threadIdx.x; m < S; m += blockDim.x) ex[m] = exp(lam[m] * t);
+  __syncthreads();
+  const double* V = evec + (size_t)de * S * S;
+  const double* Vi = ivec + (size_t)de * S * S;
+  for (int idx = threadIdx.x; idx < S * LD; idx += blockDim.x) {
+    const int i = idx / LD, j = idx - i * LD;
+    sA[idx] = j < S ? V[i * S + j] * ex[j] : 0.0;
+    sB[idx] = j < S ? Vi[i * S + j] : 0.0;
+  }
+  __syncthreads();
+  double* P = mats + (((size_t)d * B + b) * K + k) * S * S;
+  const int Q4 = LD / 4;
+  for (int item = threadIdx.x; item < S * Q4; item += blockDim.x) {
+    const int i = item / Q4, j0 = (item - i * Q4) * 4;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    mm_row4<false>(c, sA, sB, i, j0, S, LD);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (j0 + q < S) P[i * S + j0 + q] = c[q];
+  }
+}
+
+// shared: G [S][LD] | T = V^T G [S][LD] | V [S][LD] | ViT = (V^-1)^T [S][LD] | lambda [S] | ex [S]
+__global__ void __launch_bounds__(1024)
+eigen_contract_tiled_kernel(const double* __restrict__ dmat, const double* __restrict__ bl,
+                            const double* __restrict__ rates, int rateDraws,
+                            const double* __restrict__ evec, const double* __restrict__ ivec,
+                            const double* __restrict__ eval, int eigDraws,
+                            double* __restrict__ hpart, double* __restrict__ gscal, int B, int K,
+                            int S) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double red[32];
+  const int LD = (S + 3) & ~3;
+  double* sG = sm;
+  double* sT = sG + S * LD;
+  double* sV = sT + S * LD;
+  double* sViT = sV + S * LD;
+  double* sLam = sViT + S * LD;
+  double* sEx = sLam + S;
+  const int bk = blockIdx.x;
+  const int b = bk / K, k = bk - b * K;
+  const int d = blockIdx.y;
+  const int de = eigDraws > 1 ? d : 0;
+  const double tau = bl[(size_t)d * B + b] * rates[(size_t)(rateDraws > 1 ? d : 0) * K + k];
+  const size_t item0 = ((size_t)d * B + b) * K + k;
+  const double* G = dmat + item0 * S * S;
+  const double* V = evec + (size_t)de * S * S;
+  const double* Vi = ivec + (size_t)de * S * S;
+  for (int idx = threadIdx.x; idx < S * LD; idx += blockDim.x) {
+    const int i = idx / LD, j = idx - i * LD;
+    sG[idx] = j < S ? G[i * S + j] : 0.0;
+    sV[idx] = j < S ? V[i * S + j] : 0.0;
+    sViT[idx] = j < S ? Vi[j * S + i] : 0.0;   // transposed: row c, column j
+  }
+  for (int m = threadIdx.x; m < S; m += blockDim.x) {
+    const double l = eval[(size_t)de * S + m];
+    sLam[m] = l;
+    sEx[m] = exp(l * tau);
+  }
+  __syncthreads();
+  const int Q4 = LD / 4;
+  // T[i][c] = sum_a V[a][i] G[a][c]
+  for (int item = threadIdx.x; item < S * Q4; item += blockDim.x) {
+    const int i = item / Q4, j0 = (item - i * Q4) * 4;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    mm_row4<true>(c, sV, sG, i, j0, S, LD);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sT[i * LD + j0 + q] = c[q];
+  }
+  __syncthreads();
+  // M[i][j] = sum_c T[i][c] Vi[j][c];  H = M o Phi(tau)
+  double diag = 0.0;
+  double* H = hpart + item0 * S * S;
+  for (int item = threadIdx.x; item < S * Q4; item += blockDim.x) {
+    const int i = item / Q4, j0 = (item - i * Q4) * 4;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    mm_row4<false>(c, sT, sViT, i, j0, S, LD);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + q;
+      if (j >= S) continue;
+      double phi;
+      if (i == j) {
+        phi = tau * sEx[i];
+        diag = fma(c[q], sLam[i] * sEx[i], diag);
+      } else {
+        const double a = sLam[i] * tau, bb = sLam[j] * tau;
+        const double hi = a > bb ? a : bb;
+        const double x = -fabs(a - bb);  // <= 0
+        const double ratio = (x > -1e-9) ? 1.0 + 0.5 * x : expm1(x) / x;
+        phi = tau * exp(hi) * ratio;
+      }
+      H[i * S + j] = c[q] * phi;
+    }
+  }
+  const double t = block_sum256(diag, red);
+  if (threadIdx.x == 0) gscal[item0] = t;
+}
+
 // d_bl[d][b] = g[d] * sum_k r_k gscal[d][b][k]
 __global__ void branch_grad_kernel(const double* __restrict__ gscal,
                                    const double* __restrict__ rates, int rateDraws,
@@ -447,6 +586,18 @@ size_t planned_gpart_doubles(const Engine& e, int draws) {
 int small_pmatrix(Engine& e, int draws) {
   const Dims& m = e.dm;
   dim3 grid(m.B * m.K, draws);
+  if (m.S > 32) {
+    const int LD = (m.S + 3) & ~3;
+    const size_t smem = (2 * (size_t)m.S * LD + m.S) * sizeof(double);
+    if (smem > 48 * 1024)
+      TTB2_CUDA_CHECK(cudaFuncSetAttribute(pmatrix_tiled_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pmatrix_tiled_kernel<<<grid, 512, smem, e.stream>>>(
+        e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.mats, m.B, m.K, m.S);
+    ++e.launches;
+    TTB2_CUDA_CHECK(cudaGetLastError());
+    return TTB2_OK;
+  }
   const int threads = round_threads(m.S * m.S, 256);
   pmatrix_kernel<<<grid, threads, m.S * sizeof(double), e.stream>>>(
       e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.mats, m.B, m.K, m.S);
@@ -540,6 +691,17 @@ int small_eigen_contract(Engine& e, int draws) {
     const bool fused = e.gpartPending;
     e.gpartPending = false;
     const int threads = fused ? 256 : round_threads(SS, 256);
+    if (m.S > 32 && !fused) {
+      const int LD = (m.S + 3) & ~3;
+      const size_t smemT = (4 * (size_t)m.S * LD + 2 * m.S) * sizeof(double);
+      if (smemT > 48 * 1024)
+        TTB2_CUDA_CHECK(cudaFuncSetAttribute(eigen_contract_tiled_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smemT));
+      eigen_contract_tiled_kernel<<<grid, 1024, smemT, e.stream>>>(
+          e.dmat, e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.hpart, e.gscal,
+          m.B, m.K, m.S);
+    } else {
     const size_t smem = (4 * (size_t)SS + 2 * m.S + (fused ? threads : 0)) * sizeof(double);
     if (smem > 48 * 1024)
       TTB2_CUDA_CHECK(cudaFuncSetAttribute(eigen_contract_kernel,
@@ -548,6 +710,7 @@ int small_eigen_contract(Engine& e, int draws) {
     eigen_contract_kernel<<<grid, threads, smem, e.stream>>>(
         e.dmat, fused ? e.gpart : nullptr, e.chunkBase, e.chunkCount, e.chunkTotal, e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.hpart,
         e.gscal, m.B, m.K, m.S);
+    }
     ++e.launches;
   }
   {
