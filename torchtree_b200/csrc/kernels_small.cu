@@ -57,6 +57,33 @@ __global__ void pmatrix_kernel(const double* __restrict__ bl,
   }
 }
 
+// Four states: a half-warp per (draw, branch, category) matrix, lane = element (i, j), 16
+// matrices per CTA (a batch of draws otherwise launches one 32-thread CTA per matrix: 127 744 at
+// config 3).  Same FMA order as pmatrix_kernel.
+__global__ void __launch_bounds__(256)
+pmatrix4_kernel(const double* __restrict__ bl, const double* __restrict__ rates, int rateDraws,
+                const double* __restrict__ evec, const double* __restrict__ ivec,
+                const double* __restrict__ eval, int eigDraws, double* __restrict__ mats, int B,
+                int K, int draws) {
+  const int e = threadIdx.x & 15;
+  const long items = (long)draws * B * K;
+  const long item = (long)blockIdx.x * 16 + (threadIdx.x >> 4);
+  if (item >= items) return;
+  const int d = (int)(item / ((long)B * K));
+  const int bk = (int)(item - (long)d * B * K);
+  const int b = bk / K, k = bk - b * K;
+  const int de = eigDraws > 1 ? d : 0;
+  const double t = bl[(size_t)d * B + b] * rates[(size_t)(rateDraws > 1 ? d : 0) * K + k];
+  const double* lam = eval + (size_t)de * 4;
+  const double* V = evec + (size_t)de * 16;
+  const double* Vi = ivec + (size_t)de * 16;
+  const int i = e >> 2, j = e & 3;
+  double acc = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) acc = fma(V[i * 4 + m] * exp(lam[m] * t), Vi[m * 4 + j], acc);
+  mats[(size_t)item * 16 + e] = acc;
+}
+
 // out[d] = sum_j part[d][j]   (fixed order: deterministic)
 __global__ void __launch_bounds__(RED_THREADS)
 reduce_rows_kernel(const double* __restrict__ part, double* __restrict__ out, int n,
@@ -249,6 +276,70 @@ __global__ void eigen_contract_kernel(double* __restrict__ dmat,
 }
 
 // ---------------------------------------------------------------------------
+// Four states: the contraction above spends a 256-thread CTA on a 4 x 4 problem -- with a batch of
+// draws (config 3: 998 branches x 128 draws = 127 744 CTAs) 0.66 ms of launch overhead per
+// evaluation.  Here a half-warp owns one (draw, branch, category) item, lane = element (i, j);
+// the two 4 x 4 products go through half-warp shuffles, 16 items per CTA.  Same FMA order as
+// eigen_contract_kernel; the sum of the per-chunk partials of G is taken serially (fixed order).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eigen_contract4_kernel(double* __restrict__ dmat, const double* __restrict__ gpart,
+                       const int* __restrict__ chunkBase, const int* __restrict__ chunkCount,
+                       size_t chunkTotal, const double* __restrict__ bl,
+                       const double* __restrict__ rates, int rateDraws,
+                       const double* __restrict__ evec, const double* __restrict__ ivec,
+                       const double* __restrict__ eval, int eigDraws, double* __restrict__ hpart,
+                       double* __restrict__ gscal, int B, int K, int draws) {
+  const int e = threadIdx.x & 15;
+  const long items = (long)draws * B * K;
+  const long item = (long)blockIdx.x * 16 + (threadIdx.x >> 4);
+  const bool live = item < items;
+  const long it = live ? item : items - 1;   // dead half-warps shadow the last item (no stores)
+  const int d = (int)(it / ((long)B * K));
+  const int bk = (int)(it - (long)d * B * K);
+  const int b = bk / K, k = bk - b * K;
+  const int de = eigDraws > 1 ? d : 0;
+  const double tau = bl[(size_t)d * B + b] * rates[(size_t)(rateDraws > 1 ? d : 0) * K + k];
+  const int i = e >> 2, j = e & 3;
+  double G;
+  if (gpart != nullptr) {
+    const int n = chunkCount[b];
+    const double* p = gpart + ((size_t)d * chunkTotal + chunkBase[b] + (size_t)k * n) * 16 + e;
+    G = 0.0;
+    for (int c = 0; c < n; ++c) G += p[(size_t)c * 16];
+    if (live) dmat[(size_t)it * 16 + e] = G;
+  } else {
+    G = dmat[(size_t)it * 16 + e];
+  }
+  const double* V = evec + (size_t)de * 16;
+  const double* Vi = ivec + (size_t)de * 16;
+  const double* lam = eval + (size_t)de * 4;
+  double T = 0.0;   // T[i][j] = sum_a V[a][i] G[a][j]
+#pragma unroll
+  for (int a = 0; a < 4; ++a) T = fma(V[a * 4 + i], __shfl_sync(0xffffffffu, G, a * 4 + j, 16), T);
+  double M = 0.0;   // M[i][j] = sum_c T[i][c] Vi[j][c]
+#pragma unroll
+  for (int c = 0; c < 4; ++c) M = fma(__shfl_sync(0xffffffffu, T, i * 4 + c, 16), Vi[j * 4 + c], M);
+  const double li = lam[i], lj = lam[j];
+  const double exi = exp(li * tau);
+  double phi, diag = 0.0;
+  if (i == j) {
+    phi = tau * exi;
+    diag = M * (li * exi);
+  } else {
+    const double a = li * tau, bb = lj * tau;
+    const double hi = a > bb ? a : bb;
+    const double x = -fabs(a - bb);  // <= 0
+    const double ratio = (x > -1e-9) ? 1.0 + 0.5 * x : expm1(x) / x;
+    phi = tau * exp(hi) * ratio;
+  }
+  if (live) hpart[(size_t)it * 16 + e] = M * phi;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o, 16);
+  if (live && e == 0) gscal[it] = diag;
+}
+
+// ---------------------------------------------------------------------------
 // Large alphabets (S > 32: the 61-state codon path).  The two kernels above read both operands
 // of every FMA from memory (global for pmatrix, shared for the contraction: two LDS per FMA, so
 // the shared-memory pipe bounded them: 0.16 and 0.29 ms per evaluation at config 5).  Here the
@@ -403,21 +494,23 @@ __global__ void branch_grad_kernel(const double* __restrict__ gscal,
 }
 
 // d_rate[od][k] = sum_d g[d] sum_b t[d][b] gscal[d][b][k]   (one block per (k, od))
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(1024)
 rate_grad_kernel(const double* __restrict__ gscal, const double* __restrict__ bl,
                  const double* __restrict__ g, double* __restrict__ out, int B, int K,
                  int draws, int outDraws) {
-  __shared__ double red[RED_THREADS / 32];
+  __shared__ double red[32];
   const int k = blockIdx.x;
   const int od = blockIdx.y;
   const int d0 = outDraws > 1 ? od : 0;
   const int d1 = outDraws > 1 ? od + 1 : draws;
+  // (draw, branch) pairs flattened over the threads: a rate shared by a batch of draws used to
+  // walk the draws one after the other in a single block (0.26 ms at 128 draws)
   double acc = 0.0;
-  for (int d = d0; d < d1; ++d) {
-    double a = 0.0;
-    for (int b = threadIdx.x; b < B; b += blockDim.x)
-      a = fma(bl[(size_t)d * B + b], gscal[((size_t)d * B + b) * K + k], a);
-    acc = fma(g[d], a, acc);
+  const long n = (long)(d1 - d0) * B;
+  for (long idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int d = d0 + (int)(idx / B);
+    const size_t at = (size_t)d0 * B + idx;   // = d * B + b
+    acc = fma(g[d] * bl[at], gscal[at * K + k], acc);
   }
   const double t = block_sum256(acc, red);
   if (threadIdx.x == 0) out[(size_t)od * K + k] = t;
@@ -438,12 +531,15 @@ h_reduce_kernel(const double* __restrict__ hpart, const double* __restrict__ g,
   const int lo = slice * per, hi = min(items, lo + per);
   const int d0 = outDraws > 1 ? od : 0;
   const int d1 = outDraws > 1 ? od + 1 : draws;
+  // (draw, item) pairs flattened over the threads (a generator shared by a batch of draws used to
+  // walk the draws one after the other)
   double acc = 0.0;
-  for (int d = d0; d < d1; ++d) {
-    double a = 0.0;
-    for (int it = lo + threadIdx.x; it < hi; it += blockDim.x)
-      a += hpart[((size_t)d * items + it) * SS + e];
-    acc = fma(g[d], a, acc);
+  const int span = hi - lo;
+  const long n = span > 0 ? (long)(d1 - d0) * span : 0;
+  for (long idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int d = d0 + (int)(idx / span);
+    const int it = lo + (int)(idx - (long)(d - d0) * span);
+    acc = fma(g[d], hpart[((size_t)d * items + it) * SS + e], acc);
   }
   const double t = block_sum256(acc, red);
   if (threadIdx.x == 0) Hs[((size_t)od * H_SLICES + slice) * SS + e] = t;
@@ -586,6 +682,14 @@ size_t planned_gpart_doubles(const Engine& e, int draws) {
 int small_pmatrix(Engine& e, int draws) {
   const Dims& m = e.dm;
   dim3 grid(m.B * m.K, draws);
+  if (m.S == 4) {
+    const long items = (long)draws * m.B * m.K;
+    pmatrix4_kernel<<<(unsigned)((items + 15) / 16), 256, 0, e.stream>>>(
+        e.bl, e.rates, e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.mats, m.B, m.K, draws);
+    ++e.launches;
+    TTB2_CUDA_CHECK(cudaGetLastError());
+    return TTB2_OK;
+  }
   if (m.S > 32) {
     const int LD = (m.S + 3) & ~3;
     const size_t smem = (2 * (size_t)m.S * LD + m.S) * sizeof(double);
@@ -691,7 +795,12 @@ int small_eigen_contract(Engine& e, int draws) {
     const bool fused = e.gpartPending;
     e.gpartPending = false;
     const int threads = fused ? 256 : round_threads(SS, 256);
-    if (m.S > 32 && !fused) {
+    if (m.S == 4) {
+      const long items = (long)draws * m.B * m.K;
+      eigen_contract4_kernel<<<(unsigned)((items + 15) / 16), 256, 0, e.stream>>>(
+          e.dmat, fused ? e.gpart : nullptr, e.chunkBase, e.chunkCount, e.chunkTotal, e.bl, e.rates,
+          e.rateDraws, e.evec, e.ivec, e.eval, e.eigDraws, e.hpart, e.gscal, m.B, m.K, draws);
+    } else if (m.S > 32 && !fused) {
       const int LD = (m.S + 3) & ~3;
       const size_t smemT = (4 * (size_t)m.S * LD + 2 * m.S) * sizeof(double);
       if (smemT > 48 * 1024)
@@ -722,7 +831,7 @@ int small_eigen_contract(Engine& e, int draws) {
   {
     const int od = e.rateDraws > 1 ? draws : 1;
     dim3 grid(m.K, od);
-    rate_grad_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
+    rate_grad_kernel<<<grid, (draws > 8 && e.rateDraws <= 1) ? 1024 : RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
                                                         m.B, m.K, draws, od);
     ++e.launches;
   }
@@ -762,7 +871,7 @@ int small_expm_contract(Engine& e, int draws) {
   {
     const int od = e.rateDraws > 1 ? draws : 1;
     dim3 grid(m.K, od);
-    rate_grad_kernel<<<grid, RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
+    rate_grad_kernel<<<grid, (draws > 8 && e.rateDraws <= 1) ? 1024 : RED_THREADS, 0, e.stream>>>(e.gscal, e.bl, e.gradLnl, e.outRates,
                                                         m.B, m.K, draws, od);
     ++e.launches;
   }
