@@ -168,10 +168,14 @@ __global__ void root_outputs_kernel(const double* __restrict__ in, const double*
     const int d = idx / width, j = idx - d * width;
     out[idx] = g[d] * in[(size_t)d * inWidth + off + j];
   } else {
-    if (idx >= width) return;
+    // one warp per output, lanes over the draws (a parameter shared by a batch of draws)
+    const int o = idx >> 5, lane = idx & 31;
+    if (o >= width) return;   // whole warps: blockDim is a multiple of 32
     double acc = 0.0;
-    for (int d = 0; d < draws; ++d) acc = fma(g[d], in[(size_t)d * inWidth + off + idx], acc);
-    out[idx] = acc;
+    for (int d = lane; d < draws; d += 32) acc = fma(g[d], in[(size_t)d * inWidth + off + o], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) out[o] = acc;
   }
 }
 
@@ -777,7 +781,8 @@ int small_scale_dmat(Engine& e, int draws, double* out) {
 int small_root_outputs(Engine& e, int draws) {
   const Dims& m = e.dm;
   const int w = m.K + m.S;
-  const int nP = m.K * (e.propDraws > 1 ? draws : 1), nF = m.S * (e.freqDraws > 1 ? draws : 1);
+  // per-draw outputs: one thread each; shared outputs: one warp each
+  const int nP = e.propDraws > 1 ? m.K * draws : m.K * 32, nF = e.freqDraws > 1 ? m.S * draws : m.S * 32;
   dim3 grid(((nP > nF ? nP : nF) + 127) / 128, 2);
   root_outputs_kernel<<<grid, 128, 0, e.stream>>>(e.rootGrad, e.gradLnl, e.outProps, e.outFreqs,
                                                   m.K, m.S, w, draws, e.propDraws > 1 ? draws : 1,
