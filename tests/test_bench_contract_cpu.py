@@ -48,3 +48,33 @@ def test_product_arm_refuses_to_run_without_cuda():
     r = _run(["--steps", "1", "--warmup", "0", "--taxa", "10", "--patterns", "100"])
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_traffic_model_counts_what_the_sweeps_move_and_compute():
+    """bench.traffic_model: bytes / flops per (pattern, category) from the topology alone.  A
+    cherry ((4,0,1)) under a root ((5,4,2)), 3 tips; with cherry tabulation the cherry's vector is
+    never stored; with kept u (61-state path) the pre-order sweep reads u back instead of
+    recomputing it and the post-order sweep writes it."""
+    import bench
+
+    post = [(3, 0, 1), (4, 3, 2)]
+    S = 4
+    V = S * 8
+    plain = bench.traffic_model(post, 3, S, cherries=False)
+    # post-order: node 3 writes 1 vector; node 4 writes 1 and reads its stored child (node 3)
+    assert plain["post_bytes"] * 2 == 3 * V
+    # pre-order: both read q^ (2 V); node 4 reads node 3's vector and writes q^_3 (2 V)
+    assert plain["pre_bytes"] * 2 == 4 * V
+    tab = bench.traffic_model(post, 3, S, cherries=True)
+    assert tab["cherry_nodes"] == 1
+    assert tab["post_bytes"] * 2 == 1 * V          # only the root's vector is written
+    assert tab["pre_bytes"] * 2 == 3 * V           # the tabulated cherry still receives q^
+    S = 61
+    V = S * 8
+    rec = bench.traffic_model(post, 3, S, cherries=False)
+    kept = bench.traffic_model(post, 3, S, cherries=False, kept_u=True)
+    # one internal child in the tree: u = P p~ once per sweep (recompute) or once in all (kept)
+    assert rec["flops_pre"] - kept["flops_pre"] == 2 * S * S / 2
+    assert kept["flops_post"] == rec["flops_post"]
+    assert kept["post_bytes"] - rec["post_bytes"] == V / 2
+    assert kept["pre_bytes"] - rec["pre_bytes"] == V / 2
