@@ -1467,8 +1467,7 @@ bool gmma_supported(const Engine& e) {
 
 // 61 states through gm_fwd3_kernel / gm_bwd3_kernel (TTB2_GM_NO_USTORE=1: always recompute)
 bool gmma_keeps_u(const Engine& e) {
-  const char* f = getenv("TTB2_GM61F");
-  return gmma_supported(e) && e.dm.S == 61 && !(f && atoi(f) == 2) && !getenv("TTB2_GM61") &&
+  return gmma_supported(e) && e.dm.S == 61 && gm_fwd3_smem(e.dm) <= 227 * 1024 &&
          !getenv("TTB2_GM_NO_USTORE");
 }
 
@@ -1573,11 +1572,8 @@ int gmma_forward2(Engine& e, int draws) {
   // 20 states: 8 warps x 2 pattern tiles per A fragment measured best on config 4
   // (<1,4>: 26.6 ms, <1,8>: 22.5, <2,4>: 26.8, <2,8>: 21.6 per evaluation)
   if (m.S == 20) nw = 8;
-  // 61 states: <2,8>, <4,16>, <2,16> all measured within 2 % of <4,8> on config 5
-  // 61 states: the warp-specialised kernel (8 DMMA warps + 8 epilogue warps); TTB2_GM61F=2 keeps
-  // the lock-step tile kernel for A/B runs
-  const char* v61 = getenv("TTB2_GM61F");
-  const bool spec61 = m.S == 61 && !(v61 && atoi(v61) == 2) && gm_fwd3_smem(m) <= 227 * 1024;
+  // 61 states: the warp-specialised kernel (two groups of 8 DMMA warps + 8 epilogue warps)
+  const bool spec61 = m.S == 61 && gm_fwd3_smem(m) <= 227 * 1024;
   // level 1 (tip-tip nodes) as a streaming kernel when its two code tables fit in shared memory
   const bool cherryLevel = gmma_cherry_level_supported(e);
   auto launch_cherry_level = [&]() -> int { return gmma_cherry_forward_level(e, draws); };
@@ -1610,8 +1606,7 @@ int gmma_forward2(Engine& e, int draws) {
     e.uValid = e.ustore != nullptr;
     return TTB2_OK;
   }
-  auto kern = m.S == 61 ? gm_fwd2_kernel<4, 8, 61>
-              : m.S == 20 ? gm_fwd2_kernel<2, 8, 20>
+  auto kern = m.S == 20 ? gm_fwd2_kernel<2, 8, 20>
               : ntg == 4  ? gm_fwd2_kernel<4, 8, 0>
               : nw == 8   ? gm_fwd2_kernel<2, 8, 0>
               : ntg == 2  ? gm_fwd2_kernel<2, 4, 0>
@@ -1681,17 +1676,9 @@ int gmma_backward2(Engine& e, int draws) {
   // 20 states: 8 warps x 2 pattern tiles per A fragment measured best on config 4
   // (<1,4>: 26.6 ms, <1,8>: 22.5, <2,4>: 26.8, <2,8>: 21.6 per evaluation)
   if (m.S == 20) nw = 8;
-  // 61 states: <2,8>, <4,16>, <2,16> all measured within 2 % of <4,8> on config 5
-  // TTB2_GM61=16: the 16-warp instance (one (child, row tile) combo per warp), for A/B runs
-  // 61 states: 16 warps (one (child, row tile) combo of the G product per warp) keep the fp64
-  // tensor pipe busier than 8 (DMMA pipe 66 % vs 58 %, profiles/r02_codon_ncu.md); TTB2_GM61=8
-  // selects the 8-warp instance for A/B runs
-  const char* v61 = getenv("TTB2_GM61");
-  const bool wide61 = m.S == 61 && !(v61 && atoi(v61) == 8);
-  if (wide61) nw = 16;
-  auto kern = wide61 ? gm_bwd2_kernel<2, 16, 61>
-              : m.S == 61 ? gm_bwd2_kernel<4, 8, 61>
-              : m.S == 20 ? gm_bwd2_kernel<2, 8, 20>
+  // (61 states run gm_bwd3_kernel / gm_cherry_bwd_kernel below; this instance only serves the
+  // other alphabets)
+  auto kern = m.S == 20 ? gm_bwd2_kernel<2, 8, 20>
               : ntg == 4  ? gm_bwd2_kernel<4, 8, 0>
               : nw == 8   ? gm_bwd2_kernel<2, 8, 0>
               : ntg == 2  ? gm_bwd2_kernel<2, 4, 0>
@@ -1713,7 +1700,7 @@ int gmma_backward2(Engine& e, int draws) {
       if (rc) return rc;
       continue;
     }
-    if (m.S == 61 && !v61) {   // two-group kernel (TTB2_GM61=8 / 16 select the lock-step instances)
+    if (m.S == 61) {   // two-group kernel
       const size_t sm3 = gm_bwd3_smem(m.S);
       // with the u vectors of this evaluation's post-order sweep when it kept them
       auto k3 = e.uValid ? gm_bwd3_kernel<61, true> : gm_bwd3_kernel<61, false>;

@@ -688,28 +688,16 @@ bool gwarp_supported(const Engine& e, bool backward) {
 }
 
 int gwarp_forward(Engine& e, int draws) {
-  static const int ctas = getenv("TTB2_GW_FWD_CTAS") ? atoi(getenv("TTB2_GW_FWD_CTAS")) : 16;
-  static const int variant = getenv("TTB2_GW_FWD") ? atoi(getenv("TTB2_GW_FWD")) : 83;
-  switch (variant) {
-    case 44: return gw_launch_fwd<4, 4>(e, draws, ctas);
-    case 43: return gw_launch_fwd<4, 3>(e, draws, ctas);
-    case 45: return gw_launch_fwd<4, 5>(e, draws, ctas);
-    default: return gw_launch_fwd<8, 3>(e, draws, ctas);
-  }
+  // 8 warps x 3 stages, 16 CTAs per SM aimed at per launch: measured best on config 4 against
+  // <4,3>, <4,4>, <4,5> and 8 / 32 CTAs per SM (profiles/r01_config4_gwarp_tuning.log)
+  return gw_launch_fwd<8, 3>(e, draws, 16);
 }
 
 // the pre-order level sweep (the root kernel and the gpart reduction stay with the caller)
 int gwarp_backward_levels(Engine& e, int draws) {
-  static const int variant = getenv("TTB2_GW_BWD") ? atoi(getenv("TTB2_GW_BWD")) : 42;
-  switch (variant) {
-    case 82: return gw_launch_bwd<8, 2>(e, draws);
-    // 4 warps x 2 stages: 68 KB of shared memory per CTA -> 3 CTAs (12 warps) per SM; measured on
-    // config 4: <4,2> 10.0 ms, <4,3> 12.5, <4,4> 12.6, <8,3> 13.6 (profiles/r01_config4_gwarp_tuning.log)
-    case 83: return gw_launch_bwd<8, 3>(e, draws);
-    case 43: return gw_launch_bwd<4, 3>(e, draws);
-    case 44: return gw_launch_bwd<4, 4>(e, draws);
-    default: return gw_launch_bwd<4, 2>(e, draws);
-  }
+  // 4 warps x 2 stages: 68 KB of shared memory per CTA -> 3 CTAs (12 warps) per SM; measured on
+  // config 4: <4,2> 10.0 ms, <4,3> 12.5, <4,4> 12.6, <8,3> 13.6 (profiles/r01_config4_gwarp_tuning.log)
+  return gw_launch_bwd<4, 2>(e, draws);
 }
 
 }  // namespace ttb2

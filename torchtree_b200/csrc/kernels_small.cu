@@ -627,9 +627,7 @@ int plan_chunks(Engine& e, int draws, int granule, int ctasPerSm, int residentPe
   const int nLevels = (int)e.levelOff.size() - 1;
   // never less than 2 granules per chunk
   // ctasPerSm: CTAs per SM aimed at in every launch (several waves keep the tail short)
-  static const int envPerSm = getenv("TTB2_CHUNK_TARGET") ? atoi(getenv("TTB2_CHUNK_TARGET")) : 0;
-  const int perSm = envPerSm > 0 ? envPerSm : ctasPerSm;
-  const long target = (long)e.smCount * perSm;
+  const long target = (long)e.smCount * ctasPerSm;
   // never less than 2 granules per chunk; 8 for large alphabets, whose CTAs stage two S x S
   // matrices (about the cost of one 32-pattern tile) before their first pattern
   const int maxChunks = std::max(1, m.Npad / ((m.S > 32 ? 8 : 2) * granule));
